@@ -1,0 +1,212 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/libmpm_oracle.so (the CPU restatement, mpm_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The library is built on demand with the pinned flags of oracle/Makefile (gcc is on every box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpm_oracle.so")
+REF_BIN = os.path.join(HERE, "_ref", "ref_mpm")
+
+STATE_W = 35  # mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]
+COL = dict(mass=slice(0, 1), vel=slice(1, 4), volume=slice(4, 5), pos=slice(5, 8),
+           FE=slice(8, 17), FP=slice(17, 26), B=slice(26, 35))
+
+
+class OracleParams(C.Structure):
+    _fields_ = [("h", C.c_float), ("E", C.c_float), ("nu", C.c_float), ("xi", C.c_float),
+                ("theta_c", C.c_float), ("theta_s", C.c_float), ("gravity", C.c_float * 3),
+                ("friction", C.c_float)]
+
+
+class BoxCollider(C.Structure):
+    _fields_ = [("world_to_local", C.c_float * 16), ("half_extent", C.c_float * 3), ("velocity", C.c_float * 3)]
+
+
+def build(force=False):
+    src = os.path.join(HERE, "mpm_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "libmpm_oracle.so"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        fp = C.POINTER(C.c_float)
+        L.oracle_default_params.argtypes = [C.POINTER(OracleParams)]
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.c_int] * 4 + [C.POINTER(OracleParams)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_particles.argtypes = [C.c_void_p, fp]
+        L.oracle_get_particles.argtypes = [C.c_void_p, fp]
+        L.oracle_get_grid.argtypes = [C.c_void_p, fp]
+        L.oracle_num_used_cells.argtypes = [C.c_void_p]
+        L.oracle_num_out_of_grid.argtypes = [C.c_void_p]
+        L.oracle_cell_indices.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        for name in ("oracle_rasterize_particles_to_grid", "oracle_compute_particle_volumes_and_densities",
+                     "oracle_compute_explicit_grid_forces", "oracle_update_particle_velocities"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.oracle_grid_velocities_update.argtypes = [C.c_void_p, C.c_float]
+        L.oracle_grid_based_collisions.argtypes = [C.c_void_p, C.c_float, C.POINTER(BoxCollider), C.c_int]
+        L.oracle_update_deformation_gradient.argtypes = [C.c_void_p, C.c_float]
+        L.oracle_update_deformation_gradient.restype = C.c_int
+        L.oracle_update_particle_positions.argtypes = [C.c_void_p, C.c_float]
+        L.oracle_substep.argtypes = [C.c_void_p, C.c_float, C.POINTER(BoxCollider), C.c_int, C.c_int]
+        L.oracle_weight.argtypes = [C.c_float]
+        L.oracle_weight.restype = C.c_float
+        L.oracle_svd3.argtypes = [fp, fp, fp, fp]
+        L.oracle_svd3.restype = C.c_int
+        L.oracle_polar_rotation.argtypes = [fp, fp]
+        L.oracle_box_sdf.argtypes = [C.POINTER(BoxCollider), fp]
+        L.oracle_box_sdf.restype = C.c_float
+        L.oracle_body_collision.argtypes = [fp, fp, C.POINTER(BoxCollider), C.c_int, C.c_float, fp]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_params(**kw):
+    p = OracleParams()
+    lib().oracle_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "gravity":
+            p.gravity[:] = [float(x) for x in v]
+        else:
+            setattr(p, k, float(v))
+    return p
+
+
+def make_colliders(w2l, half, vel=None):
+    """w2l: (nc,16) glm column-major inverse transforms; half: (nc,3); vel: (nc,3) or None."""
+    w2l = np.asarray(w2l, np.float32).reshape(-1, 16)
+    half = np.asarray(half, np.float32).reshape(-1, 3)
+    nc = w2l.shape[0]
+    vel = np.zeros((nc, 3), np.float32) if vel is None else np.asarray(vel, np.float32).reshape(-1, 3)
+    arr = (BoxCollider * max(nc, 1))()
+    for i in range(nc):
+        arr[i].world_to_local[:] = w2l[i].tolist()
+        arr[i].half_extent[:] = half[i].tolist()
+        arr[i].velocity[:] = vel[i].tolist()
+    return arr, nc
+
+
+def colliders_from_ref_dump(raw):
+    """oracle/ref_driver.cpp colliders.f32 rows: scale[3], quat wxyz[4], translation[3], velocity[3], inverse mat4[16]."""
+    raw = np.asarray(raw, np.float32).reshape(-1, 29)
+    return make_colliders(raw[:, 13:29], raw[:, 0:3], raw[:, 10:13])
+
+
+class Oracle:
+    def __init__(self, I, J, K, n, params=None, threads=1):
+        self.L = lib()
+        self.I, self.J, self.K, self.n = I, J, K, n
+        self.params = params if params is not None else default_params()
+        self.h = self.L.oracle_create(I, J, K, n, C.byref(self.params))
+        self.L.oracle_set_threads(self.h, threads)
+
+    def close(self):
+        if self.h:
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, s):
+        s = np.ascontiguousarray(s, np.float32).reshape(self.n, STATE_W)
+        self.L.oracle_set_particles(self.h, _fp(s))
+
+    def state(self):
+        s = np.empty((self.n, STATE_W), np.float32)
+        self.L.oracle_get_particles(self.h, _fp(s))
+        return s
+
+    def grid(self):
+        g = np.empty((self.I * self.J * self.K, 7), np.float32)
+        self.L.oracle_get_grid(self.h, _fp(g))
+        return g
+
+    def cells(self):
+        c = np.empty((self.n, 3), np.int32)
+        self.L.oracle_cell_indices(self.h, c.ctypes.data_as(C.POINTER(C.c_int)))
+        return c
+
+    def num_used(self):
+        return self.L.oracle_num_used_cells(self.h)
+
+    def num_out_of_grid(self):
+        return self.L.oracle_num_out_of_grid(self.h)
+
+    def rasterize(self):
+        self.L.oracle_rasterize_particles_to_grid(self.h)
+
+    def volumes(self):
+        self.L.oracle_compute_particle_volumes_and_densities(self.h)
+
+    def forces(self):
+        self.L.oracle_compute_explicit_grid_forces(self.h)
+
+    def grid_velocities(self, dt):
+        self.L.oracle_grid_velocities_update(self.h, dt)
+
+    def collisions(self, dt, colliders, nc):
+        self.L.oracle_grid_based_collisions(self.h, dt, colliders, nc)
+
+    def fupdate(self, dt):
+        return self.L.oracle_update_deformation_gradient(self.h, dt)
+
+    def g2p(self):
+        self.L.oracle_update_particle_velocities(self.h)
+
+    def advect(self, dt):
+        self.L.oracle_update_particle_positions(self.h, dt)
+
+    def substep(self, dt, colliders, nc, nsteps=1):
+        self.L.oracle_substep(self.h, dt, colliders, nc, nsteps)
+
+
+def initial_state(pos, vel, mass):
+    """35-float state rows with FE = FP = I, B = 0, volume = 0 (set by volumes())."""
+    n = pos.shape[0]
+    s = np.zeros((n, STATE_W), np.float32)
+    s[:, COL["mass"]] = np.asarray(mass, np.float32).reshape(-1, 1) if np.ndim(mass) else mass
+    s[:, COL["vel"]] = vel
+    s[:, COL["pos"]] = pos
+    s[:, 8] = s[:, 12] = s[:, 16] = 1.0
+    s[:, 17] = s[:, 21] = s[:, 25] = 1.0
+    return s
+
+
+def svd3(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(9)
+    U = np.empty(9, np.float32); S = np.empty(3, np.float32); V = np.empty(9, np.float32)
+    rc = lib().oracle_svd3(_fp(A), _fp(U), _fp(S), _fp(V))
+    return rc, U.reshape(3, 3), S, V.reshape(3, 3)
+
+
+def polar_rotation(F):
+    F = np.ascontiguousarray(F, np.float32).reshape(9)
+    R = np.empty(9, np.float32)
+    lib().oracle_polar_rotation(_fp(F), _fp(R))
+    return R
+
+
+def have_reference_binary():
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
