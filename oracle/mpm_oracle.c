@@ -145,6 +145,16 @@ void oracle_set_particles(Oracle* o, const float* s) { memcpy(o->p, s, (size_t)o
 void oracle_get_particles(const Oracle* o, float* s) { memcpy(s, o->p, (size_t)o->n * sizeof(OParticle)); }
 void oracle_get_grid(const Oracle* o, float* g7) { memcpy(g7, o->g, (size_t)o->I * o->J * o->K * sizeof(OCell)); }
 int oracle_num_used_cells(const Oracle* o) { return o->nused; }
+/* inject a grid (stage-isolation tests); rebuilds used_cells by the reference's rule mass != 0 (cpp:105-110)
+ * and the cached neighbourhoods from the current positions */
+static void cache_neighbourhood(Oracle* o);
+void oracle_set_grid(Oracle* o, const float* g7) {
+    const size_t ncell = (size_t)o->I * o->J * o->K;
+    memcpy(o->g, g7, ncell * sizeof(OCell));
+    o->nused = 0;
+    for (size_t c = 0; c < ncell; ++c) if (o->g[c].mass != 0.0f) o->used[o->nused++] = (int)c;
+    cache_neighbourhood(o);
+}
 void oracle_cell_indices(const Oracle* o, int* c3) {
     for (int i = 0; i < o->n; ++i)
         for (int a = 0; a < 3; ++a) c3[i * 3 + a] = (int)(o->p[i].pos[a] / o->prm.h);

@@ -39,6 +39,7 @@ void oracle_set_particles(Oracle* o, const float* state35);
 void oracle_get_particles(const Oracle* o, float* state35);
 /* grid: I*J*K x 7 floats = mass, force[3], velocity[3] at node index i*J*K + j*K + k */
 void oracle_get_grid(const Oracle* o, float* grid7);
+void oracle_set_grid(Oracle* o, const float* grid7);   /* stage-isolation tests */
 int oracle_num_used_cells(const Oracle* o);
 /* per-particle cell index int(pos/h) per axis (n x 3 int32), material_point_method.cpp:83 */
 void oracle_cell_indices(const Oracle* o, int* cells3);

@@ -51,6 +51,7 @@ def lib():
         L.oracle_set_particles.argtypes = [C.c_void_p, fp]
         L.oracle_get_particles.argtypes = [C.c_void_p, fp]
         L.oracle_get_grid.argtypes = [C.c_void_p, fp]
+        L.oracle_set_grid.argtypes = [C.c_void_p, fp]
         L.oracle_num_used_cells.argtypes = [C.c_void_p]
         L.oracle_num_out_of_grid.argtypes = [C.c_void_p]
         L.oracle_cell_indices.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
@@ -142,6 +143,10 @@ class Oracle:
         g = np.empty((self.I * self.J * self.K, 7), np.float32)
         self.L.oracle_get_grid(self.h, _fp(g))
         return g
+
+    def set_grid(self, g):
+        g = np.ascontiguousarray(g, np.float32).reshape(self.I * self.J * self.K, 7)
+        self.L.oracle_set_grid(self.h, _fp(g))
 
     def cells(self):
         c = np.empty((self.n, 3), np.int32)
