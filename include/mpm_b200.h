@@ -1,0 +1,159 @@
+/* mpm_b200.h — C ABI of libmpm_b200.so, the B200-native (sm_100a) MPM substep.
+ *
+ * Drop-in boundary for the hot path of brocbyte/realtime-deformations: every entry point below replaces one
+ * member of MaterialPointMethod::LagrangeEulerView (reference realtime-deformations/material_point_method.hpp:
+ * 174-233, definitions in material_point_method.cpp) as called by the viewer loop (main.cpp:48-54, 192-218).
+ * Plain pointers and sizes only; no C++/torch types. All functions return MPM_OK (0) or a negative MpmStatus;
+ * mpm_last_error() returns the message of the last failure on the calling thread. The reference itself has no
+ * error convention (void methods that print "cudaMalloc error", hpp:125-127) — a C++ adapter that keeps those
+ * signatures is in adapter/lagrange_euler_view_b200.cpp, the binding recipe in INTEGRATION.md.
+ *
+ * Conventions
+ *   - 3x3 matrices cross the ABI as 9 floats in glm column-major order (m[c*3+r] == glm m[c][r]), i.e. exactly
+ *     the bytes of the reference's glm::mat3 members (Particle::FElastic/FPlastic/B, hpp:101-103).
+ *   - Grid nodes are addressed as in Grid::operator() (hpp:129-131): node = i*MAX_J*MAX_K + j*MAX_K + k.
+ *   - One handle per GPU (the device current at mpm_create). Handles are not thread-safe; distinct handles are
+ *     independent. All work is issued on a library-owned non-blocking stream (or the one given to
+ *     mpm_set_stream); every download_* / get_* call synchronises that stream.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with MPM_ERR_CUDA.
+ */
+#ifndef MPM_B200_H
+#define MPM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum MpmStatus {
+    MPM_OK = 0,
+    MPM_ERR_INVALID = -1,     /* bad argument / call order */
+    MPM_ERR_CUDA = -2,        /* CUDA runtime failure (message has cudaGetErrorString) */
+    MPM_ERR_CAPACITY = -3,    /* particle capacity exceeded (slab migration) */
+    MPM_ERR_SVD = -4          /* non-finite deformation gradient met by the F-update (reference: cpp:313-316) */
+} MpmStatus;
+
+/* Material / scene constants the reference hard-codes; defaults (mpm_default_params) are its values. */
+typedef struct MpmParams {
+    float h;              /* grid spacing            material_point_method.cpp:17   (0.05)   */
+    float youngs_modulus; /* E                       material_point_method.cpp:238  (1.4e5)  */
+    float poisson_ratio;  /* nu                      material_point_method.cpp:237  (0.2)    */
+    float hardening_xi;   /* xi                      material_point_method.hpp:213  (10)     */
+    float theta_c;        /* critical compression    material_point_method.cpp:320  (2.5e-2) */
+    float theta_s;        /* critical stretch        material_point_method.cpp:320  (5.0e-3) */
+    float gravity[3];     /*                         material_point_method.cpp:260  (0,-9.8,0) */
+    float friction_mu;    /*                         material_point_method.cpp:288  (0.5)    */
+    int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline) */
+    int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline) */
+    int   reserved[6];
+} MpmParams;
+
+/* Box collider = MeshCollider (hpp:74-93) reduced to what its sdf lambda uses (hpp:80-85):
+ * world_to_local = inverse(translate(mesh.translation) * toMat4(mesh.rotation)) as a glm column-major mat4,
+ * half_extent = mesh.scale, velocity = MeshCollider::velocity. The caller computes the matrix on the host
+ * exactly as the reference does, so the device evaluates the same numbers. */
+typedef struct MpmBoxCollider {
+    float world_to_local[16];
+    float half_extent[3];
+    float velocity[3];
+} MpmBoxCollider;
+#define MPM_MAX_COLLIDERS 16
+
+typedef struct MpmStats {
+    int64_t n_particles;        /* live particles on this handle */
+    int64_t n_out_of_grid;      /* particles whose stencil leaves the grid (reference would index out of bounds) */
+    int64_t n_active_nodes;     /* nodes with mass != 0 == used_cells.size() (cpp:105-110), after the last P2G */
+    int64_t n_particle_blocks;  /* occupied 4^3-cell particle blocks after the last binning */
+    int64_t n_grid_blocks;      /* active 4^3-node grid blocks after the last binning */
+    int64_t substeps_done;
+    int64_t kernel_launches;    /* CUDA kernels launched by this handle since creation */
+    float   last_ms[8];         /* device ms of the last mpm_substep call: bin, clear, p2g, grid, g2p, other, total, - */
+    int32_t svd_failed;         /* 1 if the last F-update met a non-finite matrix */
+    int32_t reserved[7];
+} MpmStats;
+
+typedef struct mpm_sim mpm_t;
+
+void        mpm_default_params(MpmParams* p);
+const char* mpm_last_error(void);
+int         mpm_device_count(void);                 /* 0 when no CUDA device is usable */
+
+/* LagrangeEulerView::LagrangeEulerView(max_i, max_j, max_k, particlesNum)  (cpp:144-154, hpp:178) */
+int mpm_create(const MpmParams* params, int max_i, int max_j, int max_k, int64_t n_particles, mpm_t** out);
+/* Slab-decomposed variant (no reference analogue): this handle owns the particle-block layers
+ * [block_lo, block_hi) along i (a layer = 4 cells) of the global max_i x max_j x max_k grid and
+ * can hold up to `capacity` particles. mpm_create == mpm_create_slab(.., 0, all layers, n_particles). */
+int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
+                    int64_t n_particles, int64_t capacity, mpm_t** out);
+/* LagrangeEulerView::~LagrangeEulerView()  (cpp:156-158) */
+int mpm_destroy(mpm_t* s);
+int mpm_set_stream(mpm_t* s, void* cuda_stream);   /* cudaStream_t; NULL restores the library-owned stream */
+int mpm_set_params(mpm_t* s, const MpmParams* params);  /* material sweep (BASELINE config 4); h must not change */
+
+/* Particle upload. Replaces initializeParticles()'s writes into std::vector<Particle> (cpp:42-53) and any
+ * later host-side edit through getParticles() (hpp:181-183).
+ *  - AoS: `particles` points at an array of the reference's own struct Particle (hpp:96-110), `stride` =
+ *    sizeof(Particle); the off_* arguments are offsetof() of mass, velocity, volume, pos, FElastic, FPlastic, B.
+ *  - SoA: n x 3 / n x 9 row arrays; FE/FP/B/volume may be NULL (identity / zero / computed by
+ *    mpm_compute_particle_volumes_and_densities). All host pointers. */
+int mpm_upload_particles_aos(mpm_t* s, const void* particles, int64_t n, size_t stride, size_t off_mass,
+                             size_t off_velocity, size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP,
+                             size_t off_B);
+int mpm_upload_particles_soa(mpm_t* s, int64_t n, const float* pos, const float* vel, const float* mass,
+                             const float* volume, const float* FE, const float* FP, const float* B);
+int mpm_download_particles_aos(mpm_t* s, void* particles, int64_t n, size_t stride, size_t off_mass,
+                               size_t off_velocity, size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP,
+                               size_t off_B);
+int mpm_download_particles_soa(mpm_t* s, int64_t n, float* pos, float* vel, float* mass, float* volume, float* FE,
+                               float* FP, float* B);
+/* What drawParticles() copies out of getParticles() each frame (main.cpp:257-271): xyz + size, rgba. Either
+ * pointer may be NULL. Particle order = upload order. */
+int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char* rgba, float size);
+
+/* One entry per reference stage (same order and meaning as main.cpp:192-218). */
+int mpm_rasterize_particles_to_grid(mpm_t* s);                   /* rasterizeParticlesToGrid        cpp:94-129  */
+int mpm_compute_particle_volumes_and_densities(mpm_t* s);        /* computeParticleVolumesAndDensities cpp:131-142 */
+int mpm_compute_explicit_grid_forces(mpm_t* s);                  /* computeExplicitGridForces       cpp:235-254 */
+int mpm_grid_velocities_update(mpm_t* s, float dt);              /* gridVelocitiesUpdate            cpp:256-262 */
+int mpm_grid_based_collisions(mpm_t* s, float dt, const MpmBoxCollider* colliders, int n_colliders);
+                                                                 /* gridBasedCollisions + bodyCollision cpp:264-304 */
+int mpm_update_deformation_gradient(mpm_t* s, float dt);         /* updateDeformationGradient       cpp:306-330 */
+int mpm_update_particle_velocities(mpm_t* s);                    /* updateParticleVelocities        cpp:332-342 */
+int mpm_update_particle_positions(mpm_t* s, float dt);           /* updateParticlePositions         cpp:344-350 */
+
+/* The fused fast path: n_substeps repetitions of the seven stages above in main.cpp's order, as
+ * bin/sort -> clear -> P2G (mass + APIC momentum + stress) -> grid update (velocity solve, gravity, collisions)
+ * -> G2P (F-update with the previous B, plasticity, gather, advect, re-sort). */
+int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* colliders, int n_colliders, int n_substeps);
+
+/* Test / diagnostics access. grid7: max_i*max_j*max_k x 7 floats = mass, force[3], velocity[3] (struct Cell,
+ * hpp:112-117, without nParticles). cells3: n x 3 int32 = ivec3(pos / h) (cpp:83), upload order. block_key: n
+ * int32 = linear particle-block id the binning stage assigned (-1 = out of grid). */
+int mpm_download_grid(mpm_t* s, float* grid7);
+int mpm_upload_grid(mpm_t* s, const float* grid7);               /* stage-isolation tests */
+int mpm_download_binning(mpm_t* s, int64_t n, int32_t* cells3, int32_t* block_key, int32_t* sorted_ids);
+int mpm_get_stats(mpm_t* s, MpmStats* out);
+int mpm_synchronize(mpm_t* s);
+
+/* ---- slab decomposition plumbing (multi-GPU; the exchange itself is done by the caller, e.g. NCCL) ----
+ * Ghost layer: the handle's grid holds one extra block layer above block_hi. After P2G (inside
+ * mpm_substep_begin) its partial sums must be added into the upper neighbour's first layer and vice versa. All
+ * pointers here are DEVICE pointers owned by the caller; *_bytes() give the sizes. */
+size_t mpm_halo_bytes(const mpm_t* s);                           /* one block layer of float4 nodes */
+int mpm_halo_pack(mpm_t* s, int upper, void* dev_buf);           /* upper=1: ghost layer (block_hi); 0: first layer (block_lo) */
+int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf);      /* add a neighbour's partial sums into that layer */
+/* split form of mpm_substep for the exchange points: begin = bin/clear/P2G, end = grid update/G2P */
+int mpm_substep_begin(mpm_t* s, float dt);
+int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* colliders, int n_colliders);
+/* Migration: after mpm_substep_end, particles that left [block_lo, block_hi) sit packed (MPM_MIGRATE_FLOATS
+ * floats each) in two device buffers; counts are returned after a stream sync. mpm_migrate_append adds received
+ * particles. */
+#define MPM_MIGRATE_FLOATS 44
+int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up);
+int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n);
+
+/* Link-compatibility with the reference's dead CUDA side-car (cudaCalc.cuh:4-7): same symbols, no-ops. */
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPM_B200_H */

@@ -1,0 +1,268 @@
+"""ctypes binding of libmpm_b200.so (include/mpm_b200.h) — the host-side mirror of the reference's
+MaterialPointMethod::LagrangeEulerView stage interface (material_point_method.hpp:174-233).
+
+There is no CPU path: if the CUDA library is missing or no device is present, calls raise MpmError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpm_b200.so")
+MIGRATE_FLOATS = 44
+
+
+class MpmError(RuntimeError):
+    pass
+
+
+class MpmParams(C.Structure):
+    _fields_ = [("h", C.c_float), ("youngs_modulus", C.c_float), ("poisson_ratio", C.c_float),
+                ("hardening_xi", C.c_float), ("theta_c", C.c_float), ("theta_s", C.c_float),
+                ("gravity", C.c_float * 3), ("friction_mu", C.c_float), ("p2g_variant", C.c_int),
+                ("g2p_variant", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class MpmBoxCollider(C.Structure):
+    _fields_ = [("world_to_local", C.c_float * 16), ("half_extent", C.c_float * 3), ("velocity", C.c_float * 3)]
+
+
+class MpmStats(C.Structure):
+    _fields_ = [("n_particles", C.c_int64), ("n_out_of_grid", C.c_int64), ("n_active_nodes", C.c_int64),
+                ("n_particle_blocks", C.c_int64), ("n_grid_blocks", C.c_int64), ("substeps_done", C.c_int64),
+                ("kernel_launches", C.c_int64), ("last_ms", C.c_float * 8), ("svd_failed", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
+
+
+EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_create", "mpm_create_slab", "mpm_destroy",
+           "mpm_set_stream", "mpm_set_params", "mpm_upload_particles_aos", "mpm_upload_particles_soa",
+           "mpm_download_particles_aos", "mpm_download_particles_soa", "mpm_download_render_buffers",
+           "mpm_rasterize_particles_to_grid", "mpm_compute_particle_volumes_and_densities",
+           "mpm_compute_explicit_grid_forces", "mpm_grid_velocities_update", "mpm_grid_based_collisions",
+           "mpm_update_deformation_gradient", "mpm_update_particle_velocities", "mpm_update_particle_positions",
+           "mpm_substep", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
+           "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
+           "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpmError(f"{LIB_PATH} is missing: build it with `python realtime-deformations_b200/build.py` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    fp, vp, i64 = C.POINTER(C.c_float), C.c_void_p, C.c_int64
+    sz = C.c_size_t
+    L.mpm_default_params.argtypes = [C.POINTER(MpmParams)]
+    L.mpm_last_error.restype = C.c_char_p
+    L.mpm_create.argtypes = [C.POINTER(MpmParams), C.c_int, C.c_int, C.c_int, i64, C.POINTER(vp)]
+    L.mpm_create_slab.argtypes = [C.POINTER(MpmParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, C.POINTER(vp)]
+    L.mpm_destroy.argtypes = [vp]
+    L.mpm_set_stream.argtypes = [vp, vp]
+    L.mpm_set_params.argtypes = [vp, C.POINTER(MpmParams)]
+    L.mpm_upload_particles_aos.argtypes = [vp, vp, i64] + [sz] * 8
+    L.mpm_download_particles_aos.argtypes = [vp, vp, i64] + [sz] * 8
+    L.mpm_upload_particles_soa.argtypes = [vp, i64] + [fp] * 7
+    L.mpm_download_particles_soa.argtypes = [vp, i64] + [fp] * 7
+    L.mpm_download_render_buffers.argtypes = [vp, i64, vp, vp, C.c_float]
+    for n in ("mpm_rasterize_particles_to_grid", "mpm_compute_particle_volumes_and_densities",
+              "mpm_compute_explicit_grid_forces", "mpm_update_particle_velocities", "mpm_synchronize"):
+        getattr(L, n).argtypes = [vp]
+    for n in ("mpm_grid_velocities_update", "mpm_update_deformation_gradient", "mpm_update_particle_positions",
+              "mpm_substep_begin"):
+        getattr(L, n).argtypes = [vp, C.c_float]
+    L.mpm_grid_based_collisions.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int]
+    L.mpm_substep_end.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int]
+    L.mpm_substep.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int, C.c_int]
+    L.mpm_download_grid.argtypes = [vp, fp]
+    L.mpm_upload_grid.argtypes = [vp, fp]
+    L.mpm_download_binning.argtypes = [vp, i64, vp, vp, vp]
+    L.mpm_get_stats.argtypes = [vp, C.POINTER(MpmStats)]
+    L.mpm_halo_bytes.argtypes = [vp]
+    L.mpm_halo_bytes.restype = sz
+    L.mpm_halo_pack.argtypes = [vp, C.c_int, vp]
+    L.mpm_halo_add.argtypes = [vp, C.c_int, vp]
+    L.mpm_migrate_outgoing.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]
+    L.mpm_migrate_append.argtypes = [vp, vp, i64]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise MpmError(f"libmpm_b200 error {rc}: {lib().mpm_last_error().decode()}")
+
+
+def default_params(**kw):
+    p = MpmParams()
+    lib().mpm_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "gravity":
+            p.gravity[:] = [float(x) for x in v]
+        elif k in ("p2g_variant", "g2p_variant"):
+            setattr(p, k, int(v))
+        else:
+            setattr(p, k, float(v))
+    return p
+
+
+def make_colliders(w2l, half, vel=None):
+    w2l = np.asarray(w2l, np.float32).reshape(-1, 16)
+    half = np.asarray(half, np.float32).reshape(-1, 3)
+    nc = w2l.shape[0]
+    vel = np.zeros((nc, 3), np.float32) if vel is None else np.asarray(vel, np.float32).reshape(-1, 3)
+    arr = (MpmBoxCollider * max(nc, 1))()
+    for i in range(nc):
+        arr[i].world_to_local[:] = w2l[i].tolist()
+        arr[i].half_extent[:] = half[i].tolist()
+        arr[i].velocity[:] = vel[i].tolist()
+    return arr, nc
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _f32(a, shape):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, np.float32)
+    assert a.size == int(np.prod(shape)), (a.shape, shape)
+    return a
+
+
+class Sim:
+    """Mirror of LagrangeEulerView (hpp:174-233): same stage names, same call order, state resident in HBM."""
+
+    def __init__(self, max_i, max_j, max_k, n_particles, params=None, slab=None, capacity=None):
+        L = lib()
+        self.L = L
+        self.MAX_I, self.MAX_J, self.MAX_K = max_i, max_j, max_k
+        self.n = int(n_particles)
+        self.params = params if params is not None else default_params()
+        h = C.c_void_p()
+        if slab is None:
+            _ck(L.mpm_create(C.byref(self.params), max_i, max_j, max_k, self.n, C.byref(h)))
+        else:
+            cap = int(capacity if capacity is not None else n_particles)
+            _ck(L.mpm_create_slab(C.byref(self.params), max_i, max_j, max_k, slab[0], slab[1], self.n, cap, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mpm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- particles -------------------------------------------------------------------------------
+    def upload(self, pos, vel, mass, volume=None, FE=None, FP=None, B=None):
+        n = self.n
+        pos = _f32(pos, (n, 3)); vel = _f32(vel, (n, 3))
+        mass = _f32(np.broadcast_to(np.asarray(mass, np.float32), (n,)), (n,))
+        volume = _f32(volume, (n,)); FE = _f32(FE, (n, 9)); FP = _f32(FP, (n, 9)); B = _f32(B, (n, 9))
+        _ck(self.L.mpm_upload_particles_soa(self.h, n, _fp(pos), _fp(vel), _fp(mass), _fp(volume), _fp(FE), _fp(FP), _fp(B)))
+
+    def upload_state35(self, s):
+        """oracle/ref_driver layout: mass, vel[3], volume, pos[3], FE[9], FP[9], B[9] — also exercises the AoS entry
+        point with the strides/offsets a struct Particle binding would pass."""
+        s = np.ascontiguousarray(s, np.float32).reshape(self.n, 35)
+        _ck(self.L.mpm_upload_particles_aos(self.h, s.ctypes.data, self.n, 140, 0, 4, 16, 20, 32, 68, 104))
+
+    def download_state35(self):
+        s = np.zeros((self.n, 35), np.float32)
+        _ck(self.L.mpm_download_particles_aos(self.h, s.ctypes.data, self.n, 140, 0, 4, 16, 20, 32, 68, 104))
+        return s
+
+    def download(self):
+        n = self.n
+        out = dict(pos=np.empty((n, 3), np.float32), vel=np.empty((n, 3), np.float32), mass=np.empty(n, np.float32),
+                   volume=np.empty(n, np.float32), FE=np.empty((n, 9), np.float32), FP=np.empty((n, 9), np.float32),
+                   B=np.empty((n, 9), np.float32))
+        _ck(self.L.mpm_download_particles_soa(self.h, n, _fp(out["pos"]), _fp(out["vel"]), _fp(out["mass"]),
+                                              _fp(out["volume"]), _fp(out["FE"]), _fp(out["FP"]), _fp(out["B"])))
+        return out
+
+    def render_buffers(self, size=0.02, xyzs=None, rgba=None):
+        xyzs = np.empty((self.n, 4), np.float32) if xyzs is None else xyzs
+        rgba = np.empty((self.n, 4), np.uint8) if rgba is None else rgba
+        _ck(self.L.mpm_download_render_buffers(self.h, self.n, xyzs.ctypes.data, rgba.ctypes.data, size))
+        return xyzs, rgba
+
+    # ---- reference stages (main.cpp:192-218) ---------------------------------------------------------
+    def rasterizeParticlesToGrid(self):
+        _ck(self.L.mpm_rasterize_particles_to_grid(self.h))
+
+    def computeParticleVolumesAndDensities(self):
+        _ck(self.L.mpm_compute_particle_volumes_and_densities(self.h))
+
+    def computeExplicitGridForces(self):
+        _ck(self.L.mpm_compute_explicit_grid_forces(self.h))
+
+    def gridVelocitiesUpdate(self, dt):
+        _ck(self.L.mpm_grid_velocities_update(self.h, dt))
+
+    def gridBasedCollisions(self, dt, colliders, nc):
+        _ck(self.L.mpm_grid_based_collisions(self.h, dt, colliders, nc))
+
+    def updateDeformationGradient(self, dt):
+        _ck(self.L.mpm_update_deformation_gradient(self.h, dt))
+
+    def updateParticleVelocities(self):
+        _ck(self.L.mpm_update_particle_velocities(self.h))
+
+    def updateParticlePositions(self, dt):
+        _ck(self.L.mpm_update_particle_positions(self.h, dt))
+
+    def staged_substep(self, dt, colliders, nc):
+        self.rasterizeParticlesToGrid(); self.computeExplicitGridForces(); self.gridVelocitiesUpdate(dt)
+        self.gridBasedCollisions(dt, colliders, nc); self.updateDeformationGradient(dt)
+        self.updateParticleVelocities(); self.updateParticlePositions(dt)
+
+    def substep(self, dt, colliders, nc, n=1):
+        _ck(self.L.mpm_substep(self.h, dt, colliders, nc, n))
+
+    def substep_begin(self, dt):
+        _ck(self.L.mpm_substep_begin(self.h, dt))
+
+    def substep_end(self, dt, colliders, nc):
+        _ck(self.L.mpm_substep_end(self.h, dt, colliders, nc))
+
+    # ---- diagnostics --------------------------------------------------------------------------------
+    def grid(self):
+        g = np.empty((self.MAX_I * self.MAX_J * self.MAX_K, 7), np.float32)
+        _ck(self.L.mpm_download_grid(self.h, _fp(g)))
+        return g
+
+    def set_grid(self, g):
+        g = np.ascontiguousarray(g, np.float32).reshape(-1, 7)
+        _ck(self.L.mpm_upload_grid(self.h, _fp(g)))
+
+    def binning(self):
+        cells = np.empty((self.n, 3), np.int32); key = np.empty(self.n, np.int32); ids = np.empty(self.n, np.int32)
+        _ck(self.L.mpm_download_binning(self.h, self.n, cells.ctypes.data, key.ctypes.data, ids.ctypes.data))
+        return cells, key, ids
+
+    def stats(self):
+        st = MpmStats()
+        _ck(self.L.mpm_get_stats(self.h, C.byref(st)))
+        return st
+
+    def synchronize(self):
+        _ck(self.L.mpm_synchronize(self.h))
+
+    def set_params(self, params):
+        self.params = params
+        _ck(self.L.mpm_set_params(self.h, C.byref(params)))
+
+    def set_stream(self, cuda_stream):
+        _ck(self.L.mpm_set_stream(self.h, C.c_void_p(cuda_stream)))

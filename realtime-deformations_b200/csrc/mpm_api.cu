@@ -1,0 +1,633 @@
+// libmpm_b200.so — host side of the C ABI declared in include/mpm_b200.h.
+// Each entry point names the reference member it replaces (material_point_method.{hpp,cpp}); the kernels are in
+// mpm_kernels.cuh / mpm_tile_kernels.cuh. No CPU fallback: every compute call needs a CUDA device.
+#include "../../include/mpm_b200.h"
+#include "mpm_kernels.cuh"
+#include "mpm_tile_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mpm;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(MPM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKLAUNCH() CK(cudaGetLastError())
+
+struct mpm_sim {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    MpmParams prm;
+    GridDims gd;
+    SimConst sc;
+    int64_t capacity = 0;      // slots per plane
+    int64_t n_uploaded = 0;    // pid space (upload order)
+    int64_t n_bound = 0;       // host-side upper bound of occupied slots
+    float4* buf[2] = { nullptr, nullptr };   // two particle buffers, NPLANES * capacity float4 each
+    int cur = 0;
+    int *key = nullptr, *sorted_ids = nullptr;
+    int *blk_count = nullptr, *blk_start = nullptr, *blk_cursor = nullptr, *pblock_list = nullptr;
+    int *gflag = nullptr, *gblock_list = nullptr;
+    int2* partial = nullptr;
+    int n_buckets = 0, n_chunks = 0;
+    float4 *grid = nullptr, *gforce = nullptr;
+    DevCounters* dc = nullptr;
+    float4* out_buf[2] = { nullptr, nullptr };   // migration: packed outgoing particles (down, up)
+    int64_t out_cap = 0;
+    void* pinned = nullptr; size_t pinned_bytes = 0;
+    bool tau_valid = false, binned = false;
+    int num_sms = 148;
+    cudaEvent_t ev[8];
+    bool ev_ok = false;
+    MpmStats stats;
+    ColliderSet colliders; int n_colliders = 0;
+
+    Planes planes(int which) const {
+        Planes P;
+        for (int k = 0; k < NPLANES; ++k) P.p[k] = buf[which] + (size_t)k * capacity;
+        return P;
+    }
+};
+
+void mpm_default_params(MpmParams* p) {
+    memset(p, 0, sizeof *p);
+    p->h = 0.05f; p->youngs_modulus = 1.4e5f; p->poisson_ratio = 0.2f; p->hardening_xi = 10.0f;
+    p->theta_c = (float)(2.5f * 1e-2); p->theta_s = (float)(5.0f * 1e-3);
+    p->gravity[0] = 0.0f; p->gravity[1] = (float)-9.8; p->gravity[2] = 0.0f;
+    p->friction_mu = 0.5f;
+}
+const char* mpm_last_error(void) { return g_last_error.c_str(); }
+int mpm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// DpInverse exactly as the reference builds it (hpp:177): inverse(mat3(1) * (1.0f/3.0f) * h * h), glm formulas
+static float dp_inverse_scalar(float h) {
+    volatile float d = 1.0f * (1.0f / 3.0f); d = d * h; d = d * h;
+    volatile float dd = d * d;                       // m11*m22 - 0*0
+    volatile float det = d * dd;                     // + d*(dd - 0) - 0 + 0
+    volatile float ood = 1.0f / det;
+    volatile float r = dd * ood;
+    return r;
+}
+
+static void fill_consts(mpm_sim* s) {
+    const MpmParams& p = s->prm;
+    SimConst& c = s->sc;
+    c.h = p.h; c.dinv = dp_inverse_scalar(p.h); c.E = p.youngs_modulus; c.nu = p.poisson_ratio; c.xi = p.hardening_xi;
+    c.clamp_lo = (float)(1.0 - (double)p.theta_c); c.clamp_hi = (float)(1.0 + (double)p.theta_s);   // cpp:320
+    c.friction = p.friction_mu;
+    for (int a = 0; a < 3; ++a) c.g[a] = p.gravity[a];
+    c.pos_lo = (float)(3 * p.h);                                                                     // cpp:383
+    c.pos_hi[0] = (float)((s->gd.I - 3) * p.h); c.pos_hi[1] = (float)((s->gd.J - 3) * p.h); c.pos_hi[2] = (float)((s->gd.K - 3) * p.h);
+    c.inv_h3 = 1.0f / (p.h * p.h * p.h);
+}
+
+static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
+                    int64_t n_particles, int64_t capacity, mpm_t** out) {
+    if (!out) return fail(MPM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (max_i < 8 || max_j < 8 || max_k < 8) return fail(MPM_ERR_INVALID, "grid must be at least 8^3 nodes");
+    if (n_particles < 0 || capacity < n_particles) return fail(MPM_ERR_INVALID, "capacity < n_particles");
+    if (capacity >= (int64_t)1 << 31) return fail(MPM_ERR_INVALID, "capacity must be < 2^31");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(MPM_ERR_CUDA, "no CUDA device: libmpm_b200 has no CPU fallback"); }
+    mpm_sim* s = new mpm_sim();
+    CK(cudaGetDevice(&s->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    s->num_sms = prop.multiProcessorCount;
+    if (params) s->prm = *params; else mpm_default_params(&s->prm);
+    GridDims& g = s->gd;
+    g.I = max_i; g.J = max_j; g.K = max_k;
+    g.npbi_global = (max_i + 3) / 4; g.npbj = (max_j + 3) / 4; g.npbk = (max_k + 3) / 4;
+    g.nbj = g.npbj + 1; g.nbk = g.npbk + 1;
+    if (block_lo < 0 || block_hi > g.npbi_global || block_lo >= block_hi) { delete s; return fail(MPM_ERR_INVALID, "bad slab [%d,%d) of %d layers", block_lo, block_hi, g.npbi_global); }
+    g.lo = block_lo; g.hi = block_hi;
+    const int64_t npb = (int64_t)(g.hi - g.lo) * g.npbj * g.npbk, ngb = (int64_t)(g.hi - g.lo + 1) * g.nbj * g.nbk;
+    if (npb + 3 >= ((int64_t)1 << 31) / 64) { delete s; return fail(MPM_ERR_INVALID, "grid too large"); }
+    g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
+    fill_consts(s);
+    s->capacity = std::max<int64_t>(capacity, 1);
+    s->n_uploaded = n_particles; s->n_bound = n_particles;
+    s->n_buckets = g.n_pblocks + 3;
+    s->n_chunks = (s->n_buckets + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&s->buf[b], sizeof(float4) * NPLANES * (size_t)s->capacity));
+    CK(cudaMalloc(&s->key, sizeof(int) * (size_t)s->capacity));
+    CK(cudaMalloc(&s->sorted_ids, sizeof(int) * (size_t)s->capacity));
+    CK(cudaMalloc(&s->blk_count, sizeof(int) * (size_t)s->n_buckets));
+    CK(cudaMalloc(&s->blk_start, sizeof(int) * (size_t)s->n_buckets));
+    CK(cudaMalloc(&s->blk_cursor, sizeof(int) * (size_t)s->n_buckets));
+    CK(cudaMalloc(&s->pblock_list, sizeof(int) * (size_t)g.n_pblocks));
+    CK(cudaMalloc(&s->gflag, sizeof(int) * (size_t)g.n_gblocks));
+    CK(cudaMalloc(&s->gblock_list, sizeof(int) * (size_t)g.n_gblocks));
+    CK(cudaMalloc(&s->partial, sizeof(int2) * (size_t)s->n_chunks));
+    CK(cudaMalloc(&s->grid, sizeof(float4) * 64 * (size_t)g.n_gblocks));
+    CK(cudaMalloc(&s->dc, sizeof(DevCounters)));
+    CK(cudaMemsetAsync(s->gflag, 0, sizeof(int) * (size_t)g.n_gblocks, s->stream));
+    CK(cudaMemsetAsync(s->grid, 0, sizeof(float4) * 64 * (size_t)g.n_gblocks, s->stream));
+    CK(cudaMemsetAsync(s->dc, 0, sizeof(DevCounters), s->stream));
+    for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s->buf[b], 0, sizeof(float4) * NPLANES * (size_t)s->capacity, s->stream));
+    for (auto& e : s->ev) CK(cudaEventCreate(&e));
+    s->ev_ok = true;
+    memset(&s->stats, 0, sizeof s->stats);
+    memset(&s->colliders, 0, sizeof s->colliders);
+    CK(tile_kernels_init());
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return MPM_OK;
+}
+
+int mpm_create(const MpmParams* params, int max_i, int max_j, int max_k, int64_t n_particles, mpm_t** out) {
+    return mpm_create_slab(params, max_i, max_j, max_k, 0, (max_i + 3) / 4, n_particles, n_particles, out);
+}
+
+int mpm_destroy(mpm_t* s) {
+    if (!s) return MPM_OK;
+    cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < 2; ++b) { cudaFree(s->buf[b]); cudaFree(s->out_buf[b]); }
+    cudaFree(s->key); cudaFree(s->sorted_ids); cudaFree(s->blk_count); cudaFree(s->blk_start); cudaFree(s->blk_cursor);
+    cudaFree(s->pblock_list); cudaFree(s->gflag); cudaFree(s->gblock_list); cudaFree(s->partial);
+    cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc);
+    if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return MPM_OK;
+}
+
+int mpm_set_stream(mpm_t* s, void* st) {
+    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    CK(cudaStreamSynchronize(s->stream));
+    s->stream = st ? (cudaStream_t)st : s->own_stream;
+    return MPM_OK;
+}
+
+int mpm_set_params(mpm_t* s, const MpmParams* p) {
+    if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
+    if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
+    s->prm = *p;
+    fill_consts(s);
+    s->tau_valid = false;
+    return MPM_OK;
+}
+
+static int ensure_pinned(mpm_sim* s, size_t bytes) {
+    if (s->pinned_bytes >= bytes) return MPM_OK;
+    if (s->pinned) cudaFreeHost(s->pinned);
+    s->pinned = nullptr; s->pinned_bytes = 0;
+    CK(cudaMallocHost(&s->pinned, bytes));
+    s->pinned_bytes = bytes;
+    return MPM_OK;
+}
+
+// ---- upload / download -----------------------------------------------------------------------------------
+struct HostFieldPtrs {   // strided views over the caller's particle memory (AoS or SoA), NULL = default
+    const char *mass, *vel, *vol, *pos, *FE, *FP, *B;
+    size_t s_mass, s_vel, s_vol, s_pos, s_FE, s_FP, s_B;
+};
+static const float ID9[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+static const float Z9[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+
+static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
+    if (n < 0 || n > s->capacity) return fail(MPM_ERR_CAPACITY, "n = %lld exceeds capacity %lld", (long long)n, (long long)s->capacity);
+    if (!f.pos || !f.vel || !f.mass) return fail(MPM_ERR_INVALID, "pos, vel and mass are required");
+    const int64_t CH = 1 << 20;
+    int rc = ensure_pinned(s, sizeof(float4) * NPLANES * (size_t)std::min<int64_t>(CH, std::max<int64_t>(n, 1)));
+    if (rc) return rc;
+    Planes P = s->planes(s->cur);
+    for (int64_t base = 0; base < n; base += CH) {
+        const int64_t m = std::min(CH, n - base);
+        CK(cudaStreamSynchronize(s->stream));      // staging buffer reuse
+        float4* st = (float4*)s->pinned;
+        for (int64_t i = 0; i < m; ++i) {
+            const int64_t p = base + i;
+            const float* pos = (const float*)(f.pos + p * f.s_pos);
+            const float* vel = (const float*)(f.vel + p * f.s_vel);
+            const float mass = *(const float*)(f.mass + p * f.s_mass);
+            const float vol = f.vol ? *(const float*)(f.vol + p * f.s_vol) : 0.0f;
+            const float* FE = f.FE ? (const float*)(f.FE + p * f.s_FE) : ID9;
+            const float* FP = f.FP ? (const float*)(f.FP + p * f.s_FP) : ID9;
+            const float* B = f.B ? (const float*)(f.B + p * f.s_B) : Z9;
+            int pid = (int)p; float pidf; memcpy(&pidf, &pid, 4);
+            st[0 * m + i] = make_float4(pos[0], pos[1], pos[2], mass);
+            st[1 * m + i] = make_float4(B[0], B[1], B[2], B[3]);
+            st[2 * m + i] = make_float4(B[4], B[5], B[6], B[7]);
+            st[3 * m + i] = make_float4(B[8], vel[0], vel[1], vel[2]);
+            st[4 * m + i] = make_float4(0, 0, 0, 0);
+            st[5 * m + i] = make_float4(0, 0, 0, 0);
+            st[6 * m + i] = make_float4(vol, pidf, FE[0], FE[1]);
+            st[7 * m + i] = make_float4(FE[2], FE[3], FE[4], FE[5]);
+            st[8 * m + i] = make_float4(FE[6], FE[7], FE[8], FP[0]);
+            st[9 * m + i] = make_float4(FP[1], FP[2], FP[3], FP[4]);
+            st[10 * m + i] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+        }
+        for (int k = 0; k < NPLANES; ++k)
+            CK(cudaMemcpyAsync(P.p[k] + base, st + (size_t)k * m, sizeof(float4) * m, cudaMemcpyHostToDevice, s->stream));
+    }
+    const int ni = (int)n;
+    CK(cudaMemcpyAsync(&s->dc->n_slots, &ni, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->n_uploaded = n; s->n_bound = n;
+    s->tau_valid = false; s->binned = false;
+    return MPM_OK;
+}
+
+struct HostFieldPtrsW { char *mass, *vel, *vol, *pos, *FE, *FP, *B; size_t s_mass, s_vel, s_vol, s_pos, s_FE, s_FP, s_B; };
+
+static int download_common(mpm_sim* s, int64_t n, const HostFieldPtrsW& f) {
+    if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "download of %lld particles but %lld were uploaded", (long long)n, (long long)s->n_uploaded);
+    const int64_t CH = 1 << 20;
+    int rc = ensure_pinned(s, sizeof(float4) * NPLANES * (size_t)std::min<int64_t>(CH, std::max<int64_t>(n, 1)));
+    if (rc) return rc;
+    Planes C = s->planes(s->cur), O = s->planes(s->cur ^ 1);    // the idle buffer is the staging area
+    k_unsort<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(C, O, s->dc);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    for (int64_t base = 0; base < n; base += CH) {
+        const int64_t m = std::min(CH, n - base);
+        float4* st = (float4*)s->pinned;
+        for (int k = 0; k < NPLANES; ++k)
+            CK(cudaMemcpyAsync(st + (size_t)k * m, O.p[k] + base, sizeof(float4) * m, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int64_t i = 0; i < m; ++i) {
+            const int64_t p = base + i;
+            const float4 a0 = st[0 * m + i], a1 = st[1 * m + i], a2 = st[2 * m + i], a3 = st[3 * m + i], a6 = st[6 * m + i],
+                         a7 = st[7 * m + i], a8 = st[8 * m + i], a9 = st[9 * m + i], a10 = st[10 * m + i];
+            if (f.pos) { float* o = (float*)(f.pos + p * f.s_pos); o[0] = a0.x; o[1] = a0.y; o[2] = a0.z; }
+            if (f.mass) *(float*)(f.mass + p * f.s_mass) = a0.w;
+            if (f.vel) { float* o = (float*)(f.vel + p * f.s_vel); o[0] = a3.y; o[1] = a3.z; o[2] = a3.w; }
+            if (f.vol) *(float*)(f.vol + p * f.s_vol) = a6.x;
+            if (f.B) { float* o = (float*)(f.B + p * f.s_B); o[0] = a1.x; o[1] = a1.y; o[2] = a1.z; o[3] = a1.w; o[4] = a2.x; o[5] = a2.y; o[6] = a2.z; o[7] = a2.w; o[8] = a3.x; }
+            if (f.FE) { float* o = (float*)(f.FE + p * f.s_FE); o[0] = a6.z; o[1] = a6.w; o[2] = a7.x; o[3] = a7.y; o[4] = a7.z; o[5] = a7.w; o[6] = a8.x; o[7] = a8.y; o[8] = a8.z; }
+            if (f.FP) { float* o = (float*)(f.FP + p * f.s_FP); o[0] = a8.w; o[1] = a9.x; o[2] = a9.y; o[3] = a9.z; o[4] = a9.w; o[5] = a10.x; o[6] = a10.y; o[7] = a10.z; o[8] = a10.w; }
+        }
+    }
+    return MPM_OK;
+}
+
+int mpm_upload_particles_aos(mpm_t* s, const void* particles, int64_t n, size_t stride, size_t off_mass, size_t off_velocity,
+                             size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP, size_t off_B) {
+    if (!s || !particles) return fail(MPM_ERR_INVALID, "null argument");
+    const char* b = (const char*)particles;
+    HostFieldPtrs f = { b + off_mass, b + off_velocity, b + off_volume, b + off_pos, b + off_FE, b + off_FP, b + off_B,
+                        stride, stride, stride, stride, stride, stride, stride };
+    return upload_common(s, n, f);
+}
+int mpm_upload_particles_soa(mpm_t* s, int64_t n, const float* pos, const float* vel, const float* mass, const float* volume,
+                             const float* FE, const float* FP, const float* B) {
+    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    HostFieldPtrs f = { (const char*)mass, (const char*)vel, (const char*)volume, (const char*)pos, (const char*)FE, (const char*)FP, (const char*)B,
+                        4, 12, 4, 12, 36, 36, 36 };
+    return upload_common(s, n, f);
+}
+int mpm_download_particles_aos(mpm_t* s, void* particles, int64_t n, size_t stride, size_t off_mass, size_t off_velocity,
+                               size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP, size_t off_B) {
+    if (!s || !particles) return fail(MPM_ERR_INVALID, "null argument");
+    char* b = (char*)particles;
+    HostFieldPtrsW f = { b + off_mass, b + off_velocity, b + off_volume, b + off_pos, b + off_FE, b + off_FP, b + off_B,
+                         stride, stride, stride, stride, stride, stride, stride };
+    return download_common(s, n, f);
+}
+int mpm_download_particles_soa(mpm_t* s, int64_t n, float* pos, float* vel, float* mass, float* volume, float* FE, float* FP, float* B) {
+    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    HostFieldPtrsW f = { (char*)mass, (char*)vel, (char*)volume, (char*)pos, (char*)FE, (char*)FP, (char*)B, 4, 12, 4, 12, 36, 36, 36 };
+    return download_common(s, n, f);
+}
+
+int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char* rgba, float size) {
+    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    if (xyzs) {
+        float4* stage = s->buf[s->cur ^ 1];     // plane 0 of the idle buffer
+        k_render<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), stage, s->dc, size);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(xyzs, stage, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    if (rgba) memset(rgba, 255, (size_t)n * 4);     // initializeParticles sets r=g=b=a=255 (cpp:48-51)
+    return MPM_OK;
+}
+
+// ---- binning / sort -----------------------------------------------------------------------------------------
+static int do_binning(mpm_sim* s) {
+    const GridDims& g = s->gd;
+    CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
+    const int nb = grid_for(s->n_bound, 256);
+    Planes C = s->planes(s->cur);
+    k_bin_count<<<nb, 256, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.h, s->key, s->blk_count);
+    CKLAUNCH();
+    k_scan_reduce<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial);
+    CKLAUNCH();
+    k_scan_partials<<<1, 1024, 0, s->stream>>>(s->partial, s->n_chunks, s->dc);
+    CKLAUNCH();
+    k_scan_apply<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial, s->blk_start,
+                                                      s->blk_cursor, s->pblock_list, s->gflag, s->gblock_list, s->dc, g);
+    CKLAUNCH();
+    k_fix_counts<<<1, 1, 0, s->stream>>>(s->blk_count, g.n_pblocks, s->dc);
+    CKLAUNCH();
+    s->stats.kernel_launches += 5;
+    const int layer_threads = g.nbj * g.nbk;
+    if (g.lo > 0) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(0, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
+    if (g.hi < g.npbi_global) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(g.hi - g.lo, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
+    k_bin_scatter<<<nb, 256, 0, s->stream>>>((int)s->n_bound, s->dc, s->key, s->blk_cursor, s->sorted_ids);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    s->binned = true;
+    return MPM_OK;
+}
+
+static int ensure_tau(mpm_sim* s) {
+    if (s->tau_valid) return MPM_OK;
+    k_stress<<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->dc, s->sc);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    s->tau_valid = true;
+    return MPM_OK;
+}
+static int ensure_gforce(mpm_sim* s) {
+    if (s->gforce) return MPM_OK;
+    CK(cudaMalloc(&s->gforce, sizeof(float4) * 64 * (size_t)s->gd.n_gblocks));
+    CK(cudaMemsetAsync(s->gforce, 0, sizeof(float4) * 64 * (size_t)s->gd.n_gblocks, s->stream));
+    return MPM_OK;
+}
+static int persistent_grid(const mpm_sim* s, int per_sm) { return s->num_sms * per_sm; }
+
+static int launch_clear(mpm_sim* s) {
+    k_grid_clear<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->gforce);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    return MPM_OK;
+}
+template <int MODE>
+static int launch_p2g(mpm_sim* s, float4* target, float dt) {
+    if (s->prm.p2g_variant == 1) {
+        k_p2g_atomic<MODE><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, target, s->gd, s->sc, dt);
+        CKLAUNCH();
+    } else {
+        CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->blk_start, s->blk_count, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
+                                  s->num_sms, (int)s->n_bound, s->stream)));
+    }
+    s->stats.kernel_launches++;
+    return MPM_OK;
+}
+template <int FLAGS>
+static int launch_grid_update(mpm_sim* s, float dt) {
+    k_grid_update<FLAGS><<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->gforce, s->gd, s->sc, dt,
+                                                                     s->colliders, s->n_colliders);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    return MPM_OK;
+}
+template <int FLAGS>
+static int launch_g2p(mpm_sim* s, float dt) {
+    Planes C = s->planes(s->cur), N = s->planes(s->cur ^ 1);
+    if (s->prm.g2p_variant == 1 || !(FLAGS & G2P_GATHER)) {
+        k_g2p_direct<FLAGS><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->grid, s->gd, s->sc, dt);
+        CKLAUNCH();
+    } else {
+        CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->blk_start, s->blk_count, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
+                                   s->num_sms, (int)s->n_bound, s->stream)));
+    }
+    s->stats.kernel_launches++;
+    if (FLAGS & G2P_REORDER) {
+        k_after_reorder<<<1, 1, 0, s->stream>>>(s->dc);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        s->cur ^= 1;
+        s->binned = false;      // sorted_ids referred to the old buffer
+    }
+    return MPM_OK;
+}
+
+static int set_colliders(mpm_sim* s, const MpmBoxCollider* c, int n) {
+    if (n < 0 || n > MPM_MAX_COLLIDERS) return fail(MPM_ERR_INVALID, "n_colliders must be in [0, %d]", MPM_MAX_COLLIDERS);
+    if (n > 0 && !c) return fail(MPM_ERR_INVALID, "colliders is NULL");
+    static_assert(sizeof(MpmBoxCollider) == sizeof(BoxCollider), "collider POD mismatch");
+    if (n) memcpy(s->colliders.c, c, sizeof(BoxCollider) * n);
+    s->n_colliders = n;
+    return MPM_OK;
+}
+#define NEED(s) do { if (!(s)) return fail(MPM_ERR_INVALID, "null handle"); CK(cudaSetDevice((s)->device)); } while (0)
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+// ---- staged API: one entry per reference stage ----------------------------------------------------------------
+int mpm_rasterize_particles_to_grid(mpm_t* s) {               // cpp:94-129
+    NEED(s);
+    TRY(do_binning(s));
+    TRY(launch_clear(s));
+    TRY((launch_p2g<P2G_MOMENTUM>(s, s->grid, 0.0f)));
+    TRY((launch_grid_update<GU_NORMALIZE | GU_COUNT>(s, 0.0f)));
+    return MPM_OK;
+}
+int mpm_compute_particle_volumes_and_densities(mpm_t* s) {     // cpp:131-142
+    NEED(s);
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first (the reference reuses its neighbour lists)");
+    k_volumes<<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->grid, s->gd, s->sc);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    s->tau_valid = false;
+    return MPM_OK;
+}
+int mpm_compute_explicit_grid_forces(mpm_t* s) {               // cpp:235-254
+    NEED(s);
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first");
+    const bool fresh = !s->gforce;
+    TRY(ensure_gforce(s));
+    (void)fresh;
+    TRY(ensure_tau(s));
+    TRY((launch_p2g<P2G_FORCE>(s, s->gforce, 0.0f)));
+    return MPM_OK;
+}
+int mpm_grid_velocities_update(mpm_t* s, float dt) {           // cpp:256-262
+    NEED(s);
+    TRY(ensure_gforce(s));
+    TRY((launch_grid_update<GU_FORCE | GU_GRAVITY>(s, dt)));
+    return MPM_OK;
+}
+int mpm_grid_based_collisions(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {   // cpp:264-304
+    NEED(s);
+    TRY(set_colliders(s, c, n));
+    TRY((launch_grid_update<GU_COLLIDE>(s, dt)));
+    return MPM_OK;
+}
+int mpm_update_deformation_gradient(mpm_t* s, float dt) {      // cpp:306-330
+    NEED(s);
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first");
+    TRY((launch_g2p<G2P_F>(s, dt)));
+    s->tau_valid = true;
+    return MPM_OK;
+}
+int mpm_update_particle_velocities(mpm_t* s) {                 // cpp:332-342
+    NEED(s);
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first");
+    TRY((launch_g2p<G2P_GATHER>(s, 0.0f)));
+    return MPM_OK;
+}
+int mpm_update_particle_positions(mpm_t* s, float dt) {        // cpp:344-350
+    NEED(s);
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first");
+    TRY((launch_g2p<G2P_ADVECT>(s, dt)));
+    return MPM_OK;
+}
+
+// ---- fused fast path --------------------------------------------------------------------------------------------
+int mpm_substep_begin(mpm_t* s, float dt) {
+    NEED(s);
+    CK(cudaEventRecord(s->ev[0], s->stream));
+    TRY(ensure_tau(s));
+    TRY(do_binning(s));
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    TRY(launch_clear(s));
+    CK(cudaEventRecord(s->ev[2], s->stream));
+    TRY((launch_p2g<P2G_FUSED>(s, s->grid, dt)));
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    return MPM_OK;
+}
+int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
+    NEED(s);
+    TRY(set_colliders(s, c, n));
+    CK(cudaEventRecord(s->ev[4], s->stream));
+    TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
+    CK(cudaEventRecord(s->ev[5], s->stream));
+    TRY((launch_g2p<G2P_F | G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));
+    CK(cudaEventRecord(s->ev[6], s->stream));
+    s->tau_valid = true;
+    s->stats.substeps_done++;
+    return MPM_OK;
+}
+int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* c, int n, int n_substeps) {
+    NEED(s);
+    if (n_substeps < 0) return fail(MPM_ERR_INVALID, "n_substeps < 0");
+    for (int i = 0; i < n_substeps; ++i) {
+        TRY(mpm_substep_begin(s, dt));
+        TRY(mpm_substep_end(s, dt, c, n));
+    }
+    return MPM_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------------------------
+int mpm_synchronize(mpm_t* s) { NEED(s); CK(cudaStreamSynchronize(s->stream)); return MPM_OK; }
+
+int mpm_get_stats(mpm_t* s, MpmStats* out) {
+    NEED(s);
+    if (!out) return fail(MPM_ERR_INVALID, "out is NULL");
+    CK(cudaStreamSynchronize(s->stream));
+    DevCounters h;
+    CK(cudaMemcpy(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost));
+    MpmStats& st = s->stats;
+    st.n_particles = h.n_slots; st.n_out_of_grid = h.n_out_of_grid; st.n_active_nodes = h.n_active_nodes;
+    st.n_particle_blocks = h.n_active_pblocks; st.n_grid_blocks = h.n_active_gblocks; st.svd_failed = h.svd_failed;
+    if (st.substeps_done > 0) {
+        float ms;
+        const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 4, 5 }, { 5, 6 }, { 3, 4 } };
+        for (int k = 0; k < 6; ++k) st.last_ms[k] = cudaEventElapsedTime(&ms, s->ev[pairs[k][0]], s->ev[pairs[k][1]]) == cudaSuccess ? ms : -1.0f;
+        st.last_ms[6] = cudaEventElapsedTime(&ms, s->ev[0], s->ev[6]) == cudaSuccess ? ms : -1.0f;
+        cudaGetLastError();
+    }
+    *out = st;
+    return MPM_OK;
+}
+
+int mpm_download_grid(mpm_t* s, float* grid7) {
+    NEED(s);
+    if (!grid7) return fail(MPM_ERR_INVALID, "grid7 is NULL");
+    const size_t n = (size_t)s->gd.I * s->gd.J * s->gd.K;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, n * 7 * sizeof(float)));
+    k_grid_export<<<grid_for((int64_t)n, 256), 256, 0, s->stream>>>(s->grid, s->gforce, s->gd, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(grid7, d, n * 7 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "download_grid: %s", cudaGetErrorString(e));
+    return MPM_OK;
+}
+int mpm_upload_grid(mpm_t* s, const float* grid7) {
+    NEED(s);
+    if (!grid7) return fail(MPM_ERR_INVALID, "grid7 is NULL");
+    TRY(ensure_gforce(s));
+    const size_t n = (size_t)s->gd.I * s->gd.J * s->gd.K;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, n * 7 * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(d, grid7, n * 7 * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->grid, 0, sizeof(float4) * 64 * (size_t)s->gd.n_gblocks, s->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->gforce, 0, sizeof(float4) * 64 * (size_t)s->gd.n_gblocks, s->stream);
+    if (e == cudaSuccess) {
+        k_grid_import<<<grid_for((int64_t)n, 256), 256, 0, s->stream>>>(s->grid, s->gforce, s->gd, d);
+        k_activate_all<<<grid_for(s->gd.n_gblocks, 256), 256, 0, s->stream>>>(s->gd.n_gblocks, s->gflag, s->gblock_list, s->dc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    s->stats.kernel_launches += 2;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "upload_grid: %s", cudaGetErrorString(e));
+    return MPM_OK;
+}
+int mpm_download_binning(mpm_t* s, int64_t n, int32_t* cells3, int32_t* block_key, int32_t* sorted_ids) {
+    NEED(s);
+    if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    if (!s->binned) return fail(MPM_ERR_INVALID, "no binning available (call mpm_rasterize_particles_to_grid)");
+    int *dc3 = nullptr, *dk = nullptr;
+    CK(cudaMalloc(&dc3, sizeof(int) * 3 * (size_t)std::max<int64_t>(n, 1)));
+    CK(cudaMalloc(&dk, sizeof(int) * (size_t)std::max<int64_t>(n, 1)));
+    k_binning_debug<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->key, s->dc, s->sc.h, dc3, dk);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && cells3) e = cudaMemcpyAsync(cells3, dc3, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && block_key) e = cudaMemcpyAsync(block_key, dk, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && sorted_ids) e = cudaMemcpyAsync(sorted_ids, s->sorted_ids, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(dc3); cudaFree(dk);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "download_binning: %s", cudaGetErrorString(e));
+    return MPM_OK;
+}
+
+// ---- slab plumbing ---------------------------------------------------------------------------------------------------
+__global__ void k_halo_add(float4* __restrict__ layer, const float4* __restrict__ buf, size_t n) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float4 a = layer[t]; const float4 b = buf[t];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    layer[t] = a;
+}
+size_t mpm_halo_bytes(const mpm_t* s) { return s ? sizeof(float4) * 64 * (size_t)s->gd.nbj * s->gd.nbk : 0; }
+int mpm_halo_pack(mpm_t* s, int upper, void* dev_buf) {
+    NEED(s);
+    const size_t n = (size_t)64 * s->gd.nbj * s->gd.nbk;
+    const float4* src = s->grid + (upper ? (size_t)(s->gd.hi - s->gd.lo) * n : 0);
+    CK(cudaMemcpyAsync(dev_buf, src, n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+    return MPM_OK;
+}
+int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
+    NEED(s);
+    const size_t n = (size_t)64 * s->gd.nbj * s->gd.nbk;
+    float4* dst = s->grid + (upper ? (size_t)(s->gd.hi - s->gd.lo) * n : 0);
+    k_halo_add<<<grid_for((int64_t)n, 256), 256, 0, s->stream>>>(dst, (const float4*)dev_buf, n);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    return MPM_OK;
+}
+int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up) {
+    NEED(s);
+    (void)n_down; (void)n_up; (void)dev_down; (void)dev_up;
+    return fail(MPM_ERR_INVALID, "migration not built yet");
+}
+int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
+    NEED(s);
+    (void)dev_buf; (void)n;
+    return fail(MPM_ERR_INVALID, "migration not built yet");
+}

@@ -1,0 +1,351 @@
+// Device-side 3x3 / weight / SVD arithmetic of the MPM substep.
+//
+// Two families live here:
+//  * "_rn" routines reproduce the reference's CPU arithmetic operation by operation (glm 0.9.7.1 association,
+//    Eigen 3.4.90 JacobiSVD control flow) with __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn, which nvcc never
+//    contracts into FMAs. They are used where the reference result is a pure function of per-particle or
+//    per-node inputs (F-update, advection, grid update, collisions, weights), so those stages are bit-exact
+//    against the CPU path given identical inputs.
+//  * plain routines (FMA allowed) are used inside the order-nondeterministic sums (P2G scatter, G2P gather).
+//
+// 3x3 matrices are float[9] in glm column-major order: m[c*3+r] == glm m[c][r].
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+
+namespace mpm {
+
+#define MPM_DI __device__ __forceinline__
+
+MPM_DI float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+MPM_DI float add_rn(float a, float b) { return __fadd_rn(a, b); }
+MPM_DI float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+MPM_DI float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+// ---- reference weightNx, material_point_method.hpp:20-31 (fp64 polynomial, rounded to fp32) ----
+MPM_DI float weight_nx(float x) {
+    const float modx = fabsf(x);
+    const float modx2 = mul_rn(modx, modx);
+    const float modx3 = mul_rn(mul_rn(modx, modx), modx);
+    if (modx < 1.0f) return (float)__dadd_rn(__dsub_rn(__dmul_rn(0.5, (double)modx3), (double)modx2), 2.0 / 3.0);
+    if (modx < 2.0f) {
+        const double a = (double)sub_rn(2.0f, modx);
+        return (float)__dmul_rn(__dmul_rn(__dmul_rn(1.0 / 6.0, a), a), a);
+    }
+    return 0.0f;
+}
+
+// cell index and the four non-zero per-axis weights (nodes cell-1 .. cell+2).
+// material_point_method.cpp:83 (ivec3(pos / h): IEEE divide + truncation), hpp:53-58 (pos/h - idx).
+MPM_DI int cell_of(float x, float h) { return __float2int_rz(div_rn(x, h)); }
+MPM_DI void axis_weights(float x, float h, int cell, float w[4]) {
+    const float q = div_rn(x, h);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) w[d] = weight_nx(sub_rn(q, (float)(cell - 1 + d)));
+}
+
+// ---- glm value-type arithmetic, reference association (see oracle/mpm_oracle.c for the file:line map) ----
+MPM_DI float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
+}
+MPM_DI void m3_mul_rn(float* R, const float* A, const float* B) {   // R may not alias A or B
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            R[c * 3 + r] = dot3_rn(A[0 + r], B[c * 3 + 0], A[3 + r], B[c * 3 + 1], A[6 + r], B[c * 3 + 2]);
+}
+#define MG(m, c, r) ((m)[(c) * 3 + (r)])
+MPM_DI float m3_det_rn(const float* m) {
+    const float t0 = mul_rn(MG(m,0,0), sub_rn(mul_rn(MG(m,1,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,1,2))));
+    const float t1 = mul_rn(MG(m,1,0), sub_rn(mul_rn(MG(m,0,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,0,2))));
+    const float t2 = mul_rn(MG(m,2,0), sub_rn(mul_rn(MG(m,0,1), MG(m,1,2)), mul_rn(MG(m,1,1), MG(m,0,2))));
+    return add_rn(sub_rn(t0, t1), t2);
+}
+MPM_DI void m3_inverse_rn(float* R, const float* m) {               // R may not alias m
+    const float ood = div_rn(1.0f, m3_det_rn(m));
+    MG(R,0,0) =  mul_rn(sub_rn(mul_rn(MG(m,1,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,1,2))), ood);
+    MG(R,1,0) = -mul_rn(sub_rn(mul_rn(MG(m,1,0), MG(m,2,2)), mul_rn(MG(m,2,0), MG(m,1,2))), ood);
+    MG(R,2,0) =  mul_rn(sub_rn(mul_rn(MG(m,1,0), MG(m,2,1)), mul_rn(MG(m,2,0), MG(m,1,1))), ood);
+    MG(R,0,1) = -mul_rn(sub_rn(mul_rn(MG(m,0,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,0,2))), ood);
+    MG(R,1,1) =  mul_rn(sub_rn(mul_rn(MG(m,0,0), MG(m,2,2)), mul_rn(MG(m,2,0), MG(m,0,2))), ood);
+    MG(R,2,1) = -mul_rn(sub_rn(mul_rn(MG(m,0,0), MG(m,2,1)), mul_rn(MG(m,2,0), MG(m,0,1))), ood);
+    MG(R,0,2) =  mul_rn(sub_rn(mul_rn(MG(m,0,1), MG(m,1,2)), mul_rn(MG(m,1,1), MG(m,0,2))), ood);
+    MG(R,1,2) = -mul_rn(sub_rn(mul_rn(MG(m,0,0), MG(m,1,2)), mul_rn(MG(m,1,0), MG(m,0,2))), ood);
+    MG(R,2,2) =  mul_rn(sub_rn(mul_rn(MG(m,0,0), MG(m,1,1)), mul_rn(MG(m,1,0), MG(m,0,1))), ood);
+}
+MPM_DI void m3_transpose(float* R, const float* A) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) R[c * 3 + r] = A[r * 3 + c];
+}
+
+// ---- Eigen 3.4.90 JacobiSVD<MatrixXf, ComputeFullU|ComputeFullV> on a 3x3, in registers ----
+// Control flow, sweep order (1,0),(2,0),(2,1), 2x2 kernel, sign fix-up and selection sort follow
+// external/Eigen/src/SVD/JacobiSVD.h:689-817, misc/RealSvd2x2.h:21-51, Jacobi/Jacobi.h:96-126,326-337
+// (restated in oracle/mpm_oracle.c: oracle_svd3). Arrays are ROW-major here (a[r*3+c] == Eigen m(r,c)).
+template <int P, int Q>
+MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxDiag, bool& finished) {
+    const float pm = mul_rn(2.0f * FLT_EPSILON, maxDiag);
+    const float threshold = (FLT_MIN < pm) ? pm : FLT_MIN;
+    if (!(fabsf(W[P * 3 + Q]) > threshold || fabsf(W[Q * 3 + P]) > threshold)) return;
+    finished = false;
+    float m00 = W[P * 3 + P], m01 = W[P * 3 + Q], m10 = W[Q * 3 + P], m11 = W[Q * 3 + Q];
+    float c1, s1;
+    const float t = add_rn(m00, m11), d = sub_rn(m10, m01);
+    if (fabsf(d) < FLT_MIN) { s1 = 0.0f; c1 = 1.0f; }
+    else {
+        const float u = div_rn(t, d);
+        const float tmp = __fsqrt_rn(add_rn(1.0f, mul_rn(u, u)));
+        s1 = div_rn(1.0f, tmp); c1 = div_rn(u, tmp);
+    }
+    if (!(c1 == 1.0f && s1 == 0.0f)) {
+        const float a0 = add_rn(mul_rn(c1, m00), mul_rn(s1, m10)), b0 = add_rn(mul_rn(-s1, m00), mul_rn(c1, m10));
+        const float a1 = add_rn(mul_rn(c1, m01), mul_rn(s1, m11)), b1 = add_rn(mul_rn(-s1, m01), mul_rn(c1, m11));
+        m00 = a0; m10 = b0; m01 = a1; m11 = b1;
+    }
+    float cr, sr;
+    const float deno = mul_rn(2.0f, fabsf(m01));
+    if (deno < FLT_MIN) { cr = 1.0f; sr = 0.0f; }
+    else {
+        const float tau = div_rn(sub_rn(m00, m11), deno);
+        const float w = __fsqrt_rn(add_rn(mul_rn(tau, tau), 1.0f));
+        const float tt = tau > 0.0f ? div_rn(1.0f, add_rn(tau, w)) : div_rn(1.0f, sub_rn(tau, w));
+        const float sign_t = tt > 0.0f ? 1.0f : -1.0f;
+        const float nn = div_rn(1.0f, __fsqrt_rn(add_rn(mul_rn(tt, tt), 1.0f)));
+        sr = mul_rn(mul_rn(mul_rn(-sign_t, div_rn(m01, fabsf(m01))), fabsf(tt)), nn);
+        cr = nn;
+    }
+    const float cl = sub_rn(mul_rn(c1, cr), mul_rn(s1, -sr));
+    const float sl = add_rn(mul_rn(c1, -sr), mul_rn(s1, cr));
+    if (!(cl == 1.0f && sl == 0.0f)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {       // W.applyOnTheLeft(p,q,j_left)
+            const float x = W[P * 3 + c], y = W[Q * 3 + c];
+            W[P * 3 + c] = add_rn(mul_rn(cl, x), mul_rn(sl, y));
+            W[Q * 3 + c] = add_rn(mul_rn(-sl, x), mul_rn(cl, y));
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {       // U.applyOnTheRight(p,q,j_left.transpose())
+            const float x = U[r * 3 + P], y = U[r * 3 + Q];
+            U[r * 3 + P] = add_rn(mul_rn(cl, x), mul_rn(sl, y));
+            U[r * 3 + Q] = add_rn(mul_rn(-sl, x), mul_rn(cl, y));
+        }
+    }
+    const float s = -sr;
+    if (!(cr == 1.0f && s == 0.0f)) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {       // W.applyOnTheRight(p,q,j_right); V.applyOnTheRight(p,q,j_right)
+            const float x = W[r * 3 + P], y = W[r * 3 + Q];
+            W[r * 3 + P] = add_rn(mul_rn(cr, x), mul_rn(s, y));
+            W[r * 3 + Q] = add_rn(mul_rn(-s, x), mul_rn(cr, y));
+            const float vx = V[r * 3 + P], vy = V[r * 3 + Q];
+            V[r * 3 + P] = add_rn(mul_rn(cr, vx), mul_rn(s, vy));
+            V[r * 3 + Q] = add_rn(mul_rn(-s, vx), mul_rn(cr, vy));
+        }
+    }
+    const float dm = fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q]));
+    if (maxDiag < dm) maxDiag = dm;
+}
+
+// returns false on non-finite input (Eigen: InvalidInput). MAX_SWEEPS only guards the GPU against a hang;
+// Eigen itself has no cap and converges in 3-5 sweeps on finite input.
+MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
+    float W[9];
+    float scale = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const float a = fabsf(A[i]); if (!(a <= scale)) scale = a; }
+    if (!isfinite(scale)) return false;
+    if (scale == 0.0f) scale = 1.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { W[i] = div_rn(A[i], scale); U[i] = (i % 4 == 0) ? 1.0f : 0.0f; V[i] = U[i]; }
+    float maxDiag = fmaxf(fmaxf(fabsf(W[0]), fabsf(W[4])), fabsf(W[8]));
+    bool finished = false;
+    constexpr int MAX_SWEEPS = 64;
+    for (int sweep = 0; sweep < MAX_SWEEPS && !finished; ++sweep) {
+        finished = true;
+        jacobi_pair<1, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 1>(W, U, V, maxDiag, finished);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = W[i * 3 + i];
+        S[i] = mul_rn(fabsf(a), scale);
+        if (a < 0.0f) { U[0 + i] = -U[0 + i]; U[3 + i] = -U[3 + i]; U[6 + i] = -U[6 + i]; }
+    }
+    // selection sort, descending, first maximum wins (JacobiSVD.h:795-814)
+#define MPM_SWAPCOL(i, j)                                                          \
+    do {                                                                           \
+        float t_ = S[i]; S[i] = S[j]; S[j] = t_;                                   \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r) {                            \
+            t_ = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + j]; U[r * 3 + j] = t_;     \
+            t_ = V[r * 3 + i]; V[r * 3 + i] = V[r * 3 + j]; V[r * 3 + j] = t_;     \
+        }                                                                          \
+    } while (0)
+    {
+        int pos = 0;
+        if (S[1] > S[pos]) pos = 1;
+        if (S[2] > S[pos]) pos = 2;
+        if (S[pos] == 0.0f) return true;
+        if (pos == 1) MPM_SWAPCOL(0, 1); else if (pos == 2) MPM_SWAPCOL(0, 2);
+        if (S[2] > S[1]) { MPM_SWAPCOL(1, 2); }
+    }
+#undef MPM_SWAPCOL
+    return true;
+}
+
+// ---- F-update of one particle, material_point_method.cpp:306-330 (bit-faithful) ----
+// in: B (previous substep's APIC matrix), FE, FP; out: FE, FP overwritten, factors of the new FE for the stress.
+// Ug/Sg: FE_new = Ug * diag(Sg) * Vg^T as glm matrices (Ug is the glm view of Eigen's U, see utils.h:25-33).
+MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], float dinv, float dt, float clamp_lo,
+                        float clamp_hi, float (&Ug)[9], float (&Sg)[3]) {
+    float T0[9], T1[9], T[9], FPinv[9], Fh[9], Vg[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {           // m3t(1.0) + B * DpInverse * dt
+        const float v = mul_rn(mul_rn(B[i], dinv), dt);
+        T0[i] = add_rn((i % 4 == 0) ? 1.0f : 0.0f, v);
+    }
+    m3_mul_rn(T1, T0, FE);
+    m3_mul_rn(T, T1, FP);                   // FPn1
+    m3_inverse_rn(FPinv, FP);
+    m3_mul_rn(Fh, T, FPinv);                // FEpKryshka
+    if (!svd3_eigen(Fh, Ug, Sg, Vg)) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { float s = Sg[k]; if (s < clamp_lo) s = clamp_lo; if (clamp_hi < s) s = clamp_hi; Sg[k] = s; }
+    float US[9], Vt[9], FEinv[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) US[c * 3 + r] = mul_rn(Ug[c * 3 + r], Sg[c]);   // U * S (S diagonal)
+    m3_transpose(Vt, Vg);
+    m3_mul_rn(FE, US, Vt);                  // U * S * transpose(V)
+    m3_inverse_rn(FEinv, FE);
+    m3_mul_rn(FP, FEinv, T);
+    return true;
+}
+
+// ---- stress term of computeExplicitGridForces (cpp:235-252) as one symmetric matrix ----
+// M = V0 * Dinv * dPsi * FE^T = A diag(d_k) A^T with FE = A diag(sig) B^T,
+// d_k = V0*dinv*(2 mu sig_k (sig_k - 1) + lambda (J - 1) J);  tau = (xx, yy, zz, xy, xz, yz)
+MPM_DI void lame(float detFP, float E, float nu, float xi, float& mu, float& lambda) {
+    const float e = expf(xi * (1.0f - detFP));
+    mu = E / (2.0f * (1.0f + nu)) * e;
+    lambda = (E * nu) / ((1.0f + nu) * (1.0f - 2.0f * nu)) * e;
+}
+MPM_DI void tau_from_factors(const float (&Ug)[9], const float (&Sg)[3], float J, float detFP, float V0, float dinv,
+                             float E, float nu, float xi, float (&tau)[6]) {
+    float mu, lambda;
+    lame(detFP, E, nu, xi, mu, lambda);
+    const float vol = V0 * dinv;
+    const float iso = lambda * (J - 1.0f) * J;
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = vol * (2.0f * mu * Sg[k] * (Sg[k] - 1.0f) + iso);
+    // A(r,k) = Ug[k*3+r]
+#define MPM_SYM(r, s) (Ug[0 + r] * d[0] * Ug[0 + s] + Ug[3 + r] * d[1] * Ug[3 + s] + Ug[6 + r] * d[2] * Ug[6 + s])
+    tau[0] = MPM_SYM(0, 0); tau[1] = MPM_SYM(1, 1); tau[2] = MPM_SYM(2, 2);
+    tau[3] = MPM_SYM(0, 1); tau[4] = MPM_SYM(0, 2); tau[5] = MPM_SYM(1, 2);
+#undef MPM_SYM
+}
+// general FE (after an upload): rotation by Newton iteration R <- (R + R^-T)/2, quadratically convergent
+MPM_DI void tau_general(const float (&FE)[9], float detFP, float V0, float dinv, float E, float nu, float xi,
+                        float (&tau)[6]) {
+    float R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = FE[i];
+    for (int it = 0; it < 40; ++it) {
+        const float c00 = MG(R,1,1) * MG(R,2,2) - MG(R,2,1) * MG(R,1,2);
+        const float c10 = MG(R,2,0) * MG(R,1,2) - MG(R,1,0) * MG(R,2,2);
+        const float c20 = MG(R,1,0) * MG(R,2,1) - MG(R,2,0) * MG(R,1,1);
+        const float det = MG(R,0,0) * c00 + MG(R,0,1) * c10 + MG(R,0,2) * c20;
+        if (det == 0.0f || !isfinite(det)) break;
+        const float id = 1.0f / det;
+        // cofactor matrix C(c,r) (glm indexing) so that R^-T = C / det
+        float C[9];
+        MG(C,0,0) = c00; MG(C,0,1) = c10; MG(C,0,2) = c20;
+        MG(C,1,0) = MG(R,2,1) * MG(R,0,2) - MG(R,0,1) * MG(R,2,2);
+        MG(C,1,1) = MG(R,0,0) * MG(R,2,2) - MG(R,2,0) * MG(R,0,2);
+        MG(C,1,2) = MG(R,2,0) * MG(R,0,1) - MG(R,0,0) * MG(R,2,1);
+        MG(C,2,0) = MG(R,0,1) * MG(R,1,2) - MG(R,1,1) * MG(R,0,2);
+        MG(C,2,1) = MG(R,1,0) * MG(R,0,2) - MG(R,0,0) * MG(R,1,2);
+        MG(C,2,2) = MG(R,0,0) * MG(R,1,1) - MG(R,1,0) * MG(R,0,1);
+        float diff = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float v = 0.5f * (R[i] + C[i] * id);
+            diff = fmaxf(diff, fabsf(v - R[i]));
+            R[i] = v;
+        }
+        if (diff < 2e-7f) break;
+    }
+    float mu, lambda;
+    lame(detFP, E, nu, xi, mu, lambda);
+    const float J = MG(FE,0,0) * (MG(FE,1,1) * MG(FE,2,2) - MG(FE,2,1) * MG(FE,1,2))
+                  - MG(FE,1,0) * (MG(FE,0,1) * MG(FE,2,2) - MG(FE,2,1) * MG(FE,0,2))
+                  + MG(FE,2,0) * (MG(FE,0,1) * MG(FE,1,2) - MG(FE,1,1) * MG(FE,0,2));
+    const float vol = V0 * dinv, iso = lambda * (J - 1.0f) * J;
+    // M(r,s) = vol * (2 mu * sum_c (FE - R)(r,c) FE(s,c) + iso * delta_rs), symmetrised
+    float M[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += (MG(FE,c,r) - MG(R,c,r)) * MG(FE,c,s);
+            M[r * 3 + s] = vol * (2.0f * mu * acc + (r == s ? iso : 0.0f));
+        }
+    tau[0] = M[0]; tau[1] = M[4]; tau[2] = M[8];
+    tau[3] = 0.5f * (M[1] + M[3]); tau[4] = 0.5f * (M[2] + M[6]); tau[5] = 0.5f * (M[5] + M[7]);
+}
+
+// ---- box collider, hpp:79-86 + mathy.hpp:40-56 + cpp:264-296 (bit-faithful) ----
+struct BoxCollider { float w2l[16]; float half[3]; float vel[3]; };
+
+MPM_DI float box_sdf_rn(const BoxCollider& c, float px, float py, float pz) {
+    float p[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        p[r] = add_rn(add_rn(mul_rn(c.w2l[0 + r], px), mul_rn(c.w2l[4 + r], py)),
+                      add_rn(mul_rn(c.w2l[8 + r], pz), mul_rn(c.w2l[12 + r], 1.0f)));
+    const float qx = sub_rn(fabsf(p[0]), c.half[0]), qy = sub_rn(fabsf(p[1]), c.half[1]), qz = sub_rn(fabsf(p[2]), c.half[2]);
+    float mx = qx; if (mx < qy) mx = qy; if (mx < qz) mx = qz; if (mx < 0.0f) mx = 0.0f;
+    float in = qy < qz ? qz : qy; in = qx < in ? in : qx; in = 0.0f < in ? 0.0f : in;
+    return add_rn(fabsf(mx), in);
+}
+
+MPM_DI void body_collision_rn(const BoxCollider* cs, int nc, float friction, float px, float py, float pz, float (&v)[3]) {
+    bool all_out = true;
+    for (int k = 0; k < nc; ++k) if (!(box_sdf_rn(cs[k], px, py, pz) > 0.0f)) { all_out = false; break; }
+    if (all_out) return;
+    const float delta = 0.001f;
+    const float two_delta = mul_rn(2.0f, delta);
+    for (int k = 0; k < nc; ++k) {
+        if (box_sdf_rn(cs[k], px, py, pz) > 0.0f) continue;
+        float n[3];
+        n[0] = div_rn(sub_rn(box_sdf_rn(cs[k], add_rn(px, delta), py, pz), box_sdf_rn(cs[k], sub_rn(px, delta), py, pz)), two_delta);
+        n[1] = div_rn(sub_rn(box_sdf_rn(cs[k], px, add_rn(py, delta), pz), box_sdf_rn(cs[k], px, sub_rn(py, delta), pz)), two_delta);
+        n[2] = div_rn(sub_rn(box_sdf_rn(cs[k], px, py, add_rn(pz, delta)), box_sdf_rn(cs[k], px, py, sub_rn(pz, delta))), two_delta);
+        float rel[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) rel[a] = sub_rn(v[a], cs[k].vel[a]);
+        const float vn = dot3_rn(rel[0], n[0], rel[1], n[1], rel[2], n[2]);
+        if (vn >= 0.0f) continue;
+        float vrel[3] = { 0.0f, 0.0f, 0.0f };
+        // cpp:290-291: vt.length() is glm's component count (3), not the norm
+        if (3.0f > mul_rn(-friction, vn)) {
+            const float s = div_rn(mul_rn(friction, vn), 3.0f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float vt = sub_rn(rel[a], mul_rn(n[a], vn));
+                vrel[a] = add_rn(vt, mul_rn(vt, s));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) v[a] = add_rn(vrel[a], cs[k].vel[a]);
+    }
+}
+
+}  // namespace mpm

@@ -1,0 +1,68 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and exports every symbol that
+include/mpm_b200.h declares; without a GPU the product fails loudly instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mpm_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    mpm_b200.build.build()
+    return mpm_b200.capi.lib()
+
+
+def test_header_symbols_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "mpm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mpm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/mpm_b200.h but not exported"
+    assert declared == set(mpm_b200.capi.EXPORTS)
+
+
+def test_default_params_are_the_reference_constants(L):
+    p = mpm_b200.capi.default_params()
+    assert p.h == np.float32(0.05) and p.youngs_modulus == np.float32(1.4e5) and p.poisson_ratio == np.float32(0.2)
+    assert p.hardening_xi == 10.0 and p.theta_c == np.float32(2.5e-2) and p.theta_s == np.float32(5e-3)
+    assert list(p.gravity) == [0.0, float(np.float32(-9.8)), 0.0] and p.friction_mu == 0.5
+
+
+def test_struct_layouts_match_header(L):
+    assert C.sizeof(mpm_b200.capi.MpmBoxCollider) == 88
+    assert C.sizeof(mpm_b200.capi.MpmParams) == 4 * 10 + 4 * 8
+    assert C.sizeof(mpm_b200.capi.MpmStats) == 8 * 7 + 4 * 8 + 4 * 8
+
+
+def test_no_cpu_fallback(L):
+    if L.mpm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(mpm_b200.MpmError, match="no CUDA device"):
+        mpm_b200.Sim(20, 20, 20, 16)
+
+
+def test_bad_arguments_are_rejected(L):
+    h = C.c_void_p()
+    p = mpm_b200.capi.default_params()
+    assert L.mpm_create(C.byref(p), 4, 20, 20, 10, C.byref(h)) != 0      # grid too small
+    assert b"grid" in L.mpm_last_error()
+    assert L.mpm_create(C.byref(p), 20, 20, 20, -1, C.byref(h)) != 0
+    assert L.mpm_substep(None, 1e-5, None, 0, 1) != 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "realtime-deformations_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/", "ORACLE_DOC_PATH/").lower() or f == "scenes.py" or \
+                    all("import" not in line and "#include" not in line and "dlopen" not in line and "CDLL" not in line
+                        for line in src.splitlines() if "oracle" in line.lower()), f"{f} references the oracle"

@@ -1,0 +1,219 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against (a) golden vectors produced by the
+unmodified reference and (b) the CPU oracle on the same seeded inputs. Tolerances are stated where used:
+bit-exact for index work and for stages that are pure per-particle / per-node functions, fp32-sum tolerances for
+the scatter / gather sums (atomic order is nondeterministic), and the reference's own noise floor x4 for
+trajectories."""
+import numpy as np
+import pytest
+
+import mpm_b200
+import oracle_py as op
+from helpers import assert_bit_exact, assert_traj_close, full_grid, traj_errors
+from scene_util import VARIANTS, gpu_colliders_from_ref_dump, oracle_from_scene, sim_from_scene, sim_from_state35
+
+pytestmark = pytest.mark.gpu
+SUM_RTOL = 2e-5      # fp32 sums of <= ~100 terms in a different order / with FMA contraction
+
+
+def close_sum(a, b, what, rtol=SUM_RTOL):
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(np.asarray(a, np.float64) - b).max())
+    assert err <= rtol * scale, f"{what}: max |d| = {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+
+
+@pytest.mark.parametrize("variants", VARIANTS)
+def test_binning_is_bit_exact_indexing(golden_c1, variants):
+    g = golden_c1
+    st = g["st120_pre"]
+    sim = sim_from_state35(st, (20, 20, 20), variants)
+    sim.rasterizeParticlesToGrid()
+    cells, key, ids = sim.binning()
+    o = op.Oracle(20, 20, 20, st.shape[0]); o.set_state(st)
+    ref_cells = o.cells()
+    assert (cells == ref_cells).all(), "cell index must equal int(pos / h) of the reference bit for bit"
+    pb = (ref_cells - 1) >> 2
+    ref_key = (pb[:, 0] * 5 + pb[:, 1]) * 5 + pb[:, 2]
+    assert (key == ref_key).all()
+    assert sorted(ids.tolist()) == list(range(st.shape[0])), "sorted_ids must be a permutation"
+    assert (np.diff(key[ids]) >= 0).all(), "particles must be ordered by grid block"
+    stt = sim.stats()
+    assert stt.n_particle_blocks == len(np.unique(ref_key)) and stt.n_out_of_grid == 0
+
+
+@pytest.mark.parametrize("variants", VARIANTS)
+@pytest.mark.parametrize("step", [1, 120])
+def test_stage_level_parity_with_reference(golden_c1, step, variants):
+    g = golden_c1
+    I = J = K = 20
+    dt = float(g["dt"])
+    used = g[f"st{step}_used"]
+    pre = g[f"st{step}_pre"]
+    cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
+    sim = sim_from_state35(pre, (I, J, K), variants)
+    # --- rasterizeParticlesToGrid
+    sim.rasterizeParticlesToGrid()
+    gr = sim.grid()
+    p2g = g[f"st{step}_p2g"]
+    assert (np.flatnonzero(gr[:, 0] != 0) == used).all(), "used_cells differ"
+    assert sim.stats().n_active_nodes == len(used)
+    close_sum(gr[used, 0], p2g[:, 0], "grid mass")
+    close_sum(gr[used][:, 4:7], p2g[:, 1:4], "grid velocity")
+    # --- computeExplicitGridForces (own polar factor; reference: Higham-Noferini in fp32)
+    sim.computeExplicitGridForces()
+    f = sim.grid()[used][:, 1:4]
+    close_sum(f, g[f"st{step}_forces"], "grid forces", rtol=2e-4 if step > 1 else 1.0)
+    if step == 1:
+        assert np.abs(f).max() == 0.0            # FE = I: R = I exactly, no stress
+    # --- grid stages from the reference's own intermediate grid: bit-exact
+    sim.set_grid(full_grid(I, J, K, used, mass=p2g[:, 0], vel=p2g[:, 1:4], force=g[f"st{step}_forces"]))
+    sim.gridVelocitiesUpdate(dt)
+    assert_bit_exact(sim.grid()[used][:, 4:7], g[f"st{step}_gridvel"], "gridVelocitiesUpdate")
+    sim.gridBasedCollisions(dt, cols, nc)
+    assert_bit_exact(sim.grid()[used][:, 4:7], g[f"st{step}_collide"], "gridBasedCollisions")
+    # --- updateDeformationGradient: bit-exact (Eigen-convention Jacobi SVD in registers)
+    sim.updateDeformationGradient(dt)
+    s = sim.download_state35()
+    assert_bit_exact(s[:, 8:26], g[f"st{step}_fupdate"], "updateDeformationGradient")
+    assert sim.stats().svd_failed == 0
+    # --- updateParticleVelocities from the reference's post-collision grid
+    sim.updateParticleVelocities()
+    s = sim.download_state35()
+    ref = g[f"st{step}_g2p"]
+    close_sum(s[:, 1:4], ref[:, 0:3], "particle velocity")
+    close_sum(s[:, 26:35], ref[:, 3:12], "APIC B")
+    # --- updateParticlePositions: bit-exact given the reference's velocities
+    st2 = pre.copy()
+    st2[:, 1:4] = ref[:, 0:3]
+    sim2 = sim_from_state35(st2, (I, J, K), variants)
+    sim2.rasterizeParticlesToGrid()
+    sim2.updateParticlePositions(dt)
+    assert_bit_exact(sim2.download_state35()[:, 5:8], g[f"st{step}_advect"], "updateParticlePositions")
+
+
+@pytest.mark.parametrize("variants", VARIANTS)
+def test_fupdate_kat_bit_exact_on_gpu(golden_kat, variants):
+    fin, fout = golden_kat["fupdate_in"], golden_kat["fupdate_out"]
+    n = fin.shape[0]
+    st = np.zeros((n, 35), np.float32)
+    st[:, 0] = 6e-5; st[:, 4] = 3e-5; st[:, 5:8] = 0.5
+    st[:, 8:35] = fin
+    sim = sim_from_state35(st, (20, 20, 20), variants)
+    sim.rasterizeParticlesToGrid()
+    sim.updateDeformationGradient(1e-5)
+    s = sim.download_state35()
+    assert_bit_exact(s[:, 8:17], fout[:, 0:9], "FElastic (degenerate / large-deformation inputs)")
+    assert_bit_exact(s[:, 17:26], fout[:, 9:18], "FPlastic")
+
+
+def test_volumes_match_reference(golden_c1):
+    s0 = golden_c1["state0"].copy()
+    ref = s0[:, 4].copy()
+    s0[:, 4] = 0
+    sim = sim_from_state35(s0, (20, 20, 20))
+    sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
+    close_sum(sim.download_state35()[:, 4], ref, "particle volumes")
+
+
+@pytest.mark.parametrize("variants", VARIANTS)
+def test_default_scene_trajectory_vs_reference(golden_c1, variants):
+    g = golden_c1
+    cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
+    sim = sim_from_state35(g["state0"], (20, 20, 20), variants)
+    done = 0
+    for n in (1, 20, 100, 200):
+        sim.substep(float(g["dt"]), cols, nc, n - done)
+        done = n
+        assert_traj_close(sim.download_state35(), g[f"state{n}"], max(n, 20), f"fused CUDA path {variants} vs reference")
+    st = sim.stats()
+    assert st.svd_failed == 0 and st.substeps_done == 200 and st.n_particles == g["state0"].shape[0]
+
+
+def test_staged_and_fused_paths_agree(golden_c1):
+    g = golden_c1
+    cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
+    a = sim_from_state35(g["state0"], (20, 20, 20))
+    b = sim_from_state35(g["state0"], (20, 20, 20))
+    for _ in range(20):
+        a.staged_substep(float(g["dt"]), cols, nc)
+    b.substep(float(g["dt"]), cols, nc, 20)
+    assert_traj_close(a.download_state35(), b.download_state35(), 20, "staged vs fused")
+    assert_traj_close(a.download_state35(), g["state20"], 20, "staged CUDA path vs reference")
+
+
+def test_fine_scene_vs_reference(golden_c1b):
+    g = golden_c1b
+    n = g["pos0"].shape[0]
+    s0 = op.initial_state(g["pos0"], g["vel0"], float(g["mass0"]))
+    s0[:, 4] = g["volume0"]
+    p = mpm_b200.capi.default_params(h=float(g["h"]))
+    sim = mpm_b200.Sim(40, 40, 40, n, p)
+    sim.upload_state35(s0)
+    cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
+    sim.substep(float(g["dt"]), cols, nc, int(g["steps"]))
+    ref = np.zeros((n, 35), np.float32)
+    ref[:, 5:8], ref[:, 1:4], ref[:, 8:17], ref[:, 17:26] = g["pos"], g["vel"], g["FE"], g["FP"]
+    assert_traj_close(sim.download_state35(), ref, int(g["steps"]), "CUDA vs reference, h=0.025, 17 100 particles")
+
+
+@pytest.mark.parametrize("variants", VARIANTS)
+def test_synthetic_ball_vs_oracle(variants):
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=5.0)
+    o, ocols, onc = oracle_from_scene(sc)
+    sim, cols, nc = sim_from_scene(sc, variants)
+    close_sum(sim.download_state35()[:, 4], o.state()[:, 4], "initial volumes")
+    for n in (20, 80):       # free fall, then first contact with the ground box
+        o.substep(float(sc["dt"]), ocols, onc, n if n == 20 else 60)
+        sim.substep(float(sc["dt"]), cols, nc, n if n == 20 else 60)
+        assert_traj_close(sim.download_state35(), o.state(), 20 if n == 20 else 100, f"CUDA {variants} vs oracle, synthetic ball")
+
+
+def test_material_sweep_vs_oracle():
+    # BASELINE config 4 in miniature: stiffer hardening, other clamp thresholds, smaller dt
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0, dt=2.5e-6)
+    for xi, tc, ts in ((5.0, 1.5e-2, 2.5e-3), (20.0, 5e-2, 7.5e-3)):
+        o, ocols, onc = oracle_from_scene(sc, xi=xi, theta_c=tc, theta_s=ts)
+        sim, cols, nc = sim_from_scene(sc, hardening_xi=xi, theta_c=tc, theta_s=ts)
+        o.substep(float(sc["dt"]), ocols, onc, 40)
+        sim.substep(float(sc["dt"]), cols, nc, 40)
+        assert_traj_close(sim.download_state35(), o.state(), 100, f"xi={xi} theta_c={tc} theta_s={ts}")
+
+
+def test_out_of_grid_particles_are_parked_not_lost():
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0, with_ground=False)
+    pos = sc["pos"].copy()
+    pos[:5] = [[0.0, 0.0, 0.0], [0.01, 0.5, 0.5], [1.59, 0.5, 0.5], [0.5, 1.58, 0.5], [0.5, 0.5, 0.06]]
+    sc["pos"] = pos
+    sim, cols, nc = sim_from_scene(sc)
+    sim.substep(float(sc["dt"]), cols, nc, 5)
+    st = sim.stats()
+    assert st.n_out_of_grid == 5 and st.n_particles == sc["n"]
+    out = sim.download()
+    assert (out["pos"][:5] == pos[:5]).all()           # untouched, still in upload order
+    o, ocols, onc = oracle_from_scene(sc)
+    assert o.num_out_of_grid() == 5
+    o.substep(float(sc["dt"]), ocols, onc, 5)
+    assert_traj_close(sim.download_state35()[5:], o.state()[5:], 20, "in-grid particles next to parked ones")
+
+
+def test_render_buffers_and_upload_order():
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0)
+    sim, cols, nc = sim_from_scene(sc)
+    tags = np.arange(sc["n"], dtype=np.float32) + 0.5
+    sim.upload(sc["pos"], sc["vel"], sc["mass"], volume=tags)       # volume rides along untouched: a permutation tag
+    sim.substep(float(sc["dt"]), cols, nc, 7)
+    out = sim.download()
+    assert (out["volume"] == tags).all(), "download order must be upload order after re-sorting substeps"
+    xyzs, rgba = sim.render_buffers(size=0.02)
+    assert (xyzs[:, :3] == out["pos"]).all() and (xyzs[:, 3] == np.float32(0.02)).all() and (rgba == 255).all()
+
+
+def test_error_paths():
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
+    sim, cols, nc = sim_from_scene(sc)
+    with pytest.raises(mpm_b200.MpmError):
+        sim.L.mpm_substep(sim.h, 1e-5, cols, 17, 1) and (_ for _ in ()).throw(mpm_b200.MpmError("x"))
+    assert sim.L.mpm_substep(sim.h, 1e-5, cols, 17, 1) != 0 and b"n_colliders" in sim.L.mpm_last_error()
+    fresh = mpm_b200.Sim(32, 32, 32, 10)
+    assert fresh.L.mpm_update_particle_velocities(fresh.h) != 0      # stage before any rasterize
+    bad = np.zeros((sc["n"] + 1, 3), np.float32)
+    assert sim.L.mpm_download_particles_soa(sim.h, sc["n"] + 1, bad.ctypes.data_as(op.C.POINTER(op.C.c_float)), None, None, None, None, None, None) != 0
