@@ -28,20 +28,35 @@ class BoxCollider(C.Structure):
     _fields_ = [("world_to_local", C.c_float * 16), ("half_extent", C.c_float * 3), ("velocity", C.c_float * 3)]
 
 
-def build(force=False):
+LIB_FMA_PATH = os.path.join(HERE, "libmpm_oracle_fma.so")
+
+
+def build(force=False, fma=False):
     src = os.path.join(HERE, "mpm_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", HERE, "libmpm_oracle.so"])
-    return LIB_PATH
+    path = LIB_FMA_PATH if fma else LIB_PATH
+    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, os.path.basename(path)])
+    return path
 
 
 _lib = None
+_lib_fma = None
 
 
-def lib():
-    global _lib
+def lib(fma=False):
+    """fma=True: the same restatement compiled with FMA contraction — only for measuring a scene's noise floor."""
+    global _lib, _lib_fma
+    if fma:
+        if _lib_fma is None:
+            _lib_fma = _bind(C.CDLL(build(fma=True)))
+        return _lib_fma
     if _lib is None:
-        L = C.CDLL(build())
+        _lib = _bind(C.CDLL(build()))
+    return _lib
+
+
+def _bind(L):
+    if True:
         fp = C.POINTER(C.c_float)
         L.oracle_default_params.argtypes = [C.POINTER(OracleParams)]
         L.oracle_create.restype = C.c_void_p
@@ -72,8 +87,7 @@ def lib():
         L.oracle_box_sdf.argtypes = [C.POINTER(BoxCollider), fp]
         L.oracle_box_sdf.restype = C.c_float
         L.oracle_body_collision.argtypes = [fp, fp, C.POINTER(BoxCollider), C.c_int, C.c_float, fp]
-        _lib = L
-    return _lib
+    return L
 
 
 def _fp(a):
@@ -112,8 +126,8 @@ def colliders_from_ref_dump(raw):
 
 
 class Oracle:
-    def __init__(self, I, J, K, n, params=None, threads=1):
-        self.L = lib()
+    def __init__(self, I, J, K, n, params=None, threads=1, fma=False):
+        self.L = lib(fma)
         self.I, self.J, self.K, self.n = I, J, K, n
         self.params = params if params is not None else default_params()
         self.h = self.L.oracle_create(I, J, K, n, C.byref(self.params))

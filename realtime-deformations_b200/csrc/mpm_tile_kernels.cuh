@@ -1,19 +1,338 @@
-// Block-tile P2G / G2P kernels (placeholder: forwards to the baseline kernels until the tile kernels land).
+// Block-tile P2G / G2P kernels: one CTA works on one occupied 4^3-cell particle block at a time
+// (persistent CTAs pulling blocks from a device-side work counter, so no host sync is needed to size the grid).
+//
+// P2G (k_p2g_tile):  no shared-memory float atomics at all (on sm_100a they are CAS loops, ATOMS.CAST.SPIN).
+//   chunk loop   : 256 particles at a time are loaded as coalesced float4 planes; each thread derives its
+//                  particle's 12 axis weights (fp64 polynomial, as the reference) and affine coefficients into smem,
+//                  and the chunk is counting-sorted by cell in smem (integer atomics only).
+//   phase 1      : thread (cell, x-slab a) walks the particles of ITS cell and accumulates the 16 stencil nodes
+//                  (a, b, c) x (mass, momentum) in 64 registers -> the cross-particle reduction happens in
+//                  registers, never between lanes.
+//   phase 2      : per-cell 64-node patches go to smem with plain stores; each tile node then gathers the <= 64
+//                  patches that cover it (plain loads, fixed order -> deterministic within a block) and issues ONE
+//                  vector red.global.add.v4.f32 per tile node (7^3 = 343 per block instead of 64 per particle).
+// G2P (k_g2p_tile):  the 2x2x2 grid blocks of the tile are eight contiguous 1 KB chunks in HBM; one thread fetches
+//   them with cp.async.bulk (TMA, mbarrier completion), double-buffered against the previous block's compute. Each
+//   thread then owns one particle: bit-faithful F-update (Jacobi SVD in registers), separable gather of v and the
+//   APIC matrix from the smem tile, advection, and the write into the other particle buffer at its sorted rank
+//   (the physical re-sort that keeps the next substep's loads coalesced).
 #pragma once
 #include "mpm_kernels.cuh"
+
 namespace mpm {
-inline cudaError_t tile_kernels_init() { return cudaSuccess; }
+
+constexpr int P2G_T = 256;         // threads per CTA = 64 cells x 4 x-slabs
+constexpr int P2G_CH = 256;        // particles per chunk
+struct P2GSmem {
+    union {
+        struct {
+            float wx[4][P2G_CH];          // wx[a][particle]
+            float4 wy[P2G_CH], wz[P2G_CH];
+            float4 qc[P2G_CH];            // (mass channel, c0.x, c0.y, c0.z)
+            float4 hA0[P2G_CH], hA1[P2G_CH];   // h*A row-major entries 0..3, 4..7
+            float hA8[P2G_CH];
+            int gid[P2G_CH];
+            unsigned char lc[P2G_CH], order[P2G_CH];
+        } c;
+        float4 patch[32][64];             // phase 2: 32 cells x 64 nodes (two rounds)
+    } u;
+    int cell_cnt[64], cell_start[65], cell_cursor[64];
+    int work;
+};
+
 template <int MODE>
-cudaError_t launch_p2g_tile(Planes P, const int* sorted_ids, const int* blk_start, const int* blk_count, const int* pblock_list,
+__global__ void __launch_bounds__(P2G_T, 2)
+k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_start, const int* __restrict__ blk_count,
+           const int* __restrict__ pblock_list, DevCounters* dc, float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    const int my_cell = t >> 2, my_a = t & 3;
+    const float fa = (float)my_a;
+    const int n_work = dc->n_active_pblocks;
+    for (;;) {
+        if (t == 0) S.work = atomicAdd(&dc->work_a, 1);
+        __syncthreads();
+        const int w = S.work;
+        if (w >= n_work) break;
+        const int b = pblock_list[w];
+        const int start = blk_start[b], cnt = blk_count[b];
+        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;   // global block coords
+        float4 acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int base = 0; base < cnt; base += P2G_CH) {
+            const int nch = min(P2G_CH, cnt - base);
+            if (t < 64) S.cell_cnt[t] = 0;
+            __syncthreads();
+            // ---- derive per-particle data ----
+            if (t < nch) {
+                const int gid = sorted_ids[start + base + t];
+                float4 xm; float mch, a0[3], A[9];
+                p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
+                const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
+                float wx[4], wy[4], wz[4];
+                axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
+                const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
+                S.u.c.wx[0][t] = wx[0]; S.u.c.wx[1][t] = wx[1]; S.u.c.wx[2][t] = wx[2]; S.u.c.wx[3][t] = wx[3];
+                S.u.c.wy[t] = make_float4(wy[0], wy[1], wy[2], wy[3]);
+                S.u.c.wz[t] = make_float4(wz[0], wz[1], wz[2], wz[3]);
+                S.u.c.qc[t] = make_float4(mch, a0[0] + A[0] * d0 + A[1] * d1 + A[2] * d2, a0[1] + A[3] * d0 + A[4] * d1 + A[5] * d2,
+                                          a0[2] + A[6] * d0 + A[7] * d1 + A[8] * d2);
+                S.u.c.hA0[t] = make_float4(A[0] * sc.h, A[1] * sc.h, A[2] * sc.h, A[3] * sc.h);
+                S.u.c.hA1[t] = make_float4(A[4] * sc.h, A[5] * sc.h, A[6] * sc.h, A[7] * sc.h);
+                S.u.c.hA8[t] = A[8] * sc.h;
+                S.u.c.gid[t] = gid;
+                const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
+                S.u.c.lc[t] = (unsigned char)lc;
+                atomicAdd(&S.cell_cnt[lc], 1);
+            }
+            __syncthreads();
+            // ---- counting sort of the chunk by cell (64 bins) ----
+            if (t < 32) {
+                const int c0 = S.cell_cnt[2 * t], c1 = S.cell_cnt[2 * t + 1];
+                int inc = c0 + c1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += v; }
+                const int ex = inc - (c0 + c1);
+                S.cell_start[2 * t] = ex; S.cell_start[2 * t + 1] = ex + c0;
+                S.cell_cursor[2 * t] = ex; S.cell_cursor[2 * t + 1] = ex + c0;
+                if (t == 31) S.cell_start[64] = inc;
+            }
+            __syncthreads();
+            if (t < nch) S.u.c.order[atomicAdd(&S.cell_cursor[S.u.c.lc[t]], 1)] = (unsigned char)t;
+            __syncthreads();
+            // keep the block's segment of sorted_ids cell-ordered: G2P lanes of one warp then share cells
+            if (t < nch) sorted_ids[start + base + t] = S.u.c.gid[S.u.c.order[t]];
+            // ---- phase 1: register accumulation over the particles of my cell ----
+            const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
+            for (int i = i0; i < i1; ++i) {
+                const int pi = S.u.c.order[i];
+                const float wxa = S.u.c.wx[my_a][pi];
+                const float4 wy = S.u.c.wy[pi], wz = S.u.c.wz[pi], qc = S.u.c.qc[pi], h0 = S.u.c.hA0[pi], h1 = S.u.c.hA1[pi];
+                const float h8 = S.u.c.hA8[pi];
+                // value(a,b,c)_r = c0_r + a*hA[r][0] + b*hA[r][1] + c*hA[r][2]
+                const float bx = qc.y + fa * h0.x, by = qc.z + fa * h0.w, bz = qc.w + fa * h1.z;
+                const float wyv[4] = { wy.x, wy.y, wy.z, wy.w }, wzv[4] = { wz.x, wz.y, wz.z, wz.w };
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const float wab = wxa * wyv[bb];
+                    float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const float wgt = wab * wzv[cc];
+                        float4& a4 = acc[bb * 4 + cc];
+                        a4.x += wgt * qc.x; a4.y += wgt * vx; a4.z += wgt * vy; a4.w += wgt * vz;
+                        vx += h0.z; vy += h1.y; vz += h8;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase 2: patches -> tile nodes -> one vector red per node ----
+        float4 out0 = make_float4(0.f, 0.f, 0.f, 0.f), out1 = out0;
+        const int n0 = t, n1 = t + P2G_T;                      // tile nodes owned by this thread (7^3 = 343)
+        const int i0n = n0 / 49, j0n = (n0 / 7) % 7, k0n = n0 % 7;
+        const int i1n = n1 / 49, j1n = (n1 / 7) % 7, k1n = n1 % 7;
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            if ((my_cell >> 5) == round) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) S.u.patch[my_cell & 31][my_a * 16 + i] = acc[i];
+            }
+            __syncthreads();
+            // cells of this round have cx in {2*round, 2*round+1}
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const int ni = which ? i1n : i0n, nj = which ? j1n : j0n, nk = which ? k1n : k0n;
+                if (which && n1 >= 343) break;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int cx = max(2 * round, ni - 3); cx <= min(2 * round + 1, ni); ++cx)
+                    for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy)
+                        for (int cz = max(0, nk - 3); cz <= min(3, nk); ++cz) {
+                            const float4 v = S.u.patch[((cx & 1) * 4 + cy) * 4 + cz][((ni - cx) * 4 + (nj - cy)) * 4 + (nk - cz)];
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        }
+                if (which) { out1.x += sum.x; out1.y += sum.y; out1.z += sum.z; out1.w += sum.w; }
+                else { out0.x += sum.x; out0.y += sum.y; out0.z += sum.z; out0.w += sum.w; }
+            }
+            __syncthreads();
+        }
+        if (out0.x != 0.f || out0.y != 0.f || out0.z != 0.f || out0.w != 0.f)
+            atomicAdd(&grid[node_index(gd, 4 * pbi + i0n, 4 * pbj + j0n, 4 * pbk + k0n)], out0);
+        if (n1 < 343 && (out1.x != 0.f || out1.y != 0.f || out1.z != 0.f || out1.w != 0.f))
+            atomicAdd(&grid[node_index(gd, 4 * pbi + i1n, 4 * pbj + j1n, 4 * pbk + k1n)], out1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G2P
+// ---------------------------------------------------------------------------------------------------------
+MPM_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+MPM_DI void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+MPM_DI void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MPM_DI void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+
+constexpr int G2P_T = 128;
+struct G2PSmem {
+    float4 tile[2][512];                 // two stages of 2x2x2 grid blocks x 64 nodes
+    unsigned long long bar[2];
+    int work[2];
+};
+
+// issue the eight 1 KB bulk copies of block b's tile into stage st (one thread)
+MPM_DI void g2p_issue_tile(G2PSmem& S, int st, int b, const float4* __restrict__ grid, const GridDims& gd) {
+    const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi_l = b / (gd.npbk * gd.npbj);
+    mbar_expect_tx(&S.bar[st], 8 * 1024);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj + ((d >> 1) & 1)) * gd.nbk + pbk + (d & 1);
+        tma_load_1d(&S.tile[st][d * 64], grid + gb * 64, 1024, &S.bar[st]);
+    }
+}
+
+template <int FLAGS>
+__global__ void __launch_bounds__(G2P_T)
+k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int* __restrict__ blk_start,
+           const int* __restrict__ blk_count, const int* __restrict__ pblock_list, DevCounters* dc,
+           const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
+    __shared__ __align__(128) G2PSmem S;
+    const int t = threadIdx.x;
+    const int n_work = dc->n_active_pblocks;
+    if (t == 0) {
+        mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.work[0] = atomicAdd(&dc->work_b, 1);
+        if (S.work[0] < n_work) g2p_issue_tile(S, 0, pblock_list[S.work[0]], grid, gd);
+    }
+    __syncthreads();
+    unsigned phase[2] = { 0, 0 };
+    for (int it = 0;; ++it) {
+        const int st = it & 1;
+        const int w = S.work[st];
+        if (w >= n_work) break;
+        // prefetch the next block's tile into the other stage (its readers finished at the end of iteration it-1)
+        if (t == 0) {
+            const int wn = atomicAdd(&dc->work_b, 1);
+            S.work[st ^ 1] = wn;
+            if (wn < n_work) g2p_issue_tile(S, st ^ 1, pblock_list[wn], grid, gd);
+        }
+        const int b = pblock_list[w];
+        const int start = blk_start[b], cnt = blk_count[b];
+        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
+        mbar_wait(&S.bar[st], phase[st]);
+        phase[st] ^= 1;
+        const float4* __restrict__ tile = S.tile[st];
+        for (int base = 0; base < cnt; base += G2P_T) {
+            const int j = start + base + t;
+            if (base + t < cnt) {
+                const int p = sorted_ids[j];
+                ParticleRegs r;
+                load_particle(cur, p, r, !(FLAGS & G2P_F));
+                if (FLAGS & G2P_F) {
+                    if (!particle_f_update(r, sc, dt)) dc->svd_failed = 1;
+                }
+                {
+                    const int cx = cell_of(r.x[0], sc.h), cy = cell_of(r.x[1], sc.h), cz = cell_of(r.x[2], sc.h);
+                    float wx[4], wy[4], wz[4];
+                    axis_weights(r.x[0], sc.h, cx, wx); axis_weights(r.x[1], sc.h, cy, wy); axis_weights(r.x[2], sc.h, cz, wz);
+                    const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
+                    int offx[4], offy[4], offz[4];
+                    float wxd[4], wyd[4], wzd[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        offx[a] = ((ox + a) >> 2) * 256 + ((ox + a) & 3) * 16;
+                        offy[a] = ((oy + a) >> 2) * 128 + ((oy + a) & 3) * 4;
+                        offz[a] = ((oz + a) >> 2) * 64 + ((oz + a) & 3);
+                        wxd[a] = wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]);
+                        wyd[a] = wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]);
+                        wzd[a] = wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]);
+                    }
+                    float v[3] = { 0, 0, 0 }, Bx[3] = { 0, 0, 0 }, By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        float t0[3] = { 0, 0, 0 }, t1y[3] = { 0, 0, 0 }, t1z[3] = { 0, 0, 0 };
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) {
+                            float s0[3] = { 0, 0, 0 }, s1[3] = { 0, 0, 0 };
+                            const int oab = offx[a] + offy[bb];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const float4 n = tile[oab + offz[cc]];
+                                s0[0] += wz[cc] * n.y; s0[1] += wz[cc] * n.z; s0[2] += wz[cc] * n.w;
+                                s1[0] += wzd[cc] * n.y; s1[1] += wzd[cc] * n.z; s1[2] += wzd[cc] * n.w;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) { t0[q] += wy[bb] * s0[q]; t1y[q] += wyd[bb] * s0[q]; t1z[q] += wy[bb] * s1[q]; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { v[q] += wx[a] * t0[q]; Bx[q] += wxd[a] * t0[q]; By[q] += wx[a] * t1y[q]; Bz[q] += wx[a] * t1z[q]; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { r.v[q] = v[q]; r.B[q] = Bx[q]; r.B[3 + q] = By[q]; r.B[6 + q] = Bz[q]; }
+                }
+                if (FLAGS & G2P_ADVECT) advect_rn(r, sc, dt);
+                store_particle((FLAGS & G2P_REORDER) ? nxt : cur, (FLAGS & G2P_REORDER) ? j : p, r);
+            }
+        }
+        __syncthreads();     // everyone is done with tile[st] and has seen work[st^1]
+    }
+}
+
+// parked (out-of-grid) particles ride along unchanged through a re-sorting G2P
+__global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const DevCounters* __restrict__ dc) {
+    const int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dc->n_sorted) return;
+    const int p = sorted_ids[j];
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
+}
+
+inline cudaError_t tile_kernels_init() {
+    cudaError_t e;
+#define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
+    MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
+#undef MPM_SET_SMEM
+    return cudaSuccess;
+}
+
+template <int MODE>
+cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int* blk_start, const int* blk_count, const int* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
-    (void)blk_start; (void)blk_count; (void)pblock_list; (void)num_sms;
-    k_p2g_atomic<MODE><<<(n_bound + 127) / 128, 128, 0, st>>>(P, sorted_ids, dc, grid, gd, sc, dt);
+    (void)n_bound;
+    cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
     return cudaGetLastError();
 }
+
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int* blk_start, const int* blk_count, const int* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
-    k_g2p_direct<FLAGS><<<(n_bound + 127) / 128, 128, 0, st>>>(C, N, sorted_ids, dc, grid, gd, sc, dt);
-    return cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_g2p_tile<FLAGS><<<num_sms * 3, G2P_T, 0, st>>>(C, N, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (FLAGS & G2P_REORDER) {
+        k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc);     // parked particles are few; 16 K slots per launch wave
+        e = cudaGetLastError();
+    }
+    return e;
 }
+
 }  // namespace mpm

@@ -7,12 +7,12 @@ import oracle_py as op
 VARIANTS = [(0, 0), (1, 1)]     # (p2g_variant, g2p_variant): tile kernels, baseline kernels
 
 
-def oracle_from_scene(sc, **prm):
+def oracle_from_scene(sc, fma=False, **prm):
     I, J, K = sc["dims"]
     p = op.default_params(h=float(sc["h"]), **prm)
     if "gravity" in sc and "gravity" not in prm:
         p.gravity[:] = [float(x) for x in sc["gravity"]]
-    o = op.Oracle(I, J, K, sc["n"], p)
+    o = op.Oracle(I, J, K, sc["n"], p, fma=fma)
     s = op.initial_state(sc["pos"], sc["vel"], sc["mass"])
     o.set_state(s)
     o.rasterize(); o.volumes()

@@ -8,15 +8,15 @@ import pytest
 
 import mpm_b200
 import oracle_py as op
-from helpers import assert_bit_exact, assert_traj_close, full_grid, traj_errors
+from helpers import assert_bit_exact, assert_traj_close, assert_traj_close_calibrated, full_grid, traj_errors
 from scene_util import VARIANTS, gpu_colliders_from_ref_dump, oracle_from_scene, sim_from_scene, sim_from_state35
 
 pytestmark = pytest.mark.gpu
 SUM_RTOL = 2e-5      # fp32 sums of <= ~100 terms in a different order / with FMA contraction
 
 
-def close_sum(a, b, what, rtol=SUM_RTOL):
-    scale = max(float(np.abs(b).max()), 1e-30)
+def close_sum(a, b, what, rtol=SUM_RTOL, scale=None):
+    scale = max(float(np.abs(b).max()), 1e-30) if scale is None else scale
     err = float(np.abs(np.asarray(a, np.float64) - b).max())
     assert err <= rtol * scale, f"{what}: max |d| = {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
 
@@ -80,7 +80,8 @@ def test_stage_level_parity_with_reference(golden_c1, step, variants):
     s = sim.download_state35()
     ref = g[f"st{step}_g2p"]
     close_sum(s[:, 1:4], ref[:, 0:3], "particle velocity")
-    close_sum(s[:, 26:35], ref[:, 3:12], "APIC B")
+    # B = sum w v_i (x_i - x_p)^T cancels to ~0 for a uniform velocity field: the error scale is |v| * stencil width
+    close_sum(s[:, 26:35], ref[:, 3:12], "APIC B", scale=float(np.abs(ref[:, 0:3]).max()) * 2 * 0.05)
     # --- updateParticlePositions: bit-exact given the reference's velocities
     st2 = pre.copy()
     st2[:, 1:4] = ref[:, 0:3]
@@ -159,12 +160,14 @@ def test_fine_scene_vs_reference(golden_c1b):
 def test_synthetic_ball_vs_oracle(variants):
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=5.0)
     o, ocols, onc = oracle_from_scene(sc)
+    of, _, _ = oracle_from_scene(sc, fma=True)       # noise-floor probe
     sim, cols, nc = sim_from_scene(sc, variants)
     close_sum(sim.download_state35()[:, 4], o.state()[:, 4], "initial volumes")
-    for n in (20, 80):       # free fall, then first contact with the ground box
-        o.substep(float(sc["dt"]), ocols, onc, n if n == 20 else 60)
-        sim.substep(float(sc["dt"]), cols, nc, n if n == 20 else 60)
-        assert_traj_close(sim.download_state35(), o.state(), 20 if n == 20 else 100, f"CUDA {variants} vs oracle, synthetic ball")
+    for n in (20, 60, 40):   # free fall, first contact with the ground box (~step 62), crushing
+        o.substep(float(sc["dt"]), ocols, onc, n)
+        of.substep(float(sc["dt"]), ocols, onc, n)
+        sim.substep(float(sc["dt"]), cols, nc, n)
+        assert_traj_close_calibrated(sim.download_state35(), o.state(), of.state(), f"CUDA {variants} vs oracle, synthetic ball")
 
 
 def test_material_sweep_vs_oracle():
@@ -172,10 +175,14 @@ def test_material_sweep_vs_oracle():
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0, dt=2.5e-6)
     for xi, tc, ts in ((5.0, 1.5e-2, 2.5e-3), (20.0, 5e-2, 7.5e-3)):
         o, ocols, onc = oracle_from_scene(sc, xi=xi, theta_c=tc, theta_s=ts)
+        of, _, _ = oracle_from_scene(sc, fma=True, xi=xi, theta_c=tc, theta_s=ts)
         sim, cols, nc = sim_from_scene(sc, hardening_xi=xi, theta_c=tc, theta_s=ts)
-        o.substep(float(sc["dt"]), ocols, onc, 40)
-        sim.substep(float(sc["dt"]), cols, nc, 40)
-        assert_traj_close(sim.download_state35(), o.state(), 100, f"xi={xi} theta_c={tc} theta_s={ts}")
+        # dt = 2.5e-6: 4x more substeps to reach the ground, so run until well into contact
+        o.substep(float(sc["dt"]), ocols, onc, 300)
+        of.substep(float(sc["dt"]), ocols, onc, 300)
+        sim.substep(float(sc["dt"]), cols, nc, 300)
+        assert_traj_close_calibrated(sim.download_state35(), o.state(), of.state(), f"xi={xi} theta_c={tc} theta_s={ts}")
+        assert np.abs(np.linalg.det(o.state()[:, 17:26].reshape(-1, 3, 3)) - 1).max() > 1e-3, "sweep never reached plasticity"
 
 
 def test_out_of_grid_particles_are_parked_not_lost():

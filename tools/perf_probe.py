@@ -1,0 +1,30 @@
+"""Quick per-phase timing probe (not the contract bench): python tools/perf_probe.py [grid n steps variants...]"""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+import mpm_b200
+
+def run(grid, n, steps, pv, gv, scene="slab"):
+    t0 = time.time()
+    sc = mpm_b200.scenes.snow_slab(grid=grid, n=n) if scene == "slab" else mpm_b200.scenes.snowball_drop(grid=grid, n=n)
+    tg = time.time() - t0
+    p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv)
+    if "gravity" in sc: p.gravity[:] = [float(x) for x in sc["gravity"]]
+    sim = mpm_b200.Sim(grid, grid, grid, sc["n"], p)
+    t0 = time.time(); sim.upload(sc["pos"], sc["vel"], sc["mass"]); tu = time.time() - t0
+    sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
+    cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
+    sim.substep(1e-5, cols, nc, 3); sim.synchronize()
+    t0 = time.time(); sim.substep(1e-5, cols, nc, steps); sim.synchronize(); dt = (time.time() - t0) / steps
+    st = sim.stats()
+    ms = list(st.last_ms)
+    print(f"{scene} grid={grid} n={sc['n']} variants=({pv},{gv}) gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
+          f"{sc['n']/dt/1e9:.3f} G upd/s  bin={ms[0]:.3f} clear={ms[1]:.3f} p2g={ms[2]:.3f} grid={ms[3]:.3f} g2p={ms[4]:.3f} total={ms[6]:.3f} "
+          f"active_nodes={st.n_active_nodes} pblocks={st.n_particle_blocks} gblocks={st.n_grid_blocks}", flush=True)
+    sim.close()
+
+if __name__ == "__main__":
+    grid, n, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    scene = sys.argv[4] if len(sys.argv) > 4 else "slab"
+    for pv, gv in ((0, 0), (1, 1), (0, 1), (1, 0)):
+        run(grid, n, steps, pv, gv, scene)
