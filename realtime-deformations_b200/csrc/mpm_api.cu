@@ -397,14 +397,14 @@ static int launch_grid_update(mpm_sim* s, float dt) {
 template <int FLAGS>
 static int launch_g2p(mpm_sim* s, float dt) {
     Planes C = s->planes(s->cur), N = s->planes(s->cur ^ 1);
-    if (s->prm.g2p_variant == 1 || !(FLAGS & G2P_GATHER)) {
+    if (s->prm.g2p_variant == 1 || !(FLAGS & (G2P_GATHER | G2P_F))) {
         k_g2p_direct<FLAGS><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->grid, s->gd, s->sc, dt);
         CKLAUNCH();
     } else {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->blk_start, s->blk_count, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream)));
     }
-    s->stats.kernel_launches++;
+    s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {
         k_after_reorder<<<1, 1, 0, s->stream>>>(s->dc);
         CKLAUNCH(); s->stats.kernel_launches++;

@@ -406,6 +406,34 @@ __global__ void k_stress(Planes P, const DevCounters* __restrict__ dc, SimConst 
     P.p[5][p] = make_float4(r.tau[4], r.tau[5], 0.0f, 0.0f);
 }
 
+// updateDeformationGradient (cpp:306-330) + next substep's stress, one thread per sorted slot. It touches only
+// B (read), FE/FP/V0 (read) and FE/FP/tau (write), i.e. planes disjoint from what the gather kernel writes, so in the
+// re-sorting fused path the two kernels split the particle record between them at no extra HBM traffic.
+template <bool REORDER>
+__global__ void __launch_bounds__(256)
+k_fupdate(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc, SimConst sc, float dt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dc->n_binned) return;
+    const int p = sorted_ids[j];
+    const float4 a1 = cur.p[1][p], a2 = cur.p[2][p], a3 = cur.p[3][p];
+    const float4 a6 = cur.p[6][p], a7 = cur.p[7][p], a8 = cur.p[8][p], a9 = cur.p[9][p], a10 = cur.p[10][p];
+    float B[9] = { a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x };
+    float FE[9] = { a6.z, a6.w, a7.x, a7.y, a7.z, a7.w, a8.x, a8.y, a8.z };
+    float FP[9] = { a8.w, a9.x, a9.y, a9.z, a9.w, a10.x, a10.y, a10.z, a10.w };
+    float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
+    if (!f_update_rn(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+    tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
+    const Planes& D = REORDER ? nxt : cur;
+    const int q = REORDER ? j : p;
+    D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
+    D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
+    D.p[6][q] = make_float4(a6.x, a6.y, FE[0], FE[1]);
+    D.p[7][q] = make_float4(FE[2], FE[3], FE[4], FE[5]);
+    D.p[8][q] = make_float4(FE[6], FE[7], FE[8], FP[0]);
+    D.p[9][q] = make_float4(FP[1], FP[2], FP[3], FP[4]);
+    D.p[10][q] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+}
+
 // computeParticleVolumesAndDensities (cpp:131-142): density = sum m_i w_ip / h^3, V0 = m / density
 __global__ void k_volumes(Planes P, const int* __restrict__ sorted_ids, const DevCounters* __restrict__ dc,
                           const float4* __restrict__ grid, GridDims gd, SimConst sc) {

@@ -21,9 +21,19 @@ MPM_DI float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 MPM_DI float add_rn(float a, float b) { return __fadd_rn(a, b); }
 MPM_DI float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 MPM_DI float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+MPM_DI float rcp_rn(float a) { return __frcp_rn(a); }      // correctly rounded 1/a == IEEE 1.0f / a
 
-// ---- reference weightNx, material_point_method.hpp:20-31 (fp64 polynomial, rounded to fp32) ----
+// ---- reference weightNx, material_point_method.hpp:20-31 ----
+// The reference evaluates the polynomial in fp64 and rounds to fp32 (weight_nx_exact reproduces that bit for bit).
+// The hot kernels use the fp32/FMA form below: it differs from the exact value by <= 1 ulp (6e-8 relative), far
+// inside the fp32 noise of the scatter/gather sums the weights feed, and avoids the F2F/FP64 pipes.
 MPM_DI float weight_nx(float x) {
+    const float m = fabsf(x);
+    if (m < 1.0f) return fmaf(fmaf(0.5f, m, -1.0f), m * m, 0.66666668653488159f);
+    if (m < 2.0f) { const float a = 2.0f - m; return 0.16666667163372040f * a * a * a; }
+    return 0.0f;
+}
+MPM_DI float weight_nx_exact(float x) {
     const float modx = fabsf(x);
     const float modx2 = mul_rn(modx, modx);
     const float modx3 = mul_rn(mul_rn(modx, modx), modx);
@@ -63,7 +73,7 @@ MPM_DI float m3_det_rn(const float* m) {
     return add_rn(sub_rn(t0, t1), t2);
 }
 MPM_DI void m3_inverse_rn(float* R, const float* m) {               // R may not alias m
-    const float ood = div_rn(1.0f, m3_det_rn(m));
+    const float ood = rcp_rn(m3_det_rn(m));
     MG(R,0,0) =  mul_rn(sub_rn(mul_rn(MG(m,1,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,1,2))), ood);
     MG(R,1,0) = -mul_rn(sub_rn(mul_rn(MG(m,1,0), MG(m,2,2)), mul_rn(MG(m,2,0), MG(m,1,2))), ood);
     MG(R,2,0) =  mul_rn(sub_rn(mul_rn(MG(m,1,0), MG(m,2,1)), mul_rn(MG(m,2,0), MG(m,1,1))), ood);
@@ -98,7 +108,7 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
     else {
         const float u = div_rn(t, d);
         const float tmp = __fsqrt_rn(add_rn(1.0f, mul_rn(u, u)));
-        s1 = div_rn(1.0f, tmp); c1 = div_rn(u, tmp);
+        s1 = rcp_rn(tmp); c1 = div_rn(u, tmp);
     }
     if (!(c1 == 1.0f && s1 == 0.0f)) {
         const float a0 = add_rn(mul_rn(c1, m00), mul_rn(s1, m10)), b0 = add_rn(mul_rn(-s1, m00), mul_rn(c1, m10));
@@ -111,10 +121,11 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
     else {
         const float tau = div_rn(sub_rn(m00, m11), deno);
         const float w = __fsqrt_rn(add_rn(mul_rn(tau, tau), 1.0f));
-        const float tt = tau > 0.0f ? div_rn(1.0f, add_rn(tau, w)) : div_rn(1.0f, sub_rn(tau, w));
-        const float sign_t = tt > 0.0f ? 1.0f : -1.0f;
-        const float nn = div_rn(1.0f, __fsqrt_rn(add_rn(mul_rn(tt, tt), 1.0f)));
-        sr = mul_rn(mul_rn(mul_rn(-sign_t, div_rn(m01, fabsf(m01))), fabsf(tt)), nn);
+        const float tt = rcp_rn(tau > 0.0f ? add_rn(tau, w) : sub_rn(tau, w));
+        const float nn = rcp_rn(__fsqrt_rn(add_rn(mul_rn(tt, tt), 1.0f)));
+        // Eigen: s = -sign_t * (y/|y|) * |t| * n. The first three factors are exact (+-1, +-1, |t|): -sign_t*|t| == -t,
+        // so s = RN((-t * sgn(y)) * n) -- one rounding, identical bits.
+        sr = mul_rn(copysignf(1.0f, m01) * -tt, nn);
         cr = nn;
     }
     const float cl = sub_rn(mul_rn(c1, cr), mul_rn(s1, -sr));

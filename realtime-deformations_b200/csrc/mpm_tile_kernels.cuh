@@ -34,20 +34,22 @@ struct P2GSmem {
             int gid[P2G_CH];
             unsigned char lc[P2G_CH], order[P2G_CH];
         } c;
-        float4 patch[32][64];             // phase 2: 32 cells x 64 nodes (two rounds)
+        float4 t1[4][4][4][4][7];         // phase 2: z-folded partial sums [cx][cy][a][b][k]
     } u;
     int cell_cnt[64], cell_start[65], cell_cursor[64];
     int work;
 };
 
+// Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
 template <int MODE>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_start, const int* __restrict__ blk_count,
            const int* __restrict__ pblock_list, DevCounters* dc, float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31;
     const int my_cell = t >> 2, my_a = t & 3;
+    const int my_cx = my_cell >> 4, my_cy = (my_cell >> 2) & 3, my_cz = my_cell & 3;
     const float fa = (float)my_a;
     const int n_work = dc->n_active_pblocks;
     for (;;) {
@@ -62,13 +64,16 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        for (int base = 0; base < cnt; base += P2G_CH) {
-            const int nch = min(P2G_CH, cnt - base);
+        // chunks take every n_chunks-th particle of the (cell-ordered) block segment, so that every chunk holds a
+        // share of every cell and all 64 (cell) thread groups have work in phase 1
+        const int n_chunks = (cnt + P2G_CH - 1) / P2G_CH;
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            const int nch = (cnt - ck + n_chunks - 1) / n_chunks;          // slots ck, ck+n_chunks, ...
             if (t < 64) S.cell_cnt[t] = 0;
             __syncthreads();
             // ---- derive per-particle data ----
             if (t < nch) {
-                const int gid = sorted_ids[start + base + t];
+                const int gid = sorted_ids[start + ck + t * n_chunks];
                 float4 xm; float mch, a0[3], A[9];
                 p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
                 const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
@@ -103,8 +108,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
             __syncthreads();
             if (t < nch) S.u.c.order[atomicAdd(&S.cell_cursor[S.u.c.lc[t]], 1)] = (unsigned char)t;
             __syncthreads();
-            // keep the block's segment of sorted_ids cell-ordered: G2P lanes of one warp then share cells
-            if (t < nch) sorted_ids[start + base + t] = S.u.c.gid[S.u.c.order[t]];
+            // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
+            // cells (smem broadcasts) and the re-sorted particle buffer stays cell-coherent for the next substep
+            if (t < nch) sorted_ids[start + ck + t * n_chunks] = S.u.c.gid[S.u.c.order[t]];
             // ---- phase 1: register accumulation over the particles of my cell ----
             const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
             for (int i = i0; i < i1; ++i) {
@@ -130,39 +136,47 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
             }
             __syncthreads();
         }
-        // ---- phase 2: patches -> tile nodes -> one vector red per node ----
-        float4 out0 = make_float4(0.f, 0.f, 0.f, 0.f), out1 = out0;
-        const int n0 = t, n1 = t + P2G_T;                      // tile nodes owned by this thread (7^3 = 343)
-        const int i0n = n0 / 49, j0n = (n0 / 7) % 7, k0n = n0 % 7;
-        const int i1n = n1 / 49, j1n = (n1 / 7) % 7, k1n = n1 % 7;
+        // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
+        // node k = cz + c; this lane ends up owning k = cz (slot 0) and k = cz + 4 (slot 1, cz <= 2)
+        float4 s0[4], s1[4];
 #pragma unroll
-        for (int round = 0; round < 2; ++round) {
-            if ((my_cell >> 5) == round) {
+        for (int bb = 0; bb < 4; ++bb) { s0[bb] = acc[bb * 4]; s1[bb] = make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) S.u.patch[my_cell & 31][my_a * 16 + i] = acc[i];
+        for (int cc = 1; cc < 4; ++cc) {
+            const int src = (lane & ~12) | (((my_cz - cc) & 3) << 2);     // the lane holding cell cz' = (cz - cc) mod 4
+            const bool lo = cc <= my_cz;                                   // cz' = cz - cc  -> k = cz ; else cz' = cz+4-cc -> k = cz+4
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                float4 v;
+                v.x = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].x, src); v.y = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].y, src);
+                v.z = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].z, src); v.w = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].w, src);
+                if (lo) { s0[bb].x += v.x; s0[bb].y += v.y; s0[bb].z += v.z; s0[bb].w += v.w; }
+                else { s1[bb].x += v.x; s1[bb].y += v.y; s1[bb].z += v.z; s1[bb].w += v.w; }
             }
-            __syncthreads();
-            // cells of this round have cx in {2*round, 2*round+1}
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                const int ni = which ? i1n : i0n, nj = which ? j1n : j0n, nk = which ? k1n : k0n;
-                if (which && n1 >= 343) break;
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int cx = max(2 * round, ni - 3); cx <= min(2 * round + 1, ni); ++cx)
-                    for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy)
-                        for (int cz = max(0, nk - 3); cz <= min(3, nk); ++cz) {
-                            const float4 v = S.u.patch[((cx & 1) * 4 + cy) * 4 + cz][((ni - cx) * 4 + (nj - cy)) * 4 + (nk - cz)];
-                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-                        }
-                if (which) { out1.x += sum.x; out1.y += sum.y; out1.z += sum.z; out1.w += sum.w; }
-                else { out0.x += sum.x; out0.y += sum.y; out0.z += sum.z; out0.w += sum.w; }
-            }
-            __syncthreads();
         }
-        if (out0.x != 0.f || out0.y != 0.f || out0.z != 0.f || out0.w != 0.f)
-            atomicAdd(&grid[node_index(gd, 4 * pbi + i0n, 4 * pbj + j0n, 4 * pbk + k0n)], out0);
-        if (n1 < 343 && (out1.x != 0.f || out1.y != 0.f || out1.z != 0.f || out1.w != 0.f))
-            atomicAdd(&grid[node_index(gd, 4 * pbi + i1n, 4 * pbj + j1n, 4 * pbk + k1n)], out1);
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            S.u.t1[my_cx][my_cy][my_a][bb][my_cz] = s0[bb];
+            if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb][my_cz + 4] = s1[bb];
+        }
+        __syncthreads();
+        // ---- phase 2b: fold x and y from smem (<= 16 terms per tile node), one vector red per node ----
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int n = t + which * P2G_T;
+            if (n < 343) {
+                const int ni = n / 49, nj = (n / 7) % 7, nk = n % 7;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int cx = max(0, ni - 3); cx <= min(3, ni); ++cx)
+                    for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy) {
+                        const float4 v = S.u.t1[cx][cy][ni - cx][nj - cy][nk];
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
+                    atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -188,7 +202,7 @@ MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) {
     }
 }
 
-constexpr int G2P_T = 128;
+constexpr int G2P_T = 256;
 struct G2PSmem {
     float4 tile[2][512];                 // two stages of 2x2x2 grid blocks x 64 nodes
     unsigned long long bar[2];
@@ -206,6 +220,7 @@ MPM_DI void g2p_issue_tile(G2PSmem& S, int st, int b, const float4* __restrict__
     }
 }
 
+// FLAGS here: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate)
 template <int FLAGS>
 __global__ void __launch_bounds__(G2P_T)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int* __restrict__ blk_start,
@@ -242,10 +257,10 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
             const int j = start + base + t;
             if (base + t < cnt) {
                 const int p = sorted_ids[j];
-                ParticleRegs r;
-                load_particle(cur, p, r, !(FLAGS & G2P_F));
-                if (FLAGS & G2P_F) {
-                    if (!particle_f_update(r, sc, dt)) dc->svd_failed = 1;
+                struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
+                {
+                    const float4 a0 = cur.p[0][p];
+                    r.x[0] = a0.x; r.x[1] = a0.y; r.x[2] = a0.z; r.m = a0.w;
                 }
                 {
                     const int cx = cell_of(r.x[0], sc.h), cy = cell_of(r.x[1], sc.h), cz = cell_of(r.x[2], sc.h);
@@ -286,8 +301,21 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { r.v[q] = v[q]; r.B[q] = Bx[q]; r.B[3 + q] = By[q]; r.B[6 + q] = Bz[q]; }
                 }
-                if (FLAGS & G2P_ADVECT) advect_rn(r, sc, dt);
-                store_particle((FLAGS & G2P_REORDER) ? nxt : cur, (FLAGS & G2P_REORDER) ? j : p, r);
+                if (FLAGS & G2P_ADVECT) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {                  // cpp:344-350, 381-388
+                        float x = add_rn(r.x[a], mul_rn(r.v[a], dt));
+                        if (x < sc.pos_lo) x = sc.pos_lo;
+                        if (sc.pos_hi[a] < x) x = sc.pos_hi[a];
+                        r.x[a] = x;
+                    }
+                }
+                const Planes& D = (FLAGS & G2P_REORDER) ? nxt : cur;
+                const int q = (FLAGS & G2P_REORDER) ? j : p;
+                if (FLAGS & (G2P_ADVECT | G2P_REORDER)) D.p[0][q] = make_float4(r.x[0], r.x[1], r.x[2], r.m);
+                D.p[1][q] = make_float4(r.B[0], r.B[1], r.B[2], r.B[3]);
+                D.p[2][q] = make_float4(r.B[4], r.B[5], r.B[6], r.B[7]);
+                D.p[3][q] = make_float4(r.B[8], r.v[0], r.v[1], r.v[2]);
             }
         }
         __syncthreads();     // everyone is done with tile[st] and has seen work[st^1]
@@ -326,8 +354,14 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_g2p_tile<FLAGS><<<num_sms * 3, G2P_T, 0, st>>>(C, N, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (FLAGS & G2P_F) {
+        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<(n_bound + 255) / 256, 256, 0, st>>>(C, N, sorted_ids, dc, sc, dt);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (FLAGS & G2P_GATHER) {
+        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * 4, G2P_T, 0, st>>>(C, N, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     if (FLAGS & G2P_REORDER) {
         k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc);     // parked particles are few; 16 K slots per launch wave
         e = cudaGetLastError();
