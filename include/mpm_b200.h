@@ -151,8 +151,11 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* colliders, int n_c
 #define MPM_MIGRATE_FLOATS 44
 int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up);
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n);
-
-/* Link-compatibility with the reference's dead CUDA side-car (cudaCalc.cuh:4-7): same symbols, no-ops. */
+/* Distributed bookkeeping: particle ids are upload indices + pid_base (set before an upload) so that they stay
+ * unique across slabs; mpm_download_live_particles returns the handle's current particles in storage order as
+ * 35-float rows (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) with their ids. */
+int mpm_set_pid_base(mpm_t* s, int64_t pid_base);
+int mpm_download_live_particles(mpm_t* s, int64_t capacity, int64_t* n_out, float* state35, int32_t* pid);
 #ifdef __cplusplus
 }
 #endif

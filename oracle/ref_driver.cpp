@@ -114,7 +114,7 @@ int main(int argc, char** argv) {
     int I = 20, J = 20, K = 20, n = 270 + 1877, steps = 0;
     float h = 0.05f, dt = 1e-5f;
     glm::vec3 origin(0.5f, 0.6f, 0.5f), v0(0.0f, -200.0f, 0.0f);
-    std::string dumpDir, loadPath, loadFullPath, katMode, katIn, katOut;
+    std::string dumpDir, loadPath, loadFullPath, katMode, katIn, katOut, collidersPath;
     std::set<int> dumpSteps, stageSteps;
     bool bench = false, quiet = false, noColliders = false;
     for (int a = 1; a < argc; ++a) {
@@ -133,6 +133,7 @@ int main(int argc, char** argv) {
         else if (is("--bench")) bench = true;
         else if (is("--quiet")) quiet = true;
         else if (is("--no-colliders")) noColliders = true;
+        else if (is("--colliders")) collidersPath = argv[++a];   // rows of 7 float32: translation[3], rotZ degrees, scale[3]
         else if (is("--load-full")) loadFullPath = argv[++a];   // n x 35 float32, same layout as the particle dumps
         else if (is("--kat-weights")) { katMode = "weights"; katIn = argv[++a]; katOut = argv[++a]; }
         else if (is("--kat-polar")) { katMode = "polar"; katIn = argv[++a]; katOut = argv[++a]; }
@@ -220,7 +221,19 @@ int main(int argc, char** argv) {
         const auto translation4 = glm::translate(glm::mat4(), { 1.0, 0.3, 0.5 });
         box4.mesh.applyMatrix4(translation4 * rotation3 * scaling3);
     }
-    if (!noColliders) {
+    std::vector<MPM::MeshCollider> customBoxes;     // built exactly like main.cpp:119-151 builds box1..box4
+    if (!collidersPath.empty()) {
+        const std::vector<float> rows = readFile(collidersPath);
+        customBoxes.reserve(rows.size() / 7);        // the sdf lambdas capture `this`: no reallocation allowed
+        for (size_t r = 0; r + 7 <= rows.size(); r += 7) {
+            customBoxes.emplace_back(0, VP, MeshPresets::Box::vertices, MeshPresets::Box::colors, glm::vec3{ 0, 0, 0 });
+            const auto rot = glm::rotate(glm::mat4(), glm::radians(rows[r + 3]), { 0, 0, 1 });
+            const auto tr = glm::translate(glm::mat4(), { rows[r + 0], rows[r + 1], rows[r + 2] });
+            const auto sc = glm::scale(glm::mat4(), glm::vec3(rows[r + 4], rows[r + 5], rows[r + 6]));
+            customBoxes.back().mesh.applyMatrix4(tr * rot * sc);
+        }
+        for (auto& b : customBoxes) solidObjects.push_back(b);
+    } else if (!noColliders) {
         solidObjects.push_back(box1);
         solidObjects.push_back(box3);
         solidObjects.push_back(box4);

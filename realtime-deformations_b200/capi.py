@@ -43,7 +43,7 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_update_deformation_gradient", "mpm_update_particle_velocities", "mpm_update_particle_positions",
            "mpm_substep", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
            "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
-           "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append"]
+           "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles"]
 
 _lib = None
 
@@ -89,6 +89,8 @@ def lib():
     L.mpm_halo_add.argtypes = [vp, C.c_int, vp]
     L.mpm_migrate_outgoing.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]
     L.mpm_migrate_append.argtypes = [vp, vp, i64]
+    L.mpm_set_pid_base.argtypes = [vp, i64]
+    L.mpm_download_live_particles.argtypes = [vp, i64, C.POINTER(i64), fp, vp]
     _lib = L
     return L
 
@@ -259,6 +261,32 @@ class Sim:
 
     def synchronize(self):
         _ck(self.L.mpm_synchronize(self.h))
+
+    # ---- slab decomposition plumbing (device pointers; the exchange itself is the caller's, see multi.py) ----
+    def halo_bytes(self):
+        return int(self.L.mpm_halo_bytes(self.h))
+
+    def halo_pack(self, upper, dev_ptr):
+        _ck(self.L.mpm_halo_pack(self.h, int(upper), C.c_void_p(dev_ptr)))
+
+    def halo_add(self, upper, dev_ptr):
+        _ck(self.L.mpm_halo_add(self.h, int(upper), C.c_void_p(dev_ptr)))
+
+    def migrate_outgoing(self):
+        nd, nu, pd, pu = C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        _ck(self.L.mpm_migrate_outgoing(self.h, C.byref(nd), C.byref(nu), C.byref(pd), C.byref(pu)))
+        return nd.value, nu.value, pd.value, pu.value
+
+    def migrate_append(self, dev_ptr, n):
+        _ck(self.L.mpm_migrate_append(self.h, C.c_void_p(dev_ptr), int(n)))
+
+    def set_pid_base(self, base):
+        _ck(self.L.mpm_set_pid_base(self.h, int(base)))
+
+    def download_live(self, capacity):
+        st = np.empty((capacity, 35), np.float32); pid = np.empty(capacity, np.int32); n = C.c_int64()
+        _ck(self.L.mpm_download_live_particles(self.h, capacity, C.byref(n), _fp(st), pid.ctypes.data))
+        return st[:n.value], pid[:n.value]
 
     def set_params(self, params):
         self.params = params

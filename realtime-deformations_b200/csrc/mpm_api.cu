@@ -48,6 +48,7 @@ struct mpm_sim {
     DevCounters* dc = nullptr;
     float4* out_buf[2] = { nullptr, nullptr };   // migration: packed outgoing particles (down, up)
     int64_t out_cap = 0;
+    int64_t pid_base = 0;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
     int num_sms = 148;
@@ -229,7 +230,7 @@ static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
             const float* FE = f.FE ? (const float*)(f.FE + p * f.s_FE) : ID9;
             const float* FP = f.FP ? (const float*)(f.FP + p * f.s_FP) : ID9;
             const float* B = f.B ? (const float*)(f.B + p * f.s_B) : Z9;
-            int pid = (int)p; float pidf; memcpy(&pidf, &pid, 4);
+            int pid = (int)(p + s->pid_base); float pidf; memcpy(&pidf, &pid, 4);
             st[0 * m + i] = make_float4(pos[0], pos[1], pos[2], mass);
             st[1 * m + i] = make_float4(B[0], B[1], B[2], B[3]);
             st[2 * m + i] = make_float4(B[4], B[5], B[6], B[7]);
@@ -256,6 +257,8 @@ static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
 struct HostFieldPtrsW { char *mass, *vel, *vol, *pos, *FE, *FP, *B; size_t s_mass, s_vel, s_vol, s_pos, s_FE, s_FP, s_B; };
 
 static int download_common(mpm_sim* s, int64_t n, const HostFieldPtrsW& f) {
+    if (s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global)
+        return fail(MPM_ERR_INVALID, "slab handles exchange particles: use mpm_download_live_particles");
     if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "download of %lld particles but %lld were uploaded", (long long)n, (long long)s->n_uploaded);
     const int64_t CH = 1 << 20;
     int rc = ensure_pinned(s, sizeof(float4) * NPLANES * (size_t)std::min<int64_t>(CH, std::max<int64_t>(n, 1)));
@@ -316,10 +319,13 @@ int mpm_download_particles_soa(mpm_t* s, int64_t n, float* pos, float* vel, floa
 
 int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char* rgba, float size) {
     if (!s) return fail(MPM_ERR_INVALID, "null handle");
-    if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+    if (!slab && n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    if (slab && (n < 0 || n > s->capacity)) return fail(MPM_ERR_INVALID, "n exceeds the slab capacity");
     if (xyzs) {
         float4* stage = s->buf[s->cur ^ 1];     // plane 0 of the idle buffer
-        k_render<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), stage, s->dc, size);
+        if (slab) k_render_slots<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), stage, s->dc, size, (int)n);
+        else k_render<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), stage, s->dc, size);
         CKLAUNCH(); s->stats.kernel_launches++;
         CK(cudaMemcpyAsync(xyzs, stage, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
@@ -623,11 +629,64 @@ int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
 }
 int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up) {
     NEED(s);
-    (void)n_down; (void)n_up; (void)dev_down; (void)dev_up;
-    return fail(MPM_ERR_INVALID, "migration not built yet");
+    if (!n_down || !n_up || !dev_down || !dev_up) return fail(MPM_ERR_INVALID, "null argument");
+    if (!s->out_buf[0]) {
+        s->out_cap = std::max<int64_t>(1 << 16, s->capacity / 16);
+        for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->out_buf[d], sizeof(float4) * NPLANES * (size_t)s->out_cap));
+    }
+    CK(cudaMemsetAsync(s->dc->n_mig, 0, 3 * sizeof(int), s->stream));
+    k_mark_outgoing<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.h, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    DevCounters h;
+    CK(cudaMemcpyAsync(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *n_down = h.n_mig[0]; *n_up = h.n_mig[1];
+    *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
+    s->n_bound = h.n_slots;          // exact after the sync
+    s->binned = false;
+    return MPM_OK;
 }
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
     NEED(s);
-    (void)dev_buf; (void)n;
-    return fail(MPM_ERR_INVALID, "migration not built yet");
+    if (n < 0 || (n > 0 && !dev_buf)) return fail(MPM_ERR_INVALID, "bad argument");
+    if (n == 0) return MPM_OK;
+    if (s->n_bound + n > s->capacity) return fail(MPM_ERR_CAPACITY, "migration overflows the slab capacity (%lld + %lld > %lld)", (long long)s->n_bound, (long long)n, (long long)s->capacity);
+    k_append_incoming<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, (int)s->n_bound, (int)n);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    s->n_bound += n;
+    s->binned = false;
+    return MPM_OK;
+}
+int mpm_set_pid_base(mpm_t* s, int64_t pid_base) {
+    NEED(s);
+    if (pid_base < 0 || pid_base >= ((int64_t)1 << 31)) return fail(MPM_ERR_INVALID, "pid_base out of range");
+    s->pid_base = pid_base;
+    return MPM_OK;
+}
+int mpm_download_live_particles(mpm_t* s, int64_t capacity, int64_t* n_out, float* state35, int32_t* pid) {
+    NEED(s);
+    if (!n_out || !state35 || !pid || capacity < 0) return fail(MPM_ERR_INVALID, "bad argument");
+    float* d35 = nullptr; int *dpid = nullptr, *dcnt = nullptr;
+    const size_t cap = (size_t)std::max<int64_t>(capacity, 1);
+    CK(cudaMalloc(&d35, cap * 35 * sizeof(float)));
+    CK(cudaMalloc(&dpid, cap * sizeof(int)));
+    CK(cudaMalloc(&dcnt, sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(dcnt, 0, sizeof(int), s->stream);
+    int cnt = 0;
+    if (e == cudaSuccess) {
+        k_export_live<<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->dc, d35, dpid, dcnt, (int)capacity);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, dcnt, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess && cnt <= capacity && cnt > 0) {
+        e = cudaMemcpy(state35, d35, (size_t)cnt * 35 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(pid, dpid, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d35); cudaFree(dpid); cudaFree(dcnt);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "download_live_particles: %s", cudaGetErrorString(e));
+    *n_out = cnt;
+    if (cnt > capacity) return fail(MPM_ERR_CAPACITY, "%d live particles exceed the caller's capacity %lld", cnt, (long long)capacity);
+    return MPM_OK;
 }

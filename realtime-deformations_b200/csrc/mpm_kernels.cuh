@@ -49,7 +49,9 @@ struct DevCounters {
     int work_a, work_b, work_c;   // dynamic work counters for persistent kernels
     int svd_failed;
     int epoch;
-    int pad[2];
+    int n_mig[2];           // particles packed for the lower / upper slab neighbour by k_mark_outgoing
+    int mig_overflow;
+    int pad[3];
 };
 
 enum { KEY_DEAD = -2 };
@@ -544,6 +546,14 @@ __global__ void k_render(Planes cur, float4* __restrict__ xyzs, const DevCounter
     const int pid = __float_as_int(cur.p[6][p].y);
     xyzs[pid] = make_float4(a0.x, a0.y, a0.z, size);
 }
+// slab mode: particles migrate between handles, so ids are not dense; render buffers come out in storage order and
+// retired slots get size 0 (an invisible billboard)
+__global__ void k_render_slots(Planes cur, float4* __restrict__ xyzs, const DevCounters* __restrict__ dc, float size, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 a0 = p < dc->n_slots ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, -1.f);
+    xyzs[p] = make_float4(a0.x, a0.y, a0.z, a0.w < 0.0f ? 0.0f : size);
+}
 __global__ void k_binning_debug(Planes cur, const int* __restrict__ key, const DevCounters* __restrict__ dc, float h,
                                 int* __restrict__ cells3, int* __restrict__ key_out) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,6 +564,50 @@ __global__ void k_binning_debug(Planes cur, const int* __restrict__ key, const D
     cells3[pid * 3 + 0] = cell_of(a0.x, h); cells3[pid * 3 + 1] = cell_of(a0.y, h); cells3[pid * 3 + 2] = cell_of(a0.z, h);
     key_out[pid] = key[p];
 }
+// ---- slab migration: pack particles whose block layer left [lo, hi) and retire their slots ----
+// record = 11 float4 (the particle's planes, particle-major) = MPM_MIGRATE_FLOATS floats
+__global__ void k_mark_outgoing(Planes cur, DevCounters* dc, GridDims gd, float h, float4* __restrict__ out_down,
+                                float4* __restrict__ out_up, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dc->n_slots) return;
+    const float4 a0 = cur.p[0][p];
+    if (a0.w < 0.0f) return;
+    int cells[3];
+    const int k = particle_key(a0, gd, h, cells);
+    if (k != gd.n_pblocks + 1 && k != gd.n_pblocks + 2) return;
+    const int dir = k - (gd.n_pblocks + 1);
+    const int idx = atomicAdd(&dc->n_mig[dir], 1);
+    if (idx >= cap) { dc->mig_overflow = 1; atomicSub(&dc->n_mig[dir], 1); return; }   // stays here one more substep
+    float4* o = (dir ? out_up : out_down) + (size_t)idx * NPLANES;
+#pragma unroll
+    for (int q = 0; q < NPLANES; ++q) o[q] = cur.p[q][p];
+    cur.p[0][p] = make_float4(a0.x, a0.y, a0.z, -1.0f);     // dead slot: skipped by the binning, dropped by the next re-sort
+}
+__global__ void k_append_incoming(Planes cur, DevCounters* dc, const float4* __restrict__ in, int base, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) dc->n_slots = base + n;
+    if (i >= n) return;
+    const float4* r = in + (size_t)i * NPLANES;
+#pragma unroll
+    for (int q = 0; q < NPLANES; ++q) cur.p[q][base + i] = r[q];
+}
+// live particles in slot order as 35-float rows (+ pid) for distributed downloads
+__global__ void k_export_live(Planes cur, const DevCounters* __restrict__ dc, float* __restrict__ out35, int* __restrict__ pid_out,
+                              int* __restrict__ counter, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dc->n_slots) return;
+    ParticleRegs r;
+    load_particle(cur, p, r, false);
+    if (r.m < 0.0f) return;
+    const int i = atomicAdd(counter, 1);
+    if (i >= cap) return;
+    float* o = out35 + (size_t)i * 35;
+    o[0] = r.m; o[1] = r.v[0]; o[2] = r.v[1]; o[3] = r.v[2]; o[4] = r.V0; o[5] = r.x[0]; o[6] = r.x[1]; o[7] = r.x[2];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { o[8 + q] = r.FE[q]; o[17 + q] = r.FP[q]; o[26 + q] = r.B[q]; }
+    pid_out[i] = r.pid;
+}
+
 // blocked <-> linear grid (download_grid / upload_grid, tests only)
 __global__ void k_grid_export(const float4* __restrict__ grid, const float4* __restrict__ gforce, GridDims gd, float* __restrict__ out7) {
     const size_t n = (size_t)gd.I * gd.J * gd.K;

@@ -1,0 +1,163 @@
+"""Slab decomposition of one scene over the GPUs of one box: one process per GPU (torch.distributed, NCCL over
+NVLink / NVSwitch), the grid split along i into contiguous runs of 4-cell block layers.
+
+Per substep each rank runs  bin/clear/P2G  ->  [halo exchange]  ->  grid update / F-update / G2P  ->  [migration].
+  halo      : a rank's P2G also writes the first block layer of its upper neighbour (its "ghost" layer). The ghost
+              layer's partial sums go up, the neighbour's own partial sums for that layer come down, both sides add
+              (a+b == b+a in IEEE), and both then run the identical grid update on it: ONE exchange, no second trip.
+              A layer is one contiguous chunk of the blocked grid (nbj*nbk*64 float4), 16.6 MB at 512^3.
+  migration : particles whose block layer left the slab are packed by the library (44 floats each), counts and
+              payloads go to the two neighbours with grouped isend/irecv, and are appended behind the live particles.
+The comm helpers below only see torch tensors, so the same code runs under gloo on CPU tensors (tests).
+"""
+import numpy as np
+
+from . import capi, scenes
+
+
+def slab_layers(n_layers, world):
+    """Contiguous, near-equal split of the particle-block layers along i: rank r owns [lo, hi)."""
+    base, rem = divmod(n_layers, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def exchange_with_neighbours(dist, torch, rank, world, send_down, send_up, recv_down, recv_up):
+    """Grouped point-to-point exchange with rank-1 (down) and rank+1 (up); any tensor may be None at the ends."""
+    ops = []
+    if rank > 0:
+        if send_down is not None: ops.append(dist.P2POp(dist.isend, send_down, rank - 1))
+        if recv_down is not None: ops.append(dist.P2POp(dist.irecv, recv_down, rank - 1))
+    if rank < world - 1:
+        if send_up is not None: ops.append(dist.P2POp(dist.isend, send_up, rank + 1))
+        if recv_up is not None: ops.append(dist.P2POp(dist.irecv, recv_up, rank + 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def exchange_counts(dist, torch, rank, world, n_down, n_up, device):
+    """Each rank tells its neighbours how many particles are coming; returns (incoming_from_down, incoming_from_up)."""
+    sd = torch.tensor([n_down], dtype=torch.int64, device=device)
+    su = torch.tensor([n_up], dtype=torch.int64, device=device)
+    rd = torch.zeros(1, dtype=torch.int64, device=device)
+    ru = torch.zeros(1, dtype=torch.int64, device=device)
+    exchange_with_neighbours(dist, torch, rank, world, sd, su, rd, ru)
+    return int(rd.item()) if rank > 0 else 0, int(ru.item()) if rank < world - 1 else 0
+
+
+class SlabRunner:
+    """Owns one rank's slab of the snow-slab scene (BASELINE config 5) and advances it substep by substep."""
+
+    def __init__(self, grid, n_particles, rank, world, torch, scene=None, dt=1e-5, variants=(0, 0)):
+        self.torch, self.rank, self.world, self.dt = torch, rank, world, float(dt)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+        n_layers = (grid + 3) // 4
+        self.lo, self.hi = slab_layers(n_layers, world)[rank]
+        # each rank generates only the cells of its own slab (counter-based RNG keyed by cell id)
+        if scene is None:
+            i_range = None if world == 1 else (max(4 * self.lo + 1, 0), 4 * self.hi + 1)   # cells c with (c-1)>>2 in [lo,hi)
+            scene = scenes.snow_slab(grid=grid, n=n_particles, i_range=i_range)
+        self.scene = scene
+        n = scene["n"]
+        p = capi.default_params(h=float(scene["h"]), p2g_variant=variants[0], g2p_variant=variants[1])
+        if "gravity" in scene:
+            p.gravity[:] = [float(x) for x in scene["gravity"]]
+        self.migrates = world > 1
+        cap = n if world == 1 else int(n * 1.5) + (1 << 16)
+        self.sim = capi.Sim(grid, grid, grid, n, p, slab=None if world == 1 else (self.lo, self.hi), capacity=cap)
+        # one stream for everything: the library's kernels and torch's NCCL calls are ordered against each other only
+        # if the library stream IS torch's current stream while the collectives are enqueued
+        self.stream = torch.cuda.Stream()
+        self.sim.set_stream(self.stream.cuda_stream)
+        with torch.cuda.stream(self.stream):
+            self._setup(scene, n, rank, world, torch)
+
+    def _setup(self, scene, n, rank, world, torch):
+        if world > 1:
+            # ids unique across ranks: exclusive prefix of the per-rank counts
+            counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+            counts[rank] = n
+            self.dist.all_reduce(counts)
+            self.sim.set_pid_base(int(counts[:rank].sum().item()))
+        self.sim.upload(scene["pos"], scene["vel"], scene["mass"])
+        self.cols, self.nc = capi.make_colliders(scene["w2l"], scene["half"], scene["cvel"])
+        self.h2d_bytes_per_step = 88 * self.nc + 4
+        if world > 1:
+            hb = self.sim.halo_bytes() // 4
+            self.h_send_up = torch.empty(hb, dtype=torch.float32, device="cuda")
+            self.h_recv_up = torch.empty(hb, dtype=torch.float32, device="cuda")
+            self.h_send_dn = torch.empty(hb, dtype=torch.float32, device="cuda")
+            self.h_recv_dn = torch.empty(hb, dtype=torch.float32, device="cuda")
+        # start-up of the reference (main.cpp:53-54): one P2G for the particle volumes; needs the halo as well
+        self.sim.rasterizeParticlesToGrid()
+        if world > 1:
+            self._halo()
+        self.sim.computeParticleVolumesAndDensities()
+
+    # ghost-layer partial sums up, first-layer partial sums down, add on both sides
+    def _halo(self):
+        t, s, r, w = self.torch, self.sim, self.rank, self.world
+        if r < w - 1:
+            s.halo_pack(1, self.h_send_up.data_ptr())
+        if r > 0:
+            s.halo_pack(0, self.h_send_dn.data_ptr())
+        exchange_with_neighbours(self.dist, t, r, w, self.h_send_dn if r > 0 else None, self.h_send_up if r < w - 1 else None,
+                                 self.h_recv_dn if r > 0 else None, self.h_recv_up if r < w - 1 else None)
+        if r < w - 1:
+            s.halo_add(1, self.h_recv_up.data_ptr())
+        if r > 0:
+            s.halo_add(0, self.h_recv_dn.data_ptr())
+
+    def _migrate(self):
+        t, s, r, w = self.torch, self.sim, self.rank, self.world
+        n_dn, n_up, p_dn, p_up = s.migrate_outgoing()
+        if r == 0 and n_dn:
+            raise capi.MpmError("particles left the domain through the lower i boundary")
+        in_dn, in_up = exchange_counts(self.dist, t, r, w, n_dn, n_up, "cuda")
+        F = capi.MIGRATE_FLOATS
+
+        def view(ptr, n):      # torch view over the library's packed device buffer (no copy)
+            if n == 0:
+                return None
+            class _A:          # minimal __cuda_array_interface__ carrier
+                pass
+            a = _A()
+            a.__cuda_array_interface__ = {"shape": (n * F,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+            return t.as_tensor(a, device="cuda")
+        send_dn, send_up = view(p_dn, n_dn), view(p_up, n_up)
+        recv_dn = t.empty(in_dn * F, dtype=t.float32, device="cuda") if in_dn else None
+        recv_up = t.empty(in_up * F, dtype=t.float32, device="cuda") if in_up else None
+        exchange_with_neighbours(self.dist, t, r, w, send_dn, send_up, recv_dn, recv_up)
+        if in_dn:
+            s.migrate_append(recv_dn.data_ptr(), in_dn)
+        if in_up:
+            s.migrate_append(recv_up.data_ptr(), in_up)
+        self._keep = (recv_dn, recv_up)      # keep alive until the append kernels ran
+
+    def substep(self, host_colliders=False):
+        if host_colliders:       # e2e arm: the per-frame host inputs are rebuilt and handed over every step
+            self.cols, self.nc = capi.make_colliders(self.scene["w2l"], self.scene["half"], self.scene["cvel"])
+        if self.world == 1:
+            self.sim.substep(self.dt, self.cols, self.nc, 1)
+            return
+        with self.torch.cuda.stream(self.stream):
+            self.sim.substep_begin(self.dt)
+            self._halo()
+            self.sim.substep_end(self.dt, self.cols, self.nc)
+            self._migrate()
+
+    def download_positions(self, pinned_xyzs):
+        n = min(pinned_xyzs.shape[0], int(self.sim.stats().n_particles))
+        self.sim.L.mpm_download_render_buffers(self.sim.h, n, pinned_xyzs.numpy().ctypes.data, None, 0.02)
+
+    def live_state(self):
+        cap = int(self.sim.stats().n_particles) + 16
+        return self.sim.download_live(cap)

@@ -147,9 +147,14 @@ def snow_slab(grid=512, n=1 << 26, h=0.05, dt=1e-5, seed=SEED, i_range=None, til
     foot = grid - 2 * margin
     thick = int(np.ceil(n / 8.0 / (foot * foot)))
     lo, hi = [margin, j0, margin], [grid - margin, min(j0 + thick, grid - 4), grid - margin]
+    per_plane = (hi[1] - lo[1]) * (hi[2] - lo[2]) * 8          # candidates per i-plane of cells (no rejection in a box)
+    n_keep = n
     if i_range is not None:
-        lo[0], hi[0] = max(lo[0], i_range[0]), min(hi[0], i_range[1])
-    pos = box_region(lo, hi, dims, h, seed, None if i_range is not None else n)
+        # the global scene keeps the first n candidates in i-major order; a slab keeps its share of exactly those
+        first = max(lo[0], i_range[0])
+        n_keep = int(np.clip(n - (first - lo[0]) * per_plane, 0, None))
+        lo[0], hi[0] = first, min(hi[0], i_range[1])
+    pos = box_region(lo, hi, dims, h, seed, n_keep) if hi[0] > lo[0] and n_keep > 0 else np.zeros((0, 3), np.float32)
     g = 9.8
     a = np.deg2rad(tilt_deg)
     return _scene(pos, (0.0, 0.0, 0.0), dims, h, dt, [ground_collider(top, dims, h)], name=f"snow_slab_{grid}",
