@@ -40,7 +40,8 @@ struct mpm_sim {
     float4* buf[2] = { nullptr, nullptr };   // two particle buffers, NPLANES * capacity float4 each
     int cur = 0;
     int *key = nullptr, *sorted_ids = nullptr;
-    int *blk_count = nullptr, *blk_start = nullptr, *blk_cursor = nullptr, *pblock_list = nullptr;
+    int *blk_count = nullptr, *blk_start = nullptr, *blk_cursor = nullptr;
+    int4* pblock_list = nullptr;      // occupied particle blocks as work items (block id, first sorted rank, count, -)
     int *gflag = nullptr, *gblock_list = nullptr;
     int2* partial = nullptr;
     int n_buckets = 0, n_chunks = 0;
@@ -139,7 +140,7 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     CK(cudaMalloc(&s->blk_count, sizeof(int) * (size_t)s->n_buckets));
     CK(cudaMalloc(&s->blk_start, sizeof(int) * (size_t)s->n_buckets));
     CK(cudaMalloc(&s->blk_cursor, sizeof(int) * (size_t)s->n_buckets));
-    CK(cudaMalloc(&s->pblock_list, sizeof(int) * (size_t)g.n_pblocks));
+    CK(cudaMalloc(&s->pblock_list, sizeof(int4) * (size_t)g.n_pblocks));
     CK(cudaMalloc(&s->gflag, sizeof(int) * (size_t)g.n_gblocks));
     CK(cudaMalloc(&s->gblock_list, sizeof(int) * (size_t)g.n_gblocks));
     CK(cudaMalloc(&s->partial, sizeof(int2) * (size_t)s->n_chunks));
@@ -387,7 +388,7 @@ static int launch_p2g(mpm_sim* s, float4* target, float dt) {
         k_p2g_atomic<MODE><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, target, s->gd, s->sc, dt);
         CKLAUNCH();
     } else {
-        CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->blk_start, s->blk_count, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
+        CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
                                   s->num_sms, (int)s->n_bound, s->stream)));
     }
     s->stats.kernel_launches++;
@@ -407,7 +408,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
         k_g2p_direct<FLAGS><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->grid, s->gd, s->sc, dt);
         CKLAUNCH();
     } else {
-        CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->blk_start, s->blk_count, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
+        CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream)));
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);

@@ -168,7 +168,7 @@ __global__ void k_scan_partials(int2* partial, int n_chunks, DevCounters* dc) {
 // pass 3: write blk_start / blk_cursor, the occupied particle-block list, and mark the 2x2x2 grid blocks of
 // every occupied particle block (appended once each to the active grid-block list through an epoch stamp)
 __global__ void k_scan_apply(const int* __restrict__ blk_count, int n, int n_real, const int2* __restrict__ partial,
-                             int* __restrict__ blk_start, int* __restrict__ blk_cursor, int* __restrict__ pblock_list,
+                             int* __restrict__ blk_start, int* __restrict__ blk_cursor, int4* __restrict__ pblock_list,
                              int* __restrict__ gflag, int* __restrict__ gblock_list, DevCounters* dc, GridDims gd) {
     __shared__ int2 sm[32];
     __shared__ int2 tot;
@@ -193,7 +193,7 @@ __global__ void k_scan_apply(const int* __restrict__ blk_count, int n, int n_rea
             if (i == n_real) dc->n_binned = ex.x;                 // start of the parked bucket
             if (i == n_real + 1) dc->n_sorted = ex.x;             // end of the parked bucket
             if (c[e] > 0 && i < n_real) {
-                pblock_list[ex.y] = i;
+                pblock_list[ex.y] = make_int4(i, ex.x, c[e], 0);      // work item: (block id, first sorted rank, count)
                 const int pbk = i % gd.npbk, pbj = (i / gd.npbk) % gd.npbj, pbi = i / (gd.npbk * gd.npbj);
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {

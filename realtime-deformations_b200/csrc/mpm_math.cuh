@@ -48,10 +48,21 @@ MPM_DI float weight_nx_exact(float x) {
 // cell index and the four non-zero per-axis weights (nodes cell-1 .. cell+2).
 // material_point_method.cpp:83 (ivec3(pos / h): IEEE divide + truncation), hpp:53-58 (pos/h - idx).
 MPM_DI int cell_of(float x, float h) { return __float2int_rz(div_rn(x, h)); }
+// The four stencil offsets are q-(cell-1) = fx+1, fx, fx-1, fx-2 with fx = q - cell in [0,1) (all exact in fp32), so
+// the reference's |x|<1 / |x|<2 branches are known statically: far, near, near, far. Branch-free, <= 1 ulp from
+// weight_nx_exact, partition of unity to fp32 rounding.
 MPM_DI void axis_weights(float x, float h, int cell, float w[4]) {
+    const float fx = sub_rn(div_rn(x, h), (float)cell);
+    const float gx = 1.0f - fx;
+    w[0] = 0.16666667163372040f * gx * gx * gx;
+    w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
+    w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
+    w[3] = 0.16666667163372040f * fx * fx * fx;
+}
+MPM_DI void axis_weights_exact(float x, float h, int cell, float w[4]) {
     const float q = div_rn(x, h);
 #pragma unroll
-    for (int d = 0; d < 4; ++d) w[d] = weight_nx(sub_rn(q, (float)(cell - 1 + d)));
+    for (int d = 0; d < 4; ++d) w[d] = weight_nx_exact(sub_rn(q, (float)(cell - 1 + d)));
 }
 
 // ---- glm value-type arithmetic, reference association (see oracle/mpm_oracle.c for the file:line map) ----

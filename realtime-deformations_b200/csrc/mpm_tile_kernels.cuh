@@ -22,7 +22,8 @@
 namespace mpm {
 
 constexpr int P2G_T = 256;         // threads per CTA = 64 cells x 4 x-slabs
-constexpr int P2G_CH = 256;        // particles per chunk
+constexpr int P2G_PPT = 2;         // particles derived per thread per chunk
+constexpr int P2G_CH = P2G_T * P2G_PPT;   // particles per chunk (a full 8-ppc block is one chunk)
 struct P2GSmem {
     union {
         struct {
@@ -32,19 +33,20 @@ struct P2GSmem {
             float4 hA0[P2G_CH], hA1[P2G_CH];   // h*A row-major entries 0..3, 4..7
             float hA8[P2G_CH];
             int gid[P2G_CH];
-            unsigned char lc[P2G_CH], order[P2G_CH];
+            unsigned short order[P2G_CH];
+            unsigned char lc[P2G_CH];
         } c;
         float4 t1[4][4][4][4][7];         // phase 2: z-folded partial sums [cx][cy][a][b][k]
     } u;
     int cell_cnt[64], cell_start[65], cell_cursor[64];
-    int work;
+    int4 work;
 };
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
 template <int MODE>
 __global__ void __launch_bounds__(P2G_T, 2)
-k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_start, const int* __restrict__ blk_count,
-           const int* __restrict__ pblock_list, DevCounters* dc, float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
+k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
+           float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31;
@@ -52,13 +54,18 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
     const int my_cx = my_cell >> 4, my_cy = (my_cell >> 2) & 3, my_cz = my_cell & 3;
     const float fa = (float)my_a;
     const int n_work = dc->n_active_pblocks;
+    int w_next = 0;
+    if (t == 0) w_next = atomicAdd(&dc->work_a, 1);
     for (;;) {
-        if (t == 0) S.work = atomicAdd(&dc->work_a, 1);
+        if (t == 0) {
+            S.work = w_next < n_work ? pblock_list[w_next] : make_int4(-1, 0, 0, 0);
+            w_next = atomicAdd(&dc->work_a, 1);       // consumed one block later: its latency hides behind this block
+        }
+        if (t < 64) S.cell_cnt[t] = 0;
         __syncthreads();
-        const int w = S.work;
-        if (w >= n_work) break;
-        const int b = pblock_list[w];
-        const int start = blk_start[b], cnt = blk_count[b];
+        const int4 wk = S.work;
+        if (wk.x < 0) break;
+        const int b = wk.x, start = wk.y, cnt = wk.z;
         const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;   // global block coords
         float4 acc[16];
 #pragma unroll
@@ -69,29 +76,35 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
         const int n_chunks = (cnt + P2G_CH - 1) / P2G_CH;
         for (int ck = 0; ck < n_chunks; ++ck) {
             const int nch = (cnt - ck + n_chunks - 1) / n_chunks;          // slots ck, ck+n_chunks, ...
-            if (t < 64) S.cell_cnt[t] = 0;
-            __syncthreads();
-            // ---- derive per-particle data ----
-            if (t < nch) {
-                const int gid = sorted_ids[start + ck + t * n_chunks];
-                float4 xm; float mch, a0[3], A[9];
-                p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
-                const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
-                float wx[4], wy[4], wz[4];
-                axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
-                const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
-                S.u.c.wx[0][t] = wx[0]; S.u.c.wx[1][t] = wx[1]; S.u.c.wx[2][t] = wx[2]; S.u.c.wx[3][t] = wx[3];
-                S.u.c.wy[t] = make_float4(wy[0], wy[1], wy[2], wy[3]);
-                S.u.c.wz[t] = make_float4(wz[0], wz[1], wz[2], wz[3]);
-                S.u.c.qc[t] = make_float4(mch, a0[0] + A[0] * d0 + A[1] * d1 + A[2] * d2, a0[1] + A[3] * d0 + A[4] * d1 + A[5] * d2,
-                                          a0[2] + A[6] * d0 + A[7] * d1 + A[8] * d2);
-                S.u.c.hA0[t] = make_float4(A[0] * sc.h, A[1] * sc.h, A[2] * sc.h, A[3] * sc.h);
-                S.u.c.hA1[t] = make_float4(A[4] * sc.h, A[5] * sc.h, A[6] * sc.h, A[7] * sc.h);
-                S.u.c.hA8[t] = A[8] * sc.h;
-                S.u.c.gid[t] = gid;
-                const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
-                S.u.c.lc[t] = (unsigned char)lc;
-                atomicAdd(&S.cell_cnt[lc], 1);
+            if (ck > 0) {
+                if (t < 64) S.cell_cnt[t] = 0;
+                __syncthreads();
+            }
+            // ---- derive per-particle data (P2G_PPT particles per thread, loads of both issued back to back) ----
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) {
+                const int q = t + u * P2G_T;
+                if (q < nch) {
+                    const int gid = sorted_ids[start + ck + q * n_chunks];
+                    float4 xm; float mch, a0[3], A[9];
+                    p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
+                    const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
+                    float wx[4], wy[4], wz[4];
+                    axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
+                    const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
+                    S.u.c.wx[0][q] = wx[0]; S.u.c.wx[1][q] = wx[1]; S.u.c.wx[2][q] = wx[2]; S.u.c.wx[3][q] = wx[3];
+                    S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
+                    S.u.c.wz[q] = make_float4(wz[0], wz[1], wz[2], wz[3]);
+                    S.u.c.qc[q] = make_float4(mch, a0[0] + A[0] * d0 + A[1] * d1 + A[2] * d2, a0[1] + A[3] * d0 + A[4] * d1 + A[5] * d2,
+                                              a0[2] + A[6] * d0 + A[7] * d1 + A[8] * d2);
+                    S.u.c.hA0[q] = make_float4(A[0] * sc.h, A[1] * sc.h, A[2] * sc.h, A[3] * sc.h);
+                    S.u.c.hA1[q] = make_float4(A[4] * sc.h, A[5] * sc.h, A[6] * sc.h, A[7] * sc.h);
+                    S.u.c.hA8[q] = A[8] * sc.h;
+                    S.u.c.gid[q] = gid;
+                    const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
+                    S.u.c.lc[q] = (unsigned char)lc;
+                    atomicAdd(&S.cell_cnt[lc], 1);
+                }
             }
             __syncthreads();
             // ---- counting sort of the chunk by cell (64 bins) ----
@@ -106,11 +119,19 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int* __restrict__ blk_s
                 if (t == 31) S.cell_start[64] = inc;
             }
             __syncthreads();
-            if (t < nch) S.u.c.order[atomicAdd(&S.cell_cursor[S.u.c.lc[t]], 1)] = (unsigned char)t;
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) {
+                const int q = t + u * P2G_T;
+                if (q < nch) S.u.c.order[atomicAdd(&S.cell_cursor[S.u.c.lc[q]], 1)] = (unsigned short)q;
+            }
             __syncthreads();
             // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
             // cells (smem broadcasts) and the re-sorted particle buffer stays cell-coherent for the next substep
-            if (t < nch) sorted_ids[start + ck + t * n_chunks] = S.u.c.gid[S.u.c.order[t]];
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) {
+                const int q = t + u * P2G_T;
+                if (q < nch) sorted_ids[start + ck + q * n_chunks] = S.u.c.gid[S.u.c.order[q]];
+            }
             // ---- phase 1: register accumulation over the particles of my cell ----
             const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
             for (int i = i0; i < i1; ++i) {
@@ -202,66 +223,69 @@ MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) {
     }
 }
 
-constexpr int G2P_T = 256;
+constexpr int G2P_WARPS = 8, G2P_T = G2P_WARPS * 32;
 struct G2PSmem {
-    float4 tile[2][512];                 // two stages of 2x2x2 grid blocks x 64 nodes
-    unsigned long long bar[2];
-    int work[2];
+    float4 tile[G2P_WARPS][512];         // one 2x2x2-grid-block tile (8 x 1 KB) per warp
+    unsigned long long bar[G2P_WARPS];
 };
 
-// issue the eight 1 KB bulk copies of block b's tile into stage st (one thread)
-MPM_DI void g2p_issue_tile(G2PSmem& S, int st, int b, const float4* __restrict__ grid, const GridDims& gd) {
-    const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi_l = b / (gd.npbk * gd.npbj);
-    mbar_expect_tx(&S.bar[st], 8 * 1024);
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-        const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj + ((d >> 1) & 1)) * gd.nbk + pbk + (d & 1);
-        tma_load_1d(&S.tile[st][d * 64], grid + gb * 64, 1024, &S.bar[st]);
-    }
-}
-
-// FLAGS here: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate)
+// Warp-per-block gather: every warp owns a whole particle block at a time (its own TMA-loaded tile, its own
+// mbarrier), so there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
+// FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate).
 template <int FLAGS>
-__global__ void __launch_bounds__(G2P_T)
-k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int* __restrict__ blk_start,
-           const int* __restrict__ blk_count, const int* __restrict__ pblock_list, DevCounters* dc,
+__global__ void __launch_bounds__(G2P_T, 2)
+k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
-    __shared__ __align__(128) G2PSmem S;
-    const int t = threadIdx.x;
+    extern __shared__ __align__(128) unsigned char g2p_smem_raw[];
+    G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_work = dc->n_active_pblocks;
-    if (t == 0) {
-        mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+    float4* __restrict__ tile = S.tile[wid];
+    unsigned long long* bar = &S.bar[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.work[0] = atomicAdd(&dc->work_b, 1);
-        if (S.work[0] < n_work) g2p_issue_tile(S, 0, pblock_list[S.work[0]], grid, gd);
     }
-    __syncthreads();
-    unsigned phase[2] = { 0, 0 };
-    for (int it = 0;; ++it) {
-        const int st = it & 1;
-        const int w = S.work[st];
-        if (w >= n_work) break;
-        // prefetch the next block's tile into the other stage (its readers finished at the end of iteration it-1)
-        if (t == 0) {
-            const int wn = atomicAdd(&dc->work_b, 1);
-            S.work[st ^ 1] = wn;
-            if (wn < n_work) g2p_issue_tile(S, st ^ 1, pblock_list[wn], grid, gd);
-        }
-        const int b = pblock_list[w];
-        const int start = blk_start[b], cnt = blk_count[b];
-        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
-        mbar_wait(&S.bar[st], phase[st]);
-        phase[st] ^= 1;
-        const float4* __restrict__ tile = S.tile[st];
-        for (int base = 0; base < cnt; base += G2P_T) {
-            const int j = start + base + t;
-            if (base + t < cnt) {
-                const int p = sorted_ids[j];
-                struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
-                {
-                    const float4 a0 = cur.p[0][p];
-                    r.x[0] = a0.x; r.x[1] = a0.y; r.x[2] = a0.z; r.m = a0.w;
+    __syncwarp();
+    unsigned phase = 0;
+    for (;;) {
+        int w = 0, b = 0, start = 0, cnt = 0;
+        if (lane == 0) {
+            w = atomicAdd(&dc->work_b, 1);
+            if (w < n_work) {
+                const int4 wk = pblock_list[w];
+                b = wk.x; start = wk.y; cnt = wk.z;
+                const int pbk0 = b % gd.npbk, pbj0 = (b / gd.npbk) % gd.npbj, pbi_l = b / (gd.npbk * gd.npbj);
+                mbar_expect_tx(bar, 8 * 1024);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj0 + ((d >> 1) & 1)) * gd.nbk + pbk0 + (d & 1);
+                    tma_load_1d(&tile[d * 64], grid + gb * 64, 1024, bar);
                 }
+            }
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_work) break;
+        b = __shfl_sync(0xffffffffu, b, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
+        // first slice's particle is requested before waiting for the tile
+        int p = (lane < cnt) ? sorted_ids[start + lane] : -1;
+        float4 a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        for (int base = 0; base < cnt; base += 32) {
+            const int j = start + base + lane;
+            const bool active = base + lane < cnt;
+            // software prefetch of the next slice
+            const int p_cur = p;
+            const float4 a_cur = a0;
+            if (base + 32 < cnt) {
+                p = (base + 32 + lane < cnt) ? sorted_ids[j + 32] : -1;
+                a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (active) {
+                struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
+                r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
                 {
                     const int cx = cell_of(r.x[0], sc.h), cy = cell_of(r.x[1], sc.h), cz = cell_of(r.x[2], sc.h);
                     float wx[4], wy[4], wz[4];
@@ -311,14 +335,14 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                     }
                 }
                 const Planes& D = (FLAGS & G2P_REORDER) ? nxt : cur;
-                const int q = (FLAGS & G2P_REORDER) ? j : p;
+                const int q = (FLAGS & G2P_REORDER) ? j : p_cur;
                 if (FLAGS & (G2P_ADVECT | G2P_REORDER)) D.p[0][q] = make_float4(r.x[0], r.x[1], r.x[2], r.m);
                 D.p[1][q] = make_float4(r.B[0], r.B[1], r.B[2], r.B[3]);
                 D.p[2][q] = make_float4(r.B[4], r.B[5], r.B[6], r.B[7]);
                 D.p[3][q] = make_float4(r.B[8], r.v[0], r.v[1], r.v[2]);
             }
         }
-        __syncthreads();     // everyone is done with tile[st] and has seen work[st^1]
+        __syncwarp();     // every lane is done with the tile before the next bulk copy overwrites it
     }
 }
 
@@ -336,21 +360,24 @@ inline cudaError_t tile_kernels_init() {
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
     MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
 #undef MPM_SET_SMEM
+#define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
+    MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
+#undef MPM_SET_SMEM2
     return cudaSuccess;
 }
 
 template <int MODE>
-cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int* blk_start, const int* blk_count, const int* pblock_list,
+cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
+    k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
     return cudaGetLastError();
 }
 
 template <int FLAGS>
-cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int* blk_start, const int* blk_count, const int* pblock_list,
+cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
@@ -359,7 +386,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_GATHER) {
-        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * 4, G2P_T, 0, st>>>(C, N, sorted_ids, blk_start, blk_count, pblock_list, dc, grid, gd, sc, dt);
+        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * 2, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_REORDER) {
