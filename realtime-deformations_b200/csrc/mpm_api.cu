@@ -99,6 +99,33 @@ static void fill_consts(mpm_sim* s) {
     c.pos_lo = (float)(3 * p.h);                                                                     // cpp:383
     c.pos_hi[0] = (float)((s->gd.I - 3) * p.h); c.pos_hi[1] = (float)((s->gd.J - 3) * p.h); c.pos_hi[2] = (float)((s->gd.K - 3) * p.h);
     c.inv_h3 = 1.0f / (p.h * p.h * p.h);
+    c.pd.h = p.h; c.pd.rh = 1.0f / p.h;
+    // the fast quotient is validated (validate_pos_div) on [2h, (max dim + 2) h]: every position whose particle is not
+    // parked anyway lies in there (cell >= 2), see particle_key
+    const int md = std::max(s->gd.I, std::max(s->gd.J, s->gd.K));
+    c.pd.lo = 2.0f * p.h; c.pd.hi = (float)(md + 2) * p.h;
+}
+
+// runs once per handle: exhaustive comparison of the pos/h shortcut with __fdiv_rn over its whole range
+static int validate_pos_div(mpm_sim* s) {
+    PosDiv& d = s->sc.pd;
+    d.fast = 0;
+    unsigned lo, hi;
+    memcpy(&lo, &d.lo, 4); memcpy(&hi, &d.hi, 4);
+    if (!(d.lo > 0.0f) || !(d.hi > d.lo)) return MPM_OK;
+    unsigned long long* bad = nullptr;
+    CK(cudaMalloc(&bad, sizeof *bad));
+    CK(cudaMemsetAsync(bad, 0, sizeof *bad, s->stream));
+    k_validate_pos_div<<<s->num_sms * 8, 256, 0, s->stream>>>(d, lo, hi, bad);
+    unsigned long long h_bad = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, sizeof h_bad, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(bad);
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "validate_pos_div: %s", cudaGetErrorString(e));
+    d.fast = (h_bad == 0) ? 1 : 0;
+    s->stats.kernel_launches++;
+    return MPM_OK;
 }
 
 static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
@@ -156,6 +183,7 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
     CK(cudaStreamSynchronize(s->stream));
+    { int rc = validate_pos_div(s); if (rc) return rc; }
     *out = s;
     return MPM_OK;
 }
@@ -189,7 +217,9 @@ int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
     if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
     s->prm = *p;
+    const int fast = s->sc.pd.fast;
     fill_consts(s);
+    s->sc.pd.fast = fast;           // h is unchanged, so the validation still holds
     s->tau_valid = false;
     return MPM_OK;
 }
@@ -341,7 +371,7 @@ static int do_binning(mpm_sim* s) {
     CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
     const int nb = grid_for(s->n_bound, 256);
     Planes C = s->planes(s->cur);
-    k_bin_count<<<nb, 256, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.h, s->key, s->blk_count);
+    k_bin_count<<<nb, 256, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.pd, s->key, s->blk_count);
     CKLAUNCH();
     k_scan_reduce<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial);
     CKLAUNCH();
@@ -538,6 +568,8 @@ int mpm_get_stats(mpm_t* s, MpmStats* out) {
     MpmStats& st = s->stats;
     st.n_particles = h.n_slots; st.n_out_of_grid = h.n_out_of_grid; st.n_active_nodes = h.n_active_nodes;
     st.n_particle_blocks = h.n_active_pblocks; st.n_grid_blocks = h.n_active_gblocks; st.svd_failed = h.svd_failed;
+    st.reserved[0] = s->sc.pd.fast;      // 1: the pos/h FMA shortcut passed its exhaustive check against __fdiv_rn
+    st.reserved[1] = h.mig_overflow;
     if (st.substeps_done > 0) {
         float ms;
         const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 4, 5 }, { 5, 6 }, { 3, 4 } };
@@ -592,7 +624,7 @@ int mpm_download_binning(mpm_t* s, int64_t n, int32_t* cells3, int32_t* block_ke
     int *dc3 = nullptr, *dk = nullptr;
     CK(cudaMalloc(&dc3, sizeof(int) * 3 * (size_t)std::max<int64_t>(n, 1)));
     CK(cudaMalloc(&dk, sizeof(int) * (size_t)std::max<int64_t>(n, 1)));
-    k_binning_debug<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->key, s->dc, s->sc.h, dc3, dk);
+    k_binning_debug<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->key, s->dc, s->sc.pd, dc3, dk);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && cells3) e = cudaMemcpyAsync(cells3, dc3, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess && block_key) e = cudaMemcpyAsync(block_key, dk, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
@@ -636,7 +668,7 @@ int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** 
         for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->out_buf[d], sizeof(float4) * NPLANES * (size_t)s->out_cap));
     }
     CK(cudaMemsetAsync(s->dc->n_mig, 0, 3 * sizeof(int), s->stream));
-    k_mark_outgoing<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.h, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
+    k_mark_outgoing<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
     DevCounters h;
     CK(cudaMemcpyAsync(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost, s->stream));

@@ -34,6 +34,7 @@ struct SimConst {
     float g[3];
     float pos_lo, pos_hi[3];   // clampPosition bounds (cpp:381-388)
     float inv_h3;              // unused by bit-faithful paths
+    PosDiv pd;                 // pos / h
 };
 
 // device-resident counters (one struct per handle); nothing here needs a host sync inside a substep
@@ -58,12 +59,25 @@ enum { KEY_DEAD = -2 };
 
 struct ColliderSet { BoxCollider c[16]; };
 
+// exhaustive check of the pos/h shortcut: every fp32 bit pattern in [lo_bits, hi_bits] against the IEEE intrinsic
+__global__ void k_validate_pos_div(PosDiv pd, unsigned lo_bits, unsigned hi_bits, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long)lo_bits + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b <= hi_bits;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)b);
+        const float q0 = mul_rn(x, pd.rh);
+        const float q = __fmaf_rn(__fmaf_rn(-q0, pd.h, x), pd.rh, q0);
+        bad += (__float_as_uint(q) != __float_as_uint(div_rn(x, pd.h)));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------------------
-MPM_DI int particle_key(float4 xm, const GridDims& gd, float h, int* cells /*3*/) {
+MPM_DI int particle_key(float4 xm, const GridDims& gd, const PosDiv& pd, int* cells /*3*/) {
     if (xm.w < 0.0f) return KEY_DEAD;
-    const int cx = cell_of(xm.x, h), cy = cell_of(xm.y, h), cz = cell_of(xm.z, h);
+    const int cx = cell_of(xm.x, pd), cy = cell_of(xm.y, pd), cz = cell_of(xm.z, pd);
     cells[0] = cx; cells[1] = cy; cells[2] = cz;
     // the reference enumerates cell-2..cell+2 without bounds checks (cpp:84-91); outside that the particle is parked
     const bool ok = cx >= 2 && cy >= 2 && cz >= 2 && cx + 2 <= gd.I - 1 && cy + 2 <= gd.J - 1 && cz + 2 <= gd.K - 1;
@@ -75,12 +89,12 @@ MPM_DI int particle_key(float4 xm, const GridDims& gd, float h, int* cells /*3*/
 }
 
 __global__ void k_bin_count(const float4* __restrict__ P0, int n_bound, const DevCounters* __restrict__ dc,
-                            GridDims gd, float h, int* __restrict__ key, int* __restrict__ blk_count) {
+                            GridDims gd, PosDiv pd, int* __restrict__ key, int* __restrict__ blk_count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int k = KEY_DEAD;
     if (j < n_bound && j < dc->n_slots) {
         int cells[3];
-        k = particle_key(P0[j], gd, h, cells);
+        k = particle_key(P0[j], gd, pd, cells);
         key[j] = k;
     }
     // warp-aggregated histogram: one atomic per distinct key per warp
@@ -326,9 +340,9 @@ __global__ void k_p2g_atomic(Planes P, const int* __restrict__ sorted_ids, const
     const int p = sorted_ids[j];
     float4 xm; float mch, a0[3], A[9];
     p2g_coeffs<MODE>(P, p, sc.dinv, dt, xm, mch, a0, A);
-    const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
+    const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
     float wx[4], wy[4], wz[4];
-    axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
+    axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const float dx = (float)(cx - 1 + a) * sc.h - xm.x;
@@ -445,9 +459,9 @@ __global__ void k_volumes(Planes P, const int* __restrict__ sorted_ids, const De
     const float4 xm = P.p[0][p];
     float density = 0.0f;
     if (j < dc->n_binned) {
-        const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
+        const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
         float wx[4], wy[4], wz[4];
-        axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
+        axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
         for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) for (int c = 0; c < 4; ++c) {
             const float w = mul_rn(mul_rn(wx[a], wy[b]), wz[c]);
             density = add_rn(density, mul_rn(grid[node_index(gd, cx - 1 + a, cy - 1 + b, cz - 1 + c)].x, w));
@@ -487,9 +501,9 @@ __global__ void k_g2p_direct(Planes cur, Planes nxt, const int* __restrict__ sor
             if (!particle_f_update(r, sc, dt)) dc->svd_failed = 1;
         }
         if (FLAGS & G2P_GATHER) {
-            const int cx = cell_of(r.x[0], sc.h), cy = cell_of(r.x[1], sc.h), cz = cell_of(r.x[2], sc.h);
+            const int cx = cell_of(r.x[0], sc.pd), cy = cell_of(r.x[1], sc.pd), cz = cell_of(r.x[2], sc.pd);
             float wx[4], wy[4], wz[4];
-            axis_weights(r.x[0], sc.h, cx, wx); axis_weights(r.x[1], sc.h, cy, wy); axis_weights(r.x[2], sc.h, cz, wz);
+            axis_weights(r.x[0], sc.pd, cx, wx); axis_weights(r.x[1], sc.pd, cy, wy); axis_weights(r.x[2], sc.pd, cz, wz);
             float v[3] = { 0, 0, 0 }, Bn[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -554,7 +568,7 @@ __global__ void k_render_slots(Planes cur, float4* __restrict__ xyzs, const DevC
     const float4 a0 = p < dc->n_slots ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, -1.f);
     xyzs[p] = make_float4(a0.x, a0.y, a0.z, a0.w < 0.0f ? 0.0f : size);
 }
-__global__ void k_binning_debug(Planes cur, const int* __restrict__ key, const DevCounters* __restrict__ dc, float h,
+__global__ void k_binning_debug(Planes cur, const int* __restrict__ key, const DevCounters* __restrict__ dc, PosDiv h,
                                 int* __restrict__ cells3, int* __restrict__ key_out) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dc->n_slots) return;
@@ -566,14 +580,14 @@ __global__ void k_binning_debug(Planes cur, const int* __restrict__ key, const D
 }
 // ---- slab migration: pack particles whose block layer left [lo, hi) and retire their slots ----
 // record = 11 float4 (the particle's planes, particle-major) = MPM_MIGRATE_FLOATS floats
-__global__ void k_mark_outgoing(Planes cur, DevCounters* dc, GridDims gd, float h, float4* __restrict__ out_down,
+__global__ void k_mark_outgoing(Planes cur, DevCounters* dc, GridDims gd, PosDiv pd, float4* __restrict__ out_down,
                                 float4* __restrict__ out_up, int cap) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dc->n_slots) return;
     const float4 a0 = cur.p[0][p];
     if (a0.w < 0.0f) return;
     int cells[3];
-    const int k = particle_key(a0, gd, h, cells);
+    const int k = particle_key(a0, gd, pd, cells);
     if (k != gd.n_pblocks + 1 && k != gd.n_pblocks + 2) return;
     const int dir = k - (gd.n_pblocks + 1);
     const int idx = atomicAdd(&dc->n_mig[dir], 1);

@@ -45,22 +45,35 @@ MPM_DI float weight_nx_exact(float x) {
     return 0.0f;
 }
 
+// pos / h must be the IEEE-754 quotient (the cell index ivec3(pos / h), material_point_method.cpp:83, is bit-exact
+// index work). h is a per-scene constant, so the quotient is formed as q0 = x*rh, q = fma(fma(-q0, h, x), rh, q0) with
+// rh = RN(1/h): three dependent FMA-pipe ops instead of the ~10-instruction __fdiv_rn sequence. That shortcut is
+// only used on [lo, hi], where mpm_create has checked it EXHAUSTIVELY (every fp32 in the range) against __fdiv_rn
+// for this h; elsewhere, or if the check ever failed, the exact intrinsic runs.
+struct PosDiv { float h, rh, lo, hi; int fast; };
+MPM_DI float pos_div(float x, const PosDiv& d) {
+    if (d.fast && x >= d.lo && x <= d.hi) {
+        const float q0 = mul_rn(x, d.rh);
+        return __fmaf_rn(__fmaf_rn(-q0, d.h, x), d.rh, q0);
+    }
+    return div_rn(x, d.h);
+}
 // cell index and the four non-zero per-axis weights (nodes cell-1 .. cell+2).
 // material_point_method.cpp:83 (ivec3(pos / h): IEEE divide + truncation), hpp:53-58 (pos/h - idx).
-MPM_DI int cell_of(float x, float h) { return __float2int_rz(div_rn(x, h)); }
+MPM_DI int cell_of(float x, const PosDiv& d) { return __float2int_rz(pos_div(x, d)); }
 // The four stencil offsets are q-(cell-1) = fx+1, fx, fx-1, fx-2 with fx = q - cell in [0,1) (all exact in fp32), so
 // the reference's |x|<1 / |x|<2 branches are known statically: far, near, near, far. Branch-free, <= 1 ulp from
 // weight_nx_exact, partition of unity to fp32 rounding.
-MPM_DI void axis_weights(float x, float h, int cell, float w[4]) {
-    const float fx = sub_rn(div_rn(x, h), (float)cell);
+MPM_DI void axis_weights(float x, const PosDiv& d, int cell, float w[4]) {
+    const float fx = sub_rn(pos_div(x, d), (float)cell);
     const float gx = 1.0f - fx;
     w[0] = 0.16666667163372040f * gx * gx * gx;
     w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
     w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
     w[3] = 0.16666667163372040f * fx * fx * fx;
 }
-MPM_DI void axis_weights_exact(float x, float h, int cell, float w[4]) {
-    const float q = div_rn(x, h);
+MPM_DI void axis_weights_exact(float x, const PosDiv& d, int cell, float w[4]) {
+    const float q = pos_div(x, d);
 #pragma unroll
     for (int d = 0; d < 4; ++d) w[d] = weight_nx_exact(sub_rn(q, (float)(cell - 1 + d)));
 }

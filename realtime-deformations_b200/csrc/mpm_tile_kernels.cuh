@@ -54,16 +54,28 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
     const int my_cx = my_cell >> 4, my_cy = (my_cell >> 2) & 3, my_cz = my_cell & 3;
     const float fa = (float)my_a;
     const int n_work = dc->n_active_pblocks;
-    int w_next = 0;
-    if (t == 0) w_next = atomicAdd(&dc->work_a, 1);
+    // work pipeline of thread 0: the atomic ticket is drawn two blocks ahead and its work item (block id, first rank,
+    // count) one block ahead, so neither latency is ever waited for; everybody else pre-loads the ids of the next
+    // block's first chunk during phase 2.
+    int w_ticket = 0;
+    int4 wk_reg = make_int4(-1, 0, 0, 0);
+    if (t == 0) {
+        const int w0 = atomicAdd(&dc->work_a, 1);
+        S.work = w0 < n_work ? pblock_list[w0] : make_int4(-1, 0, 0, 0);
+        w_ticket = atomicAdd(&dc->work_a, 1);
+    }
+    __syncthreads();
+    int gid_pref[P2G_PPT];
+    {
+        const int4 wk0 = S.work;
+        const int nck0 = (wk0.z + P2G_CH - 1) / P2G_CH, nch0 = nck0 ? (wk0.z + nck0 - 1) / nck0 : 0;
+#pragma unroll
+        for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wk0.x >= 0 && q < nch0) ? sorted_ids[wk0.y + q * nck0] : 0; }
+    }
     for (;;) {
-        if (t == 0) {
-            S.work = w_next < n_work ? pblock_list[w_next] : make_int4(-1, 0, 0, 0);
-            w_next = atomicAdd(&dc->work_a, 1);       // consumed one block later: its latency hides behind this block
-        }
-        if (t < 64) S.cell_cnt[t] = 0;
-        __syncthreads();
         const int4 wk = S.work;
+        if (t < 64) S.cell_cnt[t] = 0;
+        __syncthreads();          // also: everyone has read S.work, and phase 2b of the previous block is done with t1
         if (wk.x < 0) break;
         const int b = wk.x, start = wk.y, cnt = wk.z;
         const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;   // global block coords
@@ -85,12 +97,12 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
                 if (q < nch) {
-                    const int gid = sorted_ids[start + ck + q * n_chunks];
+                    const int gid = ck == 0 ? gid_pref[u] : sorted_ids[start + ck + q * n_chunks];
                     float4 xm; float mch, a0[3], A[9];
                     p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
-                    const int cx = cell_of(xm.x, sc.h), cy = cell_of(xm.y, sc.h), cz = cell_of(xm.z, sc.h);
+                    const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
                     float wx[4], wy[4], wz[4];
-                    axis_weights(xm.x, sc.h, cx, wx); axis_weights(xm.y, sc.h, cy, wy); axis_weights(xm.z, sc.h, cz, wz);
+                    axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
                     S.u.c.wx[0][q] = wx[0]; S.u.c.wx[1][q] = wx[1]; S.u.c.wx[2][q] = wx[2]; S.u.c.wx[3][q] = wx[3];
                     S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
@@ -157,6 +169,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             }
             __syncthreads();
         }
+        if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[w_ticket] : make_int4(-1, 0, 0, 0);   // issued here, stored below
         // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
         // node k = cz + c; this lane ends up owning k = cz (slot 0) and k = cz + 4 (slot 1, cz <= 2)
         float4 s0[4], s1[4];
@@ -180,7 +193,14 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             S.u.t1[my_cx][my_cy][my_a][bb][my_cz] = s0[bb];
             if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb][my_cz + 4] = s1[bb];
         }
+        if (t == 0) { S.work = wk_reg; w_ticket = atomicAdd(&dc->work_a, 1); }
         __syncthreads();
+        {   // ids of the next block's first chunk: in flight while this block's tile is reduced and written back
+            const int4 wn = S.work;
+            const int nckn = (wn.z + P2G_CH - 1) / P2G_CH, nchn = nckn ? (wn.z + nckn - 1) / nckn : 0;
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wn.x >= 0 && q < nchn) ? sorted_ids[wn.y + q * nckn] : 0; }
+        }
         // ---- phase 2b: fold x and y from smem (<= 16 terms per tile node), one vector red per node ----
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
@@ -197,7 +217,6 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -268,28 +287,28 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
         if (w >= n_work) break;
         b = __shfl_sync(0xffffffffu, b, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
         const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
-        // first slice's particle is requested before waiting for the tile
+        // software pipeline over the 32-particle slices: ids two slices ahead, positions one slice ahead, so neither
+        // the sorted_ids -> position dependent-load chain nor the position load is waited for
         int p = (lane < cnt) ? sorted_ids[start + lane] : -1;
+        int p_nn = (32 + lane < cnt) ? sorted_ids[start + 32 + lane] : -1;
         float4 a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(bar, phase);
         phase ^= 1;
         for (int base = 0; base < cnt; base += 32) {
             const int j = start + base + lane;
             const bool active = base + lane < cnt;
-            // software prefetch of the next slice
             const int p_cur = p;
             const float4 a_cur = a0;
-            if (base + 32 < cnt) {
-                p = (base + 32 + lane < cnt) ? sorted_ids[j + 32] : -1;
-                a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            p = p_nn;
+            a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
+            p_nn = (base + 64 + lane < cnt) ? sorted_ids[j + 64] : -1;
             if (active) {
                 struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
                 r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
                 {
-                    const int cx = cell_of(r.x[0], sc.h), cy = cell_of(r.x[1], sc.h), cz = cell_of(r.x[2], sc.h);
+                    const int cx = cell_of(r.x[0], sc.pd), cy = cell_of(r.x[1], sc.pd), cz = cell_of(r.x[2], sc.pd);
                     float wx[4], wy[4], wz[4];
-                    axis_weights(r.x[0], sc.h, cx, wx); axis_weights(r.x[1], sc.h, cy, wy); axis_weights(r.x[2], sc.h, cz, wz);
+                    axis_weights(r.x[0], sc.pd, cx, wx); axis_weights(r.x[1], sc.pd, cy, wy); axis_weights(r.x[2], sc.pd, cz, wz);
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     int offx[4], offy[4], offz[4];
                     float wxd[4], wyd[4], wzd[4];
