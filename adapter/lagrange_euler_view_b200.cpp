@@ -1,0 +1,157 @@
+// Drop-in replacement for the reference's material_point_method.cpp.
+//
+// It defines the member functions that the reference's OWN header declares (material_point_method.hpp:174-233,
+// compiled unmodified from /root/reference) by forwarding every MPM stage to libmpm_b200.so through the C ABI of
+// include/mpm_b200.h. A viewer built from the reference's main.cpp links against this file instead of
+// material_point_method.cpp and calls the very same methods (main.cpp:50-54, 192-218, 257-260):
+//
+//     reference member                              ->  C ABI entry point
+//     LagrangeEulerView(max_i,max_j,max_k,n)        ->  mpm_create
+//     ~LagrangeEulerView                            ->  mpm_destroy
+//     initializeParticles                           ->  host-side fill (same rule) + mpm_upload_particles_aos
+//     rasterizeParticlesToGrid                      ->  mpm_rasterize_particles_to_grid
+//     computeParticleVolumesAndDensities            ->  mpm_compute_particle_volumes_and_densities
+//     computeExplicitGridForces                     ->  mpm_compute_explicit_grid_forces
+//     gridVelocitiesUpdate(dt)                      ->  mpm_grid_velocities_update
+//     gridBasedCollisions(dt, objects)              ->  mpm_grid_based_collisions (MeshCollider -> MpmBoxCollider)
+//     updateDeformationGradient(dt)                 ->  mpm_update_deformation_gradient
+//     updateParticleVelocities                      ->  mpm_update_particle_velocities
+//     updateParticlePositions(dt)                   ->  mpm_update_particle_positions + mirror into std::vector<Particle>
+//     getParticles / getNumParticles (inline)       ->  unchanged: they read the mirrored host vector
+//     cuP2G / devH (cudaCalc.cuh)                   ->  link-compatibility symbols, no-ops (dead path in the reference)
+//
+// The class layout is the reference's, so per-instance adapter state lives in a side table keyed by `this`.
+#include "material_point_method.hpp"
+#include "utils.h"
+#include "cudaCalc.cuh"
+
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
+#include "../include/mpm_b200.h"
+
+ftype devH = 0.0f;
+void cuP2G(MaterialPointMethod::Particle*, MaterialPointMethod::Cell*, int, int, int, int, ftype*) {}
+
+namespace MaterialPointMethod {
+
+ftype WeightCalculator::h = 0.05f;      // same default as material_point_method.cpp:17
+
+namespace {
+struct Binding { mpm_t* sim = nullptr; bool uploaded = false; };
+std::unordered_map<const LagrangeEulerView*, Binding>& table() { static std::unordered_map<const LagrangeEulerView*, Binding> t; return t; }
+std::mutex& table_mutex() { static std::mutex m; return m; }
+Binding& binding(const LagrangeEulerView* v) { std::lock_guard<std::mutex> g(table_mutex()); return table()[v]; }
+
+void check(int rc, const char* what) {
+    // the reference's own convention: print and carry on (hpp:125-127, cpp:146-152)
+    if (rc != MPM_OK) std::printf("mpm_b200 error in %s: %s\n", what, mpm_last_error());
+}
+constexpr size_t OFF_MASS = offsetof(Particle, mass), OFF_VEL = offsetof(Particle, velocity), OFF_VOL = offsetof(Particle, volume),
+                 OFF_POS = offsetof(Particle, pos), OFF_FE = offsetof(Particle, FElastic), OFF_FP = offsetof(Particle, FPlastic),
+                 OFF_B = offsetof(Particle, B);
+}  // namespace
+
+// The dense WeightStorage / Grid members only serve the reference's dead CUDA path and its CPU loops; they are
+// constructed at 1x1x1 here instead of I*J*K*N floats.
+LagrangeEulerView::LagrangeEulerView(int max_i, int max_j, int max_k, int particlesNum)
+    : MAX_I(max_i), MAX_J(max_j), MAX_K(max_k), devParticles(nullptr), w{ 1, 1, 1, 1 }, grid{ 1, 1, 1 }, nParticles(particlesNum) {
+    particles.resize(nParticles);
+    MpmParams prm;
+    mpm_default_params(&prm);
+    prm.h = WeightCalculator::h;
+    Binding& b = binding(this);
+    check(mpm_create(&prm, max_i, max_j, max_k, particlesNum, &b.sim), "mpm_create");
+    devH = WeightCalculator::h;
+}
+
+LagrangeEulerView::~LagrangeEulerView() {
+    std::lock_guard<std::mutex> g(table_mutex());
+    auto it = table().find(this);
+    if (it != table().end()) { mpm_destroy(it->second.sim); table().erase(it); }
+}
+
+// Same fill rule as material_point_method.cpp:18-63 (8 jittered sites per cell inside a ball of radius 0.2 around the
+// origin, slots filled from the back, three colour draws per accepted particle while slots remain), so that the
+// default libc rand() stream produces the reference's particles.
+void LagrangeEulerView::initializeParticles(const v3t& particlesOrigin, const v3t& velocity) {
+    const ftype radius = 0.2;
+    const glm::ivec3 centre{ particlesOrigin / WeightCalculator::h };
+    const int reach = radius / WeightCalculator::h;
+    int free_slots = nParticles, missing = 0;
+    const glm::vec3 sites[] = { {1, 1, 1}, {1, 1, 3}, {1, 3, 1}, {1, 3, 3}, {3, 1, 1}, {3, 1, 3}, {3, 3, 1}, {3, 3, 3} };
+    for (int i = centre.x - reach; i < centre.x + reach; ++i)
+        for (int j = centre.y - reach; j < centre.y + reach; ++j)
+            for (int k = centre.z - reach; k < centre.z + reach; ++k)
+                for (const auto& site : sites) {
+                    const auto candidate = (glm::vec3(i, j, k) + site * (1 / 4.0f) + generateRandomInsideUnitBall(0.25)) * WeightCalculator::h;
+                    if (glm::length(candidate - particlesOrigin) > radius) continue;
+                    if (free_slots == 0) { ++missing; continue; }
+                    Particle& p = particles[--free_slots];
+                    p.pos = candidate;
+                    p.velocity = velocity;
+                    rand(); rand(); rand();                 // the reference draws (and then overwrites) r, g, b
+                    p.r = p.g = p.b = p.a = 255;
+                    p.size = 0.02;
+                    p.mass = 0.00006;
+                }
+    if (missing) std::cout << missing << " more!!!\n";
+    binding(this).uploaded = false;
+}
+
+void LagrangeEulerView::precalculateWeights() {}    // the reference's dead CUDA side-car (cpp:65-76): nothing to do
+
+static void upload_if_needed(LagrangeEulerView* v, Particle* particles, int n) {
+    Binding& b = binding(v);
+    if (b.uploaded) return;
+    check(mpm_upload_particles_aos(b.sim, particles, n, sizeof(Particle), OFF_MASS, OFF_VEL, OFF_VOL, OFF_POS, OFF_FE, OFF_FP, OFF_B),
+          "mpm_upload_particles_aos");
+    b.uploaded = true;
+}
+
+void LagrangeEulerView::rasterizeParticlesToGrid() {
+    upload_if_needed(this, particles.data(), nParticles);
+    check(mpm_rasterize_particles_to_grid(binding(this).sim), "rasterizeParticlesToGrid");
+}
+
+void LagrangeEulerView::computeParticleVolumesAndDensities() {
+    Binding& b = binding(this);
+    check(mpm_compute_particle_volumes_and_densities(b.sim), "computeParticleVolumesAndDensities");
+    // volumes are host-visible state in the reference (Particle::volume)
+    check(mpm_download_particles_aos(b.sim, particles.data(), nParticles, sizeof(Particle), OFF_MASS, OFF_VEL, OFF_VOL, OFF_POS, OFF_FE,
+                                     OFF_FP, OFF_B), "mpm_download_particles_aos");
+}
+
+void LagrangeEulerView::computeExplicitGridForces() { check(mpm_compute_explicit_grid_forces(binding(this).sim), "computeExplicitGridForces"); }
+void LagrangeEulerView::gridVelocitiesUpdate(ftype timeDelta) { check(mpm_grid_velocities_update(binding(this).sim, timeDelta), "gridVelocitiesUpdate"); }
+void LagrangeEulerView::timeIntegration(ftype) { logger.log(Logger::LogLevel::WARNING, "timeIntegration: the implicit integrator is not part of the live path"); }
+
+void LagrangeEulerView::gridBasedCollisions(ftype timeDelta, const std::vector<MeshCollider>& objects) {
+    std::vector<MpmBoxCollider> boxes(objects.size());
+    for (size_t k = 0; k < objects.size(); ++k) {
+        const auto& m = objects[k].mesh;
+        // exactly what MeshCollider::sdf evaluates per call (hpp:80-83), hoisted to once per collider per substep
+        const glm::mat4 inv = glm::inverse(glm::translate(glm::mat4(), m.translation) * glm::toMat4(m.rotation));
+        const glm::vec4 b4 = glm::scale(glm::mat4(), m.scale) * glm::vec4{ 1, 1, 1, 1 };
+        for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) boxes[k].world_to_local[c * 4 + r] = inv[c][r];
+        boxes[k].half_extent[0] = b4.x; boxes[k].half_extent[1] = b4.y; boxes[k].half_extent[2] = b4.z;
+        boxes[k].velocity[0] = objects[k].velocity.x; boxes[k].velocity[1] = objects[k].velocity.y; boxes[k].velocity[2] = objects[k].velocity.z;
+    }
+    check(mpm_grid_based_collisions(binding(this).sim, timeDelta, boxes.data(), (int)boxes.size()), "gridBasedCollisions");
+}
+
+void LagrangeEulerView::updateDeformationGradient(ftype timeDelta) { check(mpm_update_deformation_gradient(binding(this).sim, timeDelta), "updateDeformationGradient"); }
+void LagrangeEulerView::updateParticleVelocities() { check(mpm_update_particle_velocities(binding(this).sim), "updateParticleVelocities"); }
+
+void LagrangeEulerView::updateParticlePositions(ftype timeDelta) {
+    Binding& b = binding(this);
+    check(mpm_update_particle_positions(b.sim, timeDelta), "updateParticlePositions");
+    // getParticles() hands the viewer a pointer into `particles` (hpp:181-183, main.cpp:257-271): mirror the state
+    check(mpm_download_particles_aos(b.sim, particles.data(), nParticles, sizeof(Particle), OFF_MASS, OFF_VEL, OFF_VOL, OFF_POS, OFF_FE,
+                                     OFF_FP, OFF_B), "mpm_download_particles_aos");
+}
+
+}  // namespace MaterialPointMethod

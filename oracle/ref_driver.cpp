@@ -251,6 +251,7 @@ int main(int argc, char** argv) {
         writeFile(dumpDir + "/colliders.f32", c);
     }
 
+#ifndef DRIVER_NO_KAT                 // (the adapter build has no private bodyCollision to call)
     if (katMode == "collide") {       // material_point_method.cpp:264-296; in: m x 6 (pos, vel) -> out: m x 3
         std::vector<float> in = readFile(katIn), out(in.size() / 2);
         for (size_t i = 0; i + 6 <= in.size(); i += 6) {
@@ -259,6 +260,7 @@ int main(int argc, char** argv) {
         }
         writeFile(katOut, out); return 0;
     }
+#endif
 
     // ---- main.cpp:163-218: one substep per frame ----
     char name[256];
