@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpm_b200.so")
+LIB_PATH = os.environ.get("MPM_B200_LIB", os.path.join(HERE, "libmpm_b200.so"))   # override: A/B builds during tuning
 MIGRATE_FLOATS = 44
 
 

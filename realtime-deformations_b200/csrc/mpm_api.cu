@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,7 @@ struct mpm_sim {
     int num_sms = 148;
     cudaEvent_t ev[8];
     bool ev_ok = false;
+    SideStream side = { nullptr, nullptr, nullptr, 1 };   // F-update || gather (MPM_B200_OVERLAP=0 disables)
     MpmStats stats;
     ColliderSet colliders; int n_colliders = 0;
 
@@ -179,6 +181,16 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s->buf[b], 0, sizeof(float4) * NPLANES * (size_t)s->capacity, s->stream));
     for (auto& e : s->ev) CK(cudaEventCreate(&e));
     s->ev_ok = true;
+    {
+        const char* ov = getenv("MPM_B200_OVERLAP");
+        const int mode = ov ? atoi(ov) : 1;
+        if (mode > 0) {
+            CK(cudaStreamCreateWithFlags(&s->side.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->side.fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->side.join, cudaEventDisableTiming));
+            s->side.gather_ctas_per_sm = mode >= 2 ? 2 : 1;
+        }
+    }
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
@@ -201,6 +213,7 @@ int mpm_destroy(mpm_t* s) {
     cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
+    if (s->side.stream) { cudaStreamDestroy(s->side.stream); cudaEventDestroy(s->side.fork); cudaEventDestroy(s->side.join); }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return MPM_OK;
@@ -439,7 +452,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
         CKLAUNCH();
     } else {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
-                                   s->num_sms, (int)s->n_bound, s->stream)));
+                                   s->num_sms, (int)s->n_bound, s->stream, &s->side)));
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {

@@ -27,7 +27,7 @@ constexpr int P2G_CH = P2G_T * P2G_PPT;   // particles per chunk (a full 8-ppc b
 struct P2GSmem {
     union {
         struct {
-            float wx[4][P2G_CH];          // wx[a][particle]
+            float4 wx[P2G_CH];            // read as scalar component [a] (4 slab lanes of a cell hit 4 consecutive banks)
             float4 wy[P2G_CH], wz[P2G_CH];
             float4 qc[P2G_CH];            // (mass channel, c0.x, c0.y, c0.z)
             float4 hA0[P2G_CH], hA1[P2G_CH];   // h*A row-major entries 0..3, 4..7
@@ -36,7 +36,9 @@ struct P2GSmem {
             unsigned short order[P2G_CH];
             unsigned char lc[P2G_CH];
         } c;
-        float4 t1[4][4][4][4][7];         // phase 2: z-folded partial sums [cx][cy][a][b][k]
+        float4 t1[4][4][4][42];           // phase 2: z-folded partial sums [cx][cy][a][b*7 + k]; the a-stride is padded
+                                          // from 28 to 42 float4 (= 2 mod 8 slots) so that a quarter-warp's stores
+                                          // (a = 0..3, two consecutive k) land in 8 different 16-byte bank groups
     } u;
     int cell_cnt[64], cell_start[65], cell_cursor[64];
     int4 work;
@@ -104,7 +106,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     float wx[4], wy[4], wz[4];
                     axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
-                    S.u.c.wx[0][q] = wx[0]; S.u.c.wx[1][q] = wx[1]; S.u.c.wx[2][q] = wx[2]; S.u.c.wx[3][q] = wx[3];
+                    S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
                     S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
                     S.u.c.wz[q] = make_float4(wz[0], wz[1], wz[2], wz[3]);
                     S.u.c.qc[q] = make_float4(mch, a0[0] + A[0] * d0 + A[1] * d1 + A[2] * d2, a0[1] + A[3] * d0 + A[4] * d1 + A[5] * d2,
@@ -148,7 +150,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
             for (int i = i0; i < i1; ++i) {
                 const int pi = S.u.c.order[i];
-                const float wxa = S.u.c.wx[my_a][pi];
+                const float wxa = reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a];
                 const float4 wy = S.u.c.wy[pi], wz = S.u.c.wz[pi], qc = S.u.c.qc[pi], h0 = S.u.c.hA0[pi], h1 = S.u.c.hA1[pi];
                 const float h8 = S.u.c.hA8[pi];
                 // value(a,b,c)_r = c0_r + a*hA[r][0] + b*hA[r][1] + c*hA[r][2]
@@ -190,8 +192,8 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         }
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-            S.u.t1[my_cx][my_cy][my_a][bb][my_cz] = s0[bb];
-            if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb][my_cz + 4] = s1[bb];
+            S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz] = s0[bb];
+            if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz + 4] = s1[bb];
         }
         if (t == 0) { S.work = wk_reg; w_ticket = atomicAdd(&dc->work_a, 1); }
         __syncthreads();
@@ -202,20 +204,18 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wn.x >= 0 && q < nchn) ? sorted_ids[wn.y + q * nckn] : 0; }
         }
         // ---- phase 2b: fold x and y from smem (<= 16 terms per tile node), one vector red per node ----
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            const int n = t + which * P2G_T;
-            if (n < 343) {
-                const int ni = n / 49, nj = (n / 7) % 7, nk = n % 7;
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int cx = max(0, ni - 3); cx <= min(3, ni); ++cx)
-                    for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy) {
-                        const float4 v = S.u.t1[cx][cy][ni - cx][nj - cy][nk];
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-                    }
-                if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
-                    atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
-            }
+        // (visiting the nodes sorted by fold length to even out the trip counts was measured SLOWER than natural order:
+        // the contiguous k-runs of natural order matter more to the smem pipe than the divergence costs)
+        for (int n = t; n < 343; n += P2G_T) {
+            const int ni = n / 49, nj = (n / 7) % 7, nk = n % 7;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int cx = max(0, ni - 3); cx <= min(3, ni); ++cx)
+                for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy) {
+                    const float4 v = S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk];
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+            if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
+                atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
         }
     }
 }
@@ -395,18 +395,34 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
     return cudaGetLastError();
 }
 
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas_per_sm; };
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
-                            DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
+                            DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
+                            const SideStream* side) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
+    // The F-update (HBM-bound, 64 registers) and the gather (issue-bound) touch disjoint planes: when both run, the
+    // F-update goes to a side stream so that its CTAs share the SMs with the gather's persistent CTAs.
+    const bool overlap = side && side->stream && (FLAGS & G2P_F) && (FLAGS & G2P_GATHER);
     if (FLAGS & G2P_F) {
-        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<(n_bound + 255) / 256, 256, 0, st>>>(C, N, sorted_ids, dc, sc, dt);
+        cudaStream_t fs = st;
+        if (overlap) {
+            if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
+            fs = side->stream;
+        }
+        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<(n_bound + 255) / 256, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_GATHER) {
-        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * 2, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        const int per_sm = overlap ? side->gather_ctas_per_sm : 2;
+        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (overlap) {
+        if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_REORDER) {
         k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc);     // parked particles are few; 16 K slots per launch wave
