@@ -152,6 +152,15 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* colliders, int n_c
 #define MPM_MIGRATE_FLOATS 44
 int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up);
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n);
+/* Sync-free migration (what multi.py uses): mpm_migrate_pack fills two fixed-size device buffers of
+ * mpm_migrate_buffer_bytes(s) bytes each = one 16-byte header (first int32 = record count) + capacity records, without
+ * any host synchronisation; mpm_migrate_append_packed appends a neighbour's buffer, reading the count on the device.
+ * mpm_sync_counts is the occasional host read-back that re-tightens the launch bound and reports overflow. */
+int mpm_set_migrate_capacity(mpm_t* s, int64_t records);   /* must be IDENTICAL on neighbouring ranks (fixed-size messages) */
+size_t mpm_migrate_buffer_bytes(const mpm_t* s);
+int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up);
+int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf);
+int mpm_sync_counts(mpm_t* s);
 /* Distributed bookkeeping: particle ids are upload indices + pid_base (set before an upload) so that they stay
  * unique across slabs; mpm_download_live_particles returns the handle's current particles in storage order as
  * 35-float rows (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) with their ids. */

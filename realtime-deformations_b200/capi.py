@@ -43,7 +43,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_update_deformation_gradient", "mpm_update_particle_velocities", "mpm_update_particle_positions",
            "mpm_substep", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
            "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
-           "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles"]
+           "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
+           "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity"]
 
 _lib = None
 
@@ -89,6 +90,12 @@ def lib():
     L.mpm_halo_add.argtypes = [vp, C.c_int, vp]
     L.mpm_migrate_outgoing.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]
     L.mpm_migrate_append.argtypes = [vp, vp, i64]
+    L.mpm_set_migrate_capacity.argtypes = [vp, i64]
+    L.mpm_migrate_buffer_bytes.argtypes = [vp]
+    L.mpm_migrate_buffer_bytes.restype = sz
+    L.mpm_migrate_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mpm_migrate_append_packed.argtypes = [vp, vp]
+    L.mpm_sync_counts.argtypes = [vp]
     L.mpm_set_pid_base.argtypes = [vp, i64]
     L.mpm_download_live_particles.argtypes = [vp, i64, C.POINTER(i64), fp, vp]
     _lib = L
@@ -279,6 +286,23 @@ class Sim:
 
     def migrate_append(self, dev_ptr, n):
         _ck(self.L.mpm_migrate_append(self.h, C.c_void_p(dev_ptr), int(n)))
+
+    def set_migrate_capacity(self, records):
+        _ck(self.L.mpm_set_migrate_capacity(self.h, int(records)))
+
+    def migrate_buffer_bytes(self):
+        return int(self.L.mpm_migrate_buffer_bytes(self.h))
+
+    def migrate_pack(self):
+        pd, pu = C.c_void_p(), C.c_void_p()
+        _ck(self.L.mpm_migrate_pack(self.h, C.byref(pd), C.byref(pu)))
+        return pd.value, pu.value
+
+    def migrate_append_packed(self, dev_ptr):
+        _ck(self.L.mpm_migrate_append_packed(self.h, C.c_void_p(dev_ptr)))
+
+    def sync_counts(self):
+        _ck(self.L.mpm_sync_counts(self.h))
 
     def set_pid_base(self, base):
         _ck(self.L.mpm_set_pid_base(self.h, int(base)))

@@ -673,13 +673,11 @@ int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
+static int ensure_out_buffers(mpm_sim* s);
 int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up) {
     NEED(s);
     if (!n_down || !n_up || !dev_down || !dev_up) return fail(MPM_ERR_INVALID, "null argument");
-    if (!s->out_buf[0]) {
-        s->out_cap = std::max<int64_t>(1 << 16, s->capacity / 16);
-        for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->out_buf[d], sizeof(float4) * NPLANES * (size_t)s->out_cap));
-    }
+    TRY(ensure_out_buffers(s));
     CK(cudaMemsetAsync(s->dc->n_mig, 0, 3 * sizeof(int), s->stream));
     k_mark_outgoing<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
@@ -701,6 +699,62 @@ int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
     CKLAUNCH(); s->stats.kernel_launches++;
     s->n_bound += n;
     s->binned = false;
+    return MPM_OK;
+}
+static int64_t default_migrate_capacity(const mpm_sim* s) { return std::min<int64_t>(std::max<int64_t>(1 << 14, s->capacity / 128), 1 << 18); }
+int mpm_set_migrate_capacity(mpm_t* s, int64_t records) {
+    NEED(s);
+    if (records < 1 || records > ((int64_t)1 << 24)) return fail(MPM_ERR_INVALID, "migrate capacity out of range");
+    if (s->out_buf[0]) return fail(MPM_ERR_INVALID, "migration buffers already allocated");
+    s->out_cap = records;
+    return MPM_OK;
+}
+static int ensure_out_buffers(mpm_sim* s) {
+    if (s->out_buf[0]) return MPM_OK;
+    if (s->out_cap <= 0) s->out_cap = default_migrate_capacity(s);
+    for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->out_buf[d], sizeof(float4) * (1 + NPLANES * (size_t)s->out_cap)));
+    return MPM_OK;
+}
+size_t mpm_migrate_buffer_bytes(const mpm_t* s) {
+    if (!s) return 0;
+    const int64_t cap = s->out_cap > 0 ? s->out_cap : default_migrate_capacity(s);
+    return sizeof(float4) * (1 + NPLANES * (size_t)cap);
+}
+int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up) {
+    NEED(s);
+    if (!dev_down || !dev_up) return fail(MPM_ERR_INVALID, "null argument");
+    TRY(ensure_out_buffers(s));
+    for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(s->out_buf[d], 0, sizeof(float4), s->stream));
+    k_mark_outgoing_hdr<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
+    s->binned = false;
+    return MPM_OK;
+}
+int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
+    NEED(s);
+    if (!dev_buf) return fail(MPM_ERR_INVALID, "null buffer");
+    TRY(ensure_out_buffers(s));
+    const int cap = (int)s->out_cap;
+    k_append_incoming_hdr<<<grid_for(cap, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, cap, (int)s->capacity);
+    CKLAUNCH();
+    k_bump_slots<<<1, 1, 0, s->stream>>>(s->dc, (const float4*)dev_buf, cap, (int)s->capacity);
+    CKLAUNCH(); s->stats.kernel_launches += 2;
+    s->n_bound = std::min<int64_t>(s->capacity, s->n_bound + cap);      // upper bound; mpm_sync_counts tightens it
+    s->binned = false;
+    return MPM_OK;
+}
+int mpm_sync_counts(mpm_t* s) {
+    NEED(s);
+    DevCounters h;
+    CK(cudaMemcpyAsync(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->n_bound = h.n_slots;
+    if (h.mig_overflow) {
+        const int what = h.mig_overflow;
+        CK(cudaMemsetAsync(&s->dc->mig_overflow, 0, sizeof(int), s->stream));
+        return fail(MPM_ERR_CAPACITY, what == 2 ? "slab capacity exceeded by incoming particles" : "more particles left the slab in one substep than the migration buffer holds");
+    }
     return MPM_OK;
 }
 int mpm_set_pid_base(mpm_t* s, int64_t pid_base) {

@@ -605,6 +605,39 @@ __global__ void k_append_incoming(Planes cur, DevCounters* dc, const float4* __r
 #pragma unroll
     for (int q = 0; q < NPLANES; ++q) cur.p[q][base + i] = r[q];
 }
+// Sync-free variant: the packed buffers start with one float4 header whose first int is the record count (it IS the
+// atomic cursor), so the receiving side learns the count on the device and the host never has to.
+__global__ void k_mark_outgoing_hdr(Planes cur, DevCounters* dc, GridDims gd, PosDiv pd, float4* __restrict__ out_down,
+                                    float4* __restrict__ out_up, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dc->n_slots) return;
+    const float4 a0 = cur.p[0][p];
+    if (a0.w < 0.0f) return;
+    int cells[3];
+    const int k = particle_key(a0, gd, pd, cells);
+    if (k != gd.n_pblocks + 1 && k != gd.n_pblocks + 2) return;
+    float4* buf = (k == gd.n_pblocks + 2) ? out_up : out_down;
+    const int idx = atomicAdd(reinterpret_cast<int*>(buf), 1);
+    if (idx >= cap) { dc->mig_overflow = 1; return; }      // header count may exceed cap; the receiver clamps it
+    float4* o = buf + 1 + (size_t)idx * NPLANES;
+#pragma unroll
+    for (int q = 0; q < NPLANES; ++q) o[q] = cur.p[q][p];
+    cur.p[0][p] = make_float4(a0.x, a0.y, a0.z, -1.0f);
+}
+__global__ void k_append_incoming_hdr(Planes cur, const DevCounters* __restrict__ dc, const float4* __restrict__ in, int cap, int capacity) {
+    const int n = min(*reinterpret_cast<const int*>(in), cap);
+    const int base = dc->n_slots;          // advanced by k_bump_slots after this kernel
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || base + i >= capacity) return;
+    const float4* r = in + 1 + (size_t)i * NPLANES;
+#pragma unroll
+    for (int q = 0; q < NPLANES; ++q) cur.p[q][base + i] = r[q];
+}
+__global__ void k_bump_slots(DevCounters* dc, const float4* __restrict__ in, int cap, int capacity) {
+    const int n = min(*reinterpret_cast<const int*>(in), cap);
+    if (dc->n_slots + n > capacity) { dc->mig_overflow = 2; dc->n_slots = capacity; }
+    else dc->n_slots += n;
+}
 // live particles in slot order as 35-float rows (+ pid) for distributed downloads
 __global__ void k_export_live(Planes cur, const DevCounters* __restrict__ dc, float* __restrict__ out35, int* __restrict__ pid_out,
                               int* __restrict__ counter, int cap) {

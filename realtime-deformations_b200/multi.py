@@ -26,6 +26,25 @@ def slab_layers(n_layers, world):
     return out
 
 
+def slab_layers_balanced(layer_counts, world):
+    """Contiguous split of the block layers with near-equal PARTICLE counts (layer_counts[l] = particles whose block
+    layer is l). Every rank gets at least one layer."""
+    c = np.asarray(layer_counts, np.float64)
+    n_layers = len(c)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target))
+        # nearest layer boundary to the target, keeping at least one layer per remaining rank
+        k = k if abs(cum[min(k, n_layers)] - target) <= abs(cum[max(k - 1, 0)] - target) else k - 1
+        k = min(max(k, cuts[-1] + 1), n_layers - (world - r))
+        cuts.append(k)
+    cuts.append(n_layers)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def exchange_with_neighbours(dist, torch, rank, world, send_down, send_up, recv_down, recv_up):
     """Grouped point-to-point exchange with rank-1 (down) and rank+1 (up); any tensor may be None at the ends."""
     ops = []
@@ -60,7 +79,12 @@ class SlabRunner:
             import torch.distributed as dist
             self.dist = dist
         n_layers = (grid + 3) // 4
-        self.lo, self.hi = slab_layers(n_layers, world)[rank]
+        if scene is None and world > 1:
+            # balance by particle count: the slab scene's per-layer counts are known in closed form
+            self.lo, self.hi = slab_layers_balanced(scenes.snow_slab_layer_counts(grid, n_particles), world)[rank]
+        else:
+            self.lo, self.hi = slab_layers(n_layers, world)[rank]
+        self.sync_every = 16
         # each rank generates only the cells of its own slab (counter-based RNG keyed by cell id)
         if scene is None:
             i_range = None if world == 1 else (max(4 * self.lo + 1, 0), 4 * self.hi + 1)   # cells c with (c-1)>>2 in [lo,hi)
@@ -90,7 +114,15 @@ class SlabRunner:
         self.sim.upload(scene["pos"], scene["vel"], scene["mass"])
         self.cols, self.nc = capi.make_colliders(scene["w2l"], scene["half"], scene["cvel"])
         self.h2d_bytes_per_step = 88 * self.nc + 4
+        self.steps_done = 0
         if world > 1:
+            # the migration messages have a fixed size: every rank must use the SAME record capacity
+            cap = torch.tensor([min(max(1 << 14, n // 64), 1 << 18)], dtype=torch.int64, device="cuda")
+            self.dist.all_reduce(cap, op=self.dist.ReduceOp.MAX)
+            self.sim.set_migrate_capacity(int(cap.item()))
+            mb = self.sim.migrate_buffer_bytes() // 4
+            self.m_recv_dn = torch.empty(mb, dtype=torch.float32, device="cuda")
+            self.m_recv_up = torch.empty(mb, dtype=torch.float32, device="cuda")
             hb = self.sim.halo_bytes() // 4
             self.h_send_up = torch.empty(hb, dtype=torch.float32, device="cuda")
             self.h_recv_up = torch.empty(hb, dtype=torch.float32, device="cuda")
@@ -116,31 +148,29 @@ class SlabRunner:
         if r > 0:
             s.halo_add(0, self.h_recv_dn.data_ptr())
 
-    def _migrate(self):
-        t, s, r, w = self.torch, self.sim, self.rank, self.world
-        n_dn, n_up, p_dn, p_up = s.migrate_outgoing()
-        if r == 0 and n_dn:
-            raise capi.MpmError("particles left the domain through the lower i boundary")
-        in_dn, in_up = exchange_counts(self.dist, t, r, w, n_dn, n_up, "cuda")
-        F = capi.MIGRATE_FLOATS
+    def _view(self, ptr, n_floats):
+        """torch view over a device buffer owned by the library (no copy)."""
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        return self.torch.as_tensor(a, device="cuda")
 
-        def view(ptr, n):      # torch view over the library's packed device buffer (no copy)
-            if n == 0:
-                return None
-            class _A:          # minimal __cuda_array_interface__ carrier
-                pass
-            a = _A()
-            a.__cuda_array_interface__ = {"shape": (n * F,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-            return t.as_tensor(a, device="cuda")
-        send_dn, send_up = view(p_dn, n_dn), view(p_up, n_up)
-        recv_dn = t.empty(in_dn * F, dtype=t.float32, device="cuda") if in_dn else None
-        recv_up = t.empty(in_up * F, dtype=t.float32, device="cuda") if in_up else None
-        exchange_with_neighbours(self.dist, t, r, w, send_dn, send_up, recv_dn, recv_up)
-        if in_dn:
-            s.migrate_append(recv_dn.data_ptr(), in_dn)
-        if in_up:
-            s.migrate_append(recv_up.data_ptr(), in_up)
-        self._keep = (recv_dn, recv_up)      # keep alive until the append kernels ran
+    def _migrate(self):
+        """Fixed-size packed buffers (count in a device-side header): no host synchronisation per substep; the launch
+        bound is re-tightened and overflow checked every `sync_every` substeps."""
+        t, s, r, w = self.torch, self.sim, self.rank, self.world
+        p_dn, p_up = s.migrate_pack()
+        nf = s.migrate_buffer_bytes() // 4
+        exchange_with_neighbours(self.dist, t, r, w, self._view(p_dn, nf) if r > 0 else None, self._view(p_up, nf) if r < w - 1 else None,
+                                 self.m_recv_dn if r > 0 else None, self.m_recv_up if r < w - 1 else None)
+        if r > 0:
+            s.migrate_append_packed(self.m_recv_dn.data_ptr())
+        if r < w - 1:
+            s.migrate_append_packed(self.m_recv_up.data_ptr())
+        self.steps_done += 1
+        if self.steps_done % self.sync_every == 0:
+            s.sync_counts()
 
     def substep(self, host_colliders=False):
         if host_colliders:       # e2e arm: the per-frame host inputs are rebuilt and handed over every step

@@ -161,6 +161,31 @@ def snow_slab(grid=512, n=1 << 26, h=0.05, dt=1e-5, seed=SEED, i_range=None, til
                   gravity=(np.float32(g * np.sin(a)), np.float32(-g * np.cos(a)), np.float32(0.0)), n_target=n)
 
 
+def snow_slab_layer_counts(grid, n):
+    """Particles of snow_slab(grid, n) per particle-block layer l (cells c with (c-1)>>2 == l), in closed form."""
+    full = snow_slab_geometry(grid, n)
+    lo, hi, per_plane = full
+    counts = np.zeros((grid + 3) // 4, np.int64)
+    left = n
+    for c in range(lo[0], hi[0]):
+        k = min(per_plane, left)
+        if k <= 0:
+            break
+        counts[(c - 1) >> 2] += k
+        left -= k
+    return counts
+
+
+def snow_slab_geometry(grid, n, h=0.05):
+    top = 0.8 * (grid / 512.0) + h / 2 if grid >= 64 else 4 * h + h / 2
+    j0 = int(np.floor(top / h)) + 1
+    margin = max(4, grid // 32)
+    foot = grid - 2 * margin
+    thick = int(np.ceil(n / 8.0 / (foot * foot)))
+    lo, hi = [margin, j0, margin], [grid - margin, min(j0 + thick, grid - 4), grid - margin]
+    return lo, hi, (hi[1] - lo[1]) * (hi[2] - lo[2]) * 8
+
+
 def small_ball(grid=32, radius_cells=5.0, h=0.05, dt=1e-5, seed=SEED, v0=(0.0, -200.0, 0.0), with_ground=True):
     """Small parity scene the CPU oracle finishes in seconds."""
     dims = (grid, grid, grid)
