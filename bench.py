@@ -281,10 +281,17 @@ def main():
     except Exception:
         pass
     dom = max(("p2g", "g2p(fupdate+gather)", "bin_sort", "grid_update"), key=lambda k: kern[k])
+    # per-kernel algorithmic bytes, per GPU
+    npg, apg = n_total / world, n_active / world
+    kern_alg = {"p2g": 88 * npg + 16 * apg, "g2p(fupdate+gather)": (128 + 112) * npg + (16 + 64) * npg + 16 * apg,
+                "bin_sort": 24 * npg, "grid_update": 32 * apg}
+    dom_gbs = kern_alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
     roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "traffic": traffic, "peak_source": peak_src, "scope": "one whole substep (all kernels), per GPU",
             "algorithmic_bytes_per_substep": alg_bytes, "active_nodes": n_active,
             "kernel_ms_last_substep": kern, "dominant_kernel": dom,
+            "dominant_kernel_algorithmic_bytes": kern_alg[dom], "dominant_kernel_achieved_gbs": round(dom_gbs, 1),
+            "dominant_kernel_frac": round(dom_gbs / peak, 4),
             "dominant_share_of_substep": round(kern[dom] / max(kern["substep_total"], 1e-9), 3)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

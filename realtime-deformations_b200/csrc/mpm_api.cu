@@ -256,7 +256,7 @@ static const float Z9[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
     if (n < 0 || n > s->capacity) return fail(MPM_ERR_CAPACITY, "n = %lld exceeds capacity %lld", (long long)n, (long long)s->capacity);
-    if (!f.pos || !f.vel || !f.mass) return fail(MPM_ERR_INVALID, "pos, vel and mass are required");
+    if (n > 0 && (!f.pos || !f.vel || !f.mass)) return fail(MPM_ERR_INVALID, "pos, vel and mass are required");
     const int64_t CH = 1 << 20;
     int rc = ensure_pinned(s, sizeof(float4) * NPLANES * (size_t)std::min<int64_t>(CH, std::max<int64_t>(n, 1)));
     if (rc) return rc;
@@ -334,7 +334,7 @@ static int download_common(mpm_sim* s, int64_t n, const HostFieldPtrsW& f) {
 
 int mpm_upload_particles_aos(mpm_t* s, const void* particles, int64_t n, size_t stride, size_t off_mass, size_t off_velocity,
                              size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP, size_t off_B) {
-    if (!s || !particles) return fail(MPM_ERR_INVALID, "null argument");
+    if (!s || (!particles && n > 0)) return fail(MPM_ERR_INVALID, "null argument");
     const char* b = (const char*)particles;
     HostFieldPtrs f = { b + off_mass, b + off_velocity, b + off_volume, b + off_pos, b + off_FE, b + off_FP, b + off_B,
                         stride, stride, stride, stride, stride, stride, stride };
@@ -349,7 +349,7 @@ int mpm_upload_particles_soa(mpm_t* s, int64_t n, const float* pos, const float*
 }
 int mpm_download_particles_aos(mpm_t* s, void* particles, int64_t n, size_t stride, size_t off_mass, size_t off_velocity,
                                size_t off_volume, size_t off_pos, size_t off_FE, size_t off_FP, size_t off_B) {
-    if (!s || !particles) return fail(MPM_ERR_INVALID, "null argument");
+    if (!s || (!particles && n > 0)) return fail(MPM_ERR_INVALID, "null argument");
     char* b = (char*)particles;
     HostFieldPtrsW f = { b + off_mass, b + off_velocity, b + off_volume, b + off_pos, b + off_FE, b + off_FP, b + off_B,
                          stride, stride, stride, stride, stride, stride, stride };
@@ -382,9 +382,9 @@ int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char*
 static int do_binning(mpm_sim* s) {
     const GridDims& g = s->gd;
     CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
-    const int nb = grid_for(s->n_bound, 256);
+    const int nb = grid_for(s->n_bound, BIN_T * BIN_E);
     Planes C = s->planes(s->cur);
-    k_bin_count<<<nb, 256, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.pd, s->key, s->blk_count);
+    k_bin_count<<<nb, BIN_T, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.pd, s->key, s->blk_count);
     CKLAUNCH();
     k_scan_reduce<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial);
     CKLAUNCH();
@@ -399,7 +399,7 @@ static int do_binning(mpm_sim* s) {
     const int layer_threads = g.nbj * g.nbk;
     if (g.lo > 0) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(0, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
     if (g.hi < g.npbi_global) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(g.hi - g.lo, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
-    k_bin_scatter<<<nb, 256, 0, s->stream>>>((int)s->n_bound, s->dc, s->key, s->blk_cursor, s->sorted_ids);
+    k_bin_scatter<<<nb, BIN_T, 0, s->stream>>>((int)s->n_bound, s->dc, s->key, s->blk_cursor, s->sorted_ids);
     CKLAUNCH(); s->stats.kernel_launches++;
     s->binned = true;
     return MPM_OK;

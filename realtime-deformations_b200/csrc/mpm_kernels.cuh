@@ -88,31 +88,58 @@ MPM_DI int particle_key(float4 xm, const GridDims& gd, const PosDiv& pd, int* ce
     return ((pbi - gd.lo) * gd.npbj + pbj) * gd.npbk + pbk;
 }
 
-__global__ void k_bin_count(const float4* __restrict__ P0, int n_bound, const DevCounters* __restrict__ dc,
-                            GridDims gd, PosDiv pd, int* __restrict__ key, int* __restrict__ blk_count) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = KEY_DEAD;
-    if (j < n_bound && j < dc->n_slots) {
+// Both binning kernels handle BIN_E elements per thread (warp-coalesced, stride = blockDim) so that several
+// position loads / atomic round trips are in flight per thread: they are latency-bound, not bandwidth-bound.
+constexpr int BIN_E = 4, BIN_T = 256;
+__global__ void __launch_bounds__(BIN_T)
+k_bin_count(const float4* __restrict__ P0, int n_bound, const DevCounters* __restrict__ dc,
+            GridDims gd, PosDiv pd, int* __restrict__ key, int* __restrict__ blk_count) {
+    const int n = min(n_bound, dc->n_slots);
+    const int base = blockIdx.x * (BIN_T * BIN_E) + threadIdx.x;
+    float4 xm[BIN_E];
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) {
+        const int j = base + e * BIN_T;
+        xm[e] = j < n ? P0[j] : make_float4(0.f, 0.f, 0.f, -1.f);
+    }
+    int k[BIN_E];
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) {
+        const int j = base + e * BIN_T;
         int cells[3];
-        k = particle_key(P0[j], gd, pd, cells);
-        key[j] = k;
+        k[e] = KEY_DEAD;
+        if (j < n) { k[e] = particle_key(xm[e], gd, pd, cells); key[j] = k[e]; }
     }
     // warp-aggregated histogram: one atomic per distinct key per warp
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    if (k >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&blk_count[k], __popc(peers));
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) {
+        const unsigned peers = __match_any_sync(0xffffffffu, k[e]);
+        if (k[e] >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&blk_count[k[e]], __popc(peers));
+    }
 }
 
-__global__ void k_bin_scatter(int n_bound, const DevCounters* __restrict__ dc, const int* __restrict__ key,
-                              int* __restrict__ blk_cursor, int* __restrict__ sorted_ids) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = KEY_DEAD;
-    if (j < n_bound && j < dc->n_slots) k = key[j];
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    int base = 0;
-    if (k >= 0 && lane == leader) base = atomicAdd(&blk_cursor[k], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (k >= 0) sorted_ids[base + __popc(peers & ((1u << lane) - 1u))] = j;
+__global__ void __launch_bounds__(BIN_T)
+k_bin_scatter(int n_bound, const DevCounters* __restrict__ dc, const int* __restrict__ key,
+              int* __restrict__ blk_cursor, int* __restrict__ sorted_ids) {
+    const int n = min(n_bound, dc->n_slots);
+    const int base0 = blockIdx.x * (BIN_T * BIN_E) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int k[BIN_E], slot[BIN_E], leader[BIN_E];
+    unsigned peers[BIN_E];
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) { const int j = base0 + e * BIN_T; k[e] = j < n ? key[j] : KEY_DEAD; }
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) {               // all BIN_E atomic round trips are issued before any is consumed
+        peers[e] = __match_any_sync(0xffffffffu, k[e]);
+        leader[e] = __ffs(peers[e]) - 1;
+        slot[e] = 0;
+        if (k[e] >= 0 && lane == leader[e]) slot[e] = atomicAdd(&blk_cursor[k[e]], __popc(peers[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < BIN_E; ++e) {
+        const int b = __shfl_sync(0xffffffffu, slot[e], leader[e]);
+        if (k[e] >= 0) sorted_ids[b + __popc(peers[e] & ((1u << lane) - 1u))] = base0 + e * BIN_T;
+    }
 }
 
 // ---- exclusive scan over the per-block counts (+ compaction of the occupied blocks) ----

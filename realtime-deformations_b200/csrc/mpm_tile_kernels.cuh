@@ -242,6 +242,9 @@ MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) {
     }
 }
 
+#ifndef G2P_MIN_CTAS
+#define G2P_MIN_CTAS 2
+#endif
 constexpr int G2P_WARPS = 8, G2P_T = G2P_WARPS * 32;
 struct G2PSmem {
     float4 tile[G2P_WARPS][512];         // one 2x2x2-grid-block tile (8 x 1 KB) per warp
@@ -252,7 +255,7 @@ struct G2PSmem {
 // mbarrier), so there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
 // FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate).
 template <int FLAGS>
-__global__ void __launch_bounds__(G2P_T, 2)
+__global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
     extern __shared__ __align__(128) unsigned char g2p_smem_raw[];
@@ -412,11 +415,11 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
             if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
             fs = side->stream;
         }
-        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<(n_bound + 255) / 256, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
+        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_GATHER) {
-        const int per_sm = overlap ? side->gather_ctas_per_sm : 2;
+        const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
         k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

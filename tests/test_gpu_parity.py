@@ -298,3 +298,53 @@ def test_slab_decomposition_on_two_gpus():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "MULTI_CHECK_OK" in r.stdout, r.stdout[-3000:]
+
+
+def _crowded_scene(n, seed=3):
+    """Ragged occupancy: n particles inside ONE 4^3-cell particle block (>> 512: several P2G chunks, 32-slices with
+    a ragged tail in the gather) plus a handful of isolated ones, on a 32^3 grid."""
+    rng = np.random.default_rng(seed)
+    h = np.float32(0.05)
+    lo = np.float32(13 * 0.05 + 1e-4)                     # cells 13..16 -> block (c-1)>>2 == 3 on every axis
+    pos = (lo + rng.uniform(0, 4 * 0.05 - 2e-4, size=(n, 3))).astype(np.float32)
+    extra = np.array([[0.31, 0.52, 0.77], [1.2, 0.4, 0.9], [0.8, 1.3, 0.2]], np.float32)
+    pos = np.concatenate([pos, extra])
+    vel = rng.normal(scale=5.0, size=pos.shape).astype(np.float32)
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=2.0, with_ground=False)
+    sc.update(pos=pos, vel=vel, mass=np.full(len(pos), 6e-5, np.float32), n=len(pos))
+    return sc
+
+
+@pytest.mark.parametrize("n", [1, 31, 700, 3000])
+def test_ragged_block_occupancy_vs_oracle(n):
+    sc = _crowded_scene(n)
+    o, ocols, onc = oracle_from_scene(sc)
+    sim, cols, nc = sim_from_scene(sc)
+    close_sum(sim.grid()[:, 0], o.grid()[:, 0], "grid mass, crowded block", rtol=5e-5)
+    close_sum(sim.download_state35()[:, 4], o.state()[:, 4], "volumes, crowded block", rtol=5e-5)
+    o.substep(float(sc["dt"]), ocols, onc, 3); sim.substep(float(sc["dt"]), cols, nc, 3)
+    a, b = sim.download_state35(), o.state()
+    assert np.isfinite(a).all()
+    close_sum(a[:, 5:8], b[:, 5:8], "positions after 3 substeps", rtol=1e-5)
+    close_sum(a[:, 1:4], b[:, 1:4], "velocities after 3 substeps", rtol=1e-3)
+    assert sim.stats().n_particles == sc["n"]
+
+
+def test_empty_handle_and_two_interleaved_handles():
+    empty = mpm_b200.Sim(32, 32, 32, 0)
+    empty.upload(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    cols0, nc0 = mpm_b200.capi.make_colliders(np.zeros((0, 16)), np.zeros((0, 3)))
+    empty.substep(1e-5, cols0, nc0, 2)
+    st = empty.stats()
+    assert st.n_particles == 0 and st.n_active_nodes == 0 and st.n_particle_blocks == 0
+    assert empty.download_state35().shape == (0, 35)
+    # two independent handles advanced alternately must not disturb each other (own streams, own buffers, no globals)
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
+    a, cols, nc = sim_from_scene(sc)
+    b, _, _ = sim_from_scene(sc, hardening_xi=20.0)
+    ref, _, _ = sim_from_scene(sc)
+    for _ in range(10):
+        a.substep(float(sc["dt"]), cols, nc, 1)
+        b.substep(float(sc["dt"]), cols, nc, 1)
+    ref.substep(float(sc["dt"]), cols, nc, 10)
+    assert_traj_close(a.download_state35(), ref.download_state35(), 20, "handle advanced alone vs interleaved with another")
