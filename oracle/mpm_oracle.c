@@ -372,7 +372,11 @@ void oracle_grid_based_collisions(Oracle* o, float dt, const OracleBoxCollider* 
 int oracle_svd3(const float A[9], float U[9], float S[3], float V[9]) {
     float W[9];
     float scale = 0.0f;
-    for (int i = 0; i < 9; ++i) { const float a = fabsf(A[i]); if (!(a <= scale)) scale = a; }  /* NaN-propagating max */
+    for (int i = 0; i < 9; ++i) {                         /* maxCoeff<PropagateNaN>: a NaN, once seen, sticks */
+        const float a = fabsf(A[i]);
+        if (scale != scale) break;
+        if (a != a || a > scale) scale = a;
+    }
     if (!isfinite(scale)) return 1;
     if (scale == 0.0f) scale = 1.0f;
     for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = ID3[i]; V[i] = ID3[i]; }

@@ -190,7 +190,10 @@ MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float 
     float W[9];
     float scale = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const float a = fabsf(A[i]); if (!(a <= scale)) scale = a; }
+    for (int i = 0; i < 9; ++i) {           // maxCoeff<PropagateNaN>: a NaN, once seen, sticks
+        const float a = fabsf(A[i]);
+        if (!(scale != scale) && (a != a || a > scale)) scale = a;
+    }
     if (!isfinite(scale)) return false;
     if (scale == 0.0f) scale = 1.0f;
 #pragma unroll
