@@ -111,6 +111,13 @@ int mpm_download_particles_soa(mpm_t* s, int64_t n, float* pos, float* vel, floa
  * pointer may be NULL. Particle order = upload order. */
 int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char* rgba, float size);
 
+/* Pipelined variant for a render loop: enqueues the instance-buffer build behind the work already issued and its
+ * device->host copy on a separate copy stream, and returns at once, so the copy of frame t overlaps the substeps of
+ * frame t+1 (the copy engine and the SMs run concurrently). xyzs must be page-locked host memory and must not be
+ * read before mpm_wait_render_buffers returns. */
+int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs_pinned, float size);
+int mpm_wait_render_buffers(mpm_t* s);
+
 /* One entry per reference stage (same order and meaning as main.cpp:192-218). */
 int mpm_rasterize_particles_to_grid(mpm_t* s);                   /* rasterizeParticlesToGrid        cpp:94-129  */
 int mpm_compute_particle_volumes_and_densities(mpm_t* s);        /* computeParticleVolumesAndDensities cpp:131-142 */

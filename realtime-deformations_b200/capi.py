@@ -44,7 +44,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_substep", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
            "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
            "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
-           "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity"]
+           "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
+           "mpm_wait_render_buffers"]
 
 _lib = None
 
@@ -71,6 +72,8 @@ def lib():
     L.mpm_upload_particles_soa.argtypes = [vp, i64] + [fp] * 7
     L.mpm_download_particles_soa.argtypes = [vp, i64] + [fp] * 7
     L.mpm_download_render_buffers.argtypes = [vp, i64, vp, vp, C.c_float]
+    L.mpm_download_render_buffers_async.argtypes = [vp, i64, vp, C.c_float]
+    L.mpm_wait_render_buffers.argtypes = [vp]
     for n in ("mpm_rasterize_particles_to_grid", "mpm_compute_particle_volumes_and_densities",
               "mpm_compute_explicit_grid_forces", "mpm_update_particle_velocities", "mpm_synchronize"):
         getattr(L, n).argtypes = [vp]
@@ -206,6 +209,16 @@ class Sim:
         rgba = np.empty((self.n, 4), np.uint8) if rgba is None else rgba
         _ck(self.L.mpm_download_render_buffers(self.h, self.n, xyzs.ctypes.data, rgba.ctypes.data, size))
         return xyzs, rgba
+
+    def capacity_rows(self):
+        """Rows a render buffer needs in slab mode (storage order incl. retired slots): the current slot bound."""
+        return int(self.stats().n_particles)
+
+    def render_buffers_async(self, xyzs_pinned_ptr, n, size=0.02):
+        _ck(self.L.mpm_download_render_buffers_async(self.h, int(n), C.c_void_p(xyzs_pinned_ptr), size))
+
+    def wait_render_buffers(self):
+        _ck(self.L.mpm_wait_render_buffers(self.h))
 
     # ---- reference stages (main.cpp:192-218) ---------------------------------------------------------
     def rasterizeParticlesToGrid(self):

@@ -28,6 +28,8 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(MPM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 #define CKLAUNCH() CK(cudaGetLastError())
+#define NEED(s) do { if (!(s)) return fail(MPM_ERR_INVALID, "null handle"); CK(cudaSetDevice((s)->device)); } while (0)
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 struct mpm_sim {
     int device = 0;
@@ -51,6 +53,10 @@ struct mpm_sim {
     float4* out_buf[2] = { nullptr, nullptr };   // migration: packed outgoing particles (down, up)
     int64_t out_cap = 0;
     int64_t pid_base = 0;
+    float4* render_stage = nullptr; int64_t render_cap = 0;      // async render path: device staging + copy stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t render_ready = nullptr, copy_done = nullptr;
+    bool copy_pending = false;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
     int num_sms = 148;
@@ -213,6 +219,8 @@ int mpm_destroy(mpm_t* s) {
     cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
+    cudaFree(s->render_stage);
     if (s->side.stream) { cudaStreamDestroy(s->side.stream); cudaEventDestroy(s->side.fork); cudaEventDestroy(s->side.join); }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -378,6 +386,42 @@ int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char*
     return MPM_OK;
 }
 
+int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs, float size) {
+    NEED(s);
+    if (!xyzs || n < 0) return fail(MPM_ERR_INVALID, "bad argument");
+    const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+    if (!slab && n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    if (slab && n > s->capacity) return fail(MPM_ERR_INVALID, "n exceeds the slab capacity");
+    if (!s->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->render_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    }
+    if (s->render_cap < n) {
+        if (s->copy_pending) CK(cudaEventSynchronize(s->copy_done));
+        cudaFree(s->render_stage); s->render_stage = nullptr;
+        CK(cudaMalloc(&s->render_stage, sizeof(float4) * (size_t)std::max<int64_t>(n, 1)));
+        s->render_cap = n;
+    }
+    if (n == 0) return MPM_OK;
+    // the staging buffer is reused: the previous copy must have drained before it is overwritten (device-side wait)
+    if (s->copy_pending) CK(cudaStreamWaitEvent(s->stream, s->copy_done, 0));
+    if (slab) k_render_slots<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->render_stage, s->dc, size, (int)n);
+    else k_render<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->render_stage, s->dc, size);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    CK(cudaEventRecord(s->render_ready, s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->render_ready, 0));
+    CK(cudaMemcpyAsync(xyzs, s->render_stage, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->copy_done, s->copy_stream));
+    s->copy_pending = true;
+    return MPM_OK;
+}
+int mpm_wait_render_buffers(mpm_t* s) {
+    NEED(s);
+    if (s->copy_pending) { CK(cudaEventSynchronize(s->copy_done)); s->copy_pending = false; }
+    return MPM_OK;
+}
+
 // ---- binning / sort -----------------------------------------------------------------------------------------
 static int do_binning(mpm_sim* s) {
     const GridDims& g = s->gd;
@@ -472,8 +516,6 @@ static int set_colliders(mpm_sim* s, const MpmBoxCollider* c, int n) {
     s->n_colliders = n;
     return MPM_OK;
 }
-#define NEED(s) do { if (!(s)) return fail(MPM_ERR_INVALID, "null handle"); CK(cudaSetDevice((s)->device)); } while (0)
-#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 // ---- staged API: one entry per reference stage ----------------------------------------------------------------
 int mpm_rasterize_particles_to_grid(mpm_t* s) {               // cpp:94-129
