@@ -221,7 +221,9 @@ def test_render_buffers_and_upload_order():
     assert (pinned.numpy() == xyzs).all()
     sim.render_buffers_async(pinned.numpy().ctypes.data, sc["n"])
     sim.wait_render_buffers()
-    assert (pinned.numpy()[:, :3] == sim.download()["pos"]).all()
+    # bitwise: the tag volumes make this scene blow up after a few substeps, and NaN != NaN
+    now = np.ascontiguousarray(pinned.numpy()[:, :3]).view(np.uint32)
+    assert np.array_equal(now, np.ascontiguousarray(sim.download()["pos"]).view(np.uint32))
 
 
 def test_error_paths():
