@@ -196,8 +196,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         from datetime import timedelta
-        # a rank that dies must not leave the others waiting for NCCL's default 10-minute watchdog
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=timedelta(seconds=90))
+        # a rank that dies must not leave the others waiting for NCCL's default 10-minute watchdog (but slow first-time CUDA/NCCL start-up on a fresh box must fit)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=timedelta(seconds=240))
     workload = WORKLOAD_NAME if (args.grid == 512 and args.particles == 1 << 26) else f"snow_slab_{args.grid}: {args.particles} particles (development override)"
 
     from importlib import import_module
