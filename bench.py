@@ -110,11 +110,12 @@ def run_reference_binary(sc, steps, nproc):
     return nproc * sc["n"] * steps / max(secs), wall, max(secs)
 
 
-def run_oracle_port(sc, steps):
+def run_oracle_port(sc, steps, threads=1):
+    """The CPU restatement (oracle/mpm_oracle.c); threads > 1 uses OpenMP with per-thread grids."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as op
     I, J, K = sc["dims"]
-    o = op.Oracle(I, J, K, sc["n"], op.default_params(h=float(sc["h"])))
+    o = op.Oracle(I, J, K, sc["n"], op.default_params(h=float(sc["h"])), threads=threads)
     o.set_state(op.initial_state(sc["pos"], sc["vel"], sc["mass"]))
     o.rasterize(); o.volumes()
     cols, nc = op.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
@@ -154,9 +155,8 @@ def reference_arm(args):
         run_reference_binary(sc, max(args.warmup, 1), cores)
         v, wall, sec = run_reference_binary(sc, args.steps, cores)
     else:
-        run_oracle_port(sc, max(args.warmup, 1))
-        v, sec = run_oracle_port(sc, args.steps)
-        cores = 1
+        run_oracle_port(sc, max(args.warmup, 1), cores)
+        v, sec = run_oracle_port(sc, args.steps, cores)
     ms = sec * 1e3 / args.steps
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -124,6 +124,10 @@ def kats(tmp):
     out["collide_vel"] = vel
     out["collide_out"] = np.fromfile(tmp + "/c_out.f32", dtype=np.float32).reshape(-1, 3)
     out["colliders"] = np.fromfile(tmp + "/colliders.f32", dtype=np.float32).reshape(-1, 29)
+    # same points against MOVING colliders (MeshCollider::velocity != 0, the key_callback case of main.cpp:37-41,174-190)
+    run(["--kat-collide", tmp + "/c_in.f32", tmp + "/cm_out.f32", "--dump-dir", tmp, "--collider-vel", 3.0, -1.5, 0.75])
+    out["collide_moving_out"] = np.fromfile(tmp + "/cm_out.f32", dtype=np.float32).reshape(-1, 3)
+    out["colliders_moving"] = np.fromfile(tmp + "/colliders.f32", dtype=np.float32).reshape(-1, 29)
     # --- updateDeformationGradient (material_point_method.cpp:306-330) on synthetic particle states
     n = 4096
     st = np.zeros((n, 35), np.float32)

@@ -200,18 +200,17 @@ static void cache_neighbourhood(Oracle* o) {   /* getParticleNeighs, cpp:80-93 *
     } while (0)
 
 /* ---------------- P2G: material_point_method.cpp:94-129 ---------------- */
-void oracle_rasterize_particles_to_grid(Oracle* o) {
-    const size_t ncell = (size_t)o->I * o->J * o->K;
-    memset(o->g, 0, ncell * sizeof(OCell));                      /* grid.clear(), cpp:95 */
-    cache_neighbourhood(o);
-    OCell* g = o->g;
-    for (int i = 0; i < o->n; ++i) {                             /* cpp:99-103 */
+/* threads > 1 (timing runs only): every thread scatters a contiguous range of particles into a private grid and the
+ * private grids are summed in thread order. Deterministic, but NOT the reference's summation order; parity tests and
+ * golden checks use threads == 1. */
+static void scatter_mass(Oracle* o, OCell* g, int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {                              /* cpp:99-103 */
         if (!o->valid[i]) continue;
         FOR_NEIGHBOURS(o, i, { (void)dxi; g[node].mass += P_->mass * w; });
     }
-    o->nused = 0;                                                /* cpp:105-110 */
-    for (size_t c = 0; c < ncell; ++c) if (g[c].mass != 0.0f) o->used[o->nused++] = (int)c;
-    for (int i = 0; i < o->n; ++i) {                             /* cpp:112-117 */
+}
+static void scatter_momentum(Oracle* o, OCell* g, int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {                              /* cpp:112-117 */
         if (!o->valid[i]) continue;
         float BD[9];
         m3mul(BD, o->p[i].B, o->Dinv);
@@ -224,6 +223,42 @@ void oracle_rasterize_particles_to_grid(Oracle* o) {
             g[node].vel[2] += wm * (P_->vel[2] + a[2]);
         });
     }
+}
+typedef void (*scatter_fn)(Oracle*, OCell*, int, int);
+static void run_scatter(Oracle* o, scatter_fn fn) {
+    const int T = o->threads;
+    if (T <= 1) { fn(o, o->g, 0, o->n); return; }
+    const size_t ncell = (size_t)o->I * o->J * o->K;
+    OCell* priv = (OCell*)calloc(ncell * (size_t)T, sizeof(OCell));
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        const int i0 = (int)((long long)o->n * t / T), i1 = (int)((long long)o->n * (t + 1) / T);
+        fn(o, priv + ncell * (size_t)t, i0, i1);
+    }
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (long long c = 0; c < (long long)ncell; ++c)
+        for (int t = 0; t < T; ++t) {
+            const OCell* q = &priv[ncell * (size_t)t + (size_t)c];
+            o->g[c].mass += q->mass;
+            for (int a = 0; a < 3; ++a) { o->g[c].vel[a] += q->vel[a]; o->g[c].force[a] += q->force[a]; }
+        }
+    free(priv);
+}
+
+void oracle_rasterize_particles_to_grid(Oracle* o) {
+    const size_t ncell = (size_t)o->I * o->J * o->K;
+    memset(o->g, 0, ncell * sizeof(OCell));                      /* grid.clear(), cpp:95 */
+    cache_neighbourhood(o);
+    OCell* g = o->g;
+    run_scatter(o, scatter_mass);
+    o->nused = 0;                                                /* cpp:105-110 */
+    for (size_t c = 0; c < ncell; ++c) if (g[c].mass != 0.0f) o->used[o->nused++] = (int)c;
+    run_scatter(o, scatter_momentum);
     for (int u = 0; u < o->nused; ++u) {                         /* cpp:118-121 */
         OCell* c = &g[o->used[u]];
         c->vel[0] /= c->mass; c->vel[1] /= c->mass; c->vel[2] /= c->mass;
@@ -269,10 +304,9 @@ void oracle_polar_rotation(const float F[9], float R[9]) {
 }
 
 /* ---------------- forces: cpp:235-254 ---------------- */
-void oracle_compute_explicit_grid_forces(Oracle* o) {
+static void scatter_forces(Oracle* o, OCell* g, int i0, int i1) {
     const OracleParams* q = &o->prm;
-    OCell* g = o->g;
-    for (int i = 0; i < o->n; ++i) {
+    for (int i = i0; i < i1; ++i) {
         if (!o->valid[i]) continue;
         const OParticle* P = &o->p[i];
         const float poisson = q->nu, E = q->E;
@@ -299,6 +333,7 @@ void oracle_compute_explicit_grid_forces(Oracle* o) {
         });
     }
 }
+void oracle_compute_explicit_grid_forces(Oracle* o) { run_scatter(o, scatter_forces); }
 
 /* ---------------- grid velocities: cpp:256-262 ---------------- */
 void oracle_grid_velocities_update(Oracle* o, float dt) {
@@ -472,7 +507,10 @@ int oracle_update_deformation_gradient(Oracle* o, float dt) {
      * with theta as a float parameter the same rule is 1 -/+ theta in double, rounded once */
     const float clo = (float)(1.0 - (double)o->prm.theta_c);
     const float chi = (float)(1.0 + (double)o->prm.theta_s);
+    int failed = 0;
+#pragma omp parallel for num_threads(o->threads) schedule(static) if (o->threads > 1)
     for (int i = 0; i < o->n; ++i) {
+        if (failed) continue;
         OParticle* P = &o->p[i];
         float T[9], Fh[9], FPinv[9], U[9], S[3], V[9], Sg[9], Vt[9], FEinv[9];
         m3mul(T, P->B, o->Dinv); m3scale(T, T, dt); m3add(T, ID3, T);    /* m3t(1.0) + B * DpInverse * dt */
@@ -481,7 +519,7 @@ int oracle_update_deformation_gradient(Oracle* o, float dt) {
         m3mul(Fh, T, FPinv);                                             /* FEpKryshka */
         /* glmToEigen: Eigen m(i,j) = glm mat[i][j] -> the glm array read as a row-major matrix;
          * eigenToGlm maps back the same way, so U/V arrays are used as glm matrices unchanged */
-        if (oracle_svd3(Fh, U, S, V)) return 1;                          /* early return, cpp:313-316 */
+        if (oracle_svd3(Fh, U, S, V)) { failed = 1; continue; }          /* early return, cpp:313-316 (sequential order when threads == 1) */
         for (int k = 0; k < 3; ++k) { float s = S[k]; if (s < clo) s = clo; if (chi < s) s = chi; S[k] = s; }
         memset(Sg, 0, sizeof Sg); Sg[0] = S[0]; Sg[4] = S[1]; Sg[8] = S[2];
         m3transpose(Vt, V);
@@ -489,7 +527,7 @@ int oracle_update_deformation_gradient(Oracle* o, float dt) {
         m3inverse(FEinv, P->FE);
         m3mul(P->FP, FEinv, T);
     }
-    return 0;
+    return failed;
 }
 
 /* ---------------- G2P: cpp:332-342 ---------------- */

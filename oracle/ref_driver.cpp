@@ -116,7 +116,8 @@ int main(int argc, char** argv) {
     glm::vec3 origin(0.5f, 0.6f, 0.5f), v0(0.0f, -200.0f, 0.0f);
     std::string dumpDir, loadPath, loadFullPath, katMode, katIn, katOut, collidersPath;
     std::set<int> dumpSteps, stageSteps;
-    bool bench = false, quiet = false, noColliders = false;
+    bool bench = false, quiet = false, noColliders = false, haveColVel = false;
+    glm::vec3 colVel(0.0f);        // MeshCollider::velocity of every box (main.cpp:121-151 uses 0; key_callback flips its sign)
     for (int a = 1; a < argc; ++a) {
         auto is = [&](const char* k) { return strcmp(argv[a], k) == 0; };
         if (is("--grid")) { I = atoi(argv[++a]); J = atoi(argv[++a]); K = atoi(argv[++a]); }
@@ -133,6 +134,7 @@ int main(int argc, char** argv) {
         else if (is("--bench")) bench = true;
         else if (is("--quiet")) quiet = true;
         else if (is("--no-colliders")) noColliders = true;
+        else if (is("--collider-vel")) { colVel.x = atof(argv[++a]); colVel.y = atof(argv[++a]); colVel.z = atof(argv[++a]); haveColVel = true; }
         else if (is("--colliders")) collidersPath = argv[++a];   // rows of 7 float32: translation[3], rotZ degrees, scale[3]
         else if (is("--load-full")) loadFullPath = argv[++a];   // n x 35 float32, same layout as the particle dumps
         else if (is("--kat-weights")) { katMode = "weights"; katIn = argv[++a]; katOut = argv[++a]; }
@@ -238,6 +240,7 @@ int main(int argc, char** argv) {
         solidObjects.push_back(box3);
         solidObjects.push_back(box4);
     }
+    if (haveColVel) for (auto& o : solidObjects) o.velocity = colVel;
     if (!dumpDir.empty()) {
         // what the sdf lambda actually uses (material_point_method.hpp:80-83): scale, quat, translation
         std::vector<float> c;

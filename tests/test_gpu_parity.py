@@ -106,6 +106,25 @@ def test_fupdate_kat_bit_exact_on_gpu(golden_kat, variants):
     assert_bit_exact(s[:, 17:26], fout[:, 9:18], "FPlastic")
 
 
+def test_collisions_with_moving_colliders_bit_exact(golden_kat):
+    """bodyCollision KAT of the reference with MeshCollider::velocity = (3,-1.5,0.75) on every node of the 20^3 grid:
+    the node velocities go in through upload_grid, gridBasedCollisions runs on the device, results must match bitwise."""
+    k = golden_kat
+    n_nodes = 20 * 20 * 20
+    pos, vel, ref = k["collide_pos"][:n_nodes], k["collide_vel"][:n_nodes], k["collide_moving_out"][:n_nodes]
+    assert np.array_equal(pos[21], np.array([0, 1, 1], np.float32) * np.float32(0.05))      # rows are node positions idx * h
+    raw = k["colliders_moving"]
+    cols, nc = mpm_b200.capi.make_colliders(raw[:, 13:29], raw[:, 0:3], raw[:, 10:13])
+    sim = mpm_b200.Sim(20, 20, 20, 1)
+    sim.upload(np.full((1, 3), 0.5, np.float32), np.zeros((1, 3), np.float32), np.float32(6e-5))
+    g = np.zeros((n_nodes, 7), np.float32)
+    g[:, 0] = 1.0                      # mass != 0: every node is a used cell
+    g[:, 4:7] = vel
+    sim.set_grid(g)
+    sim.gridBasedCollisions(1e-5, cols, nc)
+    assert_bit_exact(sim.grid()[:, 4:7], ref, "gridBasedCollisions with moving colliders")
+
+
 def test_volumes_match_reference(golden_c1):
     s0 = golden_c1["state0"].copy()
     ref = s0[:, 4].copy()
