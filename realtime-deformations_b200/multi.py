@@ -170,7 +170,16 @@ class SlabRunner:
             s.migrate_append_packed(self.m_recv_up.data_ptr())
         self.steps_done += 1
         if self.steps_done % self.sync_every == 0:
-            s.sync_counts()
+            # a capacity error on ONE rank must stop ALL ranks together (otherwise the others wait in the next exchange)
+            err, msg = 0, ""
+            try:
+                s.sync_counts()
+            except capi.MpmError as exc:
+                err, msg = 1, str(exc)
+            flag = t.tensor([err], dtype=t.int32, device="cuda")
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+            if int(flag.item()):
+                raise capi.MpmError(msg or "a neighbouring rank ran out of migration / slab capacity")
 
     def substep(self, host_colliders=False):
         if host_colliders:       # e2e arm: the per-frame host inputs are rebuilt and handed over every step
