@@ -67,7 +67,8 @@ typedef struct MpmStats {
     int64_t n_grid_blocks;      /* active 4^3-node grid blocks after the last binning */
     int64_t substeps_done;
     int64_t kernel_launches;    /* CUDA kernels launched by this handle since creation */
-    float   last_ms[8];         /* device ms of the last mpm_substep call: bin, clear, p2g, grid, g2p, other, total, - */
+    float   last_ms[8];         /* device ms of the last mpm_substep call: bin, clear, p2g, grid, g2p (F-update + gather),
+                                   time between begin/end calls, total, F-update alone (-1 if it ran on the side stream) */
     int32_t svd_failed;         /* 1 if the last F-update met a non-finite matrix */
     int32_t reserved[7];        /* [0] = 1 if the pos/h shortcut passed its exhaustive check for this h,
                                    [1] = 1 if a migration buffer overflowed (particles kept one more substep) */

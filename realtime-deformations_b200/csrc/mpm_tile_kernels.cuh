@@ -398,12 +398,13 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
     return cudaGetLastError();
 }
 
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas_per_sm; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas_per_sm; cudaEvent_t mid; bool mid_recorded; };
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            const SideStream* side) {
+                            SideStream* side) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
+    if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
     // The F-update (HBM-bound, 64 registers) and the gather (issue-bound) touch disjoint planes: when both run, the
     // F-update goes to a side stream so that its CTAs share the SMs with the gather's persistent CTAs.
@@ -417,6 +418,10 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         }
         k_fupdate<(FLAGS & G2P_REORDER) != 0><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (!overlap && side && side->mid && (FLAGS & G2P_GATHER)) {      // per-kernel timing: F-update | gather
+            if ((e = cudaEventRecord(side->mid, st)) != cudaSuccess) return e;
+            side->mid_recorded = true;
+        }
     }
     if (FLAGS & G2P_GATHER) {
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
