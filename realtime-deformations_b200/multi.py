@@ -117,7 +117,10 @@ class SlabRunner:
         self.steps_done = 0
         if world > 1:
             # the migration messages have a fixed size: every rank must use the SAME record capacity
-            cap = torch.tensor([min(max(1 << 14, n // 64), 1 << 18)], dtype=torch.int64, device="cuda")
+            # (a plane of the 8-ppc slab sheds ~8 * cells_in_plane * |v| dt / h particles per substep: a few hundred at
+            # avalanche speeds, a few thousand at 200 m/s; n/512 leaves an order of magnitude of head-room while keeping
+            # the four fixed-size messages per substep at a few MB)
+            cap = torch.tensor([min(max(1 << 13, n // 512), 1 << 17)], dtype=torch.int64, device="cuda")
             self.dist.all_reduce(cap, op=self.dist.ReduceOp.MAX)
             self.sim.set_migrate_capacity(int(cap.item()))
             mb = self.sim.migrate_buffer_bytes() // 4

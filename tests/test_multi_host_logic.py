@@ -84,3 +84,18 @@ def test_neighbour_exchange_over_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def test_balanced_partition_follows_particle_counts():
+    counts = mpm_b200.scenes.snow_slab_layer_counts(512, 1 << 26)
+    assert counts.sum() == 1 << 26
+    for world in (2, 4, 8):
+        parts = multi.slab_layers_balanced(counts, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(counts)
+        assert all(a[1] == b[0] and a[1] > a[0] for a, b in zip(parts, parts[1:]))
+        per_rank = np.array([counts[lo:hi].sum() for lo, hi in parts], np.float64)
+        assert per_rank.max() / per_rank.mean() < 1.06, "particle counts per rank must be balanced to a few percent"
+    # degenerate inputs: all particles in one layer, more ranks than occupied layers
+    one = np.zeros(16, np.int64); one[5] = 1000
+    parts = multi.slab_layers_balanced(one, 4)
+    assert parts[0][0] == 0 and parts[-1][1] == 16 and all(hi > lo for lo, hi in parts)
