@@ -66,3 +66,17 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in src.replace("oracle/", "ORACLE_DOC_PATH/").lower() or f == "scenes.py" or \
                     all("import" not in line and "#include" not in line and "dlopen" not in line and "CDLL" not in line
                         for line in src.splitlines() if "oracle" in line.lower()), f"{f} references the oracle"
+
+
+def test_cxx_host_links_against_the_c_abi(tmp_path, L):
+    """examples/headless_bench.cpp is a plain C++ host (no Python, no torch) using only include/mpm_b200.h: it must
+    compile and link against the in-tree library; without a GPU it must stop with the 'no CUDA device' message."""
+    import subprocess
+    exe = str(tmp_path / "headless_bench")
+    pkg = os.path.join(ROOT, "realtime-deformations_b200")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", os.path.join(ROOT, "examples", "headless_bench.cpp"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + pkg, "-lmpm_b200", "-Wl,-rpath," + pkg, "-o", exe])
+    if L.mpm_device_count() > 0:
+        pytest.skip("a GPU is present: the run itself is covered by the gpu tests")
+    r = subprocess.run([exe, "32", "2", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr
