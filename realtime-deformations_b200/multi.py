@@ -45,6 +45,14 @@ def slab_layers_balanced(layer_counts, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def migrate_capacity_for(n_local):
+    """Records per migration message wanted by a rank holding n_local particles. A plane of the 8-ppc slab sheds about
+    8 * cells_in_plane * |v| dt / h particles per substep (hundreds at avalanche speeds, thousands at 200 m/s); n/512
+    leaves an order of magnitude of head-room while the four fixed-size messages per substep stay at a few MB. The ranks
+    then agree on the MAXIMUM of these (the message size must be identical on both ends of every exchange)."""
+    return min(max(1 << 13, n_local // 512), 1 << 17)
+
+
 def exchange_with_neighbours(dist, torch, rank, world, send_down, send_up, recv_down, recv_up):
     """Grouped point-to-point exchange with rank-1 (down) and rank+1 (up); any tensor may be None at the ends."""
     ops = []
@@ -72,8 +80,12 @@ def exchange_counts(dist, torch, rank, world, n_down, n_up, device):
 class SlabRunner:
     """Owns one rank's slab of the snow-slab scene (BASELINE config 5) and advances it substep by substep."""
 
-    def __init__(self, grid, n_particles, rank, world, torch, scene=None, dt=1e-5, variants=(0, 0)):
+    def __init__(self, grid, n_particles, rank, world, torch, scene=None, dt=1e-5, variants=(0, 0), sim_factory=None,
+                 device="cuda"):
+        """sim_factory / device exist for the CPU (gloo) tests of this protocol: a stand-in object with capi.Sim's
+        pointer-based slab methods and device="cpu"; the product path always uses capi.Sim on "cuda"."""
         self.torch, self.rank, self.world, self.dt = torch, rank, world, float(dt)
+        self.device = device
         self.dist = None
         if world > 1:
             import torch.distributed as dist
@@ -96,18 +108,25 @@ class SlabRunner:
             p.gravity[:] = [float(x) for x in scene["gravity"]]
         self.migrates = world > 1
         cap = n if world == 1 else int(n * 1.5) + (1 << 16)
-        self.sim = capi.Sim(grid, grid, grid, n, p, slab=None if world == 1 else (self.lo, self.hi), capacity=cap)
+        make = sim_factory if sim_factory is not None else capi.Sim
+        self.sim = make(grid, grid, grid, n, p, slab=None if world == 1 else (self.lo, self.hi), capacity=cap)
         # one stream for everything: the library's kernels and torch's NCCL calls are ordered against each other only
         # if the library stream IS torch's current stream while the collectives are enqueued
-        self.stream = torch.cuda.Stream()
-        self.sim.set_stream(self.stream.cuda_stream)
-        with torch.cuda.stream(self.stream):
+        self.stream = None
+        if device == "cuda":
+            self.stream = torch.cuda.Stream()
+            self.sim.set_stream(self.stream.cuda_stream)
+        with self._on_stream():
             self._setup(scene, n, rank, world, torch)
+
+    def _on_stream(self):
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def _setup(self, scene, n, rank, world, torch):
         if world > 1:
             # ids unique across ranks: exclusive prefix of the per-rank counts
-            counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+            counts = torch.zeros(world, dtype=torch.int64, device=self.device)
             counts[rank] = n
             self.dist.all_reduce(counts)
             self.sim.set_pid_base(int(counts[:rank].sum().item()))
@@ -117,20 +136,17 @@ class SlabRunner:
         self.steps_done = 0
         if world > 1:
             # the migration messages have a fixed size: every rank must use the SAME record capacity
-            # (a plane of the 8-ppc slab sheds ~8 * cells_in_plane * |v| dt / h particles per substep: a few hundred at
-            # avalanche speeds, a few thousand at 200 m/s; n/512 leaves an order of magnitude of head-room while keeping
-            # the four fixed-size messages per substep at a few MB)
-            cap = torch.tensor([min(max(1 << 13, n // 512), 1 << 17)], dtype=torch.int64, device="cuda")
+            cap = torch.tensor([migrate_capacity_for(n)], dtype=torch.int64, device=self.device)
             self.dist.all_reduce(cap, op=self.dist.ReduceOp.MAX)
             self.sim.set_migrate_capacity(int(cap.item()))
             mb = self.sim.migrate_buffer_bytes() // 4
-            self.m_recv_dn = torch.empty(mb, dtype=torch.float32, device="cuda")
-            self.m_recv_up = torch.empty(mb, dtype=torch.float32, device="cuda")
+            self.m_recv_dn = torch.empty(mb, dtype=torch.float32, device=self.device)
+            self.m_recv_up = torch.empty(mb, dtype=torch.float32, device=self.device)
             hb = self.sim.halo_bytes() // 4
-            self.h_send_up = torch.empty(hb, dtype=torch.float32, device="cuda")
-            self.h_recv_up = torch.empty(hb, dtype=torch.float32, device="cuda")
-            self.h_send_dn = torch.empty(hb, dtype=torch.float32, device="cuda")
-            self.h_recv_dn = torch.empty(hb, dtype=torch.float32, device="cuda")
+            self.h_send_up = torch.empty(hb, dtype=torch.float32, device=self.device)
+            self.h_recv_up = torch.empty(hb, dtype=torch.float32, device=self.device)
+            self.h_send_dn = torch.empty(hb, dtype=torch.float32, device=self.device)
+            self.h_recv_dn = torch.empty(hb, dtype=torch.float32, device=self.device)
         # start-up of the reference (main.cpp:53-54): one P2G for the particle volumes; needs the halo as well
         self.sim.rasterizeParticlesToGrid()
         if world > 1:
@@ -152,7 +168,10 @@ class SlabRunner:
             s.halo_add(0, self.h_recv_dn.data_ptr())
 
     def _view(self, ptr, n_floats):
-        """torch view over a device buffer owned by the library (no copy)."""
+        """torch view over a buffer owned by the library (no copy)."""
+        if self.device != "cuda":       # CPU stand-in of the tests: a plain host pointer
+            import ctypes
+            return self.torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n_floats).from_address(ptr)))
         class _A:
             pass
         a = _A()
@@ -179,7 +198,7 @@ class SlabRunner:
                 s.sync_counts()
             except capi.MpmError as exc:
                 err, msg = 1, str(exc)
-            flag = t.tensor([err], dtype=t.int32, device="cuda")
+            flag = t.tensor([err], dtype=t.int32, device=self.device)
             self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
             if int(flag.item()):
                 raise capi.MpmError(msg or "a neighbouring rank ran out of migration / slab capacity")
@@ -190,7 +209,7 @@ class SlabRunner:
         if self.world == 1:
             self.sim.substep(self.dt, self.cols, self.nc, 1)
             return
-        with self.torch.cuda.stream(self.stream):
+        with self._on_stream():
             self.sim.substep_begin(self.dt)
             self._halo()
             self.sim.substep_end(self.dt, self.cols, self.nc)

@@ -99,3 +99,118 @@ def test_balanced_partition_follows_particle_counts():
     one = np.zeros(16, np.int64); one[5] = 1000
     parts = multi.slab_layers_balanced(one, 4)
     assert parts[0][0] == 0 and parts[-1][1] == 16 and all(hi > lo for lo, hi in parts)
+
+
+# ---- the whole per-substep protocol of SlabRunner on 8 gloo ranks, against a CPU stand-in of the library -------------
+class _StandInSim:
+    """Same pointer-based slab methods as capi.Sim, backed by numpy. Every message carries (sender rank, step, kind) so
+    that the receiver can check WHO it came from and WHEN; the migration buffer size depends on the capacity the ranks
+    agreed on, exactly like the real library (unequal sizes between neighbours is the bug this test exists for)."""
+    HALO_FLOATS = 4096
+
+    def __init__(self, I, J, K, n, params, slab=None, capacity=None):
+        import ctypes
+        self.ct = ctypes
+        self.n, self.slab, self.capacity = n, slab, capacity
+        self.rank = None
+        self.step = 0            # substeps begun
+        self.halo_round = 0      # halo exchanges seen (1 at start-up + 1 per substep)
+        self.mig_round = 0
+        self.mcap = None
+        self.errors = []
+        self.out = {}
+
+    def _arr(self, ptr, n):
+        return np.ctypeslib.as_array((self.ct.c_float * n).from_address(ptr))
+
+    # set-up
+    def set_pid_base(self, base): self.pid_base = base
+    def upload(self, pos, vel, mass): assert len(pos) == self.n
+    def set_migrate_capacity(self, cap): self.mcap = int(cap)
+    def migrate_buffer_bytes(self): return 16 * (1 + 11 * self.mcap)
+    def halo_bytes(self): return 4 * self.HALO_FLOATS
+    def rasterizeParticlesToGrid(self): pass
+    def computeParticleVolumesAndDensities(self): pass
+    def stats(self): raise AssertionError("no per-step host read-back expected")
+
+    # halo: upper=1 is my ghost layer (goes to rank+1), upper=0 my first layer (goes to rank-1)
+    def halo_pack(self, upper, ptr):
+        self._arr(ptr, self.HALO_FLOATS)[:] = 1000 * self.rank + 10 * self.halo_round + upper
+    def halo_add(self, upper, ptr):
+        got = self._arr(ptr, self.HALO_FLOATS)
+        sender = self.rank + 1 if upper else self.rank - 1
+        want = 1000 * sender + 10 * self.halo_round + (0 if upper else 1)      # the neighbour's OTHER layer
+        if not (got == want).all():
+            self.errors.append(f"halo round {self.halo_round}: rank {self.rank} upper={upper} got {got[0]} want {want}")
+        if upper == 0 or self.slab[1] == self.top:          # last add of this exchange
+            pass
+
+    def substep_begin(self, dt):
+        self.step += 1
+        self.halo_round += 1
+    def substep_end(self, dt, cols, nc): pass
+
+    def migrate_pack(self):
+        nf = self.migrate_buffer_bytes() // 4
+        self.out = {d: np.full(nf, float(1000 * self.rank + d), np.float32) for d in (0, 1)}
+        for d in (0, 1):
+            self.out[d][:1].view(np.int32)[0] = (7 * self.rank + self.step + d) % 5       # header: record count
+        return self.out[0].ctypes.data, self.out[1].ctypes.data
+    def migrate_append_packed(self, ptr):
+        nf = self.migrate_buffer_bytes() // 4
+        got = self._arr(ptr, nf)
+        self.appends = getattr(self, "appends", [])
+        self.appends.append((int(got[:1].view(np.int32)[0]), float(got[-1])))
+    def sync_counts(self): self.syncs = getattr(self, "syncs", 0) + 1
+
+
+def _protocol_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sims = []
+
+        def factory(*a, **k):
+            s = _StandInSim(*a, **k); s.rank = rank; s.top = None; sims.append(s); return s
+        multi.migrate_capacity_for = lambda n_local: 16 + n_local // 64       # per-rank wishes now really differ
+        r = multi.SlabRunner(64, 60000, rank, world, torch, sim_factory=factory, device="cpu")
+        sim = sims[0]
+        # balanced slabs: unequal particle counts, yet every rank must have agreed on one migration capacity
+        caps = [None] * world
+        dist.all_gather_object(caps, (sim.n, sim.mcap, sim.slab))
+        assert len({c[1] for c in caps}) == 1, f"migration capacity differs across ranks: {caps}"
+        assert caps[0][1] == max(16 + c[0] // 64 for c in caps), "the agreed capacity is the largest wish"
+        assert len({c[0] for c in caps}) > 1, "the test needs unequal per-rank particle counts"
+        assert [c[2][0] for c in caps[1:]] == [c[2][1] for c in caps[:-1]], "slabs must be contiguous"
+        steps = 20
+        for _ in range(steps):
+            r.substep()
+            # migration: what arrived must be the neighbours' buffers of THIS step
+            want = []
+            if rank > 0:
+                want.append(((7 * (rank - 1) + sim.step + 1) % 5, float(1000 * (rank - 1) + 1)))     # lower neighbour's "up" buffer
+            if rank < world - 1:
+                want.append(((7 * (rank + 1) + sim.step + 0) % 5, float(1000 * (rank + 1) + 0)))     # upper neighbour's "down" buffer
+            assert sim.appends == want, (rank, sim.step, sim.appends, want)
+            sim.appends = []
+        assert sim.errors == [], sim.errors
+        assert getattr(sim, "syncs", 0) == steps // r.sync_every
+        out.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [3, 8])
+def test_slab_protocol_on_many_ranks_with_stand_in_library(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_protocol_worker, args=(r, world, 29650 + world, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), [r for r in res if r[1] != "ok"]
