@@ -44,7 +44,8 @@ typedef struct MpmParams {
     float gravity[3];     /*                         material_point_method.cpp:260  (0,-9.8,0) */
     float friction_mu;    /*                         material_point_method.cpp:288  (0.5)    */
     int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline) */
-    int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline) */
+    int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline),
+                             2 = experimental linear-tile gather (not validated on hardware yet) */
     int   reserved[6];
 } MpmParams;
 

@@ -18,6 +18,7 @@
 //   (the physical re-sort that keeps the next substep's loads coalesced).
 #pragma once
 #include "mpm_kernels.cuh"
+#include <type_traits>
 
 namespace mpm {
 
@@ -251,15 +252,27 @@ struct G2PSmem {
     unsigned long long bar[G2P_WARPS];
 };
 
+// EXPERIMENTAL (g2p_variant = 2, not the default, not yet validated on hardware): the tile re-laid out LINEARLY in
+// smem, slot(ti,tj,tk) = ti*73 + tj*9 + tk (rows padded 8->9, planes 72->73 so that the bank group is (ti+tj+tk) mod 8).
+// The 64 stencil reads of a particle then are LDS.128 [base + immediate] with no per-node address arithmetic
+// (the blocked tile costs ~190 integer instructions per particle, 17 % of the gather loop). The re-layout is done by
+// the copy engine: 128 bulk copies of 64 B (one 4-node k-row each), 4 per lane.
+constexpr int G2P_LIN_ROW = 9, G2P_LIN_PLANE = 73, G2P_LIN_SLOTS = 8 * G2P_LIN_PLANE;
+struct G2PSmemLinear {
+    float4 tile[G2P_WARPS][G2P_LIN_SLOTS];
+    unsigned long long bar[G2P_WARPS];
+};
+
 // Warp-per-block gather: every warp owns a whole particle block at a time (its own TMA-loaded tile, its own
 // mbarrier), so there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
 // FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate).
-template <int FLAGS>
+template <int FLAGS, bool LINEAR = false>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
     extern __shared__ __align__(128) unsigned char g2p_smem_raw[];
-    G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
+    using Smem = typename std::conditional<LINEAR, G2PSmemLinear, G2PSmem>::type;
+    Smem& S = *reinterpret_cast<Smem*>(g2p_smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_work = dc->n_active_pblocks;
     float4* __restrict__ tile = S.tile[wid];
@@ -279,10 +292,12 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 b = wk.x; start = wk.y; cnt = wk.z;
                 const int pbk0 = b % gd.npbk, pbj0 = (b / gd.npbk) % gd.npbj, pbi_l = b / (gd.npbk * gd.npbj);
                 mbar_expect_tx(bar, 8 * 1024);
+                if (!LINEAR) {
 #pragma unroll
-                for (int d = 0; d < 8; ++d) {
-                    const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj0 + ((d >> 1) & 1)) * gd.nbk + pbk0 + (d & 1);
-                    tma_load_1d(&tile[d * 64], grid + gb * 64, 1024, bar);
+                    for (int d = 0; d < 8; ++d) {
+                        const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj0 + ((d >> 1) & 1)) * gd.nbk + pbk0 + (d & 1);
+                        tma_load_1d(&tile[d * 64], grid + gb * 64, 1024, bar);
+                    }
                 }
             }
         }
@@ -290,6 +305,17 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
         if (w >= n_work) break;
         b = __shfl_sync(0xffffffffu, b, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
         const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
+        if (LINEAR) {
+            // lane 0 has armed the barrier with the byte count (ordered before the copies by the shuffles above);
+            // every lane issues 4 of the 128 row copies: row = lane & 15 of grid blocks d = (lane >> 4) + 2m
+            const int row = lane & 15, li = row >> 2, lj = row & 3;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int d = (lane >> 4) + 2 * m, di = d >> 2, dj = (d >> 1) & 1, dk = d & 1;
+                const size_t gb = ((size_t)(pbi - gd.lo + di) * gd.nbj + pbj + dj) * gd.nbk + pbk + dk;
+                tma_load_1d(&tile[(di * 4 + li) * G2P_LIN_PLANE + (dj * 4 + lj) * G2P_LIN_ROW + dk * 4], grid + gb * 64 + row * 4, 64, bar);
+            }
+        }
         // software pipeline over the 32-particle slices: ids two slices ahead, positions one slice ahead, so neither
         // the sorted_ids -> position dependent-load chain nor the position load is waited for
         int p = (lane < cnt) ? sorted_ids[start + lane] : -1;
@@ -315,11 +341,12 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     int offx[4], offy[4], offz[4];
                     float wxd[4], wyd[4], wzd[4];
+                    const float4* __restrict__ lin = tile + (LINEAR ? ox * G2P_LIN_PLANE + oy * G2P_LIN_ROW + oz : 0);
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        offx[a] = ((ox + a) >> 2) * 256 + ((ox + a) & 3) * 16;
-                        offy[a] = ((oy + a) >> 2) * 128 + ((oy + a) & 3) * 4;
-                        offz[a] = ((oz + a) >> 2) * 64 + ((oz + a) & 3);
+                        offx[a] = LINEAR ? 0 : ((ox + a) >> 2) * 256 + ((ox + a) & 3) * 16;
+                        offy[a] = LINEAR ? 0 : ((oy + a) >> 2) * 128 + ((oy + a) & 3) * 4;
+                        offz[a] = LINEAR ? 0 : ((oz + a) >> 2) * 64 + ((oz + a) & 3);
                         wxd[a] = wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]);
                         wyd[a] = wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]);
                         wzd[a] = wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]);
@@ -334,7 +361,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                             const int oab = offx[a] + offy[bb];
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                const float4 n = tile[oab + offz[cc]];
+                                const float4 n = LINEAR ? lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : tile[oab + offz[cc]];
                                 s0[0] += wz[cc] * n.y; s0[1] += wz[cc] * n.z; s0[2] += wz[cc] * n.w;
                                 s1[0] += wzd[cc] * n.y; s1[1] += wzd[cc] * n.z; s1[2] += wzd[cc] * n.w;
                             }
@@ -385,6 +412,8 @@ inline cudaError_t tile_kernels_init() {
 #define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
     MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
 #undef MPM_SET_SMEM2
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -402,7 +431,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side) {
+                            SideStream* side, bool linear_tile = false) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -425,7 +454,10 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
     }
     if (FLAGS & G2P_GATHER) {
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
-        k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        if (linear_tile)
+            k_g2p_tile<FLAGS & ~G2P_F, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmemLinear), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        else
+            k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (overlap) {

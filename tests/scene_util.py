@@ -4,7 +4,11 @@ import numpy as np
 import mpm_b200
 import oracle_py as op
 
+import os
+
 VARIANTS = [(0, 0), (1, 1)]     # (p2g_variant, g2p_variant): tile kernels, baseline kernels
+if os.environ.get("MPM_TEST_EXPERIMENTAL") == "1":
+    VARIANTS.append((0, 2))     # experimental linear-tile gather: opt-in until it has been validated on hardware
 
 
 def oracle_from_scene(sc, fma=False, **prm):
