@@ -57,6 +57,12 @@ struct mpm_sim {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t render_ready = nullptr, copy_done = nullptr;
     bool copy_pending = false;
+    // EXPERIMENTAL, opt-in (MPM_B200_GRAPH=1), not yet validated on hardware: a CUDA graph of two consecutive fused
+    // substeps (the particle buffers ping-pong, so two substeps return every host-side pointer to where it started)
+    bool graph_enabled = false, capturing = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    float graph_dt = 0.0f; int graph_nc = -1; int64_t graph_n_bound = -1; int graph_cur = -1; int graph_launches = 0;
+    ColliderSet graph_cols;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
     int num_sms = 148;
@@ -187,6 +193,7 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s->buf[b], 0, sizeof(float4) * NPLANES * (size_t)s->capacity, s->stream));
     for (auto& e : s->ev) CK(cudaEventCreate(&e));
     s->ev_ok = true;
+    { const char* g = getenv("MPM_B200_GRAPH"); s->graph_enabled = g && atoi(g) > 0; }
     {
         // Running the F-update on a side stream next to the gather was measured at <= 1.5 % (the gather's persistent CTAs
         // own the register file), so it is opt-in; the default keeps the two kernels back to back and times them apart.
@@ -224,6 +231,7 @@ int mpm_destroy(mpm_t* s) {
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
     cudaFree(s->render_stage);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->side.stream) { cudaStreamDestroy(s->side.stream); cudaEventDestroy(s->side.fork); cudaEventDestroy(s->side.join); }
     if (s->side.mid) cudaEventDestroy(s->side.mid);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -403,7 +411,8 @@ int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs, float si
     }
     if (s->render_cap < n) {
         if (s->copy_pending) CK(cudaEventSynchronize(s->copy_done));
-        cudaFree(s->render_stage); s->render_stage = nullptr;
+        cudaFree(s->render_stage);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec); s->render_stage = nullptr;
         CK(cudaMalloc(&s->render_stage, sizeof(float4) * (size_t)std::max<int64_t>(n, 1)));
         s->render_cap = n;
     }
@@ -581,33 +590,75 @@ int mpm_update_particle_positions(mpm_t* s, float dt) {        // cpp:344-350
 }
 
 // ---- fused fast path --------------------------------------------------------------------------------------------
+#define EV(i) do { if (!s->capturing) CK(cudaEventRecord(s->ev[i], s->stream)); } while (0)   // timing events are not graph nodes
 int mpm_substep_begin(mpm_t* s, float dt) {
     NEED(s);
-    CK(cudaEventRecord(s->ev[0], s->stream));
+    EV(0);
     TRY(ensure_tau(s));
     TRY(do_binning(s));
-    CK(cudaEventRecord(s->ev[1], s->stream));
+    EV(1);
     TRY(launch_clear(s));
-    CK(cudaEventRecord(s->ev[2], s->stream));
+    EV(2);
     TRY((launch_p2g<P2G_FUSED>(s, s->grid, dt)));
-    CK(cudaEventRecord(s->ev[3], s->stream));
+    EV(3);
     return MPM_OK;
 }
 int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
     NEED(s);
     TRY(set_colliders(s, c, n));
-    CK(cudaEventRecord(s->ev[4], s->stream));
+    EV(4);
     TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
-    CK(cudaEventRecord(s->ev[5], s->stream));
+    EV(5);
     TRY((launch_g2p<G2P_F | G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));
-    CK(cudaEventRecord(s->ev[6], s->stream));
+    EV(6);
     s->tau_valid = true;
     s->stats.substeps_done++;
+    return MPM_OK;
+}
+#undef EV
+
+// EXPERIMENTAL graph path: (re)capture two substeps when dt / colliders / particle bound / buffer parity changed
+static int graph_prepare(mpm_sim* s, float dt, const MpmBoxCollider* c, int n) {
+    const bool same = s->graph_exec && s->graph_dt == dt && s->graph_nc == n && s->graph_n_bound == s->n_bound && s->graph_cur == s->cur &&
+                      (n == 0 || memcmp(s->graph_cols.c, c, sizeof(BoxCollider) * n) == 0);
+    if (same) return MPM_OK;
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    TRY(ensure_tau(s));                                     // the one lazily launched kernel stays outside the capture
+    const int64_t launches0 = s->stats.kernel_launches, steps0 = s->stats.substeps_done;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    s->capturing = true;
+    int rc = MPM_OK;
+    for (int i = 0; i < 2 && rc == MPM_OK; ++i) {
+        rc = mpm_substep_begin(s, dt);
+        if (rc == MPM_OK) rc = mpm_substep_end(s, dt, c, n);
+    }
+    s->capturing = false;
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    s->graph_launches = (int)(s->stats.kernel_launches - launches0);
+    s->stats.kernel_launches = launches0; s->stats.substeps_done = steps0;      // nothing has run yet
+    if (rc != MPM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { s->graph_exec = nullptr; return fail(MPM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e2)); }
+    s->graph_dt = dt; s->graph_nc = n; s->graph_n_bound = s->n_bound; s->graph_cur = s->cur;
+    if (n) memcpy(s->graph_cols.c, c, sizeof(BoxCollider) * n);
     return MPM_OK;
 }
 int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* c, int n, int n_substeps) {
     NEED(s);
     if (n_substeps < 0) return fail(MPM_ERR_INVALID, "n_substeps < 0");
+    const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+    if (s->graph_enabled && !slab && !s->side.stream && n_substeps >= 2 && n >= 0 && n <= MPM_MAX_COLLIDERS && (n == 0 || c)) {
+        TRY(graph_prepare(s, dt, c, n));
+        const int pairs = n_substeps / 2;
+        for (int i = 0; i < pairs; ++i) CK(cudaGraphLaunch(s->graph_exec, s->stream));
+        s->stats.substeps_done += 2 * pairs;
+        s->stats.kernel_launches += (int64_t)s->graph_launches * pairs;
+        s->tau_valid = true; s->binned = false;
+        n_substeps -= 2 * pairs;                            // an odd leftover runs through the plain path below
+    }
     for (int i = 0; i < n_substeps; ++i) {
         TRY(mpm_substep_begin(s, dt));
         TRY(mpm_substep_end(s, dt, c, n));

@@ -405,3 +405,18 @@ def test_full_size_properties_config3_momentum():
     # the two balls travel +-100 m/s along i: 5 substeps move them 5 mm each
     half = n // 2
     assert abs(float((out["pos"][:half, 0] - sc["pos"][:half, 0]).mean()) - 100.0 * dt * k) < 1e-5
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental paths (CUDA-graph substeps, linear-tile gather) are opt-in until validated on hardware")
+def test_experimental_graph_substeps_match_plain_path(monkeypatch):
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0)
+    plain, cols, nc = sim_from_scene(sc)
+    monkeypatch.setenv("MPM_B200_GRAPH", "1")
+    graph, _, _ = sim_from_scene(sc)
+    monkeypatch.delenv("MPM_B200_GRAPH")
+    for k in (7, 12, 1, 4):                      # odd counts leave one plain substep and flip the buffer parity
+        plain.substep(float(sc["dt"]), cols, nc, k)
+        graph.substep(float(sc["dt"]), cols, nc, k)
+    assert_traj_close(graph.download_state35(), plain.download_state35(), 20, "CUDA-graph substeps vs plain launches")
+    assert graph.stats().substeps_done == plain.stats().substeps_done == 24
