@@ -168,6 +168,40 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def roofline_block(ms_per_step, n_total, n_active, world, phase_ms, grid, particles):
+    """The `roofline` object of the JSON line. phase_ms = MpmStats.last_ms of the last substep (max over ranks):
+    [bin, clear, p2g, grid, g2p (F-update + gather), between begin/end, total, F-update alone or -1]."""
+    peak, peak_src = measured_peak()
+    alg_bytes = ALG_BYTES_PER_PARTICLE * n_total + ALG_BYTES_PER_NODE * n_active
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9 / world      # per-GPU GB/s against a per-GPU peak
+    names = ["bin_sort", "grid_clear", "p2g", "halo_wait", "grid_update", "g2p(fupdate+gather)", "substep_total"]
+    order = [0, 1, 2, 5, 3, 4, 6]
+    kern = {names[i]: round(phase_ms[order[i]], 4) for i in range(7)}
+    if len(phase_ms) > 7 and phase_ms[7] > 0:   # the two G2P kernels timed apart (default: back to back on one stream)
+        kern["fupdate"] = round(phase_ms[7], 4)
+        kern["g2p_gather"] = round(phase_ms[4] - phase_ms[7], 4)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{grid}:{particles}")
+    except Exception:
+        pass
+    cands = ("p2g", "fupdate", "g2p_gather", "bin_sort", "grid_update") if "fupdate" in kern else ("p2g", "g2p(fupdate+gather)", "bin_sort", "grid_update")
+    dom = max(cands, key=lambda k: kern[k])
+    # per-kernel algorithmic bytes (DESIGN.md section 4), per GPU
+    npg, apg = n_total / world, n_active / world
+    kern_alg = {"p2g": 88 * npg + 16 * apg, "g2p(fupdate+gather)": (128 + 112) * npg + (16 + 64) * npg + 16 * apg,
+                "fupdate": (128 + 112) * npg, "g2p_gather": (16 + 64) * npg + 16 * apg,
+                "bin_sort": 24 * npg, "grid_update": 32 * apg}
+    dom_gbs = kern_alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
+    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": traffic, "peak_source": peak_src, "scope": "one whole substep (all kernels), per GPU",
+            "algorithmic_bytes_per_substep": alg_bytes, "active_nodes": n_active,
+            "kernel_ms_last_substep": kern, "dominant_kernel": dom,
+            "dominant_kernel_algorithmic_bytes": kern_alg[dom], "dominant_kernel_achieved_gbs": round(dom_gbs, 1),
+            "dominant_kernel_frac": round(dom_gbs / peak, 4),
+            "dominant_share_of_substep": round(kern[dom] / max(kern["substep_total"], 1e-9), 3)}
+
+
 WORKLOAD_NAME = "snow_slab_512: 64Mi-particle snow slab avalanche, 512^3 grid (BASELINE config 5)"
 
 
@@ -286,35 +320,7 @@ def main():
 
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3)
-    peak, peak_src = measured_peak()
-    alg_bytes = ALG_BYTES_PER_PARTICLE * n_total + ALG_BYTES_PER_NODE * n_active
-    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9 / world      # per-GPU GB/s against a per-GPU peak
-    names = ["bin_sort", "grid_clear", "p2g", "halo_wait", "grid_update", "g2p(fupdate+gather)", "substep_total"]
-    order = [0, 1, 2, 5, 3, 4, 6]
-    kern = {names[i]: round(phase_ms[order[i]], 4) for i in range(7)}
-    if phase_ms[7] > 0:        # the two G2P kernels timed apart (default: they run back to back on one stream)
-        kern["fupdate"] = round(phase_ms[7], 4)
-        kern["g2p_gather"] = round(phase_ms[4] - phase_ms[7], 4)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.grid}:{args.particles}")
-    except Exception:
-        pass
-    cands = ("p2g", "fupdate", "g2p_gather", "bin_sort", "grid_update") if "fupdate" in kern else ("p2g", "g2p(fupdate+gather)", "bin_sort", "grid_update")
-    dom = max(cands, key=lambda k: kern[k])
-    # per-kernel algorithmic bytes, per GPU
-    npg, apg = n_total / world, n_active / world
-    kern_alg = {"p2g": 88 * npg + 16 * apg, "g2p(fupdate+gather)": (128 + 112) * npg + (16 + 64) * npg + 16 * apg,
-                "fupdate": (128 + 112) * npg, "g2p_gather": (16 + 64) * npg + 16 * apg,
-                "bin_sort": 24 * npg, "grid_update": 32 * apg}
-    dom_gbs = kern_alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
-    roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": traffic, "peak_source": peak_src, "scope": "one whole substep (all kernels), per GPU",
-            "algorithmic_bytes_per_substep": alg_bytes, "active_nodes": n_active,
-            "kernel_ms_last_substep": kern, "dominant_kernel": dom,
-            "dominant_kernel_algorithmic_bytes": kern_alg[dom], "dominant_kernel_achieved_gbs": round(dom_gbs, 1),
-            "dominant_kernel_frac": round(dom_gbs / peak, 4),
-            "dominant_share_of_substep": round(kern[dom] / max(kern["substep_total"], 1e-9), 3)}
+    roof = roofline_block(ms_per_step, n_total, n_active, world, phase_ms, args.grid, args.particles)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(mpm_b200)

@@ -30,3 +30,22 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_reference_arm_other_ranks_exit_without_work():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_roofline_block_assembly():
+    """The roofline object is assembled by a pure function: exercise both timing layouts without a GPU."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n, a = 67108864.0, 9184376.0
+    # default: F-update and gather timed apart
+    r = bench.roofline_block(9.92, n, a, 1, [0.48, 0.03, 4.21, 0.11, 5.01, 0.003, 9.85, 2.44], 512, 1 << 26)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["dominant_kernel"] == "p2g" and r["kernel_ms_last_substep"]["g2p_gather"] == round(5.01 - 2.44, 4)
+    assert abs(r["achieved"] - (272 * n + 80 * a) / 9.92e-3 / 1e9) < 1.0
+    assert r["dominant_kernel_achieved_gbs"] == round((88 * n + 16 * a) / 4.21e-3 / 1e9, 1)
+    # side-stream overlap: only the combined G2P time exists
+    r2 = bench.roofline_block(9.92, n, a, 1, [0.48, 0.03, 4.21, 0.11, 5.01, 0.003, 9.85, -1.0], 512, 1 << 26)
+    assert r2["dominant_kernel"] == "g2p(fupdate+gather)" and "fupdate" not in r2["kernel_ms_last_substep"]
+    # 8 GPUs: per-GPU achieved against a per-GPU peak
+    r8 = bench.roofline_block(2.0, n, a, 8, [0.1, 0.01, 0.55, 0.4, 0.65, 0.3, 1.7, 0.3], 512, 1 << 26)
+    assert abs(r8["achieved"] - (272 * n + 80 * a) / 2.0e-3 / 1e9 / 8) < 1.0
