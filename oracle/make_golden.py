@@ -64,16 +64,19 @@ def c1_default(tmp):
 
 
 def c1b_fine(tmp):
-    """h = 0.025, 40^3, 17 100 particles: the largest scene the real class can hold."""
-    n, steps = 17100, 20
-    run(["--h", 0.025, "--grid", 40, 40, 40, "--n", n, "--steps", steps, "--dump-dir", tmp,
-         "--dump-steps", steps, "--quiet"])
+    """h = 0.025, 40^3, 17 100 particles: the largest scene the real class can hold. Snapshots in free
+    fall (20 substeps) and after first contact with the ground box (120 substeps)."""
+    n, steps, late = 17100, 20, 120
+    run(["--h", 0.025, "--grid", 40, 40, 40, "--n", n, "--steps", late, "--dump-dir", tmp,
+         "--dump-steps", f"{steps},{late}", "--quiet"])
     s0 = ld(tmp + "/particles_step0000.f32", 35)
     s1 = ld(f"{tmp}/particles_step{steps:04d}.f32", 35)
+    s2 = ld(f"{tmp}/particles_step{late:04d}.f32", 35)
     np.savez_compressed(os.path.join(OUT, "c1b_h0025.npz"), I=40, J=40, K=40, h=np.float32(0.025), dt=np.float32(1e-5),
                         steps=steps, colliders=np.fromfile(tmp + "/colliders.f32", dtype=np.float32).reshape(-1, 29),
                         pos0=s0[:, 5:8], vel0=s0[0, 1:4], mass0=s0[0, 0], volume0=s0[:, 4],
-                        pos=s1[:, 5:8], vel=s1[:, 1:4], FE=s1[:, 8:17], FP=s1[:, 17:26])
+                        pos=s1[:, 5:8], vel=s1[:, 1:4], FE=s1[:, 8:17], FP=s1[:, 17:26],
+                        steps_late=late, pos_late=s2[:, 5:8], vel_late=s2[:, 1:4], FE_late=s2[:, 8:17], FP_late=s2[:, 17:26])
 
 
 def rand_rot(rng, n):
