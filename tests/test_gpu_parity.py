@@ -173,6 +173,12 @@ def test_fine_scene_vs_reference(golden_c1b):
     ref = np.zeros((n, 35), np.float32)
     ref[:, 5:8], ref[:, 1:4], ref[:, 8:17], ref[:, 17:26] = g["pos"], g["vel"], g["FE"], g["FP"]
     assert_traj_close(sim.download_state35(), ref, int(g["steps"]), "CUDA vs reference, h=0.025, 17 100 particles")
+    # ... and on through first contact with the ground box (120 substeps: collisions, clamping and hardening active)
+    late = int(g["steps_late"])
+    sim.substep(float(g["dt"]), cols, nc, late - int(g["steps"]))
+    ref[:, 5:8], ref[:, 1:4], ref[:, 8:17], ref[:, 17:26] = g["pos_late"], g["vel_late"], g["FE_late"], g["FP_late"]
+    assert_traj_close(sim.download_state35(), ref, 200, "CUDA vs reference, h=0.025, through first contact")
+    assert sim.stats().svd_failed == 0
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
