@@ -144,16 +144,31 @@ static int validate_pos_div(mpm_sim* s) {
 
 static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
+static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
+                       int64_t n_particles, int64_t capacity, mpm_sim*& s);
 int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
                     int64_t n_particles, int64_t capacity, mpm_t** out) {
     if (!out) return fail(MPM_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    mpm_sim* s = nullptr;
+    const int rc = create_impl(params, max_i, max_j, max_k, block_lo, block_hi, n_particles, capacity, s);
+    if (rc != MPM_OK) {                 // release whatever was allocated before the failure (keeps the error message)
+        const std::string msg = g_last_error;
+        if (s) mpm_destroy(s);
+        g_last_error = msg;
+        return rc;
+    }
+    *out = s;
+    return MPM_OK;
+}
+static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
+                       int64_t n_particles, int64_t capacity, mpm_sim*& s) {
     if (max_i < 8 || max_j < 8 || max_k < 8) return fail(MPM_ERR_INVALID, "grid must be at least 8^3 nodes");
     if (n_particles < 0 || capacity < n_particles) return fail(MPM_ERR_INVALID, "capacity < n_particles");
     if (capacity >= (int64_t)1 << 31) return fail(MPM_ERR_INVALID, "capacity must be < 2^31");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(MPM_ERR_CUDA, "no CUDA device: libmpm_b200 has no CPU fallback"); }
-    mpm_sim* s = new mpm_sim();
+    s = new mpm_sim();
     CK(cudaGetDevice(&s->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, s->device));
@@ -163,10 +178,10 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     g.I = max_i; g.J = max_j; g.K = max_k;
     g.npbi_global = (max_i + 3) / 4; g.npbj = (max_j + 3) / 4; g.npbk = (max_k + 3) / 4;
     g.nbj = g.npbj + 1; g.nbk = g.npbk + 1;
-    if (block_lo < 0 || block_hi > g.npbi_global || block_lo >= block_hi) { delete s; return fail(MPM_ERR_INVALID, "bad slab [%d,%d) of %d layers", block_lo, block_hi, g.npbi_global); }
+    if (block_lo < 0 || block_hi > g.npbi_global || block_lo >= block_hi) return fail(MPM_ERR_INVALID, "bad slab [%d,%d) of %d layers", block_lo, block_hi, g.npbi_global);
     g.lo = block_lo; g.hi = block_hi;
     const int64_t npb = (int64_t)(g.hi - g.lo) * g.npbj * g.npbk, ngb = (int64_t)(g.hi - g.lo + 1) * g.nbj * g.nbk;
-    if (npb + 3 >= ((int64_t)1 << 31) / 64) { delete s; return fail(MPM_ERR_INVALID, "grid too large"); }
+    if (npb + 3 >= ((int64_t)1 << 31) / 64) return fail(MPM_ERR_INVALID, "grid too large");
     g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
     fill_consts(s);
     s->capacity = std::max<int64_t>(capacity, 1);
@@ -212,7 +227,6 @@ int mpm_create_slab(const MpmParams* params, int max_i, int max_j, int max_k, in
     CK(tile_kernels_init());
     CK(cudaStreamSynchronize(s->stream));
     { int rc = validate_pos_div(s); if (rc) return rc; }
-    *out = s;
     return MPM_OK;
 }
 
