@@ -43,9 +43,11 @@ typedef struct MpmParams {
     float theta_s;        /* critical stretch        material_point_method.cpp:320  (5.0e-3) */
     float gravity[3];     /*                         material_point_method.cpp:260  (0,-9.8,0) */
     float friction_mu;    /*                         material_point_method.cpp:288  (0.5)    */
-    int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline) */
+    int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline),
+                             2 = experimental: tile kernel with packed fp32 pairs (FFMA2) in the accumulation loop */
     int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline),
-                             2 = experimental linear-tile gather (not validated on hardware yet) */
+                             experimental (none validated on hardware yet): 2 = linear-tile gather,
+                             3 = packed fp32 pairs (FFMA2) in the separable gather, 4 = both */
     int   reserved[6];
 } MpmParams;
 

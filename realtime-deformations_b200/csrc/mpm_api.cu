@@ -503,7 +503,7 @@ static int launch_p2g(mpm_sim* s, float4* target, float dt) {
         CKLAUNCH();
     } else {
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
-                                  s->num_sms, (int)s->n_bound, s->stream)));
+                                  s->num_sms, (int)s->n_bound, s->stream, s->prm.p2g_variant == 2)));
     }
     s->stats.kernel_launches++;
     return MPM_OK;
@@ -523,7 +523,8 @@ static int launch_g2p(mpm_sim* s, float dt) {
         CKLAUNCH();
     } else {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
-                                   s->num_sms, (int)s->n_bound, s->stream, &s->side, s->prm.g2p_variant == 2)));
+                                   s->num_sms, (int)s->n_bound, s->stream, &s->side,
+                                   s->prm.g2p_variant == 2 || s->prm.g2p_variant == 4, s->prm.g2p_variant == 3 || s->prm.g2p_variant == 4)));
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {

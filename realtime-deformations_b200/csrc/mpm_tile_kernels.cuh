@@ -22,6 +22,19 @@
 
 namespace mpm {
 
+// packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
+// {x, x} operand into a scalar broadcast). Used only by the experimental kernel variants below.
+typedef unsigned long long f32x2_t;
+MPM_DI f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+MPM_DI float lo2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+MPM_DI float hi2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }   // c += a * b, in place
+MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 constexpr int P2G_T = 256;         // threads per CTA = 64 cells x 4 x-slabs
 constexpr int P2G_PPT = 2;         // particles derived per thread per chunk
 constexpr int P2G_CH = P2G_T * P2G_PPT;   // particles per chunk (a full 8-ppc block is one chunk)
@@ -46,7 +59,11 @@ struct P2GSmem {
 };
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
-template <int MODE>
+// PACKED (p2g_variant = 2, EXPERIMENTAL, not the default, not yet validated on hardware): phase 1 accumulates each channel
+// of two consecutive z-nodes as one fp32 pair: per node pair 1 FMUL2 + 7 FFMA2 instead of 2 FMUL + 8 FFMA + 6 FADD.
+// The affine value at node c is formed as fma(c, step, v0) instead of c repeated additions (one rounding instead
+// of c: an fp32 re-association like the tile kernel's own summation order, covered by the trajectory tolerances).
+template <int MODE, bool PACKED = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
@@ -85,6 +102,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         float4 acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        f32x2_t AM[8], AX[8], AY[8], AZ[8];     // PACKED only: channel-major pairs over (c, c+1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) AM[i] = AX[i] = AY[i] = AZ[i] = 0ull;
 
         // chunks take every n_chunks-th particle of the (cell-ordered) block segment, so that every chunk holds a
         // share of every cell and all 64 (cell) thread groups have work in phase 1
@@ -149,6 +169,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             }
             // ---- phase 1: register accumulation over the particles of my cell ----
             const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
+#pragma unroll 1
             for (int i = i0; i < i1; ++i) {
                 const int pi = S.u.c.order[i];
                 const float wxa = reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a];
@@ -157,6 +178,27 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 // value(a,b,c)_r = c0_r + a*hA[r][0] + b*hA[r][1] + c*hA[r][2]
                 const float bx = qc.y + fa * h0.x, by = qc.z + fa * h0.w, bz = qc.w + fa * h1.z;
                 const float wyv[4] = { wy.x, wy.y, wy.z, wy.w }, wzv[4] = { wz.x, wz.y, wz.z, wz.w };
+                if (PACKED) {
+                    // pairs over two consecutive z-nodes (c, c+1): weights W = wab * (wz_c, wz_c+1) straight from the aligned
+                    // halves of the wz record, channel values v0 + (c, c+1) * step by one FFMA2 with broadcast operands
+                    const f32x2_t wzp[2] = { pack2(wz.x, wz.y), pack2(wz.z, wz.w) };
+                    const f32x2_t cp2[2] = { pack2(0.f, 1.f), pack2(2.f, 3.f) };
+                    const f32x2_t mm = pack2(qc.x, qc.x), sx = pack2(h0.z, h0.z), sy = pack2(h1.y, h1.y), sz = pack2(h8, h8);
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const float wab = wxa * wyv[bb];
+                        const float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
+                        const f32x2_t wab2 = pack2(wab, wab), vx2 = pack2(vx, vx), vy2 = pack2(vy, vy), vz2 = pack2(vz, vz);
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+                            const f32x2_t W = fmul2(wzp[cp], wab2);
+                            ffma2_acc(AM[bb * 2 + cp], W, mm);
+                            ffma2_acc(AX[bb * 2 + cp], W, ffma2(cp2[cp], sx, vx2));
+                            ffma2_acc(AY[bb * 2 + cp], W, ffma2(cp2[cp], sy, vy2));
+                            ffma2_acc(AZ[bb * 2 + cp], W, ffma2(cp2[cp], sz, vz2));
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) {
                     const float wab = wxa * wyv[bb];
@@ -171,6 +213,13 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 }
             }
             __syncthreads();
+        }
+        if (PACKED) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[2 * i] = make_float4(lo2(AM[i]), lo2(AX[i]), lo2(AY[i]), lo2(AZ[i]));
+                acc[2 * i + 1] = make_float4(hi2(AM[i]), hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
+            }
         }
         if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[w_ticket] : make_int4(-1, 0, 0, 0);   // issued here, stored below
         // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
@@ -263,10 +312,15 @@ struct G2PSmemLinear {
     unsigned long long bar[G2P_WARPS];
 };
 
+// EXPERIMENTAL (g2p_variant = 3 / 4, not the default, not yet validated on hardware): the separable gather issued as
+// packed fp32 pairs. sm_100a has FFMA2 (PTX fma.rn.f32x2): two IEEE fma.rn per lane per instruction, and ptxas folds a
+// duplicated {x, x} operand into a scalar broadcast, so (s0, s1) += (wz, wz*dz) * n needs ONE instruction instead of
+// two. Same operations in the same order on every component -> results identical to the scalar code (up to the sign
+// of an exact zero); 576 FFMA per particle become 240 FFMA2 + 84 FFMA.
 // Warp-per-block gather: every warp owns a whole particle block at a time (its own TMA-loaded tile, its own
 // mbarrier), so there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
 // FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate).
-template <int FLAGS, bool LINEAR = false>
+template <int FLAGS, bool LINEAR = false, bool PACKED = false>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
@@ -352,6 +406,43 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                         wzd[a] = wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]);
                     }
                     float v[3] = { 0, 0, 0 }, Bx[3] = { 0, 0, 0 }, By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
+                    if (PACKED) {
+                        // pairs: S = (s0, s1) <- (wz, wz dz) * n ;  T = (t0, t1y) <- (wy, wy dy) * s0 ;  V = (v, Bx) <- (wx, wx dx) * t0
+                        f32x2_t WX[4], WY[4], WZ[4], V[3] = { 0ull, 0ull, 0ull };
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) { WX[a] = pack2(wx[a], wxd[a]); WY[a] = pack2(wy[a], wyd[a]); WZ[a] = pack2(wz[a], wzd[a]); }
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            f32x2_t T[3] = { 0ull, 0ull, 0ull };
+                            float t1z[3] = { 0, 0, 0 };
+#pragma unroll
+                            for (int bb = 0; bb < 4; ++bb) {
+                                f32x2_t S[3] = { 0ull, 0ull, 0ull };
+                                const int oab = offx[a] + offy[bb];
+#pragma unroll
+                                for (int cc = 0; cc < 4; ++cc) {
+                                    const float4 n = LINEAR ? lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : tile[oab + offz[cc]];
+                                    S[0] = ffma2(WZ[cc], pack2(n.y, n.y), S[0]);
+                                    S[1] = ffma2(WZ[cc], pack2(n.z, n.z), S[1]);
+                                    S[2] = ffma2(WZ[cc], pack2(n.w, n.w), S[2]);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    const float s0q = lo2(S[q]);
+                                    T[q] = ffma2(WY[bb], pack2(s0q, s0q), T[q]);
+                                    t1z[q] += lo2(WY[bb]) * hi2(S[q]);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float t0q = lo2(T[q]);
+                                V[q] = ffma2(WX[a], pack2(t0q, t0q), V[q]);
+                                By[q] += lo2(WX[a]) * hi2(T[q]); Bz[q] += lo2(WX[a]) * t1z[q];
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { v[q] = lo2(V[q]); Bx[q] = hi2(V[q]); }
+                    } else
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         float t0[3] = { 0, 0, 0 }, t1y[3] = { 0, 0, 0 }, t1z[3] = { 0, 0, 0 };
@@ -408,22 +499,31 @@ inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
     MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
+    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>));
 #undef MPM_SET_SMEM
 #define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
     MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
 #undef MPM_SET_SMEM2
     if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 template <int MODE>
 cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
-                            DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st) {
+                            DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
+                            bool packed = false) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+    if (packed)
+        k_p2g_tile<MODE, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+    else
+        k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
     return cudaGetLastError();
 }
 
@@ -431,7 +531,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side, bool linear_tile = false) {
+                            SideStream* side, bool linear_tile = false, bool packed = false) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -454,8 +554,12 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
     }
     if (FLAGS & G2P_GATHER) {
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
-        if (linear_tile)
+        if (linear_tile && packed)
+            k_g2p_tile<FLAGS & ~G2P_F, true, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmemLinear), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        else if (linear_tile)
             k_g2p_tile<FLAGS & ~G2P_F, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmemLinear), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        else if (packed)
+            k_g2p_tile<FLAGS & ~G2P_F, false, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         else
             k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -8,7 +8,9 @@ import os
 
 VARIANTS = [(0, 0), (1, 1)]     # (p2g_variant, g2p_variant): tile kernels, baseline kernels
 if os.environ.get("MPM_TEST_EXPERIMENTAL") == "1":
-    VARIANTS.append((0, 2))     # experimental linear-tile gather: opt-in until it has been validated on hardware
+    # experimental kernels, opt-in until they have been validated on hardware: linear-tile gather, packed-pair (FFMA2)
+    # P2G + gather, both gather options together
+    VARIANTS += [(0, 2), (2, 3), (0, 4)]
 
 
 def oracle_from_scene(sc, fma=False, **prm):
