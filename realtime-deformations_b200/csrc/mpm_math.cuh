@@ -72,6 +72,18 @@ MPM_DI void axis_weights(float x, const PosDiv& d, int cell, float w[4]) {
     w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
     w[3] = 0.16666667163372040f * fx * fx * fx;
 }
+// same as cell_of + axis_weights with the quotient formed once (used by the experimental kernel variants)
+MPM_DI int cell_and_weights(float x, const PosDiv& d, float w[4]) {
+    const float q = pos_div(x, d);
+    const int cell = __float2int_rz(q);
+    const float fx = sub_rn(q, (float)cell);
+    const float gx = 1.0f - fx;
+    w[0] = 0.16666667163372040f * gx * gx * gx;
+    w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
+    w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
+    w[3] = 0.16666667163372040f * fx * fx * fx;
+    return cell;
+}
 MPM_DI void axis_weights_exact(float x, const PosDiv& d, int cell, float w[4]) {
     const float q = pos_div(x, d);
 #pragma unroll

@@ -123,9 +123,14 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     const int gid = ck == 0 ? gid_pref[u] : sorted_ids[start + ck + q * n_chunks];
                     float4 xm; float mch, a0[3], A[9];
                     p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
-                    const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
                     float wx[4], wy[4], wz[4];
-                    axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
+                    int cx, cy, cz;
+                    if (PACKED) {
+                        cx = cell_and_weights(xm.x, sc.pd, wx); cy = cell_and_weights(xm.y, sc.pd, wy); cz = cell_and_weights(xm.z, sc.pd, wz);
+                    } else {
+                        cx = cell_of(xm.x, sc.pd); cy = cell_of(xm.y, sc.pd); cz = cell_of(xm.z, sc.pd);
+                        axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
+                    }
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
                     S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
                     S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
@@ -389,9 +394,14 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
                 r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
                 {
-                    const int cx = cell_of(r.x[0], sc.pd), cy = cell_of(r.x[1], sc.pd), cz = cell_of(r.x[2], sc.pd);
                     float wx[4], wy[4], wz[4];
-                    axis_weights(r.x[0], sc.pd, cx, wx); axis_weights(r.x[1], sc.pd, cy, wy); axis_weights(r.x[2], sc.pd, cz, wz);
+                    int cx, cy, cz;
+                    if (PACKED) {
+                        cx = cell_and_weights(r.x[0], sc.pd, wx); cy = cell_and_weights(r.x[1], sc.pd, wy); cz = cell_and_weights(r.x[2], sc.pd, wz);
+                    } else {
+                        cx = cell_of(r.x[0], sc.pd); cy = cell_of(r.x[1], sc.pd); cz = cell_of(r.x[2], sc.pd);
+                        axis_weights(r.x[0], sc.pd, cx, wx); axis_weights(r.x[1], sc.pd, cy, wy); axis_weights(r.x[2], sc.pd, cz, wz);
+                    }
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     int offx[4], offy[4], offz[4];
                     float wxd[4], wyd[4], wzd[4];
