@@ -43,6 +43,7 @@ def test_roofline_block_assembly():
     assert r["dominant_kernel"] == "p2g" and r["kernel_ms_last_substep"]["g2p_gather"] == round(5.01 - 2.44, 4)
     assert abs(r["achieved"] - (272 * n + 80 * a) / 9.92e-3 / 1e9) < 1.0
     assert r["dominant_kernel_achieved_gbs"] == round((88 * n + 16 * a) / 4.21e-3 / 1e9, 1)
+    assert abs(r["achieved_fp32_tflops"] - 4500 * n / 9.92e-3 / 1e12) < 0.01      # ~30 TFLOP/s of 74 nominal
     # side-stream overlap: only the combined G2P time exists
     r2 = bench.roofline_block(9.92, n, a, 1, [0.48, 0.03, 4.21, 0.11, 5.01, 0.003, 9.85, -1.0], 512, 1 << 26)
     assert r2["dominant_kernel"] == "g2p(fupdate+gather)" and "fupdate" not in r2["kernel_ms_last_substep"]
