@@ -1,12 +1,21 @@
-"""Quick per-phase timing probe (not the contract bench): python tools/perf_probe.py [grid n steps variants...]"""
+"""Quick per-phase timing probe (not the contract bench):
+  python tools/perf_probe.py GRID N STEPS [slab|ball] [p2g:g2p,p2g:g2p,...]
+e.g. A/B of the experimental kernels:  python tools/perf_probe.py 256 8388608 20 slab 0:0,0:2,0:3,0:4,2:0,2:4"""
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
 import mpm_b200
 
+_scene_cache = {}
+
+
 def run(grid, n, steps, pv, gv, scene="slab"):
     t0 = time.time()
-    sc = mpm_b200.scenes.snow_slab(grid=grid, n=n) if scene == "slab" else mpm_b200.scenes.snowball_drop(grid=grid, n=n)
+    key = (grid, n, scene)
+    if key not in _scene_cache:
+        _scene_cache.clear()
+        _scene_cache[key] = mpm_b200.scenes.snow_slab(grid=grid, n=n) if scene == "slab" else mpm_b200.scenes.snowball_drop(grid=grid, n=n)
+    sc = _scene_cache[key]
     tg = time.time() - t0
     p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv)
     if "gravity" in sc: p.gravity[:] = [float(x) for x in sc["gravity"]]
@@ -19,12 +28,15 @@ def run(grid, n, steps, pv, gv, scene="slab"):
     st = sim.stats()
     ms = list(st.last_ms)
     print(f"{scene} grid={grid} n={sc['n']} variants=({pv},{gv}) gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
-          f"{sc['n']/dt/1e9:.3f} G upd/s  bin={ms[0]:.3f} clear={ms[1]:.3f} p2g={ms[2]:.3f} grid={ms[3]:.3f} g2p={ms[4]:.3f} total={ms[6]:.3f} "
+          f"{sc['n']/dt/1e9:.3f} G upd/s  bin={ms[0]:.3f} clear={ms[1]:.3f} p2g={ms[2]:.3f} grid={ms[3]:.3f} g2p={ms[4]:.3f} (fupdate={ms[7]:.3f}) total={ms[6]:.3f} "
           f"active_nodes={st.n_active_nodes} pblocks={st.n_particle_blocks} gblocks={st.n_grid_blocks}", flush=True)
     sim.close()
 
 if __name__ == "__main__":
     grid, n, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     scene = sys.argv[4] if len(sys.argv) > 4 else "slab"
-    for pv, gv in ((0, 0), (1, 1), (0, 1), (1, 0)):
+    combos = ((0, 0), (1, 1), (0, 1), (1, 0))
+    if len(sys.argv) > 5:
+        combos = tuple(tuple(int(x) for x in c.split(":")) for c in sys.argv[5].split(","))
+    for pv, gv in combos:
         run(grid, n, steps, pv, gv, scene)
