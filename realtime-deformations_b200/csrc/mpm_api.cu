@@ -496,14 +496,21 @@ static int launch_clear(mpm_sim* s) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
+// p2g_variant: 2 = packed pairs, 3 = F-update inside the fused substep's P2G, 4 = both (all experimental)
+static bool p2g_packed(const mpm_sim* s) { return s->prm.p2g_variant == 2 || s->prm.p2g_variant == 4; }
+static bool p2g_fupd(const mpm_sim* s) { return s->prm.p2g_variant == 3 || s->prm.p2g_variant == 4; }
 template <int MODE>
 static int launch_p2g(mpm_sim* s, float4* target, float dt) {
     if (s->prm.p2g_variant == 1) {
         k_p2g_atomic<MODE><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, target, s->gd, s->sc, dt);
         CKLAUNCH();
+    } else if (MODE == P2G_FUSED && p2g_fupd(s)) {
+        const Planes nxt = s->planes(s->cur ^ 1);
+        CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
+                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), &nxt)));
     } else {
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
-                                  s->num_sms, (int)s->n_bound, s->stream, s->prm.p2g_variant == 2)));
+                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s))));
     }
     s->stats.kernel_launches++;
     return MPM_OK;
@@ -624,7 +631,8 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
     EV(4);
     TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
     EV(5);
-    TRY((launch_g2p<G2P_F | G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));
+    if (p2g_fupd(s)) TRY((launch_g2p<G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));      // the F-update already ran inside P2G
+    else TRY((launch_g2p<G2P_F | G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));
     EV(6);
     s->tau_valid = true;
     s->stats.substeps_done++;

@@ -59,14 +59,46 @@ struct P2GSmem {
 };
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
+// The F-update of one particle, split into its loads and its compute + stores so that a thread can have the loads of
+// two particles in flight (same arithmetic and plane layout as k_fupdate<true> in mpm_kernels.cuh).
+struct FUpdIn { float4 a1, a2, a3, a6, a7, a8, a9, a10; };
+MPM_DI FUpdIn fupd_load(const Planes& cur, int p) {
+    FUpdIn r;
+    r.a1 = cur.p[1][p]; r.a2 = cur.p[2][p]; r.a3 = cur.p[3][p];
+    r.a6 = cur.p[6][p]; r.a7 = cur.p[7][p]; r.a8 = cur.p[8][p]; r.a9 = cur.p[9][p]; r.a10 = cur.p[10][p];
+    return r;
+}
+MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCounters* dc, const SimConst& sc, float dt) {
+    float B[9] = { in.a1.x, in.a1.y, in.a1.z, in.a1.w, in.a2.x, in.a2.y, in.a2.z, in.a2.w, in.a3.x };
+    float FE[9] = { in.a6.z, in.a6.w, in.a7.x, in.a7.y, in.a7.z, in.a7.w, in.a8.x, in.a8.y, in.a8.z };
+    float FP[9] = { in.a8.w, in.a9.x, in.a9.y, in.a9.z, in.a9.w, in.a10.x, in.a10.y, in.a10.z, in.a10.w };
+    float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
+    if (!f_update_rn(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+    tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), in.a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
+    D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
+    D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
+    D.p[6][q] = make_float4(in.a6.x, in.a6.y, FE[0], FE[1]);
+    D.p[7][q] = make_float4(FE[2], FE[3], FE[4], FE[5]);
+    D.p[8][q] = make_float4(FE[6], FE[7], FE[8], FP[0]);
+    D.p[9][q] = make_float4(FP[1], FP[2], FP[3], FP[4]);
+    D.p[10][q] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+}
+
+// FUPD (p2g_variant = 3 / 4, EXPERIMENTAL, fused substep only, not yet validated on hardware): after a block's tile has
+// been written back, the same CTA runs the F-update (cpp:306-330) of the block's particles: it depends only on particle
+// state of the START of the substep (B of the previous gather, FE, FP), never on the grid, so it can run anywhere
+// between two gathers. Inside P2G its HBM streaming (240 B/particle, 2.4 ms as a kernel of its own) overlaps the
+// smem-bound accumulation of the SM's other CTA, and B is read once per substep instead of twice. Results go to
+// planes 4..10 of the OTHER buffer at the particle's sorted rank, exactly where k_fupdate<true> puts them; the gather
+// then runs without its F-update launch.
 // PACKED (p2g_variant = 2, EXPERIMENTAL, not the default, not yet validated on hardware): phase 1 accumulates each channel
 // of two consecutive z-nodes as one fp32 pair: per node pair 1 FMUL2 + 7 FFMA2 instead of 2 FMUL + 8 FFMA + 6 FADD.
 // The affine value at node c is formed as fma(c, step, v0) instead of c repeated additions (one rounding instead
 // of c: an fp32 re-association like the tile kernel's own summation order, covered by the trajectory tolerances).
-template <int MODE, bool PACKED = false>
+template <int MODE, bool PACKED = false, bool FUPD = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
-           float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
+           float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31;
@@ -271,6 +303,20 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 }
             if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
                 atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
+        }
+        if (FUPD) {
+            // F-update of this block's particles, two per thread and round with both particles' loads issued first.
+            // sorted_ids[start .. start+cnt) is final here (the cell-ordering writes above are behind CTA barriers).
+#pragma unroll 1
+            for (int q = t; q < cnt; q += 2 * P2G_T) {
+                const int j0 = start + q, j1 = j0 + P2G_T;
+                const bool two = q + P2G_T < cnt;
+                const int p0 = sorted_ids[j0], p1 = two ? sorted_ids[j1] : p0;
+                const FUpdIn in0 = fupd_load(P, p0);
+                const FUpdIn in1 = fupd_load(P, p1);
+                fupd_compute_store(in0, Nx, j0, dc, sc, dt);
+                if (two) fupd_compute_store(in1, Nx, j1, dc, sc, dt);
+            }
         }
     }
 }
@@ -510,6 +556,7 @@ inline cudaError_t tile_kernels_init() {
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
     MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
     MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>));
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>));
 #undef MPM_SET_SMEM
 #define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
     MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
@@ -526,14 +573,18 @@ inline cudaError_t tile_kernels_init() {
 template <int MODE>
 cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            bool packed = false) {
+                            bool packed = false, const Planes* fupd_target = nullptr) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    if (packed)
-        k_p2g_tile<MODE, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+    const Planes Nx = fupd_target ? *fupd_target : P;
+    if (fupd_target && MODE == P2G_FUSED) {       // only the fused substep moves the F-update into P2G
+        if (packed) k_p2g_tile<P2G_FUSED, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
+        else k_p2g_tile<P2G_FUSED, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
+    } else if (packed)
+        k_p2g_tile<MODE, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
     else
-        k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
     return cudaGetLastError();
 }
 

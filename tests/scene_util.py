@@ -9,8 +9,9 @@ import os
 VARIANTS = [(0, 0), (1, 1)]     # (p2g_variant, g2p_variant): tile kernels, baseline kernels
 if os.environ.get("MPM_TEST_EXPERIMENTAL") == "1":
     # experimental kernels, opt-in until they have been validated on hardware: linear-tile gather, packed-pair (FFMA2)
-    # P2G + gather, both gather options together
-    VARIANTS += [(0, 2), (2, 3), (0, 4)]
+    # P2G + gather, both gather options together, F-update inside P2G, everything together
+    VARIANTS += [(0, 2), (2, 3), (0, 4), (3, 0), (4, 4)]
+TILE_VARIANTS = [v for v in VARIANTS if v != (1, 1)]     # the tile kernels only (edge cases of block occupancy)
 
 
 def oracle_from_scene(sc, fma=False, **prm):

@@ -9,7 +9,7 @@ import pytest
 import mpm_b200
 import oracle_py as op
 from helpers import assert_bit_exact, assert_traj_close, assert_traj_close_calibrated, full_grid, traj_errors
-from scene_util import VARIANTS, gpu_colliders_from_ref_dump, oracle_from_scene, sim_from_scene, sim_from_state35
+from scene_util import TILE_VARIANTS, VARIANTS, gpu_colliders_from_ref_dump, oracle_from_scene, sim_from_scene, sim_from_state35
 
 pytestmark = pytest.mark.gpu
 SUM_RTOL = 2e-5      # fp32 sums of <= ~100 terms in a different order / with FMA contraction
@@ -210,12 +210,13 @@ def test_material_sweep_vs_oracle():
         assert np.abs(np.linalg.det(o.state()[:, 17:26].reshape(-1, 3, 3)) - 1).max() > 1e-3, "sweep never reached plasticity"
 
 
-def test_out_of_grid_particles_are_parked_not_lost():
+@pytest.mark.parametrize("variants", TILE_VARIANTS)
+def test_out_of_grid_particles_are_parked_not_lost(variants):
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0, with_ground=False)
     pos = sc["pos"].copy()
     pos[:5] = [[0.0, 0.0, 0.0], [0.01, 0.5, 0.5], [1.59, 0.5, 0.5], [0.5, 1.58, 0.5], [0.5, 0.5, 0.06]]
     sc["pos"] = pos
-    sim, cols, nc = sim_from_scene(sc)
+    sim, cols, nc = sim_from_scene(sc, variants)
     sim.substep(float(sc["dt"]), cols, nc, 5)
     st = sim.stats()
     assert st.n_out_of_grid == 5 and st.n_particles == sc["n"]
@@ -352,11 +353,12 @@ def _crowded_scene(n, seed=3):
     return sc
 
 
+@pytest.mark.parametrize("variants", TILE_VARIANTS)
 @pytest.mark.parametrize("n", [1, 31, 700, 3000])
-def test_ragged_block_occupancy_vs_oracle(n):
+def test_ragged_block_occupancy_vs_oracle(n, variants):
     sc = _crowded_scene(n)
     o, ocols, onc = oracle_from_scene(sc)
-    sim, cols, nc = sim_from_scene(sc)
+    sim, cols, nc = sim_from_scene(sc, variants)
     close_sum(sim.grid()[:, 0], o.grid()[:, 0], "grid mass, crowded block", rtol=5e-5)
     close_sum(sim.download_state35()[:, 4], o.state()[:, 4], "volumes, crowded block", rtol=5e-5)
     o.substep(float(sc["dt"]), ocols, onc, 3); sim.substep(float(sc["dt"]), cols, nc, 3)
