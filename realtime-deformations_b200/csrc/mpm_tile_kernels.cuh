@@ -22,8 +22,15 @@
 
 namespace mpm {
 
+#ifndef MPM_HOST_EMU
+#define MPM_DYN_SMEM(name, al) extern __shared__ __align__(al) unsigned char name[]
+#else
+#define MPM_DYN_SMEM(name, al) unsigned char* name = emu_dyn_smem()
+#endif
+
 // packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
 // {x, x} operand into a scalar broadcast). Used only by the experimental kernel variants below.
+#ifndef MPM_HOST_EMU
 typedef unsigned long long f32x2_t;
 MPM_DI f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 MPM_DI float lo2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
@@ -34,6 +41,16 @@ MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
 MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }   // c += a * b, in place
 MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#else   // host emulation of the kernels (tests/emu): same per-component IEEE operations
+typedef unsigned long long f32x2_t;
+MPM_DI f32x2_t pack2(float lo, float hi) { float v[2] = { lo, hi }; f32x2_t r; memcpy(&r, v, 8); return r; }
+MPM_DI float lo2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[0]; }
+MPM_DI float hi2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[1]; }
+MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) { return pack2(fmaf(lo2(a), lo2(b), lo2(c)), fmaf(hi2(a), hi2(b), hi2(c))); }
+MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { c = ffma2(a, b, c); }
+MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { return pack2(__fadd_rn(lo2(a), lo2(b)), __fadd_rn(hi2(a), hi2(b))); }
+MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { return pack2(__fmul_rn(lo2(a), lo2(b)), __fmul_rn(hi2(a), hi2(b))); }
+#endif
 
 constexpr int P2G_T = 256;         // threads per CTA = 64 cells x 4 x-slabs
 constexpr int P2G_PPT = 2;         // particles derived per thread per chunk
@@ -99,7 +116,7 @@ template <int MODE, bool PACKED = false, bool FUPD = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MPM_DYN_SMEM(smem_raw, 16);
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31;
     const int my_cell = t >> 2, my_a = t & 3;
@@ -324,6 +341,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
 // ---------------------------------------------------------------------------------------------------------
 // G2P
 // ---------------------------------------------------------------------------------------------------------
+#ifndef MPM_HOST_EMU
 MPM_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 MPM_DI void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -342,6 +360,14 @@ MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     }
 }
+MPM_DI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#else
+MPM_DI void mbar_init(unsigned long long* bar, int count) { emu::mbar_init(bar, count); }
+MPM_DI void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu::mbar_expect_tx(bar, bytes); }
+MPM_DI void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) { emu::tma_load_1d(dst_smem, src_gmem, bytes, bar); }
+MPM_DI void mbar_wait(unsigned long long* bar, unsigned phase) { emu::mbar_wait(bar, phase); }
+MPM_DI void mbar_fence_init() {}
+#endif
 
 #ifndef G2P_MIN_CTAS
 #define G2P_MIN_CTAS 2
@@ -375,7 +401,7 @@ template <int FLAGS, bool LINEAR = false, bool PACKED = false>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
-    extern __shared__ __align__(128) unsigned char g2p_smem_raw[];
+    MPM_DYN_SMEM(g2p_smem_raw, 128);
     using Smem = typename std::conditional<LINEAR, G2PSmemLinear, G2PSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(g2p_smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -384,7 +410,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
     unsigned long long* bar = &S.bar[wid];
     if (lane == 0) {
         mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncwarp();
     unsigned phase = 0;
@@ -551,6 +577,7 @@ __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ so
     for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
 }
 
+#ifndef MPM_HOST_EMU        // host launch code (nvcc only)
 inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
@@ -635,5 +662,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
     }
     return e;
 }
+
+#endif  // MPM_HOST_EMU
 
 }  // namespace mpm

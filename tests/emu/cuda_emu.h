@@ -1,0 +1,249 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the product (libmpm_b200.so is built by nvcc from the same kernel sources
+// and has no CPU path). This header lets g++ compile the CUDA kernel sources under csrc/ for the HOST so that their
+// index arithmetic, barrier structure and copy/transaction bookkeeping can be executed without a GPU:
+//   * every CUDA thread is an OS thread; the CTAs of a launch run one after the other;
+//   * __syncthreads / __syncwarp / __shfl_* are real barriers (every thread named by the mask must arrive, as on the GPU);
+//   * cp.async.bulk + mbarrier are emulated with exact transaction-byte accounting and 16-byte alignment checks;
+//   * the _rn intrinsics map to plain IEEE operations (compile with -ffp-contract=off).
+// What it cannot show: performance, the hardware memory model, real concurrency between CTAs.
+// Used by tests/emu/emu_harness.cpp (differential tests: experimental kernel variants against the hardware-validated ones).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define MPM_HOST_EMU 1
+#undef __shared__
+#define __shared__ static          /* CTAs run one at a time: a static is shared by the CTA's threads */
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+
+namespace emu {
+
+[[noreturn]] inline void die(const char* what) {
+    std::fprintf(stderr, "cuda_emu: %s\n", what);
+    std::fflush(stderr);
+    std::abort();
+}
+
+struct Barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, count = 0;
+    unsigned gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+struct Cta {
+    int nthreads = 0;
+    Barrier cta_bar;
+    std::vector<Barrier> warp_bar;
+    std::vector<unsigned long long> slot;       // shuffle exchange, one per thread
+    std::vector<unsigned char> smem;            // dynamic shared memory
+};
+
+inline thread_local Cta* cta = nullptr;
+inline thread_local int tid = 0;
+struct Idx { unsigned x = 0, y = 0, z = 0; };
+
+inline std::mutex& mbar_mutex() { static std::mutex m; return m; }
+
+// mbarrier state packed into the 64-bit shared-memory word: [0,32) pending tx bytes (signed), [32,48) pending arrivals,
+// [48,63) arrival count, bit 63 phase parity
+struct Mbar {
+    static long long tx(unsigned long long w) { return (int)(w & 0xffffffffull); }
+    static int pending(unsigned long long w) { return (int)((w >> 32) & 0xffff); }
+    static int count(unsigned long long w) { return (int)((w >> 48) & 0x7fff); }
+    static int phase(unsigned long long w) { return (int)(w >> 63); }
+    static unsigned long long pack(long long tx, int pending, int count, int phase) {
+        return ((unsigned long long)(unsigned)(int)tx) | ((unsigned long long)(pending & 0xffff) << 32) |
+               ((unsigned long long)(count & 0x7fff) << 48) | ((unsigned long long)(phase & 1) << 63);
+    }
+    static void update(unsigned long long* bar, long long dtx, int darrive) {
+        std::lock_guard<std::mutex> lk(mbar_mutex());
+        unsigned long long w = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+        long long t = tx(w) + dtx;
+        int p = pending(w) - darrive, c = count(w), ph = phase(w);
+        if (p < 0) die("mbarrier: more arrivals than the barrier was initialised for");
+        if (p == 0 && t == 0) { ph ^= 1; p = c; }
+        __atomic_store_n(bar, pack(t, p, c, ph), __ATOMIC_RELEASE);
+    }
+};
+inline void mbar_init(unsigned long long* bar, int count) { __atomic_store_n(bar, Mbar::pack(0, count, count, 0), __ATOMIC_RELEASE); }
+inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { Mbar::update(bar, bytes, 1); }
+inline long long& tma_bytes_total() { static long long b = 0; return b; }
+inline void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15) || bytes == 0) die("cp.async.bulk: address / size not a multiple of 16 bytes");
+    Cta* c = cta;
+    const unsigned char* lo = c->smem.data();
+    if ((const unsigned char*)dst < lo || (const unsigned char*)dst + bytes > lo + c->smem.size()) die("cp.async.bulk: destination outside the CTA's shared memory");
+    std::memcpy(dst, src, bytes);
+    { std::lock_guard<std::mutex> lk(mbar_mutex()); tma_bytes_total() += bytes; }
+    Mbar::update(bar, -(long long)bytes, 0);
+}
+inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+    long spins = 0;
+    while (Mbar::phase(__atomic_load_n(bar, __ATOMIC_ACQUIRE)) == (int)(parity & 1)) {
+        std::this_thread::yield();
+        if (++spins > 200000000L) die("mbarrier wait never completed (transaction bytes do not add up?)");
+    }
+}
+
+// run `body` as a grid of CTAs, one CTA at a time, `threads` OS threads per CTA
+inline void launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body);
+
+}  // namespace emu
+
+inline thread_local emu::Idx threadIdx, blockIdx, blockDim, gridDim;
+
+inline void emu::launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body) {
+    for (unsigned b = 0; b < grid; ++b) {
+        Cta c;
+        c.nthreads = (int)threads;
+        c.cta_bar.n = (int)threads;
+        c.warp_bar = std::vector<Barrier>((threads + 31) / 32);
+        for (unsigned w = 0; w < c.warp_bar.size(); ++w) c.warp_bar[w].n = (int)std::min(32u, threads - 32 * w);
+        c.slot.assign(threads, 0);
+        c.smem.assign(smem_bytes + 256, 0xcd);          // poison: uninitialised reads show up as garbage
+        std::vector<std::thread> ts;
+        ts.reserve(threads);
+        for (unsigned t = 0; t < threads; ++t)
+            ts.emplace_back([&, t, b] {
+                cta = &c; tid = (int)t;
+                threadIdx = Idx{ t, 0, 0 }; blockIdx = Idx{ b, 0, 0 }; blockDim = Idx{ threads, 1, 1 }; gridDim = Idx{ grid, 1, 1 };
+                body();
+            });
+        for (auto& t : ts) t.join();
+    }
+}
+
+// dynamic shared memory of the running CTA, 128-byte aligned
+inline unsigned char* emu_dyn_smem() {
+    unsigned char* p = emu::cta->smem.data();
+    return p + ((128 - ((uintptr_t)p & 127)) & 127);
+}
+
+// ---- synchronisation and warp collectives -------------------------------------------------------------------------
+inline void __syncthreads() { emu::cta->cta_bar.wait(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+    if (mask != 0xffffffffu) emu::die("__syncwarp with a partial mask is not emulated");
+    emu::cta->warp_bar[emu::tid >> 5].wait();
+}
+template <class T> inline T emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of a type wider than 8 bytes");
+    emu::Cta* c = emu::cta;
+    const int w = emu::tid >> 5;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    c->slot[emu::tid] = bits;
+    c->warp_bar[w].wait();
+    const unsigned long long got = c->slot[w * 32 + (src_lane & 31)];
+    c->warp_bar[w].wait();
+    T r;
+    std::memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    if (mask != 0xffffffffu || width != 32) emu::die("__shfl_sync: only full-warp shuffles are emulated");
+    return emu_exchange(v, src);
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    if (mask != 0xffffffffu || width != 32) emu::die("__shfl_up_sync: only full-warp shuffles are emulated");
+    const int lane = emu::tid & 31;
+    const T got = emu_exchange(v, lane >= (int)delta ? lane - (int)delta : lane);
+    return lane >= (int)delta ? got : v;
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    if (mask != 0xffffffffu || width != 32) emu::die("__shfl_down_sync: only full-warp shuffles are emulated");
+    const int lane = emu::tid & 31;
+    const T got = emu_exchange(v, lane + (int)delta < 32 ? lane + (int)delta : lane);
+    return lane + (int)delta < 32 ? got : v;
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int x, int width = 32) {
+    if (mask != 0xffffffffu || width != 32) emu::die("__shfl_xor_sync: only full-warp shuffles are emulated");
+    return emu_exchange(v, (emu::tid & 31) ^ x);
+}
+// collectives whose participation depends on divergence are not emulated (the binning kernels use them; the harness bins on the host)
+inline unsigned __activemask() { emu::die("__activemask is not emulated"); }
+inline unsigned __match_any_sync(unsigned, int) { emu::die("__match_any_sync is not emulated"); }
+inline unsigned __ballot_sync(unsigned, int) { emu::die("__ballot_sync is not emulated"); }
+inline int __reduce_add_sync(unsigned, int) { emu::die("__reduce_add_sync is not emulated"); }
+inline unsigned __reduce_add_sync(unsigned, unsigned) { emu::die("__reduce_add_sync is not emulated"); }
+
+// ---- atomics -------------------------------------------------------------------------------------------------------
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicSub(int* p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_RELAXED); }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline int atomicMax(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline int atomicMin(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o > v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int atomicCAS(int* p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return cmp; }
+inline float atomicAdd(float* p, float v) {
+    unsigned* u = reinterpret_cast<unsigned*>(p);
+    unsigned o = __atomic_load_n(u, __ATOMIC_RELAXED);
+    for (;;) {
+        float f; std::memcpy(&f, &o, 4);
+        const float nf = f + v;
+        unsigned n; std::memcpy(&n, &nf, 4);
+        if (__atomic_compare_exchange_n(u, &o, n, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return f;
+    }
+}
+inline float4 atomicAdd(float4* p, float4 v) {       // red.global.add.v4.f32: four independent fp32 additions
+    float4 o;
+    o.x = atomicAdd(&p->x, v.x); o.y = atomicAdd(&p->y, v.y); o.z = atomicAdd(&p->z, v.z); o.w = atomicAdd(&p->w, v.w);
+    return o;
+}
+
+// ---- arithmetic intrinsics (IEEE round-to-nearest; build with -ffp-contract=off) --------------------------------------
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+inline int __float2int_rz(float a) { return (int)a; }
+inline int __float_as_int(float a) { int r; std::memcpy(&r, &a, 4); return r; }
+inline unsigned __float_as_uint(float a) { unsigned r; std::memcpy(&r, &a, 4); return r; }
+inline float __int_as_float(int a) { float r; std::memcpy(&r, &a, 4); return r; }
+inline float __uint_as_float(unsigned a) { float r; std::memcpy(&r, &a, 4); return r; }
+inline int __popc(unsigned a) { return __builtin_popcount(a); }
+inline int __ffs(int a) { return __builtin_ffs(a); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline float min(float a, float b) { return std::fmin(a, b); }
+inline float max(float a, float b) { return std::fmax(a, b); }
+using std::isfinite;
+using std::isnan;
+using std::isinf;

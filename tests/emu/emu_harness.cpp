@@ -1,0 +1,260 @@
+// TEST INFRASTRUCTURE ONLY (see cuda_emu.h): runs the tile kernels of csrc/ on the host, compiled by g++ from the very
+// same sources, and checks the kernel VARIANTS against each other:
+//   P2G    : block-tile kernel (default) vs the per-particle-atomics baseline vs the packed-pair variant vs the variants
+//            that also run the F-update; the ids of every block must stay a permutation of the block's ids
+//   F-upd  : planes 4..10 written by P2G's F-update phase == k_fupdate<true> with the same ids, bit for bit
+//   gather : blocked tile (default) vs linear tile (bit for bit) vs packed pairs vs the direct-gather baseline
+// The default kernels are the ones validated on hardware against the oracle; this harness shows that a variant's index
+// arithmetic, barrier structure and bulk-copy byte accounting are consistent with them before any GPU time is spent.
+// Build/run: tests/test_kernel_emulation_cpu.py   (g++ -O1 -ffp-contract=off -include cuda_emu.h)
+#include "mpm_tile_kernels.cuh"
+
+#include <random>
+
+using namespace mpm;
+
+struct Host {
+    GridDims gd{};
+    SimConst sc{};
+    int n = 0, cap = 0;
+    std::vector<float4> buf[2];
+    std::vector<int> ids0;              // binned ids (before any P2G re-ordering)
+    std::vector<int4> work;
+    std::vector<float4> grid;
+    DevCounters dc{};
+    Planes planes(int b) { Planes P; for (int k = 0; k < NPLANES; ++k) P.p[k] = buf[b].data() + (size_t)k * cap; return P; }
+};
+
+static float frand(std::mt19937& g, float lo, float hi) { return lo + (hi - lo) * (float)(g() >> 8) / 16777216.0f; }
+
+static void put_particle(Host& H, int p, std::mt19937& g, float x, float y, float z) {
+    Planes P = H.planes(0);
+    float B[9], FE[9], FP[9], tau[6];
+    for (int i = 0; i < 9; ++i) {
+        B[i] = frand(g, -1e-3f, 1e-3f);
+        FE[i] = ((i % 4 == 0) ? 1.0f : 0.0f) + frand(g, -0.05f, 0.05f);
+        FP[i] = ((i % 4 == 0) ? 1.0f : 0.0f) + frand(g, -0.02f, 0.02f);
+    }
+    for (int i = 0; i < 6; ++i) tau[i] = frand(g, -2e-3f, 2e-3f);
+    const float v[3] = { frand(g, -5.f, 5.f), frand(g, -5.f, 5.f), frand(g, -5.f, 5.f) };
+    P.p[0][p] = make_float4(x, y, z, 6e-5f * frand(g, 0.5f, 1.5f));
+    P.p[1][p] = make_float4(B[0], B[1], B[2], B[3]);
+    P.p[2][p] = make_float4(B[4], B[5], B[6], B[7]);
+    P.p[3][p] = make_float4(B[8], v[0], v[1], v[2]);
+    P.p[4][p] = make_float4(tau[0], tau[1], tau[2], tau[3]);
+    P.p[5][p] = make_float4(tau[4], tau[5], 0.f, 0.f);
+    P.p[6][p] = make_float4(1.2e-5f * frand(g, 0.8f, 1.2f), __int_as_float(p), FE[0], FE[1]);
+    P.p[7][p] = make_float4(FE[2], FE[3], FE[4], FE[5]);
+    P.p[8][p] = make_float4(FE[6], FE[7], FE[8], FP[0]);
+    P.p[9][p] = make_float4(FP[1], FP[2], FP[3], FP[4]);
+    P.p[10][p] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+}
+
+// scene: sparse random fill + blocks holding exactly 1 / 512 / 513 / 1500 particles (single, full, two and three chunks)
+static void build(Host& H, int dim, unsigned seed, bool fast_div) {
+    std::mt19937 g(seed);
+    GridDims& gd = H.gd;
+    gd.I = gd.J = gd.K = dim;
+    gd.npbi_global = gd.npbj = gd.npbk = (dim + 3) / 4;
+    gd.nbj = gd.npbj + 1; gd.nbk = gd.npbk + 1;
+    gd.lo = 0; gd.hi = gd.npbi_global;
+    gd.n_pblocks = (gd.hi - gd.lo) * gd.npbj * gd.npbk;
+    gd.n_gblocks = (gd.hi - gd.lo + 1) * gd.nbj * gd.nbk;
+    SimConst& c = H.sc;
+    const float h = 0.05f;
+    c.h = h; c.dinv = 1.0f / ((1.0f / 3.0f) * h * h); c.E = 1.4e5f; c.nu = 0.2f; c.xi = 10.f;
+    c.clamp_lo = (float)(1.0 - 2.5e-2); c.clamp_hi = (float)(1.0 + 5e-3); c.friction = 0.5f;
+    c.g[0] = 0; c.g[1] = -9.8f; c.g[2] = 0;
+    c.pos_lo = 3 * h; c.pos_hi[0] = c.pos_hi[1] = c.pos_hi[2] = (dim - 3) * h;
+    c.inv_h3 = 1.0f / (h * h * h);
+    c.pd.h = h; c.pd.rh = 1.0f / h; c.pd.lo = 2.0f * h; c.pd.hi = (float)(dim + 2) * h; c.pd.fast = fast_div ? 1 : 0;
+
+    const int n_sparse = 900;
+    struct Crowd { int bi, bj, bk, n; };
+    const Crowd crowds[] = { { 1, 1, 1, 1 }, { 2, 1, 3, 512 }, { 3, 3, 2, 513 }, { 2, 3, 1, 1500 }, { 4, 2, 2, 31 } };
+    int n = n_sparse;
+    for (const Crowd& cr : crowds) n += cr.n;
+    H.n = n; H.cap = n + 64;
+    for (int b = 0; b < 2; ++b) H.buf[b].assign((size_t)NPLANES * H.cap, make_float4(NAN, NAN, NAN, NAN));
+    int p = 0;
+    const float lo = 3.0f * h, hi = (dim - 3) * h;
+    for (int i = 0; i < n_sparse; ++i) put_particle(H, p++, g, frand(g, lo, hi), frand(g, lo, hi), frand(g, lo, hi));
+    for (const Crowd& cr : crowds)          // particle block b holds cells 4b+1 .. 4b+4
+        for (int i = 0; i < cr.n; ++i)
+            put_particle(H, p++, g, (4 * cr.bi + 1 + frand(g, 0.01f, 3.99f)) * h, (4 * cr.bj + 1 + frand(g, 0.01f, 3.99f)) * h,
+                         (4 * cr.bk + 1 + frand(g, 0.01f, 3.99f)) * h);
+    // host binning with the kernels' own key function
+    std::vector<int> key(n), count(gd.n_pblocks + 3, 0), start(gd.n_pblocks + 4, 0);
+    Planes P = H.planes(0);
+    for (int q = 0; q < n; ++q) {
+        int cells[3];
+        key[q] = particle_key(P.p[0][q], gd, c.pd, cells);
+        if (key[q] < 0 || key[q] >= gd.n_pblocks) { std::fprintf(stderr, "harness scene: particle %d is not in a real block\n", q); std::exit(2); }
+        count[key[q]]++;
+    }
+    for (int b = 0; b < gd.n_pblocks + 3; ++b) start[b + 1] = start[b] + count[b];
+    H.ids0.assign(H.cap, -1);
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int q = 0; q < n; ++q) H.ids0[cur[key[q]]++] = q;
+    H.work.clear();
+    for (int b = gd.n_pblocks - 1; b >= 0; --b)            // any order is legal; use a different one than the device scan
+        if (count[b]) H.work.push_back(make_int4(b, start[b], count[b], 0));
+    H.grid.assign((size_t)gd.n_gblocks * 64, make_float4(0, 0, 0, 0));
+    std::memset(&H.dc, 0, sizeof H.dc);
+    H.dc.n_slots = n; H.dc.n_binned = n; H.dc.n_sorted = n; H.dc.n_active_pblocks = (int)H.work.size();
+}
+
+static int failures = 0;
+static void check(bool ok, const char* what) {
+    std::printf("%s  %s\n", ok ? "ok  " : "FAIL", what);
+    if (!ok) ++failures;
+}
+// max |a-b| over the four channels relative to the largest magnitude of that channel
+static double grid_rel_diff(const std::vector<float4>& a, const std::vector<float4>& b) {
+    double mx[4] = { 0, 0, 0, 0 }, d[4] = { 0, 0, 0, 0 };
+    for (size_t i = 0; i < a.size(); ++i) {
+        const float* x = &a[i].x; const float* y = &b[i].x;
+        for (int c = 0; c < 4; ++c) { mx[c] = std::max(mx[c], (double)std::fabs(x[c])); d[c] = std::max(d[c], (double)std::fabs(x[c] - y[c])); }
+    }
+    double r = 0;
+    for (int c = 0; c < 4; ++c) r = std::max(r, d[c] / std::max(mx[c], 1e-30));
+    return r;
+}
+
+template <bool PACKED, bool FUPD>
+static void run_p2g(Host& H, std::vector<int>& ids, std::vector<float4>& grid, float dt) {
+    ids = H.ids0;
+    grid.assign(H.grid.size(), make_float4(0, 0, 0, 0));
+    H.dc.work_a = 0;
+    Planes P = H.planes(0), N = H.planes(1);
+    emu::launch(3, P2G_T, sizeof(P2GSmem), [&] {
+        k_p2g_tile<P2G_FUSED, PACKED, FUPD>(P, ids.data(), H.work.data(), &H.dc, grid.data(), H.gd, H.sc, dt, FUPD ? N : P);
+    });
+}
+static bool ids_are_block_permutations(const Host& H, const std::vector<int>& ids) {
+    for (const int4& w : H.work) {
+        std::vector<int> a(H.ids0.begin() + w.y, H.ids0.begin() + w.y + w.z), b(ids.begin() + w.y, ids.begin() + w.y + w.z);
+        std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+        if (a != b) return false;
+    }
+    return true;
+}
+static void clear_planes(Host& H, int b, int k0, int k1) {
+    for (int k = k0; k <= k1; ++k) std::fill(H.buf[b].begin() + (size_t)k * H.cap, H.buf[b].begin() + (size_t)(k + 1) * H.cap, make_float4(NAN, NAN, NAN, NAN));
+}
+static bool planes_bit_equal(const std::vector<float4>& a, const std::vector<float4>& b, int cap, int n, int k0, int k1, bool allow_zero_sign) {
+    for (int k = k0; k <= k1; ++k)
+        for (int j = 0; j < n; ++j) {
+            const float* x = &a[(size_t)k * cap + j].x; const float* y = &b[(size_t)k * cap + j].x;
+            for (int c = 0; c < 4; ++c) {
+                if (std::memcmp(&x[c], &y[c], 4) == 0) continue;
+                if (allow_zero_sign && x[c] == 0.0f && y[c] == 0.0f) continue;
+                std::fprintf(stderr, "  plane %d slot %d comp %d: %.9g vs %.9g\n", k, j, c, x[c], y[c]);
+                return false;
+            }
+        }
+    return true;
+}
+static double planes_rel_diff(const std::vector<float4>& a, const std::vector<float4>& b, int cap, int n, int k0, int k1) {
+    double r = 0;
+    for (int k = k0; k <= k1; ++k) {
+        double mx = 0, d = 0;
+        for (int j = 0; j < n; ++j) {
+            const float* x = &a[(size_t)k * cap + j].x; const float* y = &b[(size_t)k * cap + j].x;
+            for (int c = 0; c < 4; ++c) { mx = std::max(mx, (double)std::fabs(x[c])); d = std::max(d, (double)std::fabs(x[c] - y[c])); }
+        }
+        r = std::max(r, d / std::max(mx, 1e-30));
+    }
+    return r;
+}
+
+template <bool LINEAR, bool PACKED>
+static std::vector<float4> run_gather(Host& H, const std::vector<int>& ids, const std::vector<float4>& vel, float dt) {
+    clear_planes(H, 1, 0, 3);
+    H.dc.work_b = 0;
+    Planes C = H.planes(0), N = H.planes(1);
+    using Smem = typename std::conditional<LINEAR, G2PSmemLinear, G2PSmem>::type;
+    const long long before = emu::tma_bytes_total();
+    emu::launch(2, G2P_T, sizeof(Smem), [&] {
+        k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, LINEAR, PACKED>(C, N, ids.data(), H.work.data(), &H.dc, vel.data(), H.gd, H.sc, dt);
+    });
+    const long long moved = emu::tma_bytes_total() - before;
+    check(moved == (long long)H.work.size() * 8192, LINEAR ? "linear tile: 8 KB of bulk copies per particle block" : "blocked tile: 8 KB of bulk copies per particle block");
+    return H.buf[1];
+}
+
+int main(int argc, char** argv) {
+    const unsigned seed = argc > 1 ? (unsigned)std::atoi(argv[1]) : 1u;
+    const bool fast_div = argc > 2 ? std::atoi(argv[2]) != 0 : true;
+    const float dt = 1e-5f;
+    Host H;
+    build(H, 24, seed, fast_div);
+    std::printf("emulated scene: %d particles, %zu occupied particle blocks, seed %u, fast pos/h %d\n", H.n, H.work.size(), seed, (int)fast_div);
+
+    // ---------------- P2G ----------------
+    std::vector<int> ids_def, ids_pk, ids_fu, ids_pkfu, ids_base = H.ids0;
+    std::vector<float4> g_def, g_pk, g_fu, g_pkfu, g_base(H.grid.size(), make_float4(0, 0, 0, 0));
+    {
+        Planes P = H.planes(0);
+        emu::launch((H.n + 127) / 128, 128, 0, [&] { k_p2g_atomic<P2G_FUSED>(P, ids_base.data(), &H.dc, g_base.data(), H.gd, H.sc, dt); });
+    }
+    run_p2g<false, false>(H, ids_def, g_def, dt);
+    check(ids_are_block_permutations(H, ids_def), "P2G default: ids stay a permutation inside every block");
+    const double e0 = grid_rel_diff(g_def, g_base);
+    std::printf("      grid, tile kernel vs per-particle atomics: rel diff %.3g\n", e0);
+    check(e0 < 2e-5, "P2G default tile kernel == baseline kernel (harness sanity)");
+    run_p2g<true, false>(H, ids_pk, g_pk, dt);
+    check(ids_are_block_permutations(H, ids_pk), "P2G packed: ids stay a permutation inside every block");
+    const double e1 = grid_rel_diff(g_pk, g_base);
+    std::printf("      grid, packed-pair tile kernel vs per-particle atomics: rel diff %.3g\n", e1);
+    check(e1 < 2e-5, "P2G packed pairs == baseline kernel");
+
+    // ---------------- F-update inside P2G ----------------
+    clear_planes(H, 1, 0, 10);
+    run_p2g<false, true>(H, ids_fu, g_fu, dt);
+    const std::vector<float4> nxt_fused = H.buf[1];
+    check(ids_are_block_permutations(H, ids_fu), "P2G + F-update: ids stay a permutation inside every block");
+    check(grid_rel_diff(g_fu, g_base) < 2e-5, "P2G + F-update: grid == baseline kernel");
+    clear_planes(H, 1, 0, 10);
+    {
+        Planes C = H.planes(0), N = H.planes(1);
+        emu::launch((H.n + 255) / 256, 256, 0, [&] { k_fupdate<true>(C, N, ids_fu.data(), &H.dc, H.sc, dt); });
+    }
+    check(planes_bit_equal(nxt_fused, H.buf[1], H.cap, H.n, 4, 10, false), "F-update inside P2G == k_fupdate<true>, planes 4..10 at every sorted rank, bit for bit");
+    check(H.dc.svd_failed == 0, "no SVD failure flagged");
+    clear_planes(H, 1, 0, 10);
+    run_p2g<true, true>(H, ids_pkfu, g_pkfu, dt);
+    const std::vector<float4> nxt_fused2 = H.buf[1];
+    check(grid_rel_diff(g_pkfu, g_base) < 2e-5, "P2G packed + F-update: grid == baseline kernel");
+    clear_planes(H, 1, 0, 10);
+    {
+        Planes C = H.planes(0), N = H.planes(1);
+        emu::launch((H.n + 255) / 256, 256, 0, [&] { k_fupdate<true>(C, N, ids_pkfu.data(), &H.dc, H.sc, dt); });
+    }
+    check(planes_bit_equal(nxt_fused2, H.buf[1], H.cap, H.n, 4, 10, false), "F-update inside packed P2G == k_fupdate<true>, bit for bit");
+
+    // ---------------- gather ----------------
+    std::vector<float4> vel = g_base;           // node velocities = momentum / mass of the scattered grid
+    for (float4& v : vel) if (v.x != 0.0f) { v.y /= v.x; v.z /= v.x; v.w /= v.x; }
+    const std::vector<float4> r_blk = run_gather<false, false>(H, ids_def, vel, dt);
+    const std::vector<float4> r_lin = run_gather<true, false>(H, ids_def, vel, dt);
+    const std::vector<float4> r_pk = run_gather<false, true>(H, ids_def, vel, dt);
+    const std::vector<float4> r_lpk = run_gather<true, true>(H, ids_def, vel, dt);
+    clear_planes(H, 1, 0, 10);
+    {
+        Planes C = H.planes(0), N = H.planes(1);
+        emu::launch((H.n + 127) / 128, 128, 0, [&] { k_g2p_direct<G2P_GATHER | G2P_ADVECT | G2P_REORDER>(C, N, ids_def.data(), &H.dc, vel.data(), H.gd, H.sc, dt); });
+    }
+    const std::vector<float4> r_dir = H.buf[1];
+    const double d0 = planes_rel_diff(r_blk, r_dir, H.cap, H.n, 0, 3);
+    std::printf("      gather, tile kernel vs direct gathers: rel diff %.3g\n", d0);
+    check(d0 < 2e-5, "gather default tile kernel == direct-gather baseline (harness sanity)");
+    check(planes_bit_equal(r_lin, r_blk, H.cap, H.n, 0, 3, false), "gather with the linear tile == blocked tile, bit for bit");
+    const double d1 = planes_rel_diff(r_pk, r_blk, H.cap, H.n, 0, 3), d2 = planes_rel_diff(r_lpk, r_blk, H.cap, H.n, 0, 3);
+    std::printf("      gather, packed pairs vs scalar: rel diff %.3g (blocked tile) %.3g (linear tile)\n", d1, d2);
+    check(d1 < 2e-5 && d2 < 2e-5, "gather with packed pairs == scalar gather");
+    check(planes_bit_equal(r_lpk, r_pk, H.cap, H.n, 0, 3, false), "packed gather: linear tile == blocked tile, bit for bit");
+
+    std::printf("%s (%d failures)\n", failures ? "EMULATION CHECKS FAILED" : "all emulation checks passed", failures);
+    return failures ? 1 : 0;
+}
