@@ -225,6 +225,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
+    if (s->prm.p2g_variant >= 2 || s->prm.g2p_variant >= 2) CK(tile_kernels_init_experimental());
     CK(cudaStreamSynchronize(s->stream));
     { int rc = validate_pos_div(s); if (rc) return rc; }
     return MPM_OK;
@@ -263,6 +264,7 @@ int mpm_set_stream(mpm_t* s, void* st) {
 int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
     if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
+    if (p->p2g_variant >= 2 || p->g2p_variant >= 2) CK(tile_kernels_init_experimental());
     s->prm = *p;
     const int fast = s->sc.pd.fast;
     fill_consts(s);

@@ -582,18 +582,23 @@ inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
     MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
-    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>));
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>)); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>));
 #undef MPM_SET_SMEM
 #define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
     MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
 #undef MPM_SET_SMEM2
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmemLinear))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+// the experimental variants are set up only when a handle selects one of them (p2g_variant >= 2 / g2p_variant >= 2), so
+// that the default path issues exactly the CUDA calls it was validated with
+inline cudaError_t tile_kernels_init_experimental() {
+    cudaError_t e;
+#define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
+    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>), P2GSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
+#undef MPM_SET_SMEM
     return cudaSuccess;
 }
 
