@@ -14,19 +14,38 @@ BUILD = os.path.join(EMU, "_build")
 CSRC = os.path.join(ROOT, "realtime-deformations_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def harness():
+def _build(name):
     os.makedirs(BUILD, exist_ok=True)
-    exe = os.path.join(BUILD, "emu_harness")
-    srcs = [os.path.join(EMU, "emu_harness.cpp"), os.path.join(EMU, "cuda_emu.h")] + \
+    exe = os.path.join(BUILD, name)
+    srcs = [os.path.join(EMU, name + ".cpp"), os.path.join(EMU, "cuda_emu.h")] + \
            [os.path.join(CSRC, f) for f in ("mpm_math.cuh", "mpm_kernels.cuh", "mpm_tile_kernels.cuh")]
     if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-pthread", "-I/usr/local/cuda/include", "-I" + CSRC,
                "-I" + os.path.join(ROOT, "include"), "-include", os.path.join(EMU, "cuda_emu.h"), "-x", "c++",
-               os.path.join(EMU, "emu_harness.cpp"), "-o", exe]
+               os.path.join(EMU, name + ".cpp"), "-o", exe]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode == 0, "host build of the kernel sources failed:\n" + r.stdout[-4000:]
     return exe
+
+
+@pytest.fixture(scope="module")
+def harness():
+    return _build("emu_harness")
+
+
+def test_device_code_reproduces_reference_kats_on_the_host(tmp_path):
+    """The reference's known-answer vectors through the device routines compiled for the host: weights, bodyCollision
+    (static and moving colliders, as a function and through k_grid_update), updateDeformationGradient (k_fupdate)."""
+    import numpy as np
+    k = np.load(os.path.join(ROOT, "tests", "golden", "kat_functions.npz"))
+    for n in ("weights_x", "weights_w", "collide_pos", "collide_vel", "collide_out", "collide_moving_out", "fupdate_in", "fupdate_out"):
+        np.ascontiguousarray(k[n], np.float32).tofile(str(tmp_path / (n + ".f32")))
+    for n in ("colliders", "colliders_moving"):       # reference dump rows -> world_to_local[16], half[3], velocity[3]
+        raw = k[n]
+        np.ascontiguousarray(np.concatenate([raw[:, 13:29], raw[:, 0:3], raw[:, 10:13]], 1), np.float32).tofile(str(tmp_path / (n + ".f32")))
+    r = subprocess.run([_build("emu_kat"), str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "all emulated known-answer tests passed" in r.stdout, r.stdout[-4000:]
+    assert r.stdout.count("ok  ") == 6
 
 
 @pytest.mark.parametrize("seed,fast_div", [(1, 1), (7, 0)])
