@@ -25,6 +25,7 @@ struct Host {
     Planes planes(int b) { Planes P; for (int k = 0; k < NPLANES; ++k) P.p[k] = buf[b].data() + (size_t)k * cap; return P; }
 };
 
+static void host_bin(Host& H, int bufi);
 static float frand(std::mt19937& g, float lo, float hi) { return lo + (hi - lo) * (float)(g() >> 8) / 16777216.0f; }
 
 static void put_particle(Host& H, int p, std::mt19937& g, float x, float y, float z) {
@@ -83,9 +84,16 @@ static void build(Host& H, int dim, unsigned seed, bool fast_div) {
         for (int i = 0; i < cr.n; ++i)
             put_particle(H, p++, g, (4 * cr.bi + 1 + frand(g, 0.01f, 3.99f)) * h, (4 * cr.bj + 1 + frand(g, 0.01f, 3.99f)) * h,
                          (4 * cr.bk + 1 + frand(g, 0.01f, 3.99f)) * h);
-    // host binning with the kernels' own key function
+    host_bin(H, 0);
+}
+
+// host binning with the kernels' own key function (stands in for k_bin_count / scan / k_bin_scatter)
+static void host_bin(Host& H, int bufi) {
+    const GridDims& gd = H.gd;
+    const SimConst& c = H.sc;
+    const int n = H.n;
     std::vector<int> key(n), count(gd.n_pblocks + 3, 0), start(gd.n_pblocks + 4, 0);
-    Planes P = H.planes(0);
+    Planes P = H.planes(bufi);
     for (int q = 0; q < n; ++q) {
         int cells[3];
         key[q] = particle_key(P.p[0][q], gd, c.pd, cells);
@@ -183,6 +191,142 @@ static std::vector<float4> run_gather(Host& H, const std::vector<int>& ids, cons
     return H.buf[1];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// whole fused substeps, kernel sequence of mpm_substep_begin/end (binning done on the host):
+//   clear -> P2G<FUSED> -> grid update -> [F-update] -> gather/advect/re-sort -> swap
+// with the default kernels and with every experimental option switched on (packed P2G that also runs the F-update,
+// gather on the linear tile with packed pairs). The particle state after several substeps must agree: this covers the
+// data flow BETWEEN substeps (tau and FE/FP written by P2G's F-update phase into the other buffer, consumed after the swap).
+// ---------------------------------------------------------------------------------------------------------------
+static void build_flow_scene(Host& H, unsigned seed) {
+    build(H, 24, seed, true);                       // dims and constants; particles replaced below
+    std::mt19937 g(seed * 7919u + 1u);
+    const float h = H.sc.h;
+    const int n = 8 * 512;
+    H.n = n; H.cap = n + 64;
+    for (int b = 0; b < 2; ++b) H.buf[b].assign((size_t)NPLANES * H.cap, make_float4(NAN, NAN, NAN, NAN));
+    Planes P = H.planes(0);
+    int p = 0;
+    for (int ci = 9; ci < 17; ++ci) for (int cj = 5; cj < 13; ++cj) for (int ck = 9; ck < 17; ++ck)     // 8^3 cells x 8 particles
+        for (int s8 = 0; s8 < 8; ++s8, ++p) {
+            const float x = (ci + 0.25f + 0.5f * (s8 & 1) + frand(g, -0.2f, 0.2f)) * h, y = (cj + 0.25f + 0.5f * ((s8 >> 1) & 1) + frand(g, -0.2f, 0.2f)) * h,
+                        z = (ck + 0.25f + 0.5f * (s8 >> 2) + frand(g, -0.2f, 0.2f)) * h;
+            P.p[0][p] = make_float4(x, y, z, 6e-5f);
+            P.p[1][p] = make_float4(0, 0, 0, 0); P.p[2][p] = make_float4(0, 0, 0, 0);
+            P.p[3][p] = make_float4(0, frand(g, -0.5f, 0.5f), -40.0f + frand(g, -0.5f, 0.5f), frand(g, -0.5f, 0.5f));
+            P.p[4][p] = make_float4(0, 0, 0, 0); P.p[5][p] = make_float4(0, 0, 0, 0);
+            // compressed, stress from the first substep on; singular values well separated (the reference re-assembles FE
+            // from transposed SVD factors, so the axis a clamped value lands on depends on the ORDER of the singular
+            // values: with nearly equal ones fp32 noise flips it -- that chaos is the reference's, not a kernel property)
+            const float c0 = 0.993f, c1 = 0.9755f, c2 = 0.986f;
+            P.p[6][p] = make_float4(1.5e-5f, __int_as_float(p), c0, 0);
+            P.p[7][p] = make_float4(0, 0, c1, 0); P.p[8][p] = make_float4(0, 0, c2, 1);
+            P.p[9][p] = make_float4(0, 0, 0, 1); P.p[10][p] = make_float4(0, 0, 0, 1);
+        }
+    H.dc.n_slots = n;
+    emu::launch((n + 127) / 128, 128, 0, [&] { k_stress(P, &H.dc, H.sc); });
+    H.grid.assign((size_t)H.gd.n_gblocks * 64, make_float4(0, 0, 0, 0));
+}
+
+template <bool PK, bool FU, bool GL, bool GP>
+static std::vector<float> run_flow(Host& H, int substeps, float dt, const ColliderSet& cs, int nc) {
+    int cur = 0;
+    std::vector<int> blocks(H.gd.n_gblocks);
+    for (int b = 0; b < H.gd.n_gblocks; ++b) blocks[b] = b;
+    for (int step = 0; step < substeps; ++step) {
+        host_bin(H, cur);
+        H.dc.n_active_gblocks = H.gd.n_gblocks;
+        std::vector<int> ids = H.ids0;
+        std::fill(H.grid.begin(), H.grid.end(), make_float4(0, 0, 0, 0));
+        Planes C = H.planes(cur), N = H.planes(cur ^ 1);
+        H.dc.work_a = 0; H.dc.work_b = 0;
+        emu::launch(3, P2G_T, sizeof(P2GSmem), [&] {
+            k_p2g_tile<P2G_FUSED, PK, FU>(C, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt, FU ? N : C);
+        });
+        emu::launch(3, 256, 0, [&] { k_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE>(blocks.data(), &H.dc, H.grid.data(), nullptr, H.gd, H.sc, dt, cs, nc); });
+        if (!FU) emu::launch((H.n + 255) / 256, 256, 0, [&] { k_fupdate<true>(C, N, ids.data(), &H.dc, H.sc, dt); });
+        using Smem = typename std::conditional<GL, G2PSmemLinear, G2PSmem>::type;
+        emu::launch(2, G2P_T, sizeof(Smem), [&] {
+            k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, GL, GP>(C, N, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt);
+        });
+        cur ^= 1;
+    }
+    // state by particle id: x y z | v | B | FE | FP | tau
+    std::vector<float> out((size_t)H.n * 36, 0.0f);
+    Planes P = H.planes(cur);
+    for (int j = 0; j < H.n; ++j) {
+        const int pid = __float_as_int(P.p[6][j].y);
+        if (pid < 0 || pid >= H.n) { std::fprintf(stderr, "flow: slot %d carries particle id %d\n", j, pid); std::exit(3); }
+        float* o = &out[(size_t)pid * 36];
+        const float4 a0 = P.p[0][j], a1 = P.p[1][j], a2 = P.p[2][j], a3 = P.p[3][j], a4 = P.p[4][j], a5 = P.p[5][j], a6 = P.p[6][j], a7 = P.p[7][j],
+                     a8 = P.p[8][j], a9 = P.p[9][j], a10 = P.p[10][j];
+        const float v[36] = { a0.x, a0.y, a0.z, a3.y, a3.z, a3.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x,
+                              a6.z, a6.w, a7.x, a7.y, a7.z, a7.w, a8.x, a8.y, a8.z, a8.w, a9.x, a9.y, a9.z, a9.w, a10.x, a10.y, a10.z, a10.w,
+                              a4.x, a4.y, a5.y };
+        std::memcpy(o, v, sizeof v);
+    }
+    return out;
+}
+
+static void check_flow(unsigned seed) {
+    const float dt = 1e-5f;
+    const int substeps = 4;
+    ColliderSet cs;
+    std::memset(&cs, 0, sizeof cs);
+    // ground box: top face at y = 5.1 cells, i.e. under the blob's lowest particles (0.1 cell away, reached in the run)
+    const float h = 0.05f;
+    BoxCollider& b = cs.c[0];
+    const float w2l[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, -0.6f, -(5.1f * h - 1.0f), -0.6f, 1 };   // translate(-centre), centre y = top - half
+    std::memcpy(b.w2l, w2l, sizeof w2l);
+    b.half[0] = 5.0f; b.half[1] = 1.0f; b.half[2] = 5.0f;
+    Host A, B;
+    build_flow_scene(A, seed);
+    build_flow_scene(B, seed);
+    const std::vector<float> ra = run_flow<false, false, false, false>(A, substeps, dt, cs, 1);
+    const char* mode = std::getenv("EMU_FLOW_MODE");
+    const int m = mode ? std::atoi(mode) : 15;
+    std::vector<float> rb;
+    switch (m) {
+    case 0: rb = run_flow<false, false, false, false>(B, substeps, dt, cs, 1); break;
+    case 1: rb = run_flow<true, false, false, false>(B, substeps, dt, cs, 1); break;
+    case 2: rb = run_flow<false, true, false, false>(B, substeps, dt, cs, 1); break;
+    case 4: rb = run_flow<false, false, true, false>(B, substeps, dt, cs, 1); break;
+    case 8: rb = run_flow<false, false, false, true>(B, substeps, dt, cs, 1); break;
+    default: rb = run_flow<true, true, true, true>(B, substeps, dt, cs, 1); break;
+    }
+    const char* names[6] = { "position", "velocity", "B", "FE", "FP", "tau" };
+    const int lo[6] = { 0, 3, 6, 15, 24, 33 }, hi[6] = { 3, 6, 15, 24, 33, 36 };
+    bool ok = true, moved = false, stressed = false, plastic = false;
+    for (int f = 0; f < 6; ++f) {
+        double mx = 0, d = 0;
+        for (int p = 0; p < A.n; ++p)
+            for (int c = lo[f]; c < hi[f]; ++c) {
+                const double x = ra[(size_t)p * 36 + c], y = rb[(size_t)p * 36 + c];
+                if (!(std::isfinite(x) && std::isfinite(y))) ok = false;
+                mx = std::max(mx, std::fabs(x)); d = std::max(d, std::fabs(x - y));
+            }
+        std::printf("      %d substeps, default vs all experimental options: %-8s max |d| %.3g (scale %.3g)\n", substeps, names[f], d, mx);
+        if (!(d <= 2e-4 * mx)) ok = false;
+        if (f == 5 && mx > 0) stressed = true;
+    }
+    for (int p = 0; p < A.n; ++p) {
+        if (std::fabs(ra[(size_t)p * 36 + 4] + 40.0f) > 5.0f) moved = true;                 // some particle has hit the ground box
+        if (std::fabs(ra[(size_t)p * 36 + 28] - 1.0f) > 1e-4f) plastic = true;             // FP_yy left 1: clamping happened
+    }
+    if (std::getenv("EMU_FLOW_DEBUG")) {
+        int worst = 0; double wd = 0;
+        for (int p = 0; p < A.n; ++p) for (int c = 15; c < 24; ++c) { const double d = std::fabs(ra[(size_t)p * 36 + c] - rb[(size_t)p * 36 + c]); if (d > wd) { wd = d; worst = p; } }
+        std::printf("worst FE particle %d:\n", worst);
+        for (int c = 0; c < 36; ++c) std::printf("  [%2d] %.9g  %.9g\n", c, ra[(size_t)worst * 36 + c], rb[(size_t)worst * 36 + c]);
+        int cnt = 0;
+        for (int p = 0; p < A.n; ++p) { double d = 0; for (int c = 15; c < 24; ++c) d = std::max(d, (double)std::fabs(ra[(size_t)p * 36 + c] - rb[(size_t)p * 36 + c])); cnt += d > 1e-5; }
+        std::printf("particles with |dFE| > 1e-5: %d of %d\n", cnt, A.n);
+    }
+    check(ok, "whole substeps: default kernels == packed P2G with in-kernel F-update + linear/packed gather");
+    if (!(moved && stressed && plastic)) std::printf("      moved %d stressed %d plastic %d\n", (int)moved, (int)stressed, (int)plastic);
+    check(moved && stressed && plastic, "flow scene exercises collision, stress and plastic clamping");
+}
+
 int main(int argc, char** argv) {
     const unsigned seed = argc > 1 ? (unsigned)std::atoi(argv[1]) : 1u;
     const bool fast_div = argc > 2 ? std::atoi(argv[2]) != 0 : true;
@@ -254,6 +398,8 @@ int main(int argc, char** argv) {
     std::printf("      gather, packed pairs vs scalar: rel diff %.3g (blocked tile) %.3g (linear tile)\n", d1, d2);
     check(d1 < 2e-5 && d2 < 2e-5, "gather with packed pairs == scalar gather");
     check(planes_bit_equal(r_lpk, r_pk, H.cap, H.n, 0, 3, false), "packed gather: linear tile == blocked tile, bit for bit");
+
+    check_flow(seed);
 
     std::printf("%s (%d failures)\n", failures ? "EMULATION CHECKS FAILED" : "all emulation checks passed", failures);
     return failures ? 1 : 0;
