@@ -58,6 +58,9 @@ def lib():
         raise MpmError(f"{LIB_PATH} is missing: build it with `python realtime-deformations_b200/build.py` "
                        "(there is no CPU fallback)")
     L = C.CDLL(LIB_PATH)
+    if hasattr(L, "mpm_emulated_build") and os.environ.get("MPM_B200_ALLOW_EMULATION") != "1":
+        # tests/emu builds a host emulation of the kernels for logic checks; it must never stand in for the CUDA library
+        raise MpmError(f"{LIB_PATH} is the host-emulation test build, not the CUDA library (there is no CPU fallback)")
     fp, vp, i64 = C.POINTER(C.c_float), C.c_void_p, C.c_int64
     sz = C.c_size_t
     L.mpm_default_params.argtypes = [C.POINTER(MpmParams)]

@@ -691,6 +691,11 @@ int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* c, int n, int n_subste
     return MPM_OK;
 }
 
+#ifdef MPM_HOST_EMU
+// only the host-emulation build of tests/emu has this symbol; capi refuses such a library unless a test asks for it
+extern "C" int mpm_emulated_build(void) { return 1; }
+#endif
+
 // ---- diagnostics ---------------------------------------------------------------------------------------------------
 int mpm_synchronize(mpm_t* s) { NEED(s); CK(cudaStreamSynchronize(s->stream)); return MPM_OK; }
 

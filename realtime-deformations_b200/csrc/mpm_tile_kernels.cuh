@@ -577,7 +577,7 @@ __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ so
     for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
 }
 
-#ifndef MPM_HOST_EMU        // host launch code (nvcc only)
+#if !defined(MPM_HOST_EMU) || defined(MPM_HOST_EMU_API)        // host launch code (nvcc; or the whole-library emulation build of tests/emu)
 inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
@@ -668,6 +668,6 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
     return e;
 }
 
-#endif  // MPM_HOST_EMU
+#endif  // host launch code
 
 }  // namespace mpm

@@ -1,8 +1,11 @@
 // TEST INFRASTRUCTURE ONLY -- never part of the product (libmpm_b200.so is built by nvcc from the same kernel sources
 // and has no CPU path). This header lets g++ compile the CUDA kernel sources under csrc/ for the HOST so that their
 // index arithmetic, barrier structure and copy/transaction bookkeeping can be executed without a GPU:
-//   * every CUDA thread is an OS thread; the CTAs of a launch run one after the other;
-//   * __syncthreads / __syncwarp / __shfl_* are real barriers (every thread named by the mask must arrive, as on the GPU);
+//   * every CUDA thread is a fiber (own stack, hand-written context switch) of the launching OS thread; the CTAs of a
+//     launch run one after the other; fibers are resumed in a seeded pseudo-random order (EMU_SEED) at every barrier /
+//     wait, so that a missing barrier shows up as a poisoned or stale read for some seed;
+//   * __syncthreads / __syncwarp / __shfl_* are real barriers (every live thread of the CTA / warp must arrive); if no
+//     fiber can make progress the launch dies with "deadlock" (e.g. an mbarrier whose byte count never completes);
 //   * cp.async.bulk + mbarrier are emulated with exact transaction-byte accounting and 16-byte alignment checks;
 //   * the _rn intrinsics map to plain IEEE operations (compile with -ffp-contract=off).
 // What it cannot show: performance, the hardware memory model, real concurrency between CTAs.
@@ -19,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -41,16 +45,19 @@ namespace emu {
     std::abort();
 }
 
-struct Barrier {
-    std::mutex m;
-    std::condition_variable cv;
-    int n = 0, count = 0;
+void yield();                       // hand the OS thread to another fiber of the running CTA
+void note_progress();
+struct Barrier {                    // n = live participants; a participant that exits stops counting (leave())
+    int n = 0, arrived = 0;
     unsigned gen = 0;
     void wait() {
-        std::unique_lock<std::mutex> lk(m);
         const unsigned g = gen;
-        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        if (++arrived >= n) { arrived = 0; ++gen; note_progress(); return; }
+        while (gen == g) yield();
+    }
+    void leave() {
+        --n;
+        if (n > 0 && arrived >= n) { arrived = 0; ++gen; note_progress(); }
     }
 };
 
@@ -102,21 +109,137 @@ inline void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned lon
     Mbar::update(bar, -(long long)bytes, 0);
 }
 inline void mbar_wait(unsigned long long* bar, unsigned parity) {
-    long spins = 0;
-    while (Mbar::phase(__atomic_load_n(bar, __ATOMIC_ACQUIRE)) == (int)(parity & 1)) {
-        std::this_thread::yield();
-        if (++spins > 200000000L) die("mbarrier wait never completed (transaction bytes do not add up?)");
-    }
+    while (Mbar::phase(__atomic_load_n(bar, __ATOMIC_ACQUIRE)) == (int)(parity & 1)) yield();    // a wait that can never complete ends in "deadlock"
+    note_progress();
 }
 
 // run `body` as a grid of CTAs, one CTA at a time, `threads` OS threads per CTA
-inline void launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body);
+inline void launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body, const char* name = "");
 
 }  // namespace emu
 
 inline thread_local emu::Idx threadIdx, blockIdx, blockDim, gridDim;
 
-inline void emu::launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body) {
+// ---- fibers ------------------------------------------------------------------------------------------------------------
+#if !defined(__x86_64__)
+#error "tests/emu: the fiber context switch is written for x86-64"
+#endif
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace emu {
+struct Sched {
+    static constexpr size_t STACK = 256 * 1024;
+    struct Fiber { void* sp = nullptr; char* stack = nullptr; bool done = true; };
+    std::vector<Fiber> fib;
+    void* main_sp = nullptr;
+    int cur = -1, live = 0;
+    bool progress = false;
+    Cta* c = nullptr;
+    const std::function<void()>* body = nullptr;
+    Idx block, bdim, gdim;
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    Sched() { if (const char* e = std::getenv("EMU_SEED")) rng ^= (unsigned long long)std::atoll(e) * 0xD1B54A32D192ED03ull; }
+    ~Sched() { for (Fiber& f : fib) std::free(f.stack); }
+    static void entry();
+    void prepare(int i) {
+        Fiber& f = fib[i];
+        if (!f.stack) f.stack = (char*)std::aligned_alloc(64, STACK);
+        uintptr_t top = ((uintptr_t)(f.stack + STACK)) & ~(uintptr_t)15;
+        void** sp = (void**)top;
+        *--sp = nullptr;                    // return address of entry(): never used
+        *--sp = (void*)&Sched::entry;       // popped by emu_switch's ret
+        for (int r = 0; r < 6; ++r) *--sp = nullptr;
+        f.sp = sp; f.done = false;
+    }
+    void resume(int i) {
+        cur = i;
+        cta = c; tid = i;
+        threadIdx = Idx{ (unsigned)i, 0, 0 }; blockIdx = block; blockDim = bdim; gridDim = gdim;
+        emu_switch(&main_sp, fib[i].sp);
+    }
+    void run_cta(Cta* cta_, int threads, Idx b, Idx bd, Idx gd, const std::function<void()>& f, const char* name) {
+        if (cur >= 0) die("nested launch");
+        if ((int)fib.size() < threads) fib.resize(threads);
+        c = cta_; body = &f; block = b; bdim = bd; gdim = gd;
+        for (int i = 0; i < threads; ++i) prepare(i);
+        live = threads;
+        std::vector<int> order(threads);
+        for (int i = 0; i < threads; ++i) order[i] = i;
+        int idle_rounds = 0;
+        while (live > 0) {
+            progress = false;
+            // a fresh pseudo-random resume order every round (xorshift, Fisher-Yates)
+            for (int i = threads - 1; i > 0; --i) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                std::swap(order[i], order[(int)(rng % (unsigned long long)(i + 1))]);
+            }
+            for (int k = 0; k < threads; ++k) if (!fib[order[k]].done) resume(order[k]);
+            cur = -1;
+            idle_rounds = progress ? 0 : idle_rounds + 1;
+            if (idle_rounds > 3) {
+                std::fprintf(stderr, "cuda_emu: deadlock in %s, block %u: %d threads blocked, none can make progress\n", name, b.x, live);
+                die("deadlock");
+            }
+        }
+    }
+};
+inline Sched& sched() { static thread_local Sched s; return s; }
+inline void Sched::entry() {
+    Sched& s = sched();
+    (*s.body)();
+    const int i = s.cur;
+    s.fib[i].done = true;
+    --s.live;
+    s.progress = true;
+    s.c->cta_bar.leave();
+    s.c->warp_bar[i >> 5].leave();
+    void* dummy;
+    emu_switch(&dummy, s.main_sp);
+    die("resumed a finished fiber");
+}
+inline void yield() { Sched& s = sched(); if (s.cur < 0) die("yield outside a kernel"); emu_switch(&s.fib[s.cur].sp, s.main_sp); }
+inline void note_progress() { sched().progress = true; }
+}  // namespace emu
+
+#include <chrono>
+#include <map>
+#include <string>
+namespace emu {
+struct Profile {       // EMU_PROFILE=1: seconds per kernel name, printed at exit
+    std::map<std::string, std::pair<double, long>> t;
+    bool on = std::getenv("EMU_PROFILE") != nullptr;
+    ~Profile() { if (on) for (auto& kv : t) std::fprintf(stderr, "emu profile %-28s %8.3f s %6ld launches\n", kv.first.c_str(), kv.second.first, kv.second.second); }
+};
+inline Profile& profile() { static Profile p; return p; }
+}
+inline void emu::launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body, const char* name) {
+    if (threads == 0 || threads > 1024) die("launch: bad block size");
+    struct Timer {
+        const char* n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Timer() { if (profile().on) { auto& e = profile().t[n]; e.first += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); e.second++; } }
+    } timer{ name };
     for (unsigned b = 0; b < grid; ++b) {
         Cta c;
         c.nthreads = (int)threads;
@@ -125,17 +248,11 @@ inline void emu::launch(unsigned grid, unsigned threads, size_t smem_bytes, cons
         for (unsigned w = 0; w < c.warp_bar.size(); ++w) c.warp_bar[w].n = (int)std::min(32u, threads - 32 * w);
         c.slot.assign(threads, 0);
         c.smem.assign(smem_bytes + 256, 0xcd);          // poison: uninitialised reads show up as garbage
-        std::vector<std::thread> ts;
-        ts.reserve(threads);
-        for (unsigned t = 0; t < threads; ++t)
-            ts.emplace_back([&, t, b] {
-                cta = &c; tid = (int)t;
-                threadIdx = Idx{ t, 0, 0 }; blockIdx = Idx{ b, 0, 0 }; blockDim = Idx{ threads, 1, 1 }; gridDim = Idx{ grid, 1, 1 };
-                body();
-            });
-        for (auto& t : ts) t.join();
+        sched().run_cta(&c, (int)threads, Idx{ b, 0, 0 }, Idx{ threads, 1, 1 }, Idx{ grid, 1, 1 }, body, name);
     }
 }
+
+template <class F> inline cudaError_t emu_func_set_attribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // dynamic shared memory of the running CTA, 128-byte aligned
 inline unsigned char* emu_dyn_smem() {
@@ -183,12 +300,37 @@ template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int x, int width
     if (mask != 0xffffffffu || width != 32) emu::die("__shfl_xor_sync: only full-warp shuffles are emulated");
     return emu_exchange(v, (emu::tid & 31) ^ x);
 }
-// collectives whose participation depends on divergence are not emulated (the binning kernels use them; the harness bins on the host)
+// full-warp collectives (every lane of the warp must call them, as the kernels do); partial masks are not emulated
 inline unsigned __activemask() { emu::die("__activemask is not emulated"); }
-inline unsigned __match_any_sync(unsigned, int) { emu::die("__match_any_sync is not emulated"); }
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    if (mask != 0xffffffffu) emu::die("__match_any_sync: only the full mask is emulated");
+    emu::Cta* c = emu::cta;
+    const int w = emu::tid >> 5, nl = c->warp_bar[w].n;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    c->slot[emu::tid] = bits;
+    c->warp_bar[w].wait();
+    unsigned peers = 0;
+    for (int l = 0; l < nl; ++l) if (c->slot[w * 32 + l] == bits) peers |= 1u << l;
+    c->warp_bar[w].wait();
+    return peers;
+}
 inline unsigned __ballot_sync(unsigned, int) { emu::die("__ballot_sync is not emulated"); }
-inline int __reduce_add_sync(unsigned, int) { emu::die("__reduce_add_sync is not emulated"); }
-inline unsigned __reduce_add_sync(unsigned, unsigned) { emu::die("__reduce_add_sync is not emulated"); }
+template <class T> inline T emu_reduce_add(unsigned mask, T v) {
+    if (mask != 0xffffffffu) emu::die("__reduce_add_sync: only the full mask is emulated");
+    emu::Cta* c = emu::cta;
+    const int w = emu::tid >> 5, nl = c->warp_bar[w].n;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    c->slot[emu::tid] = bits;
+    c->warp_bar[w].wait();
+    T sum = 0;
+    for (int l = 0; l < nl; ++l) { T x; std::memcpy(&x, &c->slot[w * 32 + l], sizeof(T)); sum += x; }
+    c->warp_bar[w].wait();
+    return sum;
+}
+inline int __reduce_add_sync(unsigned mask, int v) { return emu_reduce_add(mask, v); }
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emu_reduce_add(mask, v); }
 
 // ---- atomics -------------------------------------------------------------------------------------------------------
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -1,0 +1,72 @@
+"""The GPU parity tests' logic, run without a GPU: tests/emu builds the WHOLE library (C ABI, host orchestration, kernels)
+for the host -- kernel launches become emulated launches where every CUDA thread is a fiber -- and this file points
+tests/test_gpu_parity.py at that build in a subprocess. It pre-validates what the `-m gpu` run then confirms on hardware:
+index arithmetic, barrier structure, bulk-copy byte counts, the host-side launch sequences of the staged and fused paths,
+and the experimental kernel variants. It is test infrastructure: capi refuses the emulated build unless
+MPM_B200_ALLOW_EMULATION=1 (set only here), and nothing in the package, bench.py or smoke() can select it."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+# the full-size configs, the 2-GPU test and the C++ adapter need the real device; graphs are refused by the fake runtime
+NEEDS_DEVICE = "not full_size and not two_gpus and not adapter and not graph"
+QUICK = "binning or stage_level or fupdate_kat or moving or volumes or staged_and_fused or parked or render or error_paths or ragged or empty_handle"
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    import emu_build
+    return emu_build.build()
+
+
+def _run_gpu_suite(emu_lib, select, experimental=False, timeout=1500):
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1")
+    env.pop("MPM_TEST_EXPERIMENTAL", None)
+    if experimental:
+        env["MPM_TEST_EXPERIMENTAL"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", f"({select}) and {NEEDS_DEVICE}"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env, cwd=ROOT)
+    return r
+
+
+def test_loader_refuses_the_emulated_build(emu_lib):
+    env = dict(os.environ, MPM_B200_LIB=emu_lib)
+    env.pop("MPM_B200_ALLOW_EMULATION", None)
+    code = "import sys; sys.path.insert(0, %r); import mpm_b200\ntry:\n    mpm_b200.Sim(20, 20, 20, 1)\nexcept mpm_b200.capi.MpmError as e:\n    print('REFUSED', e)" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+    assert "REFUSED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout[-2000:]
+
+
+def test_gpu_parity_logic_on_emulated_library(emu_lib):
+    """Stage-level parity with the reference at substeps 1 and 120, F-update and collision KATs, staged vs fused, parked
+    particles, render buffers, error paths, ragged block occupancy, empty / interleaved handles."""
+    r = _run_gpu_suite(emu_lib, QUICK)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-4000:]
+
+
+def test_default_scene_trajectory_on_emulated_library(emu_lib):
+    """400 substeps of the reference's default scene through the fused path, against the reference's own trajectory."""
+    r = _run_gpu_suite(emu_lib, "default_scene_trajectory and variants0")
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-4000:]
+
+
+def test_experimental_variants_on_emulated_library(emu_lib):
+    """Every experimental kernel variant (linear gather tile, packed fp32 pairs, F-update inside P2G) through the C ABI:
+    stage-level parity, KATs, edge cases; and the synthetic-ball trajectory against the oracle for the variant that
+    switches everything on."""
+    r = _run_gpu_suite(emu_lib, "binning or stage_level or fupdate_kat or parked or ragged", experimental=True)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-4000:]
+    r = _run_gpu_suite(emu_lib, "synthetic_ball and variants6", experimental=True)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.skipif(os.environ.get("MPM_EMU_FULL") != "1", reason="the whole emulated suite takes ~5 min: MPM_EMU_FULL=1")
+def test_whole_gpu_suite_on_emulated_library(emu_lib):
+    r = _run_gpu_suite(emu_lib, "test_", experimental=True, timeout=3400)
+    assert r.returncode == 0, r.stdout[-4000:]

@@ -240,7 +240,7 @@ def test_render_buffers_and_upload_order():
     assert (xyzs[:, :3] == out["pos"]).all() and (xyzs[:, 3] == np.float32(0.02)).all() and (rgba == 255).all()
     # pipelined variant: the copy runs on its own stream while the next substeps are computed
     import torch
-    pinned = torch.zeros((sc["n"], 4), dtype=torch.float32, pin_memory=True)
+    pinned = torch.zeros((sc["n"], 4), dtype=torch.float32, pin_memory=torch.cuda.is_available())   # (host emulation runs: no driver)
     sim.render_buffers_async(pinned.numpy().ctypes.data, sc["n"])
     sim.substep(float(sc["dt"]), cols, nc, 2)            # overlaps the copy; must not disturb frame t's buffer
     sim.wait_render_buffers()
