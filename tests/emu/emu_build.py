@@ -105,7 +105,7 @@ def build(force=False):
         total += n
         open(os.path.join(SRC_OUT, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w").write(text)
     assert total >= 40, f"only {total} launches rewritten"
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-DMPM_HOST_EMU_API=1",
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-DMPM_HOST_EMU_API=1",   # -Bsymbolic: the fake runtime wins even if torch has loaded libcudart
            "-I/usr/local/cuda/include", "-I" + SRC_OUT, "-I" + os.path.join(ROOT, "include"), "-include", os.path.join(HERE, "cuda_emu.h"),
            os.path.join(SRC_OUT, "mpm_api.cpp"), os.path.join(HERE, "fake_cudart.cpp"), "-o", LIB]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -66,6 +66,19 @@ def test_experimental_variants_on_emulated_library(emu_lib):
     assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-4000:]
 
 
+@pytest.mark.parametrize("world,balanced,port", [(8, 0, 29731), (8, 1, 29732)])
+def test_slab_protocol_with_the_real_library_over_gloo(emu_lib, world, balanced, port):
+    """realtime-deformations_b200/multi.py (halo exchange, fixed-size migration messages, collective count checks) with
+    the library's own slab entry points on 8 ranks: equal layers with particles driven across the slab boundaries
+    (ranks that start empty receive particles), and the bench's balanced partition. Against the same scene in one domain."""
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "emu", "multi_check_emulated.py"), "64", "16384", "12", str(balanced)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "MULTI_CHECK_OK" in r.stdout, r.stdout[-4000:]
+    assert "unique ids 16384" in r.stdout
+
+
 @pytest.mark.skipif(os.environ.get("MPM_EMU_FULL") != "1", reason="the whole emulated suite takes ~5 min: MPM_EMU_FULL=1")
 def test_whole_gpu_suite_on_emulated_library(emu_lib):
     r = _run_gpu_suite(emu_lib, "test_", experimental=True, timeout=3400)
