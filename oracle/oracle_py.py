@@ -97,7 +97,10 @@ def _fp(a):
 def default_params(**kw):
     p = OracleParams()
     lib().oracle_default_params(C.byref(p))
+    known = {f[0] for f in OracleParams._fields_}
     for k, v in kw.items():
+        if k not in known:          # a ctypes Structure would silently grow a Python attribute instead
+            raise TypeError(f"unknown parameter {k!r}; fields are {sorted(known)}")
         if k == "gravity":
             p.gravity[:] = [float(x) for x in v]
         else:

@@ -116,7 +116,10 @@ def _ck(rc):
 def default_params(**kw):
     p = MpmParams()
     lib().mpm_default_params(C.byref(p))
+    known = {f[0] for f in MpmParams._fields_}
     for k, v in kw.items():
+        if k not in known:          # a ctypes Structure would silently grow a Python attribute instead
+            raise TypeError(f"unknown parameter {k!r}; fields are {sorted(known)}")
         if k == "gravity":
             p.gravity[:] = [float(x) for x in v]
         elif k in ("p2g_variant", "g2p_variant"):

@@ -83,3 +83,12 @@ def test_slab_protocol_with_the_real_library_over_gloo(emu_lib, world, balanced,
 def test_whole_gpu_suite_on_emulated_library(emu_lib):
     r = _run_gpu_suite(emu_lib, "test_", experimental=True, timeout=3400)
     assert r.returncode == 0, r.stdout[-4000:]
+
+
+def test_randomized_scenes_against_the_oracle_on_emulated_library(emu_lib):
+    """tests/emu/fuzz_vs_oracle.py: non-cubic grids, particles on cell faces / at the clamp / outside the grid, crowded
+    cells, moving rotated colliders, random FE / FP, every kernel variant -- a dozen seeded cases per run."""
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_vs_oracle.py"), "14", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "FUZZ_OK 14 cases" in r.stdout, r.stdout[-4000:]
