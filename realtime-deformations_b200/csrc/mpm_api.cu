@@ -428,7 +428,7 @@ int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs, float si
     if (s->render_cap < n) {
         if (s->copy_pending) CK(cudaEventSynchronize(s->copy_done));
         cudaFree(s->render_stage);
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec); s->render_stage = nullptr;
+        s->render_stage = nullptr;
         CK(cudaMalloc(&s->render_stage, sizeof(float4) * (size_t)std::max<int64_t>(n, 1)));
         s->render_cap = n;
     }
