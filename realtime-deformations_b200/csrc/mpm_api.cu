@@ -65,6 +65,7 @@ struct mpm_sim {
     ColliderSet graph_cols;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
+    bool fupd_pending = false;  // experimental p2g_variant 3/4: P2G has put the F-update results into the idle buffer (until substep_end)
     int num_sms = 148;
     cudaEvent_t ev[8];
     bool ev_ok = false;
@@ -340,6 +341,7 @@ static int download_common(mpm_sim* s, int64_t n, const HostFieldPtrsW& f) {
     if (s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global)
         return fail(MPM_ERR_INVALID, "slab handles exchange particles: use mpm_download_live_particles");
     if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "download of %lld particles but %lld were uploaded", (long long)n, (long long)s->n_uploaded);
+    if (s->fupd_pending) return fail(MPM_ERR_INVALID, "mpm_substep_begin is pending: call mpm_substep_end before downloading (the idle buffer is in use)");
     const int64_t CH = 1 << 20;
     int rc = ensure_pinned(s, sizeof(float4) * NPLANES * (size_t)std::min<int64_t>(CH, std::max<int64_t>(n, 1)));
     if (rc) return rc;
@@ -624,6 +626,7 @@ int mpm_substep_begin(mpm_t* s, float dt) {
     TRY(launch_clear(s));
     EV(2);
     TRY((launch_p2g<P2G_FUSED>(s, s->grid, dt)));
+    s->fupd_pending = p2g_fupd(s);
     EV(3);
     return MPM_OK;
 }
@@ -633,8 +636,9 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
     EV(4);
     TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
     EV(5);
-    if (p2g_fupd(s)) TRY((launch_g2p<G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));      // the F-update already ran inside P2G
+    if (s->fupd_pending) TRY((launch_g2p<G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));      // the F-update already ran inside P2G
     else TRY((launch_g2p<G2P_F | G2P_GATHER | G2P_ADVECT | G2P_REORDER>(s, dt)));
+    s->fupd_pending = false;
     EV(6);
     s->tau_valid = true;
     s->stats.substeps_done++;
