@@ -124,6 +124,12 @@ int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char*
 int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs_pinned, float size);
 int mpm_wait_render_buffers(mpm_t* s);
 
+/* Viewer hand-off without the host round trip (replaces the copy loop + glBufferSubData of
+ * main.cpp:255-286): writes the same instance data straight into DEVICE memory owned by the caller, e.g. the pointer
+ * cudaGraphicsResourceGetMappedPointer returns for the viewer's GL instance buffers. d_xyzs: n float4 (x, y, z, size);
+ * d_rgba: n uchar4 (255,255,255,255) or NULL. Asynchronous on the handle's stream (mpm_synchronize before unmapping). */
+int mpm_write_render_buffers_device(mpm_t* s, int64_t n, void* d_xyzs, void* d_rgba, float size);
+
 /* One entry per reference stage (same order and meaning as main.cpp:192-218). */
 int mpm_rasterize_particles_to_grid(mpm_t* s);                   /* rasterizeParticlesToGrid        cpp:94-129  */
 int mpm_compute_particle_volumes_and_densities(mpm_t* s);        /* computeParticleVolumesAndDensities cpp:131-142 */

@@ -41,7 +41,7 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_rasterize_particles_to_grid", "mpm_compute_particle_volumes_and_densities",
            "mpm_compute_explicit_grid_forces", "mpm_grid_velocities_update", "mpm_grid_based_collisions",
            "mpm_update_deformation_gradient", "mpm_update_particle_velocities", "mpm_update_particle_positions",
-           "mpm_substep", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
+           "mpm_substep", "mpm_write_render_buffers_device", "mpm_download_grid", "mpm_upload_grid", "mpm_download_binning", "mpm_get_stats",
            "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
            "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
            "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
@@ -76,6 +76,7 @@ def lib():
     L.mpm_download_particles_soa.argtypes = [vp, i64] + [fp] * 7
     L.mpm_download_render_buffers.argtypes = [vp, i64, vp, vp, C.c_float]
     L.mpm_download_render_buffers_async.argtypes = [vp, i64, vp, C.c_float]
+    L.mpm_write_render_buffers_device.argtypes = [vp, i64, vp, vp, C.c_float]
     L.mpm_wait_render_buffers.argtypes = [vp]
     for n in ("mpm_rasterize_particles_to_grid", "mpm_compute_particle_volumes_and_densities",
               "mpm_compute_explicit_grid_forces", "mpm_update_particle_velocities", "mpm_synchronize"):
@@ -222,6 +223,11 @@ class Sim:
 
     def render_buffers_async(self, xyzs_pinned_ptr, n, size=0.02):
         _ck(self.L.mpm_download_render_buffers_async(self.h, int(n), C.c_void_p(xyzs_pinned_ptr), size))
+
+    def write_render_buffers_device(self, d_xyzs_ptr, d_rgba_ptr=None, n=None, size=0.02):
+        """Instance buffers straight into caller-owned device memory (mapped GL buffers, torch tensors ...)."""
+        _ck(self.L.mpm_write_render_buffers_device(self.h, int(self.n if n is None else n), C.c_void_p(d_xyzs_ptr),
+                                                   C.c_void_p(d_rgba_ptr) if d_rgba_ptr else None, size))
 
     def wait_render_buffers(self):
         _ck(self.L.mpm_wait_render_buffers(self.h))

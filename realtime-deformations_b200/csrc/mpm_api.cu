@@ -416,6 +416,21 @@ int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char*
     return MPM_OK;
 }
 
+int mpm_write_render_buffers_device(mpm_t* s, int64_t n, void* d_xyzs, void* d_rgba, float size) {
+    NEED(s);
+    const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+    if (!slab && n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
+    if (slab && (n < 0 || n > s->capacity)) return fail(MPM_ERR_INVALID, "n exceeds the slab capacity");
+    if (n == 0) return MPM_OK;
+    if (d_xyzs) {
+        if (slab) k_render_slots<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), (float4*)d_xyzs, s->dc, size, (int)n);
+        else k_render<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), (float4*)d_xyzs, s->dc, size);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    }
+    if (d_rgba) CK(cudaMemsetAsync(d_rgba, 255, (size_t)n * 4, s->stream));     // initializeParticles: r = g = b = a = 255 (cpp:48-51)
+    return MPM_OK;
+}
+
 int mpm_download_render_buffers_async(mpm_t* s, int64_t n, float* xyzs, float size) {
     NEED(s);
     if (!xyzs || n < 0) return fail(MPM_ERR_INVALID, "bad argument");

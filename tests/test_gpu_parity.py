@@ -252,6 +252,26 @@ def test_render_buffers_and_upload_order():
     assert np.array_equal(now, np.ascontiguousarray(sim.download()["pos"]).view(np.uint32))
 
 
+def test_render_buffers_written_to_device_memory():
+    """the instance buffers go straight into caller-owned device memory (what a mapped GL buffer is)."""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"          # (host emulation runs: "device" memory is host memory)
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
+    sim, cols, nc = sim_from_scene(sc)
+    sim.substep(float(sc["dt"]), cols, nc, 3)
+    d_xyzs = torch.full((sc["n"], 4), -7.0, dtype=torch.float32, device=dev)
+    d_rgba = torch.zeros((sc["n"], 4), dtype=torch.uint8, device=dev)
+    sim.write_render_buffers_device(d_xyzs.data_ptr(), d_rgba.data_ptr(), size=0.03)
+    sim.synchronize()
+    xyzs, rgba = sim.render_buffers(size=0.03)
+    assert np.array_equal(d_xyzs.cpu().numpy().view(np.uint32), xyzs.view(np.uint32)) and np.array_equal(d_rgba.cpu().numpy(), rgba)
+    sim.write_render_buffers_device(d_xyzs.data_ptr(), None, size=0.01)       # rgba is optional
+    sim.synchronize()
+    assert (d_xyzs[:, 3].cpu().numpy() == np.float32(0.01)).all()
+    with pytest.raises(mpm_b200.capi.MpmError):
+        sim.write_render_buffers_device(d_xyzs.data_ptr(), None, n=sc["n"] + 1)
+
+
 def test_error_paths():
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
     sim, cols, nc = sim_from_scene(sc)
