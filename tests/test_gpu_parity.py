@@ -261,6 +261,8 @@ def test_render_buffers_written_to_device_memory():
     sim.substep(float(sc["dt"]), cols, nc, 3)
     d_xyzs = torch.full((sc["n"], 4), -7.0, dtype=torch.float32, device=dev)
     d_rgba = torch.zeros((sc["n"], 4), dtype=torch.uint8, device=dev)
+    if dev == "cuda":
+        torch.cuda.synchronize()          # torch's fill kernels run on torch's stream, the library writes on its own
     sim.write_render_buffers_device(d_xyzs.data_ptr(), d_rgba.data_ptr(), size=0.03)
     sim.synchronize()
     xyzs, rgba = sim.render_buffers(size=0.03)
