@@ -32,6 +32,28 @@ def make_scene(i_range):
 
 
 n_layers = (grid + 3) // 4
+if balanced == 2:
+    # failure path: migration messages far too small for what crosses the slab boundaries -> the library flags the overflow,
+    # the next collective count check must raise on EVERY rank in the same substep (nobody is left waiting in an exchange)
+    multi.migrate_capacity_for = lambda n_local: 4
+    lo, hi = multi.slab_layers(n_layers, world)[rank]
+    r = multi.SlabRunner(grid, n, rank, world, torch, scene=make_scene((4 * lo + 1, 4 * hi + 1)), device="cpu")
+    r.sync_every = 4
+    caught_at = -1
+    try:
+        for k in range(steps):
+            r.substep()
+    except mpm_b200.capi.MpmError as exc:
+        caught_at = r.steps_done
+        print(f"rank {rank} raised at substep {caught_at}: {exc}", flush=True)
+    got = [None] * world
+    dist.all_gather_object(got, caught_at)
+    if rank == 0:
+        print("substep of the error per rank:", got)
+        print("OVERFLOW_HANDLED" if (min(got) > 0 and len(set(got)) == 1) else "OVERFLOW_NOT_HANDLED")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 if balanced:      # the bench's configuration: partition balanced by particle count, each rank generates its own cells
     r = multi.SlabRunner(grid, n, rank, world, torch, device="cpu")
 else:

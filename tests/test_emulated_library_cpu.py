@@ -79,6 +79,16 @@ def test_slab_protocol_with_the_real_library_over_gloo(emu_lib, world, balanced,
     assert "unique ids 16384" in r.stdout
 
 
+def test_migration_overflow_stops_every_rank_together(emu_lib):
+    """Failure path of the slab protocol with the real library: migration messages too small -> the library flags the
+    overflow, and the collective check raises on all ranks in the same substep (no rank is left waiting)."""
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "3", "--master-addr", "127.0.0.1",
+                        "--master-port", "29733", os.path.join(ROOT, "tests", "emu", "multi_check_emulated.py"), "64", "16384", "12", "2"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "OVERFLOW_HANDLED" in r.stdout, r.stdout[-4000:]
+
+
 @pytest.mark.skipif(os.environ.get("MPM_EMU_FULL") != "1", reason="the whole emulated suite takes ~5 min: MPM_EMU_FULL=1")
 def test_whole_gpu_suite_on_emulated_library(emu_lib):
     r = _run_gpu_suite(emu_lib, "test_", experimental=True, timeout=3400)
