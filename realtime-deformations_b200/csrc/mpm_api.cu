@@ -113,7 +113,9 @@ static void fill_consts(mpm_sim* s) {
     for (int a = 0; a < 3; ++a) c.g[a] = p.gravity[a];
     c.pos_lo = (float)(3 * p.h);                                                                     // cpp:383
     c.pos_hi[0] = (float)((s->gd.I - 3) * p.h); c.pos_hi[1] = (float)((s->gd.J - 3) * p.h); c.pos_hi[2] = (float)((s->gd.K - 3) * p.h);
-    c.inv_h3 = 1.0f / (p.h * p.h * p.h);
+    // P2G accumulation loop: rotated record walk (see k_p2g_tile). On by default; MPM_B200_P2G_ROTATE=0 restores the
+    // aligned walk of the round-1 measurements for A/B timing.
+    { const char* r = getenv("MPM_B200_P2G_ROTATE"); c.p2g_rotate = (r && atoi(r) == 0) ? 0 : 1; }
     c.pd.h = p.h; c.pd.rh = 1.0f / p.h;
     // the fast quotient is validated (validate_pos_div) on [2h, (max dim + 2) h]: every position whose particle is not
     // parked anyway lies in there (cell >= 2), see particle_key

@@ -33,7 +33,7 @@ struct SimConst {
     float h, dinv, E, nu, xi, clamp_lo, clamp_hi, friction;
     float g[3];
     float pos_lo, pos_hi[3];   // clampPosition bounds (cpp:381-388)
-    float inv_h3;              // unused by bit-faithful paths
+    int p2g_rotate;            // k_p2g_tile: start each cell's record walk at a different record (bank-conflict fix), 0 = off
     PosDiv pd;                 // pos / h
 };
 

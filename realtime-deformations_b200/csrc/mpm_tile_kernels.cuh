@@ -24,8 +24,14 @@ namespace mpm {
 
 #ifndef MPM_HOST_EMU
 #define MPM_DYN_SMEM(name, al) extern __shared__ __align__(al) unsigned char name[]
+#define MPM_SMEM_PROBE(site, key, ptr, bytes)          /* nothing in the product build */
+#define MPM_SMEM_EPOCH()
 #else
 #define MPM_DYN_SMEM(name, al) unsigned char* name = emu_dyn_smem()
+// tests/emu only: records which shared-memory words the lanes of a warp touch in one instruction (site, key = loop
+// iteration) so that the emulator can count wavefronts under a bank model
+#define MPM_SMEM_PROBE(site, key, ptr, bytes) emu::smem_probe(site, key, ptr, bytes)
+#define MPM_SMEM_EPOCH() emu::smem_epoch()
 #endif
 
 // packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
@@ -160,6 +166,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         const int n_chunks = (cnt + P2G_CH - 1) / P2G_CH;
         for (int ck = 0; ck < n_chunks; ++ck) {
             const int nch = (cnt - ck + n_chunks - 1) / n_chunks;          // slots ck, ck+n_chunks, ...
+            MPM_SMEM_EPOCH();
             if (ck > 0) {
                 if (t < 64) S.cell_cnt[t] = 0;
                 __syncthreads();
@@ -181,6 +188,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                         axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
                     }
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
+                    MPM_SMEM_PROBE(1, u, &S.u.c.wx[q], 16); MPM_SMEM_PROBE(2, u, &S.u.c.hA8[q], 4); MPM_SMEM_PROBE(3, u, &S.u.c.lc[q], 1);
                     S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
                     S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
                     S.u.c.wz[q] = make_float4(wz[0], wz[1], wz[2], wz[3]);
@@ -211,7 +219,11 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
-                if (q < nch) S.u.c.order[atomicAdd(&S.cell_cursor[S.u.c.lc[q]], 1)] = (unsigned short)q;
+                if (q < nch) {
+                    const int slot = atomicAdd(&S.cell_cursor[S.u.c.lc[q]], 1);
+                    MPM_SMEM_PROBE(5, u, &S.u.c.order[slot], 2);
+                    S.u.c.order[slot] = (unsigned short)q;
+                }
             }
             __syncthreads();
             // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
@@ -219,13 +231,30 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
-                if (q < nch) sorted_ids[start + ck + q * n_chunks] = S.u.c.gid[S.u.c.order[q]];
+                if (q < nch) {
+                    MPM_SMEM_PROBE(6, u, &S.u.c.gid[S.u.c.order[q]], 4);
+                    sorted_ids[start + ck + q * n_chunks] = S.u.c.gid[S.u.c.order[q]];
+                }
             }
             // ---- phase 1: register accumulation over the particles of my cell ----
+            // The 8 cells of a warp read 8 different records per iteration; a record's 16-byte bank group is its slot
+            // mod 8. Once the ids are cell-ordered (after the first substep) a cell's records sit in consecutive slots, and
+            // in an 8-particles-per-cell scene every cell's run starts at a multiple of 8: walking all runs from their
+            // first record puts the 8 reads of EVERY iteration into the same bank group (8 wavefronts per LDS instead of
+            // 1-2; 2.4 k of the 2.9 k bank-conflict wavefronts per block ncu counted at 64 Mi, profiles/r1_analysis.md).
+            // So cell c starts its (cyclic) walk at record c mod 8: with runs of 8 the reads of an iteration then hit 8
+            // different bank groups, and ragged runs are no worse off than before. Only the summation order changes.
             const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
+            int i = i0;
+            if (sc.p2g_rotate && i1 - i0 > 1) i += (my_cell & 7) % (i1 - i0);
 #pragma unroll 1
-            for (int i = i0; i < i1; ++i) {
+            for (int k = 0; k < i1 - i0; ++k) {
+                MPM_SMEM_PROBE(10, k, &S.u.c.order[i], 2);
                 const int pi = S.u.c.order[i];
+                i = (i + 1 == i1) ? i0 : i + 1;
+                MPM_SMEM_PROBE(11, k, &reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a], 4);
+                MPM_SMEM_PROBE(12, k, &S.u.c.wy[pi], 16); MPM_SMEM_PROBE(13, k, &S.u.c.wz[pi], 16); MPM_SMEM_PROBE(14, k, &S.u.c.qc[pi], 16);
+                MPM_SMEM_PROBE(15, k, &S.u.c.hA0[pi], 16); MPM_SMEM_PROBE(16, k, &S.u.c.hA1[pi], 16); MPM_SMEM_PROBE(17, k, &S.u.c.hA8[pi], 4);
                 const float wxa = reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a];
                 const float4 wy = S.u.c.wy[pi], wz = S.u.c.wz[pi], qc = S.u.c.qc[pi], h0 = S.u.c.hA0[pi], h1 = S.u.c.hA1[pi];
                 const float h8 = S.u.c.hA8[pi];
@@ -296,8 +325,12 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         }
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
+            MPM_SMEM_PROBE(20, bb, &S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz], 16);
             S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz] = s0[bb];
-            if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz + 4] = s1[bb];
+            if (my_cz < 3) {
+                MPM_SMEM_PROBE(21, bb, &S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz + 4], 16);
+                S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz + 4] = s1[bb];
+            }
         }
         if (t == 0) { S.work = wk_reg; w_ticket = atomicAdd(&dc->work_a, 1); }
         __syncthreads();
@@ -315,6 +348,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int cx = max(0, ni - 3); cx <= min(3, ni); ++cx)
                 for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy) {
+                    MPM_SMEM_PROBE(30, ((n / P2G_T) * 4 + (cx - max(0, ni - 3))) * 4 + (cy - max(0, nj - 3)), &S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk], 16);
                     const float4 v = S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk];
                     sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                 }

@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <tuple>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -113,6 +115,52 @@ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
     note_progress();
 }
 
+// ---- shared-memory wavefront model -------------------------------------------------------------------------------
+// The kernels mark shared-memory instructions with MPM_SMEM_PROBE(site, key, ptr, bytes) (a no-op in the nvcc build). With
+// EMU_SMEM_PROFILE set (or SmemProbe::on), the emulator groups the lanes of a warp that execute the same (site, key) in the
+// same epoch -- the fibers run one after the other, so the grouping is by key, not by time -- and counts the wavefronts that
+// request costs under this bank model: 32 banks of 4 bytes; a request is served in phases of 32 lanes (<= 4-byte accesses)
+// or 16 lanes (8- and 16-byte accesses); a phase costs max over banks of the number of DISTINCT words it needs from that
+// bank (same word = broadcast). Calibration: ncu counts 2.01 wavefronts per LDS.128 and no bank conflicts for the gather
+// kernel at 64 Mi particles, 8 per cell (lanes of a half-warp read 2 different 16-byte nodes), which this model reproduces;
+// a strict quarter-warp model would give 4.
+struct SmemProbe {
+    struct Req { int lane; long long off; int bytes; };
+    struct Site { long long requests = 0, wavefronts = 0, lanes = 0; };
+    bool on = std::getenv("EMU_SMEM_PROFILE") != nullptr;
+    std::map<std::tuple<int, int, long long, int>, std::vector<Req>> open;     // (warp, site, key, epoch) of the running CTA
+    std::map<int, Site> sites;
+    std::vector<int> epoch;                                                     // per thread of the running CTA
+    static int wavefronts_of(const std::vector<Req>& rq) {
+        if (rq.empty()) return 0;
+        const int per_phase = rq[0].bytes > 4 ? 16 : 32;
+        int total = 0;
+        for (int l0 = 0; l0 < 32; l0 += per_phase) {
+            std::vector<long long> words;
+            for (const Req& r : rq)
+                if (r.lane >= l0 && r.lane < l0 + per_phase)
+                    for (long long w = r.off / 4; w <= (r.off + r.bytes - 1) / 4; ++w) words.push_back(w);
+            std::sort(words.begin(), words.end());
+            words.erase(std::unique(words.begin(), words.end()), words.end());
+            int per_bank[32] = { 0 }, mx = 0;
+            for (long long w : words) mx = std::max(mx, ++per_bank[(int)(w & 31)]);
+            total += mx;
+        }
+        return total;
+    }
+    void flush() {
+        for (auto& kv : open) {
+            Site& st = sites[std::get<1>(kv.first)];
+            st.requests++; st.lanes += (long long)kv.second.size(); st.wavefronts += wavefronts_of(kv.second);
+        }
+        open.clear();
+    }
+    void reset() { open.clear(); sites.clear(); }
+};
+inline SmemProbe& smem_probe_state() { static thread_local SmemProbe s; return s; }
+void smem_probe(int site, long long key, const void* p, int bytes);
+void smem_epoch();
+
 // run `body` as a grid of CTAs, one CTA at a time, `threads` OS threads per CTA
 inline void launch(unsigned grid, unsigned threads, size_t smem_bytes, const std::function<void()>& body, const char* name = "");
 
@@ -156,6 +204,7 @@ struct Sched {
     void* main_sp = nullptr;
     int cur = -1, live = 0;
     bool progress = false;
+    bool lane_order = false;            // resume the fibers in thread order instead of a random order (used by the bank-model profile)
     Cta* c = nullptr;
     const std::function<void()>* body = nullptr;
     Idx block, bdim, gdim;
@@ -191,6 +240,8 @@ struct Sched {
         while (live > 0) {
             progress = false;
             // a fresh pseudo-random resume order every round (xorshift, Fisher-Yates)
+            if (lane_order) std::sort(order.begin(), order.end());     // hardware-like: same-address shared atomics of a warp are served in lane order
+            else
             for (int i = threads - 1; i > 0; --i) {
                 rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
                 std::swap(order[i], order[(int)(rng % (unsigned long long)(i + 1))]);
@@ -249,6 +300,7 @@ inline void emu::launch(unsigned grid, unsigned threads, size_t smem_bytes, cons
         c.slot.assign(threads, 0);
         c.smem.assign(smem_bytes + 256, 0xcd);          // poison: uninitialised reads show up as garbage
         sched().run_cta(&c, (int)threads, Idx{ b, 0, 0 }, Idx{ threads, 1, 1 }, Idx{ grid, 1, 1 }, body, name);
+        if (smem_probe_state().on) { smem_probe_state().flush(); smem_probe_state().epoch.clear(); }
     }
 }
 
@@ -258,6 +310,21 @@ template <class F> inline cudaError_t emu_func_set_attribute(F, cudaFuncAttribut
 inline unsigned char* emu_dyn_smem() {
     unsigned char* p = emu::cta->smem.data();
     return p + ((128 - ((uintptr_t)p & 127)) & 127);
+}
+
+inline void emu::smem_probe(int site, long long key, const void* p, int bytes) {
+    SmemProbe& s = smem_probe_state();
+    if (!s.on) return;
+    const long long off = (const unsigned char*)p - emu_dyn_smem();
+    if (off < 0 || off + bytes > (long long)cta->smem.size()) die("smem probe: address outside the CTA's dynamic shared memory");
+    if ((int)s.epoch.size() < cta->nthreads) s.epoch.assign(cta->nthreads, 0);
+    s.open[std::make_tuple(tid >> 5, site, key, s.epoch[tid])].push_back(SmemProbe::Req{ tid & 31, off, bytes });
+}
+inline void emu::smem_epoch() {
+    SmemProbe& s = smem_probe_state();
+    if (!s.on) return;
+    if ((int)s.epoch.size() < cta->nthreads) s.epoch.assign(cta->nthreads, 0);
+    ++s.epoch[tid];
 }
 
 // ---- synchronisation and warp collectives -------------------------------------------------------------------------

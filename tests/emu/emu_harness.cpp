@@ -67,7 +67,7 @@ static void build(Host& H, int dim, unsigned seed, bool fast_div) {
     c.clamp_lo = (float)(1.0 - 2.5e-2); c.clamp_hi = (float)(1.0 + 5e-3); c.friction = 0.5f;
     c.g[0] = 0; c.g[1] = -9.8f; c.g[2] = 0;
     c.pos_lo = 3 * h; c.pos_hi[0] = c.pos_hi[1] = c.pos_hi[2] = (dim - 3) * h;
-    c.inv_h3 = 1.0f / (h * h * h);
+    c.p2g_rotate = 1;
     c.pd.h = h; c.pd.rh = 1.0f / h; c.pd.lo = 2.0f * h; c.pd.hi = (float)(dim + 2) * h; c.pd.fast = fast_div ? 1 : 0;
 
     const int n_sparse = 900;
@@ -327,8 +327,94 @@ static void check_flow(unsigned seed) {
     check(moved && stressed && plastic, "flow scene exercises collision, stress and plastic clamping");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory wavefronts of P2G under the emulator's bank model (cuda_emu.h: SmemProbe), on the layout the benchmark
+// scene has: 8 particles in every cell, ids cell-ordered by the previous substep's P2G and re-sorted by the gather.
+// Prints wavefronts per 512-particle block for every probed instruction, with the aligned record walk (the kernel
+// measured in round 1) and with the rotated walk, and checks the model against the ncu count of the aligned walk.
+// ---------------------------------------------------------------------------------------------------------------
+struct SmemRun { std::map<int, emu::SmemProbe::Site> sites; size_t blocks = 0; };
+static SmemRun smem_profile_run(unsigned seed, int rotate) {
+    const float dt = 1e-5f;
+    Host H;
+    build_flow_scene(H, seed);
+    H.sc.p2g_rotate = rotate;
+    ColliderSet cs;
+    std::memset(&cs, 0, sizeof cs);
+    int cur = 0;
+    std::vector<int> blocks(H.gd.n_gblocks);
+    for (int b = 0; b < H.gd.n_gblocks; ++b) blocks[b] = b;
+    emu::SmemProbe& pr = emu::smem_probe_state();
+    SmemRun out;
+    for (int step = 0; step < 3; ++step) {
+        host_bin(H, cur);
+        H.dc.n_active_gblocks = H.gd.n_gblocks;
+        std::vector<int> ids = H.ids0;
+        std::fill(H.grid.begin(), H.grid.end(), make_float4(0, 0, 0, 0));
+        Planes C = H.planes(cur), N = H.planes(cur ^ 1);
+        H.dc.work_a = 0; H.dc.work_b = 0;
+        pr.reset();
+        pr.on = step == 2;               // steady state: the ids were cell-ordered by two earlier P2G passes
+        // the lanes of a warp reach the counting sort's shared atomics together and the 8 particles of a cell are 8
+        // consecutive lanes: served in lane order (as the hardware's measured conflict count implies, see below) every
+        // cell keeps its particles in the same relative order -> the runs stay aligned
+        emu::sched().lane_order = true;
+        emu::launch(3, P2G_T, sizeof(P2GSmem), [&] {
+            k_p2g_tile<P2G_FUSED, false, false>(C, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt, C);
+        });
+        pr.on = false;
+        if (step == 2) { out.sites = pr.sites; out.blocks = H.work.size(); }
+        emu::launch(3, 256, 0, [&] { k_grid_update<GU_NORMALIZE | GU_GRAVITY>(blocks.data(), &H.dc, H.grid.data(), nullptr, H.gd, H.sc, dt, cs, 0); });
+        emu::launch((H.n + 255) / 256, 256, 0, [&] { k_fupdate<true>(C, N, ids.data(), &H.dc, H.sc, dt); });
+        emu::launch(2, G2P_T, sizeof(G2PSmem), [&] {
+            k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, false>(C, N, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt);
+        });
+        cur ^= 1;
+    }
+    pr.reset();
+    emu::sched().lane_order = false;
+    return out;
+}
+static int smem_profile(unsigned seed) {
+    static const struct { int site; const char* what; int mult; } names[] = {
+        { 1, "derive: STS.128 record part (x6)", 6 }, { 2, "derive: STS.32 hA8 / gid (x2)", 2 }, { 3, "derive: STS.U8 cell", 1 },
+        { 5, "sort: STS.U16 order", 1 }, { 6, "sort: LDS.32 gid[order]", 1 },
+        { 10, "phase 1: LDS.U16 order[i]", 1 }, { 11, "phase 1: LDS.32 wx[a]", 1 }, { 12, "phase 1: LDS.128 wy", 1 }, { 13, "phase 1: LDS.128 wz", 1 },
+        { 14, "phase 1: LDS.128 qc", 1 }, { 15, "phase 1: LDS.128 hA0", 1 }, { 16, "phase 1: LDS.128 hA1", 1 }, { 17, "phase 1: LDS.32 hA8", 1 },
+        { 20, "phase 2a: STS.128 t1 (k = cz)", 1 }, { 21, "phase 2a: STS.128 t1 (k = cz+4)", 1 }, { 30, "phase 2b: LDS.128 t1", 1 } };
+    const SmemRun a = smem_profile_run(seed, 0), r = smem_profile_run(seed, 1);
+    std::printf("P2G shared-memory wavefronts per 512-particle block (8 per cell, %zu blocks; model: cuda_emu.h SmemProbe)\n", a.blocks);
+    std::printf("  %-36s %10s %12s %12s\n", "instruction", "requests", "aligned walk", "rotated walk");
+    double ta = 0, tr = 0, p1a = 0, p1r = 0, ideal_p1 = 0;
+    for (const auto& nm : names) {
+        const auto ia = a.sites.find(nm.site), ir = r.sites.find(nm.site);
+        if (ia == a.sites.end() || ir == r.sites.end()) continue;
+        const double req = (double)ia->second.requests * nm.mult / a.blocks, wa = (double)ia->second.wavefronts * nm.mult / a.blocks,
+                     wr = (double)ir->second.wavefronts * nm.mult / r.blocks;
+        std::printf("  %-36s %10.1f %12.1f %12.1f\n", nm.what, req, wa, wr);
+        ta += wa; tr += wr;
+        if (nm.site >= 10 && nm.site <= 17) { p1a += wa; p1r += wr; ideal_p1 += req * (nm.site >= 12 && nm.site <= 16 ? 2 : 1); }
+    }
+    std::printf("  %-36s %10s %12.1f %12.1f\n", "sum of the probed instructions", "", ta, tr);
+    std::printf("  phase 1 alone: %.0f -> %.0f wavefronts per block (conflict-free: %.0f)\n", p1a, p1r, ideal_p1);
+    // ncu at 64 Mi particles (profiles/ncu_r1_64M_top_kernels.csv): 703.3 M shared wavefronts, 382.7 M of them bank conflicts,
+    // 131072 blocks -> 5366 and 2920 per block. The probed instructions of the aligned walk must account for most of both.
+    const double ncu_wf = 703320466.0 / 131072.0, ncu_conf = 382739298.0 / 131072.0;
+    std::printf("  ncu, aligned walk, per block: %.0f wavefronts, %.0f of them bank conflicts; model: %.0f wavefronts, %.0f above conflict-free in phase 1\n",
+                ncu_wf, ncu_conf, ta, p1a - ideal_p1);
+    check(p1a - ideal_p1 > 0.7 * ncu_conf && p1a - ideal_p1 < 1.1 * ncu_conf, "bank model: the aligned walk's phase-1 conflicts account for 70-110 % of ncu's bank-conflict wavefronts");
+    check(p1r <= 1.05 * ideal_p1, "rotated walk: phase 1 is conflict-free on the 8-per-cell layout");
+    check(tr < 0.62 * ta, "rotated walk: >= 38 % fewer shared-memory wavefronts per block");
+    return failures;
+}
+
 int main(int argc, char** argv) {
     const unsigned seed = argc > 1 ? (unsigned)std::atoi(argv[1]) : 1u;
+    if (argc > 3 && std::strcmp(argv[3], "smem") == 0) {
+        const int f = smem_profile(seed);
+        std::printf("%s (%d failures)\n", f ? "EMULATION CHECKS FAILED" : "all emulation checks passed", f);
+        return f ? 1 : 0;
+    }
     const bool fast_div = argc > 2 ? std::atoi(argv[2]) != 0 : true;
     const float dt = 1e-5f;
     Host H;

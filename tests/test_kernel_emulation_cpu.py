@@ -55,6 +55,14 @@ def test_kernel_variants_agree_under_host_emulation(harness, seed, fast_div):
     assert r.stdout.count("\nok  ") >= 20          # every check ran
 
 
+def test_p2g_shared_memory_wavefront_model(harness):
+    """Bank model of the emulator on the benchmark layout (8 particles in every cell): the aligned record walk measured
+    in round 1 reproduces most of ncu's bank-conflict count, the rotated walk (the default) is conflict-free in phase 1."""
+    r = subprocess.run([harness, "1", "1", "smem"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "all emulation checks passed" in r.stdout, r.stdout[-4000:]
+    assert r.stdout.count("\nok  ") == 3
+
+
 def test_product_cannot_reach_the_emulator():
     """The shim and harness live under tests/ only; the package and the C ABI never mention them."""
     for base in (os.path.join(ROOT, "realtime-deformations_b200"), os.path.join(ROOT, "include"), os.path.join(ROOT, "adapter")):
