@@ -470,6 +470,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
         if (w >= n_work) break;
         b = __shfl_sync(0xffffffffu, b, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
         const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
+        MPM_SMEM_EPOCH();
         if (LINEAR) {
             // lane 0 has armed the barrier with the byte count (ordered before the copies by the shuffles above);
             // every lane issues 4 of the 128 row copies: row = lane & 15 of grid blocks d = (lane >> 4) + 2m
@@ -568,6 +569,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                             const int oab = offx[a] + offy[bb];
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
+                                MPM_SMEM_PROBE(40, (base / 32) * 64 + (a * 4 + bb) * 4 + cc, LINEAR ? &lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : &tile[oab + offz[cc]], 16);
                                 const float4 n = LINEAR ? lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : tile[oab + offz[cc]];
                                 s0[0] += wz[cc] * n.y; s0[1] += wz[cc] * n.z; s0[2] += wz[cc] * n.w;
                                 s1[0] += wzd[cc] * n.y; s1[1] += wzd[cc] * n.z; s1[2] += wzd[cc] * n.w;

@@ -333,7 +333,7 @@ static void check_flow(unsigned seed) {
 // Prints wavefronts per 512-particle block for every probed instruction, with the aligned record walk (the kernel
 // measured in round 1) and with the rotated walk, and checks the model against the ncu count of the aligned walk.
 // ---------------------------------------------------------------------------------------------------------------
-struct SmemRun { std::map<int, emu::SmemProbe::Site> sites; size_t blocks = 0; };
+struct SmemRun { std::map<int, emu::SmemProbe::Site> sites; emu::SmemProbe::Site gather; size_t blocks = 0; };
 static SmemRun smem_profile_run(unsigned seed, int rotate) {
     const float dt = 1e-5f;
     Host H;
@@ -366,9 +366,13 @@ static SmemRun smem_profile_run(unsigned seed, int rotate) {
         if (step == 2) { out.sites = pr.sites; out.blocks = H.work.size(); }
         emu::launch(3, 256, 0, [&] { k_grid_update<GU_NORMALIZE | GU_GRAVITY>(blocks.data(), &H.dc, H.grid.data(), nullptr, H.gd, H.sc, dt, cs, 0); });
         emu::launch((H.n + 255) / 256, 256, 0, [&] { k_fupdate<true>(C, N, ids.data(), &H.dc, H.sc, dt); });
+        pr.reset();
+        pr.on = step == 2;
         emu::launch(2, G2P_T, sizeof(G2PSmem), [&] {
             k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, false>(C, N, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt);
         });
+        pr.on = false;
+        if (step == 2) out.gather = pr.sites[40];
         cur ^= 1;
     }
     pr.reset();
@@ -402,6 +406,10 @@ static int smem_profile(unsigned seed) {
     const double ncu_wf = 703320466.0 / 131072.0, ncu_conf = 382739298.0 / 131072.0;
     std::printf("  ncu, aligned walk, per block: %.0f wavefronts, %.0f of them bank conflicts; model: %.0f wavefronts, %.0f above conflict-free in phase 1\n",
                 ncu_wf, ncu_conf, ta, p1a - ideal_p1);
+    // second calibration point: the gather's tile reads. ncu: 270 289 023 wavefronts for 64 Mi particles x 64 LDS.128 / 32 lanes
+    const double g_model = (double)r.gather.wavefronts / (double)r.gather.requests, g_ncu = 270289023.0 / (67108864.0 * 64.0 / 32.0);
+    std::printf("  gather LDS.128 of the tile: model %.2f wavefronts per request, ncu %.2f\n", g_model, g_ncu);
+    check(std::fabs(g_model - g_ncu) < 0.15, "bank model: wavefronts per tile read of the gather match ncu");
     check(p1a - ideal_p1 > 0.7 * ncu_conf && p1a - ideal_p1 < 1.1 * ncu_conf, "bank model: the aligned walk's phase-1 conflicts account for 70-110 % of ncu's bank-conflict wavefronts");
     check(p1r <= 1.05 * ideal_p1, "rotated walk: phase 1 is conflict-free on the 8-per-cell layout");
     check(tr < 0.62 * ta, "rotated walk: >= 38 % fewer shared-memory wavefronts per block");
