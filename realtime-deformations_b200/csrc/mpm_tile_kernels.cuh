@@ -180,13 +180,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     float4 xm; float mch, a0[3], A[9];
                     p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
                     float wx[4], wy[4], wz[4];
-                    int cx, cy, cz;
-                    if (PACKED) {
-                        cx = cell_and_weights(xm.x, sc.pd, wx); cy = cell_and_weights(xm.y, sc.pd, wy); cz = cell_and_weights(xm.z, sc.pd, wz);
-                    } else {
-                        cx = cell_of(xm.x, sc.pd); cy = cell_of(xm.y, sc.pd); cz = cell_of(xm.z, sc.pd);
-                        axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
-                    }
+                    // cell index and weights from ONE pos/h quotient per axis (the same operations as cell_of + axis_weights,
+                    // which form the quotient twice: identical bits, 68 fewer instructions per particle)
+                    const int cx = cell_and_weights(xm.x, sc.pd, wx), cy = cell_and_weights(xm.y, sc.pd, wy), cz = cell_and_weights(xm.z, sc.pd, wz);
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
                     MPM_SMEM_PROBE(1, u, &S.u.c.wx[q], 16); MPM_SMEM_PROBE(2, u, &S.u.c.hA8[q], 4); MPM_SMEM_PROBE(3, u, &S.u.c.lc[q], 1);
                     S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
@@ -502,13 +498,8 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
                 {
                     float wx[4], wy[4], wz[4];
-                    int cx, cy, cz;
-                    if (PACKED) {
-                        cx = cell_and_weights(r.x[0], sc.pd, wx); cy = cell_and_weights(r.x[1], sc.pd, wy); cz = cell_and_weights(r.x[2], sc.pd, wz);
-                    } else {
-                        cx = cell_of(r.x[0], sc.pd); cy = cell_of(r.x[1], sc.pd); cz = cell_of(r.x[2], sc.pd);
-                        axis_weights(r.x[0], sc.pd, cx, wx); axis_weights(r.x[1], sc.pd, cy, wy); axis_weights(r.x[2], sc.pd, cz, wz);
-                    }
+                    // one pos/h quotient per axis feeds the cell index and the weights (same bits as cell_of + axis_weights)
+                    const int cx = cell_and_weights(r.x[0], sc.pd, wx), cy = cell_and_weights(r.x[1], sc.pd, wy), cz = cell_and_weights(r.x[2], sc.pd, wz);
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     int offx[4], offy[4], offz[4];
                     float wxd[4], wyd[4], wzd[4];

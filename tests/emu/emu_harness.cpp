@@ -429,6 +429,21 @@ int main(int argc, char** argv) {
     build(H, 24, seed, fast_div);
     std::printf("emulated scene: %d particles, %zu occupied particle blocks, seed %u, fast pos/h %d\n", H.n, H.work.size(), seed, (int)fast_div);
 
+    // ---------------- weights: one quotient per axis == cell_of + axis_weights ----------------
+    {
+        std::mt19937 g(seed * 31u + 5u);
+        bool same = true;
+        for (int i = 0; i < 2000000 && same; ++i) {
+            // inside the validated range of the fast quotient, just outside it, and far outside (exact-division fallback)
+            const float x = i % 16 == 0 ? frand(g, -1.0f, 3.0f * H.sc.pd.hi) : frand(g, H.sc.pd.lo * 0.9f, H.sc.pd.hi * 1.05f);
+            float w1[4], w2[4];
+            const int c1 = cell_and_weights(x, H.sc.pd, w1), c2 = cell_of(x, H.sc.pd);
+            axis_weights(x, H.sc.pd, c2, w2);
+            same = c1 == c2 && std::memcmp(w1, w2, sizeof w1) == 0;
+        }
+        check(same, "cell_and_weights == cell_of + axis_weights, bit for bit (2 M positions, fast and exact quotient)");
+    }
+
     // ---------------- P2G ----------------
     std::vector<int> ids_def, ids_pk, ids_fu, ids_pkfu, ids_base = H.ids0;
     std::vector<float4> g_def, g_pk, g_fu, g_pkfu, g_base(H.grid.size(), make_float4(0, 0, 0, 0));
