@@ -185,6 +185,8 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     g.lo = block_lo; g.hi = block_hi;
     const int64_t npb = (int64_t)(g.hi - g.lo) * g.npbj * g.npbk, ngb = (int64_t)(g.hi - g.lo + 1) * g.nbj * g.nbk;
     if (npb + 3 >= ((int64_t)1 << 31) / 64) return fail(MPM_ERR_INVALID, "grid too large");
+    if (g.hi - g.lo > PB_COORD_MAX || g.npbj > PB_COORD_MAX || g.npbk > PB_COORD_MAX)       // work items carry 10-bit block coordinates
+        return fail(MPM_ERR_INVALID, "grid too large: at most %d particle blocks (%d nodes) per axis and slab", PB_COORD_MAX, 4 * PB_COORD_MAX);
     g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
     fill_consts(s);
     s->capacity = std::max<int64_t>(capacity, 1);

@@ -57,6 +57,10 @@ struct DevCounters {
 
 enum { KEY_DEAD = -2 };
 
+// slab-local particle-block coordinates in one int (10 bits each; mpm_create refuses grids beyond 1024 blocks per axis)
+constexpr int PB_COORD_BITS = 10, PB_COORD_MAX = 1 << PB_COORD_BITS;
+__host__ __device__ inline int pack_block_coords(int pbi_local, int pbj, int pbk) { return (pbi_local << (2 * PB_COORD_BITS)) | (pbj << PB_COORD_BITS) | pbk; }
+
 struct ColliderSet { BoxCollider c[16]; };
 
 // exhaustive check of the pos/h shortcut: every fp32 bit pattern in [lo_bits, hi_bits] against the IEEE intrinsic
@@ -234,8 +238,10 @@ __global__ void k_scan_apply(const int* __restrict__ blk_count, int n, int n_rea
             if (i == n_real) dc->n_binned = ex.x;                 // start of the parked bucket
             if (i == n_real + 1) dc->n_sorted = ex.x;             // end of the parked bucket
             if (c[e] > 0 && i < n_real) {
-                pblock_list[ex.y] = make_int4(i, ex.x, c[e], 0);      // work item: (block id, first sorted rank, count)
                 const int pbk = i % gd.npbk, pbj = (i / gd.npbk) % gd.npbj, pbi = i / (gd.npbk * gd.npbj);
+                // work item: (block id, first sorted rank, count, slab-local block coordinates) -- the tile kernels read the
+                // coordinates instead of dividing the block id again in every thread of every block
+                pblock_list[ex.y] = make_int4(i, ex.x, c[e], pack_block_coords(pbi, pbj, pbk));
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
                     const int gb = ((pbi + (d >> 2)) * gd.nbj + pbj + ((d >> 1) & 1)) * gd.nbk + pbk + (d & 1);

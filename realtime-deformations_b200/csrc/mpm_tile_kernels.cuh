@@ -152,8 +152,8 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         if (t < 64) S.cell_cnt[t] = 0;
         __syncthreads();          // also: everyone has read S.work, and phase 2b of the previous block is done with t1
         if (wk.x < 0) break;
-        const int b = wk.x, start = wk.y, cnt = wk.z;
-        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;   // global block coords
+        const int start = wk.y, cnt = wk.z;
+        const int pbk = wk.w & (PB_COORD_MAX - 1), pbj = (wk.w >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (wk.w >> (2 * PB_COORD_BITS)) + gd.lo;   // global block coords
         float4 acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,13 +445,13 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
     __syncwarp();
     unsigned phase = 0;
     for (;;) {
-        int w = 0, b = 0, start = 0, cnt = 0;
+        int w = 0, bc = 0, start = 0, cnt = 0;
         if (lane == 0) {
             w = atomicAdd(&dc->work_b, 1);
             if (w < n_work) {
                 const int4 wk = pblock_list[w];
-                b = wk.x; start = wk.y; cnt = wk.z;
-                const int pbk0 = b % gd.npbk, pbj0 = (b / gd.npbk) % gd.npbj, pbi_l = b / (gd.npbk * gd.npbj);
+                bc = wk.w; start = wk.y; cnt = wk.z;
+                const int pbk0 = bc & (PB_COORD_MAX - 1), pbj0 = (bc >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi_l = bc >> (2 * PB_COORD_BITS);
                 mbar_expect_tx(bar, 8 * 1024);
                 if (!LINEAR) {
 #pragma unroll
@@ -464,8 +464,8 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
         }
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_work) break;
-        b = __shfl_sync(0xffffffffu, b, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
-        const int pbk = b % gd.npbk, pbj = (b / gd.npbk) % gd.npbj, pbi = b / (gd.npbk * gd.npbj) + gd.lo;
+        bc = __shfl_sync(0xffffffffu, bc, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        const int pbk = bc & (PB_COORD_MAX - 1), pbj = (bc >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (bc >> (2 * PB_COORD_BITS)) + gd.lo;
         MPM_SMEM_EPOCH();
         if (LINEAR) {
             // lane 0 has armed the barrier with the byte count (ordered before the copies by the shuffles above);

@@ -106,7 +106,7 @@ static void host_bin(Host& H, int bufi) {
     for (int q = 0; q < n; ++q) H.ids0[cur[key[q]]++] = q;
     H.work.clear();
     for (int b = gd.n_pblocks - 1; b >= 0; --b)            // any order is legal; use a different one than the device scan
-        if (count[b]) H.work.push_back(make_int4(b, start[b], count[b], 0));
+        if (count[b]) H.work.push_back(make_int4(b, start[b], count[b], pack_block_coords(b / (gd.npbk * gd.npbj), (b / gd.npbk) % gd.npbj, b % gd.npbk)));
     H.grid.assign((size_t)gd.n_gblocks * 64, make_float4(0, 0, 0, 0));
     std::memset(&H.dc, 0, sizeof H.dc);
     H.dc.n_slots = n; H.dc.n_binned = n; H.dc.n_sorted = n; H.dc.n_active_pblocks = (int)H.work.size();
