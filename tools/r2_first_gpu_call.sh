@@ -1,10 +1,24 @@
 #!/bin/bash
-# First GPU call of the next round: validate the experimental kernels prepared at the end of round 1 and A/B them.
-#   gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_call.sh'
+# First GPU call of the next round: confirm what was changed or prepared after round 1's GPU budget ran out.
+#   gpurun --timeout 1800 -- 'bash tools/r2_first_gpu_call.sh'
 # Everything is wrapped in `timeout`; outputs land in gpurun_out/.
 mkdir -p gpurun_out
+# 1. parity suite: default path (rotated P2G record walk, single-quotient weights, block coordinates in the work items)
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1
+echo "default gpu tests: exit $?" | tee -a gpurun_out/gpu_tests.log
+# 2. A/B of the rotated record walk (MPM_B200_P2G_ROTATE=0 restores the aligned walk measured in round 1)
+for rot in 0 1; do
+  MPM_B200_P2G_ROTATE=$rot timeout 300 python tools/perf_probe.py 512 67108864 10 slab 0:0 > gpurun_out/rotate_${rot}_64M.log 2>&1
+done
+# 3. shared-memory wavefronts / bank conflicts of P2G with and without the rotation (model: tests/emu smem profile)
+for rot in 0 1; do
+  MPM_B200_P2G_ROTATE=$rot timeout 400 ncu --clock-control none -k regex:k_p2g_tile -c 2 --csv \
+    --metrics gpu__time_duration.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \
+    --log-file gpurun_out/ncu_p2g_rotate_${rot}.csv python tools/profile_step.py 512 67108864 2 > gpurun_out/ncu_p2g_rotate_${rot}.log 2>&1
+done
+# 4. experimental kernels: parity, then A/B timing
 timeout 600 env MPM_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -x -q > gpurun_out/exp_tests.log 2>&1
 echo "experimental gpu tests: exit $?" | tee -a gpurun_out/exp_tests.log
 timeout 300 python tools/perf_probe.py 256 8388608 20 slab 0:0,0:2,0:3,0:4,2:0,3:0,4:4 > gpurun_out/ab_8M.log 2>&1
 timeout 480 python tools/perf_probe.py 512 67108864 10 slab 0:0,4:4,3:0,2:0,0:4 > gpurun_out/ab_64M.log 2>&1
-tail -n 8 gpurun_out/exp_tests.log gpurun_out/ab_8M.log gpurun_out/ab_64M.log
+tail -n 8 gpurun_out/gpu_tests.log gpurun_out/rotate_*_64M.log gpurun_out/exp_tests.log gpurun_out/ab_8M.log gpurun_out/ab_64M.log
