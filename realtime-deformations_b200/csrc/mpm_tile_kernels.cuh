@@ -4,7 +4,8 @@
 // P2G (k_p2g_tile):  no shared-memory float atomics at all (on sm_100a they are CAS loops, ATOMS.CAST.SPIN).
 //   chunk loop   : 256 particles at a time are loaded as coalesced float4 planes; each thread derives its
 //                  particle's 12 axis weights (fp64 polynomial, as the reference) and affine coefficients into smem,
-//                  and the chunk is counting-sorted by cell in smem (integer atomics only).
+//                  and the chunk is counting-sorted by cell in smem (one round of integer atomics: the count's return
+//                  value is the particle's rank inside its cell).
 //   phase 1      : thread (cell, x-slab a) walks the particles of ITS cell and accumulates the 16 stencil nodes
 //                  (a, b, c) x (mass, momentum) in 64 registers -> the cross-particle reduction happens in
 //                  registers, never between lanes.
@@ -71,13 +72,12 @@ struct P2GSmem {
             float hA8[P2G_CH];
             int gid[P2G_CH];
             unsigned short order[P2G_CH];
-            unsigned char lc[P2G_CH];
         } c;
         float4 t1[4][4][4][42];           // phase 2: z-folded partial sums [cx][cy][a][b*7 + k]; the a-stride is padded
                                           // from 28 to 42 float4 (= 2 mod 8 slots) so that a quarter-warp's stores
                                           // (a = 0..3, two consecutive k) land in 8 different 16-byte bank groups
     } u;
-    int cell_cnt[64], cell_start[65], cell_cursor[64];
+    int cell_cnt[64], cell_start[65];
     int4 work;
 };
 
@@ -172,6 +172,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 __syncthreads();
             }
             // ---- derive per-particle data (P2G_PPT particles per thread, loads of both issued back to back) ----
+            int cell_rank[P2G_PPT];          // cell (low 8 bits) and rank inside the cell: the counting atomic's return value
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
@@ -184,7 +185,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     // which form the quotient twice: identical bits, 68 fewer instructions per particle)
                     const int cx = cell_and_weights(xm.x, sc.pd, wx), cy = cell_and_weights(xm.y, sc.pd, wy), cz = cell_and_weights(xm.z, sc.pd, wz);
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
-                    MPM_SMEM_PROBE(1, u, &S.u.c.wx[q], 16); MPM_SMEM_PROBE(2, u, &S.u.c.hA8[q], 4); MPM_SMEM_PROBE(3, u, &S.u.c.lc[q], 1);
+                    MPM_SMEM_PROBE(1, u, &S.u.c.wx[q], 16); MPM_SMEM_PROBE(2, u, &S.u.c.hA8[q], 4);
                     S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
                     S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
                     S.u.c.wz[q] = make_float4(wz[0], wz[1], wz[2], wz[3]);
@@ -195,8 +196,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     S.u.c.hA8[q] = A[8] * sc.h;
                     S.u.c.gid[q] = gid;
                     const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
-                    S.u.c.lc[q] = (unsigned char)lc;
-                    atomicAdd(&S.cell_cnt[lc], 1);
+                    cell_rank[u] = lc | (atomicAdd(&S.cell_cnt[lc], 1) << 8);
                 }
             }
             __syncthreads();
@@ -208,15 +208,14 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += v; }
                 const int ex = inc - (c0 + c1);
                 S.cell_start[2 * t] = ex; S.cell_start[2 * t + 1] = ex + c0;
-                S.cell_cursor[2 * t] = ex; S.cell_cursor[2 * t + 1] = ex + c0;
                 if (t == 31) S.cell_start[64] = inc;
             }
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
-                if (q < nch) {
-                    const int slot = atomicAdd(&S.cell_cursor[S.u.c.lc[q]], 1);
+                if (q < nch) {           // sorted slot = start of my cell + my rank in it (no second round of atomics)
+                    const int slot = S.cell_start[cell_rank[u] & 255] + (cell_rank[u] >> 8);
                     MPM_SMEM_PROBE(5, u, &S.u.c.order[slot], 2);
                     S.u.c.order[slot] = (unsigned short)q;
                 }

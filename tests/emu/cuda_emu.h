@@ -49,12 +49,16 @@ namespace emu {
 
 void yield();                       // hand the OS thread to another fiber of the running CTA
 void note_progress();
+// Resume the fibers in thread order instead of a random order, and let the thread that completes a barrier wait for its
+// turn too: same-address shared atomics of a warp are then served in lane order, as on the hardware (used by the
+// bank-model profile; the differential tests keep the random order, which is what finds missing barriers).
+inline thread_local bool lane_order = false;
 struct Barrier {                    // n = live participants; a participant that exits stops counting (leave())
     int n = 0, arrived = 0;
     unsigned gen = 0;
     void wait() {
         const unsigned g = gen;
-        if (++arrived >= n) { arrived = 0; ++gen; note_progress(); return; }
+        if (++arrived >= n) { arrived = 0; ++gen; note_progress(); if (lane_order) yield(); return; }
         while (gen == g) yield();
     }
     void leave() {
@@ -204,7 +208,6 @@ struct Sched {
     void* main_sp = nullptr;
     int cur = -1, live = 0;
     bool progress = false;
-    bool lane_order = false;            // resume the fibers in thread order instead of a random order (used by the bank-model profile)
     Cta* c = nullptr;
     const std::function<void()>* body = nullptr;
     Idx block, bdim, gdim;
@@ -240,7 +243,7 @@ struct Sched {
         while (live > 0) {
             progress = false;
             // a fresh pseudo-random resume order every round (xorshift, Fisher-Yates)
-            if (lane_order) std::sort(order.begin(), order.end());     // hardware-like: same-address shared atomics of a warp are served in lane order
+            if (lane_order) std::sort(order.begin(), order.end());
             else
             for (int i = threads - 1; i > 0; --i) {
                 rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;

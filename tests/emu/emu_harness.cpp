@@ -358,7 +358,7 @@ static SmemRun smem_profile_run(unsigned seed, int rotate) {
         // the lanes of a warp reach the counting sort's shared atomics together and the 8 particles of a cell are 8
         // consecutive lanes: served in lane order (as the hardware's measured conflict count implies, see below) every
         // cell keeps its particles in the same relative order -> the runs stay aligned
-        emu::sched().lane_order = true;
+        emu::lane_order = true;
         emu::launch(3, P2G_T, sizeof(P2GSmem), [&] {
             k_p2g_tile<P2G_FUSED, false, false>(C, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt, C);
         });
@@ -376,12 +376,12 @@ static SmemRun smem_profile_run(unsigned seed, int rotate) {
         cur ^= 1;
     }
     pr.reset();
-    emu::sched().lane_order = false;
+    emu::lane_order = false;
     return out;
 }
 static int smem_profile(unsigned seed) {
     static const struct { int site; const char* what; int mult; } names[] = {
-        { 1, "derive: STS.128 record part (x6)", 6 }, { 2, "derive: STS.32 hA8 / gid (x2)", 2 }, { 3, "derive: STS.U8 cell", 1 },
+        { 1, "derive: STS.128 record part (x6)", 6 }, { 2, "derive: STS.32 hA8 / gid (x2)", 2 },
         { 5, "sort: STS.U16 order", 1 }, { 6, "sort: LDS.32 gid[order]", 1 },
         { 10, "phase 1: LDS.U16 order[i]", 1 }, { 11, "phase 1: LDS.32 wx[a]", 1 }, { 12, "phase 1: LDS.128 wy", 1 }, { 13, "phase 1: LDS.128 wz", 1 },
         { 14, "phase 1: LDS.128 qc", 1 }, { 15, "phase 1: LDS.128 hA0", 1 }, { 16, "phase 1: LDS.128 hA1", 1 }, { 17, "phase 1: LDS.32 hA8", 1 },
