@@ -411,6 +411,33 @@ def test_empty_handle_and_two_interleaved_handles():
     assert_traj_close(a.download_state35(), ref.download_state35(), 20, "handle advanced alone vs interleaved with another")
 
 
+def test_p2g_rotated_record_walk_on_eight_per_cell_slab(monkeypatch):
+    """The benchmark layout (8 particles in every cell of an axis-aligned slab): P2G's rotated record walk (default) and
+    the aligned walk (MPM_B200_P2G_ROTATE=0, the kernel measured in round 1) differ only in the summation order inside a
+    cell, and both follow the oracle."""
+    sc = mpm_b200.scenes.snow_slab(grid=32, n=8192)
+    o, ocols, onc = oracle_from_scene(sc)
+    of, _, _ = oracle_from_scene(sc, fma=True)
+    rot, cols, nc = sim_from_scene(sc)
+    monkeypatch.setenv("MPM_B200_P2G_ROTATE", "0")
+    ali, _, _ = sim_from_scene(sc)
+    monkeypatch.delenv("MPM_B200_P2G_ROTATE")
+    dt = float(sc["dt"])
+    # the first substeps order the ids by cell (the layout with the aligned runs of 8 records); then compare one P2G
+    rot.substep(dt, cols, nc, 3); ali.substep(dt, cols, nc, 3); o.substep(dt, ocols, onc, 3); of.substep(dt, ocols, onc, 3)
+    for sim in (rot, ali):
+        sim.rasterizeParticlesToGrid()
+    gr, ga, go = rot.grid(), ali.grid(), o.grid()
+    occupied = np.flatnonzero(go[:, 0] != 0)
+    assert (np.flatnonzero(gr[:, 0] != 0) == occupied).all() and (np.flatnonzero(ga[:, 0] != 0) == occupied).all()
+    close_sum(gr[:, 0], ga[:, 0], "grid mass, rotated vs aligned walk")
+    close_sum(gr[:, 4:7], ga[:, 4:7], "grid velocity, rotated vs aligned walk", rtol=1e-4)    # v = p / m of sums that differ by 2e-5
+    rot.substep(dt, cols, nc, 17); ali.substep(dt, cols, nc, 17); o.substep(dt, ocols, onc, 17); of.substep(dt, ocols, onc, 17)
+    assert_traj_close_calibrated(rot.download_state35(), o.state(), of.state(), "rotated walk vs oracle, 20 substeps")
+    assert_traj_close_calibrated(ali.download_state35(), o.state(), of.state(), "aligned walk vs oracle, 20 substeps")
+    assert rot.stats().n_particles == ali.stats().n_particles == sc["n"]
+
+
 def test_full_size_properties_config3_momentum():
     """BASELINE config 3 (two colliding snowballs, 8 Mi particles, 256^3, no ground): APIC transfers conserve linear
     momentum, so over k substeps the total particle momentum changes by exactly M * g * dt * k; nothing is lost or
