@@ -1,0 +1,105 @@
+"""Code-generation contract of the hot kernels, checked on the built library without a GPU (cuobjdump -sass / -res-usage):
+the properties DESIGN.md section 4 relies on -- bulk-copy (TMA) tile loads completing on an mbarrier, one vector
+red.global per tile node, no shared-memory float atomics (CAS loops on sm_100a), 128-bit shared/global accesses, register
+budgets that give the designed occupancy, no spills -- so that a source change that silently loses one of them fails here
+instead of showing up as a slower bench line."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+LIB = os.path.join(ROOT, "realtime-deformations_b200", "libmpm_b200.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"),
+                                reason="cuobjdump not available")
+
+
+@pytest.fixture(scope="module")
+def kernels():
+    import mpm_b200
+    mpm_b200.build.build()
+    os.environ["PATH"] = os.environ.get("PATH", "") + ":/usr/local/cuda/bin"
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, text=True, check=True).stdout
+    res = subprocess.run(["cuobjdump", "-res-usage", LIB], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    usage = {m.group(1): (int(m.group(2)), int(m.group(3)), int(m.group(4)))
+             for m in re.finditer(r"Function (\S+):\n\s*REG:(\d+).*?SHARED:(\d+).*?LOCAL:(\d+)", res)}
+    out = {}
+    for part in re.split(r"\n\s*Function : ", sass)[1:]:
+        name = part.split("\n", 1)[0].strip()
+        ops = []
+        for ins in re.findall(r"/\*[0-9a-f]{4}\*/\s+(.*?);", part):
+            t = re.sub(r"^@!?U?P\d+\s+", "", ins).split()
+            if t:
+                ops.append(t[0])
+        out[name] = {"ops": ops, "regs": usage.get(name, (None, None, None))[0], "local": usage.get(name, (None, None, None))[2]}
+    return out
+
+
+def _one(kernels, *needles):
+    hits = [k for k in kernels if all(n in k for n in needles)]
+    assert len(hits) == 1, (needles, hits)
+    return kernels[hits[0]]
+
+
+def _count(k, prefix):
+    return sum(o.startswith(prefix) for o in k["ops"])
+
+
+def test_built_for_sm_100a_only():
+    r = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", LIB], stdout=subprocess.PIPE, text=True)
+    elfs = [l for l in r.stdout.splitlines() if "ELF file" in l]
+    assert elfs and all("sm_100a" in l for l in elfs), r.stdout
+
+
+def test_no_kernel_spills_to_local_memory(kernels):
+    spilled = {k: v["local"] for k, v in kernels.items() if v["local"]}
+    assert not spilled, spilled
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_p2g_tile_kernel_contract(kernels, mode):
+    k = _one(kernels, f"k_p2g_tileILi{mode}ELb0ELb0")
+    assert k["regs"] <= 128, "2 CTAs of 256 threads per SM need <= 128 registers"
+    assert _count(k, "REDG.E.ADD.F32x4") == 1, "one vector red.global.add.v4.f32 per tile node"
+    assert not any("CAST" in o for o in k["ops"]), "no shared-memory float atomics (ATOMS.CAST.SPIN loops)"
+    assert _count(k, "ATOMS") <= 2, "the counting sort uses one round of integer shared atomics (two unrolled particles)"
+    assert _count(k, "LDS.128") >= 5 and _count(k, "STS.128") >= 6, "records and fold buffers move as 128-bit accesses"
+    assert _count(k, "LDG.E.128") >= (6, 6, 12)[mode], "particle planes are read as float4 (2 particles x 4 / 3 / 6 planes)"
+    assert _count(k, "SHFL.IDX") == 48, "z-fold: 3 rounds x 16 values by warp shuffles"
+    assert _count(k, "BAR.SYNC") <= 8
+
+
+@pytest.mark.parametrize("flags", [4, 14])
+def test_gather_kernel_contract(kernels, flags):
+    k = _one(kernels, f"k_g2p_tileILi{flags}ELb0ELb0")
+    assert k["regs"] <= 128
+    assert _count(k, "UBLKCP") == 8, "the 2x2x2 grid blocks of a tile arrive as eight 1 KB bulk copies (TMA)"
+    assert _count(k, "SYNCS.ARRIVE.TRANS64") == 1 and any("TRYWAIT" in o for o in k["ops"]), "mbarrier expect_tx + try_wait"
+    assert _count(k, "LDS.128") == 64, "64 stencil nodes, one LDS.128 each"
+    assert _count(k, "BAR.SYNC") == 0, "warp-per-block: no CTA barrier"
+    ffma = sum(o == "FFMA" or o.startswith("FFMA.") for o in k["ops"])
+    assert 576 <= ffma <= 700, f"separable gather: 576 FMA per particle in the loop, found {ffma} in the kernel"
+
+
+def test_fupdate_kernel_contract(kernels):
+    k = _one(kernels, "k_fupdateILb1")
+    assert k["regs"] <= 64, "4 CTAs of 256 threads per SM"
+    assert _count(k, "LDG.E.128") >= 7 and _count(k, "STG.E.128") == 7, "eight planes in, seven planes out, all float4"
+    assert not any(o.startswith(("LDS", "STS", "BAR")) for o in k["ops"])
+
+
+def test_packed_variants_use_ffma2(kernels):
+    p2g = _one(kernels, "k_p2g_tileILi2ELb1ELb0")
+    g2p = _one(kernels, "k_g2p_tileILi14ELb0ELb1")
+    assert _count(p2g, "FFMA2") >= 40 and _count(g2p, "FFMA2") >= 200
+
+
+def test_binning_uses_warp_aggregated_atomics(kernels):
+    for name in ("k_bin_count", "k_bin_scatter"):
+        k = _one(kernels, name)
+        assert _count(k, "MATCH.ANY") == 4, "4 elements per thread, each warp-aggregated with match.any"
