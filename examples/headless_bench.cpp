@@ -61,11 +61,12 @@ int main(int argc, char** argv) {
     CHECK(mpm_rasterize_particles_to_grid(sim));                    // main.cpp:53-54
     CHECK(mpm_compute_particle_volumes_and_densities(sim));
 
-    MpmBoxCollider ground = {};
-    for (int d = 0; d < 4; ++d) ground.world_to_local[d * 5] = 1.0f;             // identity rotation
+    // ground box through the scene front-end: pose = what a reference MeshCollider's sdf reads (scale, quaternion,
+    // translation; hpp:80-83); the library forms the world-to-local matrix in glm's operation order
     const float top = (j0 - 0.5f) * h;
-    ground.world_to_local[12] = -grid * h * 0.5f; ground.world_to_local[13] = -(top - 2.0f); ground.world_to_local[14] = -grid * h * 0.5f;
-    ground.half_extent[0] = grid * h; ground.half_extent[1] = 2.0f; ground.half_extent[2] = grid * h;
+    MpmBoxTransform pose = { { grid * h, 2.0f, grid * h }, { 1.0f, 0.0f, 0.0f, 0.0f }, { grid * h * 0.5f, top - 2.0f, grid * h * 0.5f }, { 0.0f, 0.0f, 0.0f } };
+    MpmBoxCollider ground;
+    CHECK(mpm_box_collider_from_transform(&pose, &ground));
 
     CHECK(mpm_substep(sim, dt, &ground, 1, 5));                     // warm-up
     CHECK(mpm_synchronize(sim));

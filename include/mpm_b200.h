@@ -64,6 +64,15 @@ typedef struct MpmBoxCollider {
 } MpmBoxCollider;
 #define MPM_MAX_COLLIDERS 16
 
+/* Scene front-end for hosts without glm: the pose a MeshCollider's sdf lambda reads (hpp:80-83) --
+ * mesh.scale, mesh.rotation (glm::quat, stored w x y z here), mesh.translation -- and MeshCollider::velocity. */
+typedef struct MpmBoxTransform {
+    float scale[3];
+    float rotation_wxyz[4];
+    float translation[3];
+    float velocity[3];
+} MpmBoxTransform;
+
 typedef struct MpmStats {
     int64_t n_particles;        /* live particles on this handle */
     int64_t n_out_of_grid;      /* particles whose stencil leaves the grid (reference would index out of bounds) */
@@ -154,6 +163,19 @@ int mpm_upload_grid(mpm_t* s, const float* grid7);               /* stage-isolat
 int mpm_download_binning(mpm_t* s, int64_t n, int32_t* cells3, int32_t* block_key, int32_t* sorted_ids);
 int mpm_get_stats(mpm_t* s, MpmStats* out);
 int mpm_synchronize(mpm_t* s);
+
+/* ---- scene front-end: host-only helpers, no handle, no device ----
+ * mpm_box_collider_from_transform: world_to_local = inverse(translate(mat4(), translation) * toMat4(rotation)) with glm
+ * 0.9.7.1's operation order (gtc/quaternion.inl mat3_cast, gtc/matrix_transform.inl translate, detail/type_mat4x4.inl
+ * operator* and compute_inverse), half_extent = scale, velocity copied: bit for bit what the reference's sdf lambda
+ * (hpp:80-83) computes from the same pose. mpm_box_transform_move: MeshCollider::move (hpp:90-92), i.e.
+ * applyMatrix4(translate(dt * velocity)) followed by glm::decompose (mesh.hpp:20-23): translation += dt * velocity,
+ * scale and rotation unchanged. mpm_box_transform_flip_velocity: the key_callback case (main.cpp:37-41,174-180).
+ * (In the reference the boxes pushed into solidObjects are copies whose sdf lambdas still read the ORIGINAL objects, so
+ * its collisions never see a move; through this ABI a collider is wherever the host's transform says it is.) */
+int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out);
+int mpm_box_transform_move(MpmBoxTransform* t, float time_delta);
+int mpm_box_transform_flip_velocity(MpmBoxTransform* t);
 
 /* ---- slab decomposition plumbing (multi-GPU; the exchange itself is done by the caller, e.g. NCCL) ----
  * Ghost layer: the handle's grid holds one extra block layer above block_hi. After P2G (inside

@@ -290,6 +290,18 @@ int main(int argc, char** argv) {
         }
     }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!dumpDir.empty()) {
+        // the colliders once more, after `steps` calls of MeshCollider::move (hpp:90-92: applyMatrix4 + glm::decompose)
+        std::vector<float> c;
+        for (auto& o : solidObjects) {
+            const auto& m = o.mesh;
+            c.insert(c.end(), { m.scale.x, m.scale.y, m.scale.z, m.rotation.w, m.rotation.x, m.rotation.y, m.rotation.z,
+                                m.translation.x, m.translation.y, m.translation.z, o.velocity.x, o.velocity.y, o.velocity.z });
+            const glm::mat4 inv = glm::inverse(glm::translate(glm::mat4(), m.translation) * glm::toMat4(m.rotation));
+            for (int cc = 0; cc < 4; ++cc) for (int rr = 0; rr < 4; ++rr) c.push_back(inv[cc][rr]);
+        }
+        writeFile(dumpDir + "/colliders_final.f32", c);
+    }
     if (bench || !quiet) {
         printf("{\"impl\": \"reference\", \"n_particles\": %d, \"grid\": [%d, %d, %d], \"steps\": %d, \"seconds\": %.6f, "
                "\"particle_updates_per_s\": %.3f, \"stage_ms\": [%.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f]}\n",

@@ -28,6 +28,11 @@ class MpmBoxCollider(C.Structure):
     _fields_ = [("world_to_local", C.c_float * 16), ("half_extent", C.c_float * 3), ("velocity", C.c_float * 3)]
 
 
+class MpmBoxTransform(C.Structure):
+    _fields_ = [("scale", C.c_float * 3), ("rotation_wxyz", C.c_float * 4), ("translation", C.c_float * 3),
+                ("velocity", C.c_float * 3)]
+
+
 class MpmStats(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("n_out_of_grid", C.c_int64), ("n_active_nodes", C.c_int64),
                 ("n_particle_blocks", C.c_int64), ("n_grid_blocks", C.c_int64), ("substeps_done", C.c_int64),
@@ -45,7 +50,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_synchronize", "mpm_halo_bytes", "mpm_halo_pack", "mpm_halo_add", "mpm_substep_begin",
            "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
            "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
-           "mpm_wait_render_buffers"]
+           "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
+           "mpm_box_transform_flip_velocity"]
 
 _lib = None
 
@@ -105,6 +111,9 @@ def lib():
     L.mpm_sync_counts.argtypes = [vp]
     L.mpm_set_pid_base.argtypes = [vp, i64]
     L.mpm_download_live_particles.argtypes = [vp, i64, C.POINTER(i64), fp, vp]
+    L.mpm_box_collider_from_transform.argtypes = [C.POINTER(MpmBoxTransform), C.POINTER(MpmBoxCollider)]
+    L.mpm_box_transform_move.argtypes = [C.POINTER(MpmBoxTransform), C.c_float]
+    L.mpm_box_transform_flip_velocity.argtypes = [C.POINTER(MpmBoxTransform)]
     _lib = L
     return L
 
@@ -140,6 +149,25 @@ def make_colliders(w2l, half, vel=None):
         arr[i].world_to_local[:] = w2l[i].tolist()
         arr[i].half_extent[:] = half[i].tolist()
         arr[i].velocity[:] = vel[i].tolist()
+    return arr, nc
+
+
+def box_transform(scale, rotation_wxyz, translation, velocity=(0.0, 0.0, 0.0)):
+    """The pose a reference MeshCollider's sdf reads (hpp:80-83) + its velocity, as the C ABI's MpmBoxTransform."""
+    t = MpmBoxTransform()
+    t.scale[:] = [float(np.float32(x)) for x in scale]
+    t.rotation_wxyz[:] = [float(np.float32(x)) for x in rotation_wxyz]
+    t.translation[:] = [float(np.float32(x)) for x in translation]
+    t.velocity[:] = [float(np.float32(x)) for x in velocity]
+    return t
+
+
+def colliders_from_transforms(transforms):
+    """MpmBoxCollider array from MpmBoxTransform poses through the library's own glm-order arithmetic."""
+    nc = len(transforms)
+    arr = (MpmBoxCollider * max(nc, 1))()
+    for i, t in enumerate(transforms):
+        _ck(lib().mpm_box_collider_from_transform(C.byref(t), C.byref(arr[i])))
     return arr, nc
 
 

@@ -722,6 +722,95 @@ extern "C" int mpm_emulated_build(void) { return 1; }
 // ---- diagnostics ---------------------------------------------------------------------------------------------------
 int mpm_synchronize(mpm_t* s) { NEED(s); CK(cudaStreamSynchronize(s->stream)); return MPM_OK; }
 
+// ---- scene front-end (host only; include/mpm_b200.h) ---------------------------------------------------------------
+// glm 0.9.7.1 value arithmetic restated on plain arrays, one rounding per source-level operation (volatile keeps the host
+// compiler from contracting or re-associating). m[c][r] is glm's m[c][r] (column c, row r).
+namespace scene_fe {
+typedef volatile float vf;
+struct V4 { float v[4]; };
+struct M4 { V4 c[4]; };
+static V4 mul(const V4& a, float s) { V4 r; for (int i = 0; i < 4; ++i) { vf t = a.v[i] * s; r.v[i] = t; } return r; }
+static V4 mul(const V4& a, const V4& b) { V4 r; for (int i = 0; i < 4; ++i) { vf t = a.v[i] * b.v[i]; r.v[i] = t; } return r; }
+static V4 add(const V4& a, const V4& b) { V4 r; for (int i = 0; i < 4; ++i) { vf t = a.v[i] + b.v[i]; r.v[i] = t; } return r; }
+static V4 sub(const V4& a, const V4& b) { V4 r; for (int i = 0; i < 4; ++i) { vf t = a.v[i] - b.v[i]; r.v[i] = t; } return r; }
+static float mm(float a, float b) { vf t = a * b; return t; }
+static float ss(float a, float b) { vf t = a - b; return t; }
+static float aa(float a, float b) { vf t = a + b; return t; }
+static M4 identity() { M4 m; for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) m.c[c].v[r] = c == r ? 1.0f : 0.0f; return m; }
+// gtc/quaternion.inl:598-622 (mat3_cast) widened to mat4 (mat4_cast)
+static M4 to_mat4(const float q[4] /* w x y z */) {
+    const float w = q[0], x = q[1], y = q[2], z = q[3];
+    const float qxx = mm(x, x), qyy = mm(y, y), qzz = mm(z, z), qxz = mm(x, z), qxy = mm(x, y), qyz = mm(y, z), qwx = mm(w, x), qwy = mm(w, y), qwz = mm(w, z);
+    M4 m = identity();
+    m.c[0].v[0] = ss(1.0f, mm(2.0f, aa(qyy, qzz))); m.c[0].v[1] = mm(2.0f, aa(qxy, qwz)); m.c[0].v[2] = mm(2.0f, ss(qxz, qwy));
+    m.c[1].v[0] = mm(2.0f, ss(qxy, qwz)); m.c[1].v[1] = ss(1.0f, mm(2.0f, aa(qxx, qzz))); m.c[1].v[2] = mm(2.0f, aa(qyz, qwx));
+    m.c[2].v[0] = mm(2.0f, aa(qxz, qwy)); m.c[2].v[1] = mm(2.0f, ss(qyz, qwx)); m.c[2].v[2] = ss(1.0f, mm(2.0f, aa(qxx, qyy)));
+    return m;
+}
+// gtc/matrix_transform.inl:40-49
+static M4 translate(const M4& m, const float t[3]) {
+    M4 r = m;
+    r.c[3] = add(add(add(mul(m.c[0], t[0]), mul(m.c[1], t[1])), mul(m.c[2], t[2])), m.c[3]);
+    return r;
+}
+// detail/type_mat4x4.inl:704-722
+static M4 mul(const M4& a, const M4& b) {
+    M4 r;
+    for (int c = 0; c < 4; ++c)
+        r.c[c] = add(add(add(mul(a.c[0], b.c[c].v[0]), mul(a.c[1], b.c[c].v[1])), mul(a.c[2], b.c[c].v[2])), mul(a.c[3], b.c[c].v[3]));
+    return r;
+}
+// detail/type_mat4x4.inl:37-92 (cofactor expansion; the 2x2 sub-determinants are shared between the columns)
+static M4 inverse(const M4& M) {
+#define E(col_, row_) M.c[col_].v[row_]
+    const float c00 = ss(mm(E(2,2), E(3,3)), mm(E(3,2), E(2,3))), c02 = ss(mm(E(1,2), E(3,3)), mm(E(3,2), E(1,3))), c03 = ss(mm(E(1,2), E(2,3)), mm(E(2,2), E(1,3)));
+    const float c04 = ss(mm(E(2,1), E(3,3)), mm(E(3,1), E(2,3))), c06 = ss(mm(E(1,1), E(3,3)), mm(E(3,1), E(1,3))), c07 = ss(mm(E(1,1), E(2,3)), mm(E(2,1), E(1,3)));
+    const float c08 = ss(mm(E(2,1), E(3,2)), mm(E(3,1), E(2,2))), c10 = ss(mm(E(1,1), E(3,2)), mm(E(3,1), E(1,2))), c11 = ss(mm(E(1,1), E(2,2)), mm(E(2,1), E(1,2)));
+    const float c12 = ss(mm(E(2,0), E(3,3)), mm(E(3,0), E(2,3))), c14 = ss(mm(E(1,0), E(3,3)), mm(E(3,0), E(1,3))), c15 = ss(mm(E(1,0), E(2,3)), mm(E(2,0), E(1,3)));
+    const float c16 = ss(mm(E(2,0), E(3,2)), mm(E(3,0), E(2,2))), c18 = ss(mm(E(1,0), E(3,2)), mm(E(3,0), E(1,2))), c19 = ss(mm(E(1,0), E(2,2)), mm(E(2,0), E(1,2)));
+    const float c20 = ss(mm(E(2,0), E(3,1)), mm(E(3,0), E(2,1))), c22 = ss(mm(E(1,0), E(3,1)), mm(E(3,0), E(1,1))), c23 = ss(mm(E(1,0), E(2,1)), mm(E(2,0), E(1,1)));
+    const V4 f0 = { { c00, c00, c02, c03 } }, f1 = { { c04, c04, c06, c07 } }, f2 = { { c08, c08, c10, c11 } };
+    const V4 f3 = { { c12, c12, c14, c15 } }, f4 = { { c16, c16, c18, c19 } }, f5 = { { c20, c20, c22, c23 } };
+    const V4 v0 = { { E(1,0), E(0,0), E(0,0), E(0,0) } }, v1 = { { E(1,1), E(0,1), E(0,1), E(0,1) } };
+    const V4 v2 = { { E(1,2), E(0,2), E(0,2), E(0,2) } }, v3 = { { E(1,3), E(0,3), E(0,3), E(0,3) } };
+    const V4 i0 = add(sub(mul(v1, f0), mul(v2, f1)), mul(v3, f2)), i1 = add(sub(mul(v0, f0), mul(v2, f3)), mul(v3, f4));
+    const V4 i2 = add(sub(mul(v0, f1), mul(v1, f3)), mul(v3, f5)), i3 = add(sub(mul(v0, f2), mul(v1, f4)), mul(v2, f5));
+    const V4 sa = { { 1.0f, -1.0f, 1.0f, -1.0f } }, sb = { { -1.0f, 1.0f, -1.0f, 1.0f } };
+    M4 inv;
+    inv.c[0] = mul(i0, sa); inv.c[1] = mul(i1, sb); inv.c[2] = mul(i2, sa); inv.c[3] = mul(i3, sb);
+    const V4 row0 = { { inv.c[0].v[0], inv.c[1].v[0], inv.c[2].v[0], inv.c[3].v[0] } };
+    const V4 d0 = mul(M.c[0], row0);
+    const float det = aa(aa(d0.v[0], d0.v[1]), aa(d0.v[2], d0.v[3]));
+    vf ood = 1.0f / det;
+    for (int c = 0; c < 4; ++c) inv.c[c] = mul(inv.c[c], (float)ood);
+#undef E
+    return inv;
+}
+}  // namespace scene_fe
+
+int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out) {
+    if (!t || !out) return fail(MPM_ERR_INVALID, "null argument");
+    using namespace scene_fe;
+    const M4 w2l = inverse(mul(translate(identity(), t->translation), to_mat4(t->rotation_wxyz)));    // hpp:82
+    for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) out->world_to_local[c * 4 + r] = w2l.c[c].v[r];
+    // hpp:80-81: b = (scale(mat4(), mesh.scale) * vec4(1,1,1,1)).xyz = mesh.scale (products with 0 and 1 are exact)
+    for (int a = 0; a < 3; ++a) { out->half_extent[a] = t->scale[a]; out->velocity[a] = t->velocity[a]; }
+    return MPM_OK;
+}
+int mpm_box_transform_move(MpmBoxTransform* t, float time_delta) {
+    if (!t) return fail(MPM_ERR_INVALID, "null argument");
+    // matrixWorld = translate(mat4(1), timeDelta * velocity) * matrixWorld changes only the last column:
+    // x' = ((1*x + 0*y) + 0*z) + (timeDelta*vx)*1; glm::decompose then reads the translation back from that column and
+    // re-derives scale / rotation from the untouched 3x3 part
+    for (int a = 0; a < 3; ++a) t->translation[a] = scene_fe::aa(t->translation[a], scene_fe::mm(time_delta, t->velocity[a]));
+    return MPM_OK;
+}
+int mpm_box_transform_flip_velocity(MpmBoxTransform* t) {
+    if (!t) return fail(MPM_ERR_INVALID, "null argument");
+    for (int a = 0; a < 3; ++a) t->velocity[a] = scene_fe::mm(t->velocity[a], -1.0f);     // main.cpp:176-177: velocity *= -1
+    return MPM_OK;
+}
+
 int mpm_get_stats(mpm_t* s, MpmStats* out) {
     NEED(s);
     if (!out) return fail(MPM_ERR_INVALID, "out is NULL");

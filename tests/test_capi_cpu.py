@@ -41,6 +41,36 @@ def test_struct_layouts_match_header(L):
     assert C.sizeof(mpm_b200.capi.MpmStats) == 8 * 7 + 4 * 8 + 4 * 8
 
 
+def test_scene_front_end_reproduces_reference_collider_poses(L):
+    """mpm_box_collider_from_transform / mpm_box_transform_move against poses dumped by the UNMODIFIED
+    reference (oracle/make_golden_colliders.py: 24 boxes built like main.cpp:119-151, moved 25 times by
+    MeshCollider::move): the world-to-local matrix of the sdf lambda (hpp:82) and the moved translation, bit for bit.
+    Host-only functions: no device needed."""
+    capi = mpm_b200.capi
+    k = np.load(os.path.join(ROOT, "tests", "golden", "kat_colliders.npz"))
+    first, last, steps, dt = k["first"], k["last"], int(k["steps"]), float(k["dt"])
+    assert C.sizeof(capi.MpmBoxTransform) == 52
+    # glm::decompose of an unchanged 3x3 part: scale and rotation do not drift under move()
+    assert np.array_equal(first[:, 0:7].view(np.uint32), last[:, 0:7].view(np.uint32))
+    for row0, row1 in zip(first, last):
+        t = capi.box_transform(row0[0:3], row0[3:7], row0[7:10], row0[10:13])
+        c = capi.MpmBoxCollider()
+        assert L.mpm_box_collider_from_transform(C.byref(t), C.byref(c)) == 0
+        assert np.array_equal(np.array(c.world_to_local[:], np.float32).view(np.uint32), row0[13:29].view(np.uint32))
+        assert list(c.half_extent) == row0[0:3].tolist() and list(c.velocity) == row0[10:13].tolist()
+        for _ in range(steps):
+            assert L.mpm_box_transform_move(C.byref(t), dt) == 0
+        assert np.array_equal(np.array(t.translation[:], np.float32).view(np.uint32), row1[7:10].view(np.uint32))
+        assert L.mpm_box_collider_from_transform(C.byref(t), C.byref(c)) == 0
+        assert np.array_equal(np.array(c.world_to_local[:], np.float32).view(np.uint32), row1[13:29].view(np.uint32))
+        assert L.mpm_box_transform_flip_velocity(C.byref(t)) == 0 and list(t.velocity) == (-row0[10:13]).tolist()
+    # the reference's own three boxes (main.cpp:119-156) from the stage-level golden file
+    for row in np.load(os.path.join(ROOT, "tests", "golden", "kat_functions.npz"))["colliders"]:
+        arr, nc = capi.colliders_from_transforms([capi.box_transform(row[0:3], row[3:7], row[7:10], row[10:13])])
+        assert nc == 1 and np.array_equal(np.array(arr[0].world_to_local[:], np.float32).view(np.uint32), row[13:29].view(np.uint32))
+    assert L.mpm_box_collider_from_transform(None, None) != 0
+
+
 def test_no_cpu_fallback(L):
     if L.mpm_device_count() > 0:
         pytest.skip("a GPU is present")
