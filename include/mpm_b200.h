@@ -172,7 +172,18 @@ int mpm_synchronize(mpm_t* s);
  * applyMatrix4(translate(dt * velocity)) followed by glm::decompose (mesh.hpp:20-23): translation += dt * velocity,
  * scale and rotation unchanged. mpm_box_transform_flip_velocity: the key_callback case (main.cpp:37-41,174-180).
  * (In the reference the boxes pushed into solidObjects are copies whose sdf lambdas still read the ORIGINAL objects, so
- * its collisions never see a move; through this ABI a collider is wherever the host's transform says it is.) */
+ * its collisions never see a move; through this ABI a collider is wherever the host's transform says it is.)
+ * mpm_fill_ball: LagrangeEulerView::initializeParticles (cpp:18-63) with the ball radius as a parameter (the reference
+ * hard-codes 0.2): every cell of the cube of +-int(radius/h) cells around ivec3(origin/h) gets 8 candidate sites
+ * (cell + {1/4,3/4}^3 + generateRandomInsideUnitBall(0.25), utils.h:114-127) * h, kept if within `radius` of the origin.
+ * Accepted positions are written in acceptance order (the reference stores the k-th one in slot nParticles-1-k); once
+ * `capacity` positions are stored further candidates are only counted in *n_missing (its "k more!!!"), and -- as in the
+ * reference -- three more random numbers are drawn per STORED particle (its discarded colour). rnd has libc rand()'s
+ * contract (NULL = rand() itself: with the default seed this is the reference's start-up scene, particle for particle).
+ * Several bodies = several calls into one position array. */
+typedef int (*MpmRandFn)(void* user);
+int mpm_fill_ball(const float origin[3], float radius, float h, MpmRandFn rnd, void* user,
+                  float* pos_xyz, int64_t capacity, int64_t* n_written, int64_t* n_missing);
 int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out);
 int mpm_box_transform_move(MpmBoxTransform* t, float time_delta);
 int mpm_box_transform_flip_velocity(MpmBoxTransform* t);

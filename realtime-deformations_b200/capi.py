@@ -51,7 +51,7 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
            "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
-           "mpm_box_transform_flip_velocity"]
+           "mpm_box_transform_flip_velocity", "mpm_fill_ball"]
 
 _lib = None
 
@@ -114,6 +114,7 @@ def lib():
     L.mpm_box_collider_from_transform.argtypes = [C.POINTER(MpmBoxTransform), C.POINTER(MpmBoxCollider)]
     L.mpm_box_transform_move.argtypes = [C.POINTER(MpmBoxTransform), C.c_float]
     L.mpm_box_transform_flip_velocity.argtypes = [C.POINTER(MpmBoxTransform)]
+    L.mpm_fill_ball.argtypes = [fp, C.c_float, C.c_float, vp, vp, fp, i64, C.POINTER(i64), C.POINTER(i64)]
     _lib = L
     return L
 
@@ -160,6 +161,21 @@ def box_transform(scale, rotation_wxyz, translation, velocity=(0.0, 0.0, 0.0)):
     t.translation[:] = [float(np.float32(x)) for x in translation]
     t.velocity[:] = [float(np.float32(x)) for x in velocity]
     return t
+
+
+RAND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+def fill_ball(origin, radius, h, capacity, rnd=None):
+    """LagrangeEulerView::initializeParticles' fill rule (cpp:18-63) through the C ABI: (positions (n, 3) in acceptance
+    order, candidates that did not fit). rnd: Python callable with libc rand()'s contract, None = libc rand() itself."""
+    o = np.ascontiguousarray(origin, np.float32)
+    pos = np.zeros((max(int(capacity), 1), 3), np.float32)
+    n, miss = C.c_int64(0), C.c_int64(0)
+    cb = RAND_FN(lambda _user: int(rnd())) if rnd is not None else None
+    _ck(lib().mpm_fill_ball(_fp(o), float(radius), float(h), C.cast(cb, C.c_void_p) if cb is not None else None, None, _fp(pos),
+                            int(capacity), C.byref(n), C.byref(miss)))
+    return pos[:n.value].copy(), miss.value
 
 
 def colliders_from_transforms(transforms):

@@ -6,6 +6,7 @@
 #include "mpm_tile_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -787,6 +788,56 @@ static M4 inverse(const M4& M) {
     return inv;
 }
 }  // namespace scene_fe
+
+// utils.h:110-112: the arguments are floats, the arithmetic is double (the literal 2000.0), the result a float
+static float fe_rand_float(MpmRandFn rnd, void* user, float low, float high) {
+    const int r = rnd ? rnd(user) : rand();
+    volatile double t = (double)(r % 2000) / 2000.0;
+    volatile double d = (double)(volatile float)(high - low);
+    volatile double v = (double)low + t * d;
+    return (float)v;
+}
+int mpm_fill_ball(const float origin[3], float radius, float h, MpmRandFn rnd, void* user,
+                  float* pos_xyz, int64_t capacity, int64_t* n_written, int64_t* n_missing) {
+    if (!origin || !(h > 0.0f) || !(radius >= 0.0f) || capacity < 0 || (capacity > 0 && !pos_xyz)) return fail(MPM_ERR_INVALID, "bad argument");
+    using scene_fe::mm; using scene_fe::aa; using scene_fe::ss;
+    int centre[3];
+    for (int a = 0; a < 3; ++a) { volatile float q = origin[a] / h; centre[a] = (int)q; }      // cpp:20: ivec3(origin / h)
+    volatile float reach_f = radius / h;                                                       // cpp:25
+    const int reach = (int)reach_f;
+    static const float sites[8][3] = { {1, 1, 1}, {1, 1, 3}, {1, 3, 1}, {1, 3, 3}, {3, 1, 1}, {3, 1, 3}, {3, 3, 1}, {3, 3, 3} };
+    int64_t stored = 0, missing = 0;
+    for (int i = centre[0] - reach; i < centre[0] + reach; ++i)
+        for (int j = centre[1] - reach; j < centre[1] + reach; ++j)
+            for (int k = centre[2] - reach; k < centre[2] + reach; ++k)
+                for (int d = 0; d < 8; ++d) {
+                    // utils.h:114-127, generateRandomInsideUnitBall(0.25): phi and u are floats, cos(theta) - 1.0 is a double
+                    const float phi = fe_rand_float(rnd, user, 0.0f, (float)(2.0 * 3.1415));
+                    volatile double costheta = (double)fe_rand_float(rnd, user, 0.0f, 2.0f) - 1.0;
+                    const float u = fe_rand_float(rnd, user, 0.0f, 1.0f);
+                    const double theta = acos(costheta);
+                    const float r = mm(0.25f, cbrtf(u));
+                    volatile double rs = (double)r * sin(theta);
+                    volatile double bx = rs * cos((double)phi), by = rs * sin((double)phi), bz = (double)r * cos(theta);   // unqualified cos/sin: the double versions
+                    const float ball[3] = { (float)bx, (float)by, (float)bz };
+                    const int cell[3] = { i, j, k };
+                    float cand[3], dist2 = 0.0f;
+                    for (int a = 0; a < 3; ++a) {
+                        cand[a] = mm(aa(aa((float)cell[a], mm(sites[d][a], 0.25f)), ball[a]), h);      // cpp:35
+                        const float df = ss(cand[a], origin[a]);
+                        dist2 = a == 0 ? mm(df, df) : aa(dist2, mm(df, df));
+                    }
+                    volatile float dist = sqrtf(dist2);
+                    if (dist > radius) continue;                                                       // cpp:36
+                    if (stored == capacity) { ++missing; continue; }                                   // cpp:38-41
+                    for (int a = 0; a < 3; ++a) pos_xyz[3 * stored + a] = cand[a];
+                    ++stored;
+                    for (int c = 0; c < 3; ++c) { if (rnd) rnd(user); else rand(); }                   // cpp:45-47: r, g, b (then overwritten)
+                }
+    if (n_written) *n_written = stored;
+    if (n_missing) *n_missing = missing;
+    return MPM_OK;
+}
 
 int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out) {
     if (!t || !out) return fail(MPM_ERR_INVALID, "null argument");

@@ -71,6 +71,34 @@ def test_scene_front_end_reproduces_reference_collider_poses(L):
     assert L.mpm_box_collider_from_transform(None, None) != 0
 
 
+def test_fill_ball_reproduces_the_reference_start_up_scene(L):
+    """SURVEY 8 (f2): mpm_fill_ball = LagrangeEulerView::initializeParticles (cpp:18-63, utils.h:110-127) with the radius
+    as a parameter. With libc rand() at its default seed it must give the reference's own start-up scene (golden state 0
+    from the unmodified class: 2147 particles, '3 more!!!'), position for position, bit for bit."""
+    capi = mpm_b200.capi
+    s0 = np.load(os.path.join(ROOT, "tests", "golden", "c1_default.npz"))["state0"]
+    C.CDLL("libc.so.6").srand(1)                        # glibc: rand() without srand() behaves as srand(1)
+    pos, missing = capi.fill_ball((0.5, 0.6, 0.5), 0.2, 0.05, s0.shape[0])
+    assert pos.shape == (2147, 3) and missing == 3
+    ref = np.ascontiguousarray(s0[::-1, 5:8])           # the reference fills its slots from the back
+    assert np.array_equal(pos.view(np.uint32), ref.view(np.uint32))
+    # generalised: another radius, a caller-supplied generator (libc rand() contract), two bodies in one array
+    state = [12345]
+
+    def lcg():
+        state[0] = (state[0] * 1103515245 + 12345) & 0x7FFFFFFF
+        return state[0]
+    a, miss_a = capi.fill_ball((1.0, 1.0, 1.0), 0.35, 0.05, 100000, rnd=lcg)
+    assert miss_a == 0 and len(a) > 0
+    assert (np.linalg.norm(a.astype(np.float64) - 1.0, axis=1) <= 0.35 * (1 + 1e-6)).all()
+    expect = 8 * 4.0 / 3.0 * np.pi * (0.35 / 0.05) ** 3
+    assert abs(len(a) - expect) < 0.1 * expect, (len(a), expect)
+    state[0] = 12345
+    b, miss_b = capi.fill_ball((1.0, 1.0, 1.0), 0.35, 0.05, 1000, rnd=lcg)       # capacity reached: the rest is only counted
+    assert len(b) == 1000 and miss_b > 0 and np.array_equal(b, a[:1000])
+    assert L.mpm_fill_ball(None, 0.2, 0.05, None, None, None, 0, None, None) != 0
+
+
 def test_no_cpu_fallback(L):
     if L.mpm_device_count() > 0:
         pytest.skip("a GPU is present")
