@@ -8,7 +8,7 @@
 //     reference member                              ->  C ABI entry point
 //     LagrangeEulerView(max_i,max_j,max_k,n)        ->  mpm_create
 //     ~LagrangeEulerView                            ->  mpm_destroy
-//     initializeParticles                           ->  host-side fill (same rule) + mpm_upload_particles_aos
+//     initializeParticles                           ->  mpm_fill_ball (same rule, libc rand()) + mpm_upload_particles_aos
 //     rasterizeParticlesToGrid                      ->  mpm_rasterize_particles_to_grid
 //     computeParticleVolumesAndDensities            ->  mpm_compute_particle_volumes_and_densities
 //     computeExplicitGridForces                     ->  mpm_compute_explicit_grid_forces
@@ -30,6 +30,9 @@
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
+#include <algorithm>
+#include <iostream>
 
 #include "../include/mpm_b200.h"
 
@@ -74,30 +77,22 @@ LagrangeEulerView::~LagrangeEulerView() {
     if (it != table().end()) { mpm_destroy(it->second.sim); table().erase(it); }
 }
 
-// Same fill rule as material_point_method.cpp:18-63 (8 jittered sites per cell inside a ball of radius 0.2 around the
-// origin, slots filled from the back, three colour draws per accepted particle while slots remain), so that the
-// default libc rand() stream produces the reference's particles.
+// material_point_method.cpp:18-63 through the C ABI: mpm_fill_ball applies the reference's fill rule (radius 0.2, cpp:19)
+// with libc rand(), so the default rand() stream produces the reference's particles; they go into the slots from the
+// back, like the reference's particles[--particlesLeft].
 void LagrangeEulerView::initializeParticles(const v3t& particlesOrigin, const v3t& velocity) {
-    const ftype radius = 0.2;
-    const glm::ivec3 centre{ particlesOrigin / WeightCalculator::h };
-    const int reach = radius / WeightCalculator::h;
-    int free_slots = nParticles, missing = 0;
-    const glm::vec3 sites[] = { {1, 1, 1}, {1, 1, 3}, {1, 3, 1}, {1, 3, 3}, {3, 1, 1}, {3, 1, 3}, {3, 3, 1}, {3, 3, 3} };
-    for (int i = centre.x - reach; i < centre.x + reach; ++i)
-        for (int j = centre.y - reach; j < centre.y + reach; ++j)
-            for (int k = centre.z - reach; k < centre.z + reach; ++k)
-                for (const auto& site : sites) {
-                    const auto candidate = (glm::vec3(i, j, k) + site * (1 / 4.0f) + generateRandomInsideUnitBall(0.25)) * WeightCalculator::h;
-                    if (glm::length(candidate - particlesOrigin) > radius) continue;
-                    if (free_slots == 0) { ++missing; continue; }
-                    Particle& p = particles[--free_slots];
-                    p.pos = candidate;
-                    p.velocity = velocity;
-                    rand(); rand(); rand();                 // the reference draws (and then overwrites) r, g, b
-                    p.r = p.g = p.b = p.a = 255;
-                    p.size = 0.02;
-                    p.mass = 0.00006;
-                }
+    const float origin[3] = { particlesOrigin.x, particlesOrigin.y, particlesOrigin.z };
+    std::vector<float> pos(3 * (size_t)std::max(nParticles, 1));
+    int64_t stored = 0, missing = 0;
+    check(mpm_fill_ball(origin, 0.2f, WeightCalculator::h, nullptr, nullptr, pos.data(), nParticles, &stored, &missing), "initializeParticles");
+    for (int64_t k = 0; k < stored; ++k) {
+        Particle& p = particles[nParticles - 1 - k];
+        p.pos = { pos[3 * k], pos[3 * k + 1], pos[3 * k + 2] };
+        p.velocity = velocity;
+        p.r = p.g = p.b = p.a = 255;        // cpp:48-51
+        p.size = 0.02;
+        p.mass = 0.00006;
+    }
     if (missing) std::cout << missing << " more!!!\n";
     binding(this).uploaded = false;
 }

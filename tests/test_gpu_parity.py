@@ -295,8 +295,12 @@ def test_adapter_drop_in_through_reference_class_interface(golden_c1, tmp_path):
     exe = os.path.join(os.path.dirname(op.HERE), "oracle", "_ref", "adapter_mpm")
     if not os.path.exists(exe):
         pytest.skip("adapter binary not built (needs /root/reference headers at build time)")
+    env = dict(os.environ)
+    if os.environ.get("MPM_B200_LIB"):        # the CPU run of this suite (tests/emu): the binary loads that build instead
+        os.symlink(os.environ["MPM_B200_LIB"], str(tmp_path / "libmpm_b200.so"))
+        env["LD_LIBRARY_PATH"] = str(tmp_path) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     r = subprocess.run([exe, "--steps", "100", "--dump-dir", str(tmp_path), "--dump-steps", "1,20,100", "--quiet"],
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout
     assert "mpm_b200 error" not in r.stdout, r.stdout
     s0 = np.fromfile(str(tmp_path / "particles_step0000.f32"), dtype=np.float32).reshape(-1, 35)
