@@ -168,7 +168,15 @@ class SlabRunner:
             s.halo_add(0, self.h_recv_dn.data_ptr())
 
     def _view(self, ptr, n_floats):
-        """torch view over a buffer owned by the library (no copy)."""
+        """torch view over a buffer owned by the library (no copy); the library's buffers keep their addresses, so the
+        views are built once (a few tens of microseconds each, every substep otherwise)."""
+        cache = self.__dict__.setdefault("_views", {})
+        key = (ptr, n_floats)
+        if key not in cache:
+            cache[key] = self._make_view(ptr, n_floats)
+        return cache[key]
+
+    def _make_view(self, ptr, n_floats):
         if self.device != "cuda":       # CPU stand-in of the tests: a plain host pointer
             import ctypes
             return self.torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n_floats).from_address(ptr)))
