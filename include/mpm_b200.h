@@ -85,7 +85,8 @@ typedef struct MpmStats {
                                    time between begin/end calls, total, F-update alone (-1 if it ran on the side stream) */
     int32_t svd_failed;         /* 1 if the last F-update met a non-finite matrix */
     int32_t reserved[7];        /* [0] = 1 if the pos/h shortcut passed its exhaustive check for this h,
-                                   [1] = 1 if a migration buffer overflowed (particles kept one more substep) */
+                                   [1] = 1 if a migration buffer overflowed (particles kept one more substep),
+                                   [2] = 1 if a peer-memory halo wait gave up (experimental mpm_substep_begin_peer) */
 } MpmStats;
 
 typedef struct mpm_sim mpm_t;
@@ -213,6 +214,20 @@ size_t mpm_migrate_buffer_bytes(const mpm_t* s);
 int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up);
 int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf);
 int mpm_sync_counts(mpm_t* s);
+/* EXPERIMENTAL (opt-in, not yet run on hardware) -- peer-memory halo: the ghost-layer reduction done by P2G itself. Every
+ * rank exports its grid allocation (mpm_peer_export: a cudaIpcMemHandle_t), the host exchanges the handles and each rank
+ * opens its neighbours' (mpm_peer_connect; *_layers = the neighbour's block_hi - block_lo; NULL at the ends of the chain).
+ * P2G then adds every tile node of a shared block layer to the local copy and, through NVLink, to the neighbour's copy;
+ * mpm_substep_begin_peer(s, dt, 0), (.., 1), (.., 2) called back to back replace mpm_substep_begin + the halo exchange
+ * (device-side flags between the phases, no host synchronisation, no message); mpm_substep_end follows unchanged.
+ * mpm_peer_connect_ptr takes neighbour grids that live in THIS process (mpm_grid_device_ptr of another handle on the same
+ * or a peer-enabled device): used by the single-process test of the protocol. */
+#define MPM_IPC_HANDLE_BYTES 64
+int mpm_peer_export(mpm_t* s, unsigned char* handle);
+int mpm_peer_connect(mpm_t* s, const unsigned char* lower_handle, int lower_layers, const unsigned char* upper_handle, int upper_layers);
+int mpm_peer_connect_ptr(mpm_t* s, void* lower_grid, int lower_layers, void* upper_grid, int upper_layers);
+int mpm_grid_device_ptr(mpm_t* s, void** grid);
+int mpm_substep_begin_peer(mpm_t* s, float dt, int phase);
 /* Distributed bookkeeping: particle ids are upload indices + pid_base (set before an upload) so that they stay
  * unique across slabs; mpm_download_live_particles returns the handle's current particles in storage order as
  * 35-float rows (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) with their ids. */

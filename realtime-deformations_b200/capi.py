@@ -51,7 +51,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_substep_end", "mpm_migrate_outgoing", "mpm_migrate_append", "mpm_set_pid_base", "mpm_download_live_particles", "mpm_migrate_buffer_bytes", "mpm_migrate_pack",
            "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
-           "mpm_box_transform_flip_velocity", "mpm_fill_ball"]
+           "mpm_box_transform_flip_velocity", "mpm_fill_ball", "mpm_peer_export", "mpm_peer_connect", "mpm_peer_connect_ptr",
+           "mpm_grid_device_ptr", "mpm_substep_begin_peer"]
 
 _lib = None
 
@@ -114,6 +115,11 @@ def lib():
     L.mpm_box_collider_from_transform.argtypes = [C.POINTER(MpmBoxTransform), C.POINTER(MpmBoxCollider)]
     L.mpm_box_transform_move.argtypes = [C.POINTER(MpmBoxTransform), C.c_float]
     L.mpm_box_transform_flip_velocity.argtypes = [C.POINTER(MpmBoxTransform)]
+    L.mpm_peer_export.argtypes = [vp, vp]
+    L.mpm_peer_connect.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.mpm_peer_connect_ptr.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.mpm_grid_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.mpm_substep_begin_peer.argtypes = [vp, C.c_float, C.c_int]
     L.mpm_fill_ball.argtypes = [fp, C.c_float, C.c_float, vp, vp, fp, i64, C.POINTER(i64), C.POINTER(i64)]
     _lib = L
     return L
@@ -314,6 +320,30 @@ class Sim:
 
     def substep_end(self, dt, colliders, nc):
         _ck(self.L.mpm_substep_end(self.h, dt, colliders, nc))
+
+    # ---- experimental peer-memory halo (include/mpm_b200.h) -------------------------------------------
+    def peer_export(self):
+        h = (C.c_ubyte * 64)()
+        _ck(self.L.mpm_peer_export(self.h, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def peer_connect(self, lower_handle, lower_layers, upper_handle, upper_layers):
+        lo = (C.c_ubyte * 64).from_buffer_copy(lower_handle) if lower_handle is not None else None
+        up = (C.c_ubyte * 64).from_buffer_copy(upper_handle) if upper_handle is not None else None
+        _ck(self.L.mpm_peer_connect(self.h, C.cast(lo, C.c_void_p) if lo is not None else None, int(lower_layers),
+                                    C.cast(up, C.c_void_p) if up is not None else None, int(upper_layers)))
+
+    def peer_connect_ptr(self, lower_grid, lower_layers, upper_grid, upper_layers):
+        _ck(self.L.mpm_peer_connect_ptr(self.h, C.c_void_p(lower_grid) if lower_grid else None, int(lower_layers),
+                                        C.c_void_p(upper_grid) if upper_grid else None, int(upper_layers)))
+
+    def grid_device_ptr(self):
+        p = C.c_void_p()
+        _ck(self.L.mpm_grid_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def substep_begin_peer(self, dt, phase):
+        _ck(self.L.mpm_substep_begin_peer(self.h, dt, int(phase)))
 
     # ---- diagnostics --------------------------------------------------------------------------------
     def grid(self):

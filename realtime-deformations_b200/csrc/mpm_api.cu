@@ -32,6 +32,8 @@ static int fail(int code, const char* fmt, ...) {
 #define NEED(s) do { if (!(s)) return fail(MPM_ERR_INVALID, "null handle"); CK(cudaSetDevice((s)->device)); } while (0)
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
+constexpr size_t PEER_FLAG_BYTES = 256;      // 4 flag words used: [0]/[1] cleared by lower/upper neighbour, [2]/[3] P2G done by lower/upper
+
 struct mpm_sim {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -66,6 +68,12 @@ struct mpm_sim {
     ColliderSet graph_cols;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
+    // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
+    PeerLayers peer = { nullptr, nullptr };
+    int* peer_flags_dn = nullptr; int* peer_flags_up = nullptr;      // the neighbours' flag words (peer-mapped)
+    void* ipc_dn = nullptr; void* ipc_up = nullptr;                  // mappings opened by mpm_peer_connect (closed in destroy)
+    bool peer_connected = false;
+    int peer_epoch = 0;
     bool fupd_pending = false;  // experimental p2g_variant 3/4: P2G has put the F-update results into the idle buffer (until substep_end)
     int num_sms = 148;
     cudaEvent_t ev[8];
@@ -206,7 +214,8 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     CK(cudaMalloc(&s->gflag, sizeof(int) * (size_t)g.n_gblocks));
     CK(cudaMalloc(&s->gblock_list, sizeof(int) * (size_t)g.n_gblocks));
     CK(cudaMalloc(&s->partial, sizeof(int2) * (size_t)s->n_chunks));
-    CK(cudaMalloc(&s->grid, sizeof(float4) * 64 * (size_t)g.n_gblocks));
+    CK(cudaMalloc(&s->grid, sizeof(float4) * 64 * (size_t)g.n_gblocks + PEER_FLAG_BYTES));     // + the peer-halo flag words (same IPC handle)
+    CK(cudaMemsetAsync(s->grid + 64 * (size_t)g.n_gblocks, 0, PEER_FLAG_BYTES, s->stream));
     CK(cudaMalloc(&s->dc, sizeof(DevCounters)));
     CK(cudaMemsetAsync(s->gflag, 0, sizeof(int) * (size_t)g.n_gblocks, s->stream));
     CK(cudaMemsetAsync(s->grid, 0, sizeof(float4) * 64 * (size_t)g.n_gblocks, s->stream));
@@ -253,6 +262,8 @@ int mpm_destroy(mpm_t* s) {
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
     cudaFree(s->render_stage);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->ipc_dn) cudaIpcCloseMemHandle(s->ipc_dn);
+    if (s->ipc_up) cudaIpcCloseMemHandle(s->ipc_up);
     if (s->side.stream) { cudaStreamDestroy(s->side.stream); cudaEventDestroy(s->side.fork); cudaEventDestroy(s->side.join); }
     if (s->side.mid) cudaEventDestroy(s->side.mid);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -873,6 +884,7 @@ int mpm_get_stats(mpm_t* s, MpmStats* out) {
     st.n_particle_blocks = h.n_active_pblocks; st.n_grid_blocks = h.n_active_gblocks; st.svd_failed = h.svd_failed;
     st.reserved[0] = s->sc.pd.fast;      // 1: the pos/h FMA shortcut passed its exhaustive check against __fdiv_rn
     st.reserved[1] = h.mig_overflow;
+    st.reserved[2] = h.peer_timeout;     // experimental peer-memory halo: a neighbour's flag never arrived
     if (st.substeps_done > 0) {
         float ms;
         const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 4, 5 }, { 5, 6 }, { 3, 4 } };
@@ -964,6 +976,106 @@ int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
+// ---- EXPERIMENTAL peer-memory halo: the ghost-layer reduction inside P2G over NVLink-mapped neighbour grids --------------
+// Protocol of substep number e (identical on every rank), all on the handle's stream, no host synchronisation:
+//   phase 0:  bin, clear (the shared layers are always in the active list)        -> signal "cleared(e)" to both neighbours
+//   phase 1:  wait for the neighbours' "cleared(e)"; P2G with remote reds (k_p2g_tile<.., PEER>) -> signal "p2g done(e)"
+//   phase 2:  wait for the neighbours' "p2g done(e)"; from here mpm_substep_end runs unchanged (both copies of a shared layer
+//             hold the complete sums, both ranks update it redundantly as with the message-based halo)
+// A neighbour clears its copy of a shared layer for substep e+1 only after phase 2 of substep e, i.e. after my remote reds of
+// substep e are complete, and my reds of substep e+1 wait for its "cleared(e+1)". The flag kernels are one thread each;
+// a wait gives up after ~2^23 polls and raises DevCounters::peer_timeout (reported by mpm_sync_counts / mpm_get_stats)
+// instead of hanging the device.
+__global__ void k_peer_signal(int* flag_a, int* flag_b, int epoch) {
+    __threadfence_system();                       // everything this stream did before is visible system-wide first
+    if (flag_a) *(volatile int*)flag_a = epoch;
+    if (flag_b) *(volatile int*)flag_b = epoch;
+    __threadfence_system();
+}
+__global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, DevCounters* dc) {
+    const int* flags[2] = { flag_a, flag_b };
+    for (int f = 0; f < 2; ++f) {
+        if (!flags[f]) continue;
+        bool ok = false;
+        for (int poll = 0; poll < (1 << 23) && !ok; ++poll) ok = *(const volatile int*)flags[f] >= epoch;
+        if (!ok) dc->peer_timeout = 1;
+    }
+    __threadfence_system();
+}
+int mpm_peer_export(mpm_t* s, unsigned char* handle) {
+    NEED(s);
+    if (!handle) return fail(MPM_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPM_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->grid));
+    memcpy(handle, &h, sizeof h);
+    return MPM_OK;
+}
+int mpm_peer_connect_ptr(mpm_t* s, void* lower_grid, int lower_layers, void* upper_grid, int upper_layers) {
+    NEED(s);
+    const size_t layer_nodes = (size_t)64 * s->gd.nbj * s->gd.nbk;
+    if ((lower_grid && lower_layers < 1) || (upper_grid && upper_layers < 1)) return fail(MPM_ERR_INVALID, "a neighbour slab has at least one block layer");
+    if ((lower_grid != nullptr) != (s->gd.lo > 0) || (upper_grid != nullptr) != (s->gd.hi < s->gd.npbi_global))
+        return fail(MPM_ERR_INVALID, "peer grids must be given exactly for the neighbours this slab has");
+    // a neighbour's grid holds its block layers [lo', hi'] (hi'-lo'+1 layers) followed by its flag words
+    s->peer.dn = lower_grid ? (float4*)lower_grid + (size_t)lower_layers * layer_nodes : nullptr;           // its ghost layer == my first layer
+    s->peer_flags_dn = lower_grid ? (int*)((float4*)lower_grid + (size_t)(lower_layers + 1) * layer_nodes) : nullptr;
+    s->peer.up = upper_grid ? (float4*)upper_grid : nullptr;                                                // its first layer == my ghost layer
+    s->peer_flags_up = upper_grid ? (int*)((float4*)upper_grid + (size_t)(upper_layers + 1) * layer_nodes) : nullptr;
+    CK(tile_kernels_init_experimental());
+    s->peer_connected = true;
+    s->peer_epoch = 0;
+    return MPM_OK;
+}
+int mpm_peer_connect(mpm_t* s, const unsigned char* lower_handle, int lower_layers, const unsigned char* upper_handle, int upper_layers) {
+    NEED(s);
+    void *lo_ptr = nullptr, *up_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    if (lower_handle) { memcpy(&h, lower_handle, sizeof h); CK(cudaIpcOpenMemHandle(&lo_ptr, h, cudaIpcMemLazyEnablePeerAccess)); s->ipc_dn = lo_ptr; }
+    if (upper_handle) { memcpy(&h, upper_handle, sizeof h); CK(cudaIpcOpenMemHandle(&up_ptr, h, cudaIpcMemLazyEnablePeerAccess)); s->ipc_up = up_ptr; }
+    return mpm_peer_connect_ptr(s, lo_ptr, lower_layers, up_ptr, upper_layers);
+}
+int mpm_grid_device_ptr(mpm_t* s, void** grid) {
+    NEED(s);
+    if (!grid) return fail(MPM_ERR_INVALID, "null argument");
+    *grid = s->grid;
+    return MPM_OK;
+}
+#define EVP(i) CK(cudaEventRecord(s->ev[i], s->stream))
+int mpm_substep_begin_peer(mpm_t* s, float dt, int phase) {
+    NEED(s);
+    if (!s->peer_connected) return fail(MPM_ERR_INVALID, "mpm_peer_connect first");
+    if (p2g_fupd(s) || s->prm.p2g_variant == 1) return fail(MPM_ERR_INVALID, "the peer-memory halo runs with the default tile P2G");
+    int* mine = (int*)(s->grid + 64 * (size_t)s->gd.n_gblocks);          // my flag words, written by the neighbours
+    // my lower neighbour sees me as ITS upper neighbour: I write its flags [1] / [3]; my upper neighbour's [0] / [2]
+    if (phase == 0) {
+        ++s->peer_epoch;
+        EVP(0);
+        TRY(ensure_tau(s));
+        TRY(do_binning(s));
+        EVP(1);
+        TRY(launch_clear(s));
+        EVP(2);
+        k_peer_signal<<<1, 1, 0, s->stream>>>(s->peer_flags_dn ? s->peer_flags_dn + 1 : nullptr, s->peer_flags_up ? s->peer_flags_up + 0 : nullptr, s->peer_epoch);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    } else if (phase == 1) {
+        k_peer_wait<<<1, 1, 0, s->stream>>>(s->peer.dn ? mine + 0 : nullptr, s->peer.up ? mine + 1 : nullptr, s->peer_epoch, s->dc);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        CK((launch_p2g_tile<P2G_FUSED>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
+                                       s->num_sms, (int)s->n_bound, s->stream, false, nullptr, &s->peer)));
+        s->stats.kernel_launches++;
+        s->fupd_pending = false;
+        k_peer_signal<<<1, 1, 0, s->stream>>>(s->peer_flags_dn ? s->peer_flags_dn + 3 : nullptr, s->peer_flags_up ? s->peer_flags_up + 2 : nullptr, s->peer_epoch);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    } else if (phase == 2) {
+        k_peer_wait<<<1, 1, 0, s->stream>>>(s->peer.dn ? mine + 2 : nullptr, s->peer.up ? mine + 3 : nullptr, s->peer_epoch, s->dc);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        EVP(3);
+    } else return fail(MPM_ERR_INVALID, "phase must be 0, 1 or 2");
+    return MPM_OK;
+}
+#undef EVP
+
 static int ensure_out_buffers(mpm_sim* s);
 int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** dev_down, const void** dev_up) {
     NEED(s);
@@ -1041,6 +1153,7 @@ int mpm_sync_counts(mpm_t* s) {
     CK(cudaMemcpyAsync(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->n_bound = h.n_slots;
+    if (h.peer_timeout) return fail(MPM_ERR_CUDA, "peer-memory halo: a neighbour's flag never arrived (the grids of this substep are incomplete)");
     if (h.mig_overflow) {
         const int what = h.mig_overflow;
         CK(cudaMemsetAsync(&s->dc->mig_overflow, 0, sizeof(int), s->stream));

@@ -52,7 +52,8 @@ struct DevCounters {
     int epoch;
     int n_mig[2];           // particles packed for the lower / upper slab neighbour by k_mark_outgoing
     int mig_overflow;
-    int pad[3];
+    int peer_timeout;       // experimental peer-memory halo: a neighbour's flag did not arrive (k_peer_wait gave up)
+    int pad[2];
 };
 
 enum { KEY_DEAD = -2 };

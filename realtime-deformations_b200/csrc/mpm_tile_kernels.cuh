@@ -118,10 +118,17 @@ MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCoun
 // of two consecutive z-nodes as one fp32 pair: per node pair 1 FMUL2 + 7 FFMA2 instead of 2 FMUL + 8 FFMA + 6 FADD.
 // The affine value at node c is formed as fma(c, step, v0) instead of c repeated additions (one rounding instead
 // of c: an fp32 re-association like the tile kernel's own summation order, covered by the trajectory tolerances).
-template <int MODE, bool PACKED = false, bool FUPD = false>
+// PEER (EXPERIMENTAL, opt-in through mpm_substep_begin_peer, not yet run on hardware): the ghost-layer reduction of the slab
+// decomposition done by this kernel itself. A tile node that lies in a block layer shared with a neighbouring slab (my
+// ghost layer = the upper neighbour's first layer; my first layer = the lower neighbour's ghost layer) is added to the
+// local copy AND, with the same vector red, to the neighbour's copy through its peer-mapped grid (NVLink atomics execute
+// at the owning GPU's L2), so that after both P2G kernels both copies hold the complete sums: no halo message, no pack /
+// add kernels, and the remote reds of a block overlap the accumulation of the next ones.
+struct PeerLayers { float4* dn; float4* up; };      // lower neighbour's ghost layer, upper neighbour's first layer (or null)
+template <int MODE, bool PACKED = false, bool FUPD = false, bool PEER = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
-           float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx) {
+           float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx, PeerLayers peer = PeerLayers{ nullptr, nullptr }) {
     MPM_DYN_SMEM(smem_raw, 16);
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31;
@@ -347,8 +354,16 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     const float4 v = S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk];
                     sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                 }
-            if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
-                atomicAdd(&grid[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
+            if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) {
+                const size_t idx = node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk);
+                atomicAdd(&grid[idx], sum);
+                if (PEER) {
+                    const int layer = ((4 * pbi + ni) >> 2) - gd.lo;                   // block layer of the node inside my slab
+                    const size_t layer_nodes = (size_t)gd.nbj * gd.nbk * 64;
+                    if (layer == gd.hi - gd.lo) { if (peer.up) atomicAdd(&peer.up[idx - (size_t)layer * layer_nodes], sum); }
+                    else if (layer == 0) { if (peer.dn) atomicAdd(&peer.dn[idx], sum); }
+                }
+            }
         }
         if (FUPD) {
             // F-update of this block's particles, two per thread and round with both particles' loads issued first.
@@ -621,6 +636,7 @@ inline cudaError_t tile_kernels_init_experimental() {
 #define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
     MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>), P2GSmem);
     MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, false, true>), P2GSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
@@ -631,11 +647,15 @@ inline cudaError_t tile_kernels_init_experimental() {
 template <int MODE>
 cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            bool packed = false, const Planes* fupd_target = nullptr) {
+                            bool packed = false, const Planes* fupd_target = nullptr, const PeerLayers* peer = nullptr) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const Planes Nx = fupd_target ? *fupd_target : P;
+    if (peer && MODE == P2G_FUSED) {              // experimental peer-memory halo: plain accumulation loop, F-update in its own kernel
+        k_p2g_tile<P2G_FUSED, false, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
+        return cudaGetLastError();
+    }
     if (fupd_target && MODE == P2G_FUSED) {       // only the fused substep moves the F-update into P2G
         if (packed) k_p2g_tile<P2G_FUSED, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
         else k_p2g_tile<P2G_FUSED, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);

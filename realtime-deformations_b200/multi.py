@@ -152,6 +152,18 @@ class SlabRunner:
         if world > 1:
             self._halo()
         self.sim.computeParticleVolumesAndDensities()
+        # EXPERIMENTAL, opt-in (MPM_B200_PEER_HALO=1, not yet run on hardware): the per-substep ghost-layer reduction done by
+        # P2G itself over NVLink (CUDA IPC mappings of the neighbours' grids, device-side flags) instead of halo messages
+        import os
+        self.peer_halo = world > 1 and self.device == "cuda" and os.environ.get("MPM_B200_PEER_HALO") == "1"
+        if self.peer_halo:
+            mine = (self.sim.peer_export(), self.hi - self.lo)
+            everyone = [None] * world
+            self.dist.all_gather_object(everyone, mine)
+            lower = everyone[rank - 1] if rank > 0 else (None, 0)
+            upper = everyone[rank + 1] if rank < world - 1 else (None, 0)
+            self.sim.peer_connect(lower[0], lower[1], upper[0], upper[1])
+            self.dist.barrier()            # every rank has mapped its neighbours before the first remote red
 
     # ghost-layer partial sums up, first-layer partial sums down, add on both sides
     def _halo(self):
@@ -218,8 +230,12 @@ class SlabRunner:
             self.sim.substep(self.dt, self.cols, self.nc, 1)
             return
         with self._on_stream():
-            self.sim.substep_begin(self.dt)
-            self._halo()
+            if getattr(self, "peer_halo", False):
+                for phase in (0, 1, 2):
+                    self.sim.substep_begin_peer(self.dt, phase)
+            else:
+                self.sim.substep_begin(self.dt)
+                self._halo()
             self.sim.substep_end(self.dt, self.cols, self.nc)
             self._migrate()
 

@@ -402,6 +402,9 @@ template <class T> inline T emu_reduce_add(unsigned mask, T v) {
 inline int __reduce_add_sync(unsigned mask, int v) { return emu_reduce_add(mask, v); }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emu_reduce_add(mask, v); }
 
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
 // ---- atomics -------------------------------------------------------------------------------------------------------
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

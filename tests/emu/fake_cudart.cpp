@@ -41,6 +41,11 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free((void*)e); return cudaSu
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+// "IPC" inside one process: the handle carries the pointer itself (the emulated multi-rank tests are separate processes
+// and do not use the peer-memory halo; the single-process protocol test connects with mpm_peer_connect_ptr)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h, &p, sizeof p); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof *p); return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime error"; }

@@ -442,6 +442,84 @@ def test_p2g_rotated_record_walk_on_eight_per_cell_slab(monkeypatch):
     assert rot.stats().n_particles == ali.stats().n_particles == sc["n"]
 
 
+def test_peer_memory_halo_two_slabs_in_one_process():
+    """EXPERIMENTAL peer-memory halo (mpm_substep_begin_peer): P2G adds the tile nodes of a shared block layer to the local
+    grid AND to the neighbour slab's grid, device-side flags replace the halo messages. Two slab handles in ONE process
+    (neighbour grids connected by pointer, migration buffers handed over directly) against the same scene in one domain,
+    with the tile-vs-baseline difference of the single domain as the noise floor."""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"          # (host emulation runs: "device" memory is host memory)
+    grid, n, steps, mid = 32, 8192, 16, 4
+    sc = mpm_b200.scenes.snow_slab(grid=grid, n=n)
+    sc["vel"][:] = (150.0, -20.0, 0.0)                            # drive particles across the slab boundary
+    dt = float(sc["dt"])
+    n_layers = (grid + 3) // 4
+
+    def params(variants=(0, 0)):
+        p = mpm_b200.capi.default_params(h=float(sc["h"]), p2g_variant=variants[0], g2p_variant=variants[1])
+        p.gravity[:] = [float(x) for x in sc["gravity"]]
+        return p
+
+    layer = ((sc["pos"][:, 0] / np.float32(sc["h"])).astype(np.int32) - 1) >> 2
+    parts, base = [], 0
+    for lo, hi in ((0, mid), (mid, n_layers)):
+        sel = np.flatnonzero((layer >= lo) & (layer < hi))
+        sim = mpm_b200.Sim(grid, grid, grid, len(sel), params(), slab=(lo, hi), capacity=n + 1024)
+        sim.set_pid_base(base)
+        sim.upload(sc["pos"][sel], sc["vel"][sel], sc["mass"][sel])
+        sim.set_migrate_capacity(4096)
+        parts.append((sim, sel, lo, hi))
+        base += len(sel)
+    (A, sel_a, _, _), (B, sel_b, _, _) = parts
+    assert len(sel_a) > 0 and len(sel_b) > 0
+    cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
+    # start-up (main.cpp:53-54) with the message-style halo through two staging buffers
+    hb = A.halo_bytes() // 4
+    buf_up, buf_dn = torch.zeros(hb, dtype=torch.float32, device=dev), torch.zeros(hb, dtype=torch.float32, device=dev)
+    if dev == "cuda":
+        torch.cuda.synchronize()
+    A.rasterizeParticlesToGrid(); B.rasterizeParticlesToGrid()
+    A.halo_pack(1, buf_up.data_ptr()); B.halo_pack(0, buf_dn.data_ptr())
+    A.synchronize(); B.synchronize()
+    B.halo_add(0, buf_up.data_ptr()); A.halo_add(1, buf_dn.data_ptr())
+    A.computeParticleVolumesAndDensities(); B.computeParticleVolumesAndDensities()
+    A.synchronize(); B.synchronize()
+    # connect the neighbour grids and run with the peer-memory halo
+    A.peer_connect_ptr(None, 0, B.grid_device_ptr(), n_layers - mid)
+    B.peer_connect_ptr(A.grid_device_ptr(), mid, None, 0)
+    for _ in range(steps):
+        for phase in (0, 1, 2):
+            A.substep_begin_peer(dt, phase); B.substep_begin_peer(dt, phase)
+        A.substep_end(dt, cols, nc); B.substep_end(dt, cols, nc)
+        _, a_up = A.migrate_pack()
+        b_dn, _ = B.migrate_pack()
+        A.synchronize(); B.synchronize()                          # the packed buffers change hands between two streams
+        B.migrate_append_packed(a_up); A.migrate_append_packed(b_dn)
+        A.synchronize(); B.synchronize()
+    A.sync_counts(); B.sync_counts()
+    assert A.stats().reserved[2] == 0 and B.stats().reserved[2] == 0, "a peer-halo wait timed out"
+    sa, pa = A.download_live(n + 1024)
+    sb, pb = B.download_live(n + 1024)
+    S, P = np.concatenate([sa, sb]), np.concatenate([pa, pb])
+    assert len(P) == n and len(np.unique(P)) == n
+    assert len(pa) != len(sel_a), "no particle crossed the slab boundary: the scene does not exercise migration"
+    S = S[np.argsort(P)]
+    order = np.concatenate([sel_a, sel_b])                        # pid -> index in the scene arrays
+    one = mpm_b200.Sim(grid, grid, grid, n, params())
+    one.upload(sc["pos"][order], sc["vel"][order], sc["mass"][order])
+    one.rasterizeParticlesToGrid(); one.computeParticleVolumesAndDensities()
+    one.substep(dt, cols, nc, steps)
+    ref = one.download_state35()
+    alt = mpm_b200.Sim(grid, grid, grid, n, params((1, 1)))
+    alt.upload(sc["pos"][order], sc["vel"][order], sc["mass"][order])
+    alt.rasterizeParticlesToGrid(); alt.computeParticleVolumesAndDensities()
+    alt.substep(dt, cols, nc, steps)
+    e, f = traj_errors(S, ref), traj_errors(alt.download_state35(), ref)
+    assert np.abs(S[:, 4] / ref[:, 4] - 1).max() < 1e-5, "particle volumes (start-up halo)"
+    for name, got, floor, absf in zip(("pos", "vel", "detF"), e, f, (1e-6, 1e-3, 1e-5)):
+        assert got <= 4 * max(floor, absf), f"peer-memory halo vs one domain: max |d {name}| = {got:.3e}, noise floor {floor:.3e}"
+
+
 def test_full_size_properties_config3_momentum():
     """BASELINE config 3 (two colliding snowballs, 8 Mi particles, 256^3, no ground): APIC transfers conserve linear
     momentum, so over k substeps the total particle momentum changes by exactly M * g * dt * k; nothing is lost or

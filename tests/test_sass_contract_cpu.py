@@ -63,7 +63,7 @@ def test_no_kernel_spills_to_local_memory(kernels):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_p2g_tile_kernel_contract(kernels, mode):
-    k = _one(kernels, f"k_p2g_tileILi{mode}ELb0ELb0")
+    k = _one(kernels, f"k_p2g_tileILi{mode}ELb0ELb0ELb0E")
     assert k["regs"] <= 128, "2 CTAs of 256 threads per SM need <= 128 registers"
     assert _count(k, "REDG.E.ADD.F32x4") == 1, "one vector red.global.add.v4.f32 per tile node"
     assert not any("CAST" in o for o in k["ops"]), "no shared-memory float atomics (ATOMS.CAST.SPIN loops)"
@@ -94,9 +94,15 @@ def test_fupdate_kernel_contract(kernels):
 
 
 def test_packed_variants_use_ffma2(kernels):
-    p2g = _one(kernels, "k_p2g_tileILi2ELb1ELb0")
+    p2g = _one(kernels, "k_p2g_tileILi2ELb1ELb0ELb0E")
     g2p = _one(kernels, "k_g2p_tileILi14ELb0ELb1")
     assert _count(p2g, "FFMA2") >= 40 and _count(g2p, "FFMA2") >= 200
+
+
+def test_peer_halo_p2g_issues_remote_vector_reds(kernels):
+    k = _one(kernels, "k_p2g_tileILi2ELb0ELb0ELb1E")
+    assert _count(k, "REDG.E.ADD.F32x4") == 3, "local copy + the upper / lower neighbour's copy of a shared layer"
+    assert k["regs"] <= 128 and not any("CAST" in o for o in k["ops"])
 
 
 def test_binning_uses_warp_aggregated_atomics(kernels):

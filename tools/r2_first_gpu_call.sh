@@ -21,4 +21,15 @@ timeout 600 env MPM_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -x -q > gp
 echo "experimental gpu tests: exit $?" | tee -a gpurun_out/exp_tests.log
 timeout 300 python tools/perf_probe.py 256 8388608 20 slab 0:0,0:2,0:3,0:4,2:0,3:0,4:4 > gpurun_out/ab_8M.log 2>&1
 timeout 480 python tools/perf_probe.py 512 67108864 10 slab 0:0,4:4,3:0,2:0,0:4 > gpurun_out/ab_64M.log 2>&1
+# 5. (needs `gpurun --gpus 2`) peer-memory halo: first the single-process protocol test is part of step 1; then 2 ranks with
+#    CUDA IPC against one domain, with and without MPM_B200_PEER_HALO, every multi-rank command under `timeout`
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  for peer in 0 1; do
+    MPM_B200_PEER_HALO=$peer timeout 300 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 \
+      tools/multi_check.py 128 2097152 30 > gpurun_out/multi_check_peer_${peer}.log 2>&1
+    MPM_B200_PEER_HALO=$peer timeout 420 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29712 \
+      bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_2gpu_peer_${peer}.log 2>&1
+  done
+  tail -n 3 gpurun_out/multi_check_peer_*.log gpurun_out/bench_2gpu_peer_*.log
+fi
 tail -n 8 gpurun_out/gpu_tests.log gpurun_out/rotate_*_64M.log gpurun_out/exp_tests.log gpurun_out/ab_8M.log gpurun_out/ab_64M.log
