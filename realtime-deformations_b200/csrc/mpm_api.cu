@@ -997,7 +997,11 @@ __global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, Dev
     for (int f = 0; f < 2; ++f) {
         if (!flags[f]) continue;
         bool ok = false;
+#ifndef MPM_HOST_EMU
         for (int poll = 0; poll < (1 << 23) && !ok; ++poll) ok = *(const volatile int*)flags[f] >= epoch;
+#else   // tests/emu: the neighbour is another PROCESS whose emulated kernels take seconds; poll politely for up to 5 minutes
+        for (int poll = 0; poll < 300000 && !ok; ++poll) { ok = *(const volatile int*)flags[f] >= epoch; if (!ok) emu_sleep_ms(1); }
+#endif
         if (!ok) dc->peer_timeout = 1;
     }
     __threadfence_system();

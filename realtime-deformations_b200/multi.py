@@ -155,7 +155,8 @@ class SlabRunner:
         # EXPERIMENTAL, opt-in (MPM_B200_PEER_HALO=1, not yet run on hardware): the per-substep ghost-layer reduction done by
         # P2G itself over NVLink (CUDA IPC mappings of the neighbours' grids, device-side flags) instead of halo messages
         import os
-        self.peer_halo = world > 1 and self.device == "cuda" and os.environ.get("MPM_B200_PEER_HALO") == "1"
+        self.peer_halo = world > 1 and os.environ.get("MPM_B200_PEER_HALO") == "1" and \
+            (self.device == "cuda" or os.environ.get("MPM_B200_ALLOW_EMULATION") == "1")     # (tests/emu: shared-memory "IPC")
         if self.peer_halo:
             mine = (self.sim.peer_export(), self.hi - self.lo)
             everyone = [None] * world

@@ -402,6 +402,7 @@ template <class T> inline T emu_reduce_add(unsigned mask, T v) {
 inline int __reduce_add_sync(unsigned mask, int v) { return emu_reduce_add(mask, v); }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emu_reduce_add(mask, v); }
 
+inline void emu_sleep_ms(int ms) { std::this_thread::sleep_for(std::chrono::milliseconds(ms)); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 

@@ -60,6 +60,8 @@ else:
     lo, hi = multi.slab_layers(n_layers, world)[rank]
     r = multi.SlabRunner(grid, n, rank, world, torch, scene=make_scene((4 * lo + 1, 4 * hi + 1)), device="cpu")
 r.sync_every = 4              # several collective count / overflow checks inside the run
+if rank == 0:
+    print("peer-memory halo:", bool(getattr(r, "peer_halo", False)))
 n0 = r.sim.stats().n_particles
 for _ in range(steps):
     r.substep()

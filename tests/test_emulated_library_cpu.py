@@ -80,6 +80,19 @@ def test_slab_protocol_with_the_real_library_over_gloo(emu_lib, world, balanced,
     assert "unique ids 16384" in r.stdout
 
 
+@pytest.mark.parametrize("world,balanced,port", [(3, 0, 29734), (8, 1, 29735)])
+def test_peer_memory_halo_protocol_across_processes(emu_lib, world, balanced, port):
+    """The EXPERIMENTAL peer-memory halo end to end across processes: handle exchange and mapping in multi.py
+    (all_gather_object, unequal slab sizes, ranks that start empty), remote reds from P2G into the neighbours' grids and the
+    device-side flag protocol under real concurrency -- the fake runtime backs "device" memory with POSIX shared memory so
+    that cudaIpcOpenMemHandle maps another rank's grid (EMU_SHM_IPC=1). Against the same scene in one domain."""
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1", OMP_NUM_THREADS="1", EMU_SHM_IPC="1", MPM_B200_PEER_HALO="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "emu", "multi_check_emulated.py"), "64", "16384", "12", str(balanced)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "MULTI_CHECK_OK" in r.stdout and "peer-memory halo: True" in r.stdout, r.stdout[-4000:]
+
+
 def test_migration_overflow_stops_every_rank_together(emu_lib):
     """Failure path of the slab protocol with the real library: migration messages too small -> the library flags the
     overflow, and the collective check raises on all ranks in the same substep (no rank is left waiting)."""
