@@ -334,7 +334,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload, "particles": int(n_total), "grid": [args.grid] * 3, "dt": 1e-5, "stencil": "cubic (reference)",
-                       "decomposition": f"{world} slab(s) along i", "l2_policy": "inputs (22 GB particle state) >> 126 MB L2, no flush needed",
+                       "decomposition": f"{world} slab(s) along i" + ("" if world == 1 else (", ghost layer reduced by P2G over peer memory (experimental)"
+                                                                                   if getattr(runner, "peer_halo", False) else ", halo over NCCL send/recv")), "l2_policy": "inputs (22 GB particle state) >> 126 MB L2, no flush needed",
                        "timing": "CUDA events on the library stream, max over ranks"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
