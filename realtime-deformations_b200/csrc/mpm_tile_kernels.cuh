@@ -125,6 +125,10 @@ MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCoun
 // at the owning GPU's L2), so that after both P2G kernels both copies hold the complete sums: no halo message, no pack /
 // add kernels, and the remote reds of a block overlap the accumulation of the next ones.
 struct PeerLayers { float4* dn; float4* up; };      // lower neighbour's ghost layer, upper neighbour's first layer (or null)
+// The work list is in block order (lowest i first). With remote reds the blocks of BOTH boundary layers go first -- tickets
+// alternate between the front and the back of the list -- so that the NVLink traffic overlaps the interior blocks and the
+// neighbours' waits end early.
+MPM_DI int peer_work_order(int ticket, int n_work) { return (ticket & 1) ? n_work - 1 - (ticket >> 1) : (ticket >> 1); }
 template <int MODE, bool PACKED = false, bool FUPD = false, bool PEER = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
@@ -143,7 +147,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
     int4 wk_reg = make_int4(-1, 0, 0, 0);
     if (t == 0) {
         const int w0 = atomicAdd(&dc->work_a, 1);
-        S.work = w0 < n_work ? pblock_list[w0] : make_int4(-1, 0, 0, 0);
+        S.work = w0 < n_work ? pblock_list[PEER ? peer_work_order(w0, n_work) : w0] : make_int4(-1, 0, 0, 0);
         w_ticket = atomicAdd(&dc->work_a, 1);
     }
     __syncthreads();
@@ -306,7 +310,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 acc[2 * i + 1] = make_float4(hi2(AM[i]), hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
             }
         }
-        if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[w_ticket] : make_int4(-1, 0, 0, 0);   // issued here, stored below
+        if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[PEER ? peer_work_order(w_ticket, n_work) : w_ticket] : make_int4(-1, 0, 0, 0);   // issued here, stored below
         // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
         // node k = cz + c; this lane ends up owning k = cz (slot 0) and k = cz + 4 (slot 1, cz <= 2)
         float4 s0[4], s1[4];
