@@ -228,6 +228,13 @@ int mpm_peer_connect(mpm_t* s, const unsigned char* lower_handle, int lower_laye
 int mpm_peer_connect_ptr(mpm_t* s, void* lower_grid, int lower_layers, void* upper_grid, int upper_layers);
 int mpm_grid_device_ptr(mpm_t* s, void** grid);
 int mpm_substep_begin_peer(mpm_t* s, float dt, int phase);
+/* The migration without messages (after mpm_peer_connect): every rank exports its two packed buffers, opens the lower
+ * neighbour's UP and the upper neighbour's DOWN buffer, and mpm_migrate_peer(s, 0), (s, 1) called back to back replace
+ * mpm_migrate_pack + the exchange + mpm_migrate_append_packed (pull over NVLink, flags "packed" / "consumed"). */
+int mpm_peer_export_migration(mpm_t* s, unsigned char* handle_down, unsigned char* handle_up);
+int mpm_peer_connect_migration(mpm_t* s, const unsigned char* lower_up_handle, const unsigned char* upper_down_handle);
+int mpm_peer_connect_migration_ptr(mpm_t* s, const void* lower_up_buf, const void* upper_down_buf);
+int mpm_migrate_peer(mpm_t* s, int phase);
 /* Distributed bookkeeping: particle ids are upload indices + pid_base (set before an upload) so that they stay
  * unique across slabs; mpm_download_live_particles returns the handle's current particles in storage order as
  * 35-float rows (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) with their ids. */

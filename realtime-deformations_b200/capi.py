@@ -52,7 +52,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_migrate_append_packed", "mpm_sync_counts", "mpm_set_migrate_capacity", "mpm_download_render_buffers_async",
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
            "mpm_box_transform_flip_velocity", "mpm_fill_ball", "mpm_peer_export", "mpm_peer_connect", "mpm_peer_connect_ptr",
-           "mpm_grid_device_ptr", "mpm_substep_begin_peer"]
+           "mpm_grid_device_ptr", "mpm_substep_begin_peer", "mpm_peer_export_migration", "mpm_peer_connect_migration",
+           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer"]
 
 _lib = None
 
@@ -120,6 +121,10 @@ def lib():
     L.mpm_peer_connect_ptr.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.mpm_grid_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.mpm_substep_begin_peer.argtypes = [vp, C.c_float, C.c_int]
+    L.mpm_peer_export_migration.argtypes = [vp, vp, vp]
+    L.mpm_peer_connect_migration.argtypes = [vp, vp, vp]
+    L.mpm_peer_connect_migration_ptr.argtypes = [vp, vp, vp]
+    L.mpm_migrate_peer.argtypes = [vp, C.c_int]
     L.mpm_fill_ball.argtypes = [fp, C.c_float, C.c_float, vp, vp, fp, i64, C.POINTER(i64), C.POINTER(i64)]
     _lib = L
     return L
@@ -344,6 +349,24 @@ class Sim:
 
     def substep_begin_peer(self, dt, phase):
         _ck(self.L.mpm_substep_begin_peer(self.h, dt, int(phase)))
+
+    def peer_export_migration(self):
+        d, u = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+        _ck(self.L.mpm_peer_export_migration(self.h, C.cast(d, C.c_void_p), C.cast(u, C.c_void_p)))
+        return bytes(d), bytes(u)
+
+    def peer_connect_migration(self, lower_up_handle, upper_down_handle):
+        lo = (C.c_ubyte * 64).from_buffer_copy(lower_up_handle) if lower_up_handle is not None else None
+        up = (C.c_ubyte * 64).from_buffer_copy(upper_down_handle) if upper_down_handle is not None else None
+        _ck(self.L.mpm_peer_connect_migration(self.h, C.cast(lo, C.c_void_p) if lo is not None else None,
+                                              C.cast(up, C.c_void_p) if up is not None else None))
+
+    def peer_connect_migration_ptr(self, lower_up_buf, upper_down_buf):
+        _ck(self.L.mpm_peer_connect_migration_ptr(self.h, C.c_void_p(lower_up_buf) if lower_up_buf else None,
+                                                  C.c_void_p(upper_down_buf) if upper_down_buf else None))
+
+    def migrate_peer(self, phase):
+        _ck(self.L.mpm_migrate_peer(self.h, int(phase)))
 
     # ---- diagnostics --------------------------------------------------------------------------------
     def grid(self):

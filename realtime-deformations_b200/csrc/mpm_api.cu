@@ -32,7 +32,7 @@ static int fail(int code, const char* fmt, ...) {
 #define NEED(s) do { if (!(s)) return fail(MPM_ERR_INVALID, "null handle"); CK(cudaSetDevice((s)->device)); } while (0)
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
-constexpr size_t PEER_FLAG_BYTES = 256;      // 4 flag words used: [0]/[1] cleared by lower/upper neighbour, [2]/[3] P2G done by lower/upper
+constexpr size_t PEER_FLAG_BYTES = 256;      // flag words: [0]/[1] cleared by lower/upper neighbour, [2]/[3] P2G done, [4]/[5] migration packed, [6]/[7] migration consumed
 
 struct mpm_sim {
     int device = 0;
@@ -74,6 +74,10 @@ struct mpm_sim {
     void* ipc_dn = nullptr; void* ipc_up = nullptr;                  // mappings opened by mpm_peer_connect (closed in destroy)
     bool peer_connected = false;
     int peer_epoch = 0;
+    const float4* peer_in_dn = nullptr; const float4* peer_in_up = nullptr;   // lower neighbour's UP buffer, upper neighbour's DOWN buffer
+    void* ipc_mig_dn = nullptr; void* ipc_mig_up = nullptr;
+    bool peer_mig_connected = false;
+    int peer_mig_epoch = 0;
     bool fupd_pending = false;  // experimental p2g_variant 3/4: P2G has put the F-update results into the idle buffer (until substep_end)
     int num_sms = 148;
     cudaEvent_t ev[8];
@@ -264,6 +268,8 @@ int mpm_destroy(mpm_t* s) {
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->ipc_dn) cudaIpcCloseMemHandle(s->ipc_dn);
     if (s->ipc_up) cudaIpcCloseMemHandle(s->ipc_up);
+    if (s->ipc_mig_dn) cudaIpcCloseMemHandle(s->ipc_mig_dn);
+    if (s->ipc_mig_up) cudaIpcCloseMemHandle(s->ipc_mig_up);
     if (s->side.stream) { cudaStreamDestroy(s->side.stream); cudaEventDestroy(s->side.fork); cudaEventDestroy(s->side.join); }
     if (s->side.mid) cudaEventDestroy(s->side.mid);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -1149,6 +1155,62 @@ int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
     CKLAUNCH(); s->stats.kernel_launches += 2;
     s->n_bound = std::min<int64_t>(s->capacity, s->n_bound + cap);      // upper bound; mpm_sync_counts tightens it
     s->binned = false;
+    return MPM_OK;
+}
+// EXPERIMENTAL peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own
+// two buffers as before; the neighbours READ them through their IPC mappings (pull), so no message is sent.
+//   phase 0: wait until both neighbours have consumed my buffers of the previous substep; pack; signal "packed(e)"
+//   phase 1: wait for the neighbours' "packed(e)"; append from the lower neighbour's UP and the upper neighbour's DOWN buffer;
+//            signal "consumed(e)"
+int mpm_peer_export_migration(mpm_t* s, unsigned char* handle_down, unsigned char* handle_up) {
+    NEED(s);
+    if (!handle_down || !handle_up) return fail(MPM_ERR_INVALID, "null argument");
+    TRY(ensure_out_buffers(s));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->out_buf[0])); memcpy(handle_down, &h, sizeof h);
+    CK(cudaIpcGetMemHandle(&h, s->out_buf[1])); memcpy(handle_up, &h, sizeof h);
+    return MPM_OK;
+}
+int mpm_peer_connect_migration_ptr(mpm_t* s, const void* lower_up_buf, const void* upper_down_buf) {
+    NEED(s);
+    if (!s->peer_connected) return fail(MPM_ERR_INVALID, "mpm_peer_connect first (the flag words live behind the neighbours' grids)");
+    if ((lower_up_buf != nullptr) != (s->gd.lo > 0) || (upper_down_buf != nullptr) != (s->gd.hi < s->gd.npbi_global))
+        return fail(MPM_ERR_INVALID, "neighbour buffers must be given exactly for the neighbours this slab has");
+    TRY(ensure_out_buffers(s));
+    s->peer_in_dn = (const float4*)lower_up_buf; s->peer_in_up = (const float4*)upper_down_buf;
+    s->peer_mig_connected = true;
+    s->peer_mig_epoch = 0;
+    return MPM_OK;
+}
+int mpm_peer_connect_migration(mpm_t* s, const unsigned char* lower_up_handle, const unsigned char* upper_down_handle) {
+    NEED(s);
+    void *lo_ptr = nullptr, *up_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    if (lower_up_handle) { memcpy(&h, lower_up_handle, sizeof h); CK(cudaIpcOpenMemHandle(&lo_ptr, h, cudaIpcMemLazyEnablePeerAccess)); s->ipc_mig_dn = lo_ptr; }
+    if (upper_down_handle) { memcpy(&h, upper_down_handle, sizeof h); CK(cudaIpcOpenMemHandle(&up_ptr, h, cudaIpcMemLazyEnablePeerAccess)); s->ipc_mig_up = up_ptr; }
+    return mpm_peer_connect_migration_ptr(s, lo_ptr, up_ptr);
+}
+int mpm_migrate_peer(mpm_t* s, int phase) {
+    NEED(s);
+    if (!s->peer_mig_connected) return fail(MPM_ERR_INVALID, "mpm_peer_connect_migration first");
+    int* mine = (int*)(s->grid + 64 * (size_t)s->gd.n_gblocks);
+    const bool has_dn = s->gd.lo > 0, has_up = s->gd.hi < s->gd.npbi_global;
+    if (phase == 0) {
+        ++s->peer_mig_epoch;
+        k_peer_wait<<<1, 1, 0, s->stream>>>(has_dn ? mine + 6 : nullptr, has_up ? mine + 7 : nullptr, s->peer_mig_epoch - 1, s->dc);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        const void *d0, *d1;
+        TRY(mpm_migrate_pack(s, &d0, &d1));
+        k_peer_signal<<<1, 1, 0, s->stream>>>(has_dn ? s->peer_flags_dn + 5 : nullptr, has_up ? s->peer_flags_up + 4 : nullptr, s->peer_mig_epoch);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    } else if (phase == 1) {
+        k_peer_wait<<<1, 1, 0, s->stream>>>(has_dn ? mine + 4 : nullptr, has_up ? mine + 5 : nullptr, s->peer_mig_epoch, s->dc);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        if (has_dn) TRY(mpm_migrate_append_packed(s, s->peer_in_dn));
+        if (has_up) TRY(mpm_migrate_append_packed(s, s->peer_in_up));
+        k_peer_signal<<<1, 1, 0, s->stream>>>(has_dn ? s->peer_flags_dn + 7 : nullptr, has_up ? s->peer_flags_up + 6 : nullptr, s->peer_mig_epoch);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    } else return fail(MPM_ERR_INVALID, "phase must be 0 or 1");
     return MPM_OK;
 }
 int mpm_sync_counts(mpm_t* s) {

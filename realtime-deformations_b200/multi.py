@@ -164,6 +164,10 @@ class SlabRunner:
             lower = everyone[rank - 1] if rank > 0 else (None, 0)
             upper = everyone[rank + 1] if rank < world - 1 else (None, 0)
             self.sim.peer_connect(lower[0], lower[1], upper[0], upper[1])
+            # the migration the same way: neighbours READ the packed buffers through their mappings (pull), no message
+            mig = [None] * world
+            self.dist.all_gather_object(mig, self.sim.peer_export_migration())          # (down buffer, up buffer) handles
+            self.sim.peer_connect_migration(mig[rank - 1][1] if rank > 0 else None, mig[rank + 1][0] if rank < world - 1 else None)
             self.dist.barrier()            # every rank has mapped its neighbours before the first remote red
 
     # ghost-layer partial sums up, first-layer partial sums down, add on both sides
@@ -203,6 +207,9 @@ class SlabRunner:
         """Fixed-size packed buffers (count in a device-side header): no host synchronisation per substep; the launch
         bound is re-tightened and overflow checked every `sync_every` substeps."""
         t, s, r, w = self.torch, self.sim, self.rank, self.world
+        if getattr(self, "peer_halo", False):
+            s.migrate_peer(0); s.migrate_peer(1)
+            return self._after_migration()
         p_dn, p_up = s.migrate_pack()
         nf = s.migrate_buffer_bytes() // 4
         exchange_with_neighbours(self.dist, t, r, w, self._view(p_dn, nf) if r > 0 else None, self._view(p_up, nf) if r < w - 1 else None,
@@ -211,6 +218,10 @@ class SlabRunner:
             s.migrate_append_packed(self.m_recv_dn.data_ptr())
         if r < w - 1:
             s.migrate_append_packed(self.m_recv_up.data_ptr())
+        self._after_migration()
+
+    def _after_migration(self):
+        t, s = self.torch, self.sim
         self.steps_done += 1
         if self.steps_done % self.sync_every == 0:
             # a capacity error on ONE rank must stop ALL ranks together (otherwise the others wait in the next exchange)

@@ -489,15 +489,16 @@ def test_peer_memory_halo_two_slabs_in_one_process():
     # connect the neighbour grids and run with the peer-memory halo
     A.peer_connect_ptr(None, 0, B.grid_device_ptr(), n_layers - mid)
     B.peer_connect_ptr(A.grid_device_ptr(), mid, None, 0)
+    _, a_up = A.migrate_pack()                                    # (addresses of the packed buffers; this pack is discarded)
+    b_dn, _ = B.migrate_pack()
+    A.peer_connect_migration_ptr(None, b_dn)                      # A reads B's DOWN buffer, B reads A's UP buffer
+    B.peer_connect_migration_ptr(a_up, None)
     for _ in range(steps):
         for phase in (0, 1, 2):
             A.substep_begin_peer(dt, phase); B.substep_begin_peer(dt, phase)
         A.substep_end(dt, cols, nc); B.substep_end(dt, cols, nc)
-        _, a_up = A.migrate_pack()
-        b_dn, _ = B.migrate_pack()
-        A.synchronize(); B.synchronize()                          # the packed buffers change hands between two streams
-        B.migrate_append_packed(a_up); A.migrate_append_packed(b_dn)
-        A.synchronize(); B.synchronize()
+        for phase in (0, 1):                                      # migration by pull through the neighbour's buffer, flag-ordered
+            A.migrate_peer(phase); B.migrate_peer(phase)
     A.sync_counts(); B.sync_counts()
     assert A.stats().reserved[2] == 0 and B.stats().reserved[2] == 0, "a peer-halo wait timed out"
     sa, pa = A.download_live(n + 1024)
