@@ -154,7 +154,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
     int gid_pref[P2G_PPT];
     {
         const int4 wk0 = S.work;
-        const int nck0 = (wk0.z + P2G_CH - 1) / P2G_CH, nch0 = nck0 ? (wk0.z + nck0 - 1) / nck0 : 0;
+        const int nck0 = (wk0.z + P2G_CH - 1) / P2G_CH, nch0 = nck0 <= 1 ? wk0.z : (wk0.z + nck0 - 1) / nck0;     // (one chunk: no division by a variable)
 #pragma unroll
         for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wk0.x >= 0 && q < nch0) ? sorted_ids[wk0.y + q * nck0] : 0; }
     }
@@ -176,7 +176,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         // share of every cell and all 64 (cell) thread groups have work in phase 1
         const int n_chunks = (cnt + P2G_CH - 1) / P2G_CH;
         for (int ck = 0; ck < n_chunks; ++ck) {
-            const int nch = (cnt - ck + n_chunks - 1) / n_chunks;          // slots ck, ck+n_chunks, ...
+            const int nch = n_chunks == 1 ? cnt : (cnt - ck + n_chunks - 1) / n_chunks;          // slots ck, ck+n_chunks, ...
             MPM_SMEM_EPOCH();
             if (ck > 0) {
                 if (t < 64) S.cell_cnt[t] = 0;
@@ -342,7 +342,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         __syncthreads();
         {   // ids of the next block's first chunk: in flight while this block's tile is reduced and written back
             const int4 wn = S.work;
-            const int nckn = (wn.z + P2G_CH - 1) / P2G_CH, nchn = nckn ? (wn.z + nckn - 1) / nckn : 0;
+            const int nckn = (wn.z + P2G_CH - 1) / P2G_CH, nchn = nckn <= 1 ? wn.z : (wn.z + nckn - 1) / nckn;
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wn.x >= 0 && q < nchn) ? sorted_ids[wn.y + q * nckn] : 0; }
         }
