@@ -336,7 +336,8 @@ def main():
             "config": {"workload": workload, "particles": int(n_total), "grid": [args.grid] * 3, "dt": 1e-5, "stencil": "cubic (reference)",
                        "decomposition": f"{world} slab(s) along i" + ("" if world == 1 else (", ghost layer reduced by P2G over peer memory (experimental)"
                                                                                    if getattr(runner, "peer_halo", False) else ", halo over NCCL send/recv")), "l2_policy": "inputs (22 GB particle state) >> 126 MB L2, no flush needed",
-                       "timing": "CUDA events on the library stream, max over ranks"},
+                       "timing": "CUDA events on the library stream, max over ranks",
+                       "p2g_record_walk": "aligned (MPM_B200_P2G_ROTATE=0)" if os.environ.get("MPM_B200_P2G_ROTATE") == "0" else "rotated (default)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
                     "d2h_bytes_per_step": int(16 * n_dl_total), "ms_per_step": e2e_ms,
