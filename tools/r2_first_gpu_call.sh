@@ -13,7 +13,7 @@ done
 # 3. shared-memory wavefronts / bank conflicts of P2G with and without the rotation (model: tests/emu smem profile)
 for rot in 0 1; do
   MPM_B200_P2G_ROTATE=$rot timeout 400 ncu --clock-control none -k regex:k_p2g_tile -c 2 --csv \
-    --metrics gpu__time_duration.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \
+    --metrics gpu__time_duration.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \
     --log-file gpurun_out/ncu_p2g_rotate_${rot}.csv python tools/profile_step.py 512 67108864 2 > gpurun_out/ncu_p2g_rotate_${rot}.log 2>&1
 done
 # 4. experimental kernels: parity, then A/B timing
