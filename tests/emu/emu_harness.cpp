@@ -444,6 +444,17 @@ int main(int argc, char** argv) {
         check(same, "cell_and_weights == cell_of + axis_weights, bit for bit (2 M positions, fast and exact quotient)");
     }
 
+    // ---------------- peer-halo work order: a permutation that visits both ends of the block list first ----------------
+    {
+        bool perm = true;
+        for (int n = 1; n <= 67 && perm; ++n) {
+            std::vector<int> seen(n, 0);
+            for (int w = 0; w < n; ++w) { const int i = peer_work_order(w, n); if (i < 0 || i >= n || seen[i]++) perm = false; }
+            if (n >= 2 && (peer_work_order(0, n) != 0 || peer_work_order(1, n) != n - 1)) perm = false;
+        }
+        check(perm, "peer_work_order is a permutation of the work list starting with its two ends");
+    }
+
     // ---------------- P2G ----------------
     std::vector<int> ids_def, ids_pk, ids_fu, ids_pkfu, ids_base = H.ids0;
     std::vector<float4> g_def, g_pk, g_fu, g_pkfu, g_base(H.grid.size(), make_float4(0, 0, 0, 0));
