@@ -990,7 +990,7 @@ int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
 //             hold the complete sums, both ranks update it redundantly as with the message-based halo)
 // A neighbour clears its copy of a shared layer for substep e+1 only after phase 2 of substep e, i.e. after my remote reds of
 // substep e are complete, and my reds of substep e+1 wait for its "cleared(e+1)". The flag kernels are one thread each;
-// a wait gives up after ~2^23 polls and raises DevCounters::peer_timeout (reported by mpm_sync_counts / mpm_get_stats)
+// a wait gives up after ~30 s and raises DevCounters::peer_timeout (reported by mpm_sync_counts / mpm_get_stats)
 // instead of hanging the device.
 __global__ void k_peer_signal(int* flag_a, int* flag_b, int epoch) {
     __threadfence_system();                       // everything this stream did before is visible system-wide first
@@ -1004,7 +1004,10 @@ __global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, Dev
         if (!flags[f]) continue;
         bool ok = false;
 #ifndef MPM_HOST_EMU
-        for (int poll = 0; poll < (1 << 23) && !ok; ++poll) ok = *(const volatile int*)flags[f] >= epoch;
+        // bounded by time, not by polls: ranks legitimately drift apart by seconds between timed regions (pinned allocations,
+        // host-side bookkeeping); ~30 s of SM clock is far below every watchdog above us (NCCL, the job's own timeout)
+        const long long t0 = clock64();
+        do { ok = *(const volatile int*)flags[f] >= epoch; } while (!ok && clock64() - t0 < 60000000000ll);
 #else   // tests/emu: the neighbour is another PROCESS whose emulated kernels take seconds; poll politely for up to 5 minutes
         for (int poll = 0; poll < 300000 && !ok; ++poll) { ok = *(const volatile int*)flags[f] >= epoch; if (!ok) emu_sleep_ms(1); }
 #endif
