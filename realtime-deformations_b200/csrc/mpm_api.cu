@@ -1000,6 +1000,7 @@ __global__ void k_peer_signal(int* flag_a, int* flag_b, int epoch) {
 }
 __global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, DevCounters* dc) {
     const int* flags[2] = { flag_a, flag_b };
+    if (dc->peer_timeout) return;                 // a neighbour is already known to be gone: do not wait for it again and again
     for (int f = 0; f < 2; ++f) {
         if (!flags[f]) continue;
         bool ok = false;
