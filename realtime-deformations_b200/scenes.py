@@ -114,6 +114,23 @@ def snowball_drop(grid=128, n=1 << 20, h=0.05, dt=1e-5, seed=SEED):
     return _scene(pos[:n], (0.0, -200.0, 0.0), dims, h, dt, [ground_collider(top, dims, h)], name=f"snowball_drop_{grid}")
 
 
+def stiff_snowball(grid=256, n=1 << 22, h=0.05, dt=2.5e-6, seed=SEED, gap_cells=0.25):
+    """Config 4: one snowball at small dt for the stiff-snow parameter sweep (hardening xi, theta_c, theta_s). Same ground
+    box as config 2; the ball starts `gap_cells` above it, so that at 200 m/s the first contact comes after
+    gap_cells * h / (200 dt) substeps (25 by default) and the plasticity clamps are active within a short run."""
+    dims = (grid, grid, grid)
+    L = grid * h
+    top = 0.125 * L + h / 2
+    radius = (n / 8.0 * 3.0 / (4.0 * np.pi)) ** (1.0 / 3.0) * h
+    while True:
+        center = (0.5 * L, top + radius + gap_cells * h, 0.5 * L)
+        pos = ball(center, radius, dims, h, seed)
+        if len(pos) >= n:
+            break
+        radius *= 1.01
+    return _scene(pos[:n], (0.0, -200.0, 0.0), dims, h, dt, [ground_collider(top, dims, h)], name=f"stiff_snowball_{grid}")
+
+
 def snowball_collision(grid=256, n=1 << 23, h=0.05, dt=1e-5, seed=SEED):
     """Config 3: two snowballs colliding head-on along i, no ground."""
     dims = (grid, grid, grid)

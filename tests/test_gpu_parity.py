@@ -549,6 +549,51 @@ def test_full_size_properties_config3_momentum():
     assert abs(float((out["pos"][:half, 0] - sc["pos"][:half, 0]).mean()) - 100.0 * dt * k) < 1e-5
 
 
+def _stiff_sweep_properties(grid, n, substeps, compare_baseline):
+    """BASELINE config 4 (stiff-snow sweep at dt = 2.5e-6) through size-independent properties: every particle's elastic
+    singular values stay inside [1 - theta_c, 1 + theta_s] of ITS parameter set and reach the compression clamp once the
+    ball is in contact, nothing is lost or non-finite, identities survive the re-sorting, tile == baseline kernels."""
+    sc = mpm_b200.scenes.stiff_snowball(grid=grid, n=n)
+    assert sc["n"] == n
+    dt = float(sc["dt"])
+    tags = (np.arange(n, dtype=np.float32) * np.float32(1e-9) + np.float32(3e-5))
+    for xi, tc, ts in ((5.0, 1.5e-2, 2.5e-3), (10.0, 2.5e-2, 5e-3), (20.0, 5e-2, 7.5e-3)):
+        sim, cols, nc = sim_from_scene(sc, hardening_xi=xi, theta_c=tc, theta_s=ts)
+        sim.upload(sc["pos"], sc["vel"], sc["mass"], volume=tags)
+        sim.substep(dt, cols, nc, substeps)
+        a = sim.download_state35()
+        st = sim.stats()
+        assert np.isfinite(a).all() and st.svd_failed == 0 and st.n_particles == n and st.n_out_of_grid == 0
+        assert (a[:, 4] == tags).all(), "identity (volume tag) must survive the re-sorting substeps"
+        # a strided sample of the whole ball plus the particles nearest the ground (where the contact is)
+        idx = np.union1d(np.arange(0, n, max(1, n // 65536)), np.argpartition(a[:, 6], min(n, 65536) - 1)[:65536])
+        sv = np.linalg.svd(a[idx, 8:17].reshape(-1, 3, 3).astype(np.float64), compute_uv=False)
+        assert sv.min() >= 1 - tc - 1e-5 and sv.max() <= 1 + ts + 1e-5, f"xi={xi}: singular values [{sv.min()}, {sv.max()}] leave the clamp interval"
+        assert sv.min() <= 1 - tc + 1e-4, f"xi={xi}: the compression clamp was never reached (no contact?)"
+        if compare_baseline and xi == 10.0:
+            base, _, _ = sim_from_scene(sc, (1, 1), hardening_xi=xi, theta_c=tc, theta_s=ts)
+            base.upload(sc["pos"], sc["vel"], sc["mass"], volume=tags)
+            base.substep(dt, cols, nc, substeps)
+            b = base.download_state35()
+            # in contact the dynamics amplify summation-order noise (the reference against itself: SURVEY App. C), so the two
+            # kernel families are compared in the mean tightly and in the maximum loosely
+            e = traj_errors(a, b)
+            mean = (float(np.abs(a[:, 5:8] - b[:, 5:8]).mean()), float(np.abs(a[:, 1:4] - b[:, 1:4]).mean()))
+            assert mean[0] <= 5e-7 and mean[1] <= 1e-2, f"tile vs baseline kernels, stiff sweep, mean |d pos|, |d vel|: {mean}"
+            assert e[0] <= 5e-5 and e[1] <= 1.0 and e[2] <= 5e-3, f"tile vs baseline kernels, stiff sweep, max: {e}"
+            base.close()
+        sim.close()
+
+
+def test_stiff_sweep_properties_small():
+    _stiff_sweep_properties(32, 4096, 80, compare_baseline=True)
+
+
+def test_full_size_properties_config4_stiff_sweep():
+    """BASELINE config 4 at full size: 4 Mi particles, 256^3, dt = 2.5e-6, three (xi, theta_c, theta_s) sets."""
+    _stiff_sweep_properties(256, 1 << 22, 60, compare_baseline=True)
+
+
 @pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1",
                     reason="experimental paths (CUDA-graph substeps, linear-tile gather) are opt-in until validated on hardware")
 def test_experimental_graph_substeps_match_plain_path(monkeypatch):
