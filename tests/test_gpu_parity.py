@@ -556,10 +556,10 @@ def _stiff_sweep_properties(grid, n, substeps, compare_baseline):
     sc = mpm_b200.scenes.stiff_snowball(grid=grid, n=n)
     assert sc["n"] == n
     dt = float(sc["dt"])
-    tags = (np.arange(n, dtype=np.float32) * np.float32(1e-9) + np.float32(3e-5))
     for xi, tc, ts in ((5.0, 1.5e-2, 2.5e-3), (10.0, 2.5e-2, 5e-3), (20.0, 5e-2, 7.5e-3)):
         sim, cols, nc = sim_from_scene(sc, hardening_xi=xi, theta_c=tc, theta_s=ts)
-        sim.upload(sc["pos"], sc["vel"], sc["mass"], volume=tags)
+        tags = sim.download_state35()[:, 4].copy()            # the particle volumes of the start-up pass double as identity tags
+        assert len(np.unique(tags)) > n // 4
         sim.substep(dt, cols, nc, substeps)
         a = sim.download_state35()
         st = sim.stats()
@@ -572,7 +572,6 @@ def _stiff_sweep_properties(grid, n, substeps, compare_baseline):
         assert sv.min() <= 1 - tc + 1e-4, f"xi={xi}: the compression clamp was never reached (no contact?)"
         if compare_baseline and xi == 10.0:
             base, _, _ = sim_from_scene(sc, (1, 1), hardening_xi=xi, theta_c=tc, theta_s=ts)
-            base.upload(sc["pos"], sc["vel"], sc["mass"], volume=tags)
             base.substep(dt, cols, nc, substeps)
             b = base.download_state35()
             # in contact the dynamics amplify summation-order noise (the reference against itself: SURVEY App. C), so the two
