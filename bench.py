@@ -78,6 +78,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_sample_scene(mpm_b200):
     """Bounded sample of the slab workload for the CPU arms: same generator, 8 ppc slab, 32^3 grid (the largest the
     reference's own class can allocate comfortably: its WeightStorage holds I*J*K*N floats)."""
@@ -132,11 +142,13 @@ def cpu_baseline(mpm_b200, budget_steps=150):
     if os.path.exists(ref):
         try:
             v, wall, sec = run_reference_binary(sc, budget_steps, 1)
-            return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample, "seconds": sec}
+            return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample, "seconds": sec,
+                    "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
         except Exception as e:   # fall through to the port
             sample += f" (reference binary unusable: {e})"
     v, sec = run_oracle_port(sc, budget_steps)
-    return {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": sec}
+    return {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": sec,
+            "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
 
 
 def reference_arm(args):
@@ -163,7 +175,7 @@ def reference_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "cpu_sample": f"{cores} independent replicas of a {sc['n']}-particle 32^3 slab sample"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": f"{sc['n']} particles x {args.steps} substeps per core, {cores} cores"},
+                             "sample": f"{sc['n']} particles x {args.steps} substeps per core, {cores} cores", "cpu_model": cpu_model()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
