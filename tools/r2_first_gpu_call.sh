@@ -6,10 +6,8 @@ mkdir -p gpurun_out
 # 1. parity suite: default path (rotated P2G record walk, single-quotient weights, block coordinates in the work items)
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1
 echo "default gpu tests: exit $?" | tee -a gpurun_out/gpu_tests.log
-# 2. A/B of the rotated record walk (MPM_B200_P2G_ROTATE=0 restores the aligned walk measured in round 1)
-for rot in 0 1; do
-  MPM_B200_P2G_ROTATE=$rot timeout 300 python tools/perf_probe.py 512 67108864 10 slab 0:0 > gpurun_out/rotate_${rot}_64M.log 2>&1
-done
+# 2. A/B of the rotated record walk at 64 Mi (third field 0 = the aligned walk measured in round 1); one process, one scene
+timeout 420 python tools/perf_probe.py 512 67108864 10 slab 0:0:0,0:0:1 > gpurun_out/rotate_64M.log 2>&1
 # 3. shared-memory wavefronts / bank conflicts of P2G with and without the rotation (model: tests/emu smem profile)
 for rot in 0 1; do
   MPM_B200_P2G_ROTATE=$rot timeout 400 ncu --clock-control none -k regex:k_p2g_tile -c 2 --csv \
@@ -32,4 +30,4 @@ if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   done
   tail -n 3 gpurun_out/multi_check_peer_*.log gpurun_out/bench_2gpu_peer_*.log
 fi
-tail -n 8 gpurun_out/gpu_tests.log gpurun_out/rotate_*_64M.log gpurun_out/exp_tests.log gpurun_out/ab_8M.log gpurun_out/ab_64M.log
+tail -n 8 gpurun_out/gpu_tests.log gpurun_out/rotate_64M.log gpurun_out/exp_tests.log gpurun_out/ab_8M.log gpurun_out/ab_64M.log
