@@ -333,7 +333,7 @@ static void check_flow(unsigned seed) {
 // Prints wavefronts per 512-particle block for every probed instruction, with the aligned record walk (the kernel
 // measured in round 1) and with the rotated walk, and checks the model against the ncu count of the aligned walk.
 // ---------------------------------------------------------------------------------------------------------------
-struct SmemRun { std::map<int, emu::SmemProbe::Site> sites; emu::SmemProbe::Site gather; size_t blocks = 0; };
+struct SmemRun { std::map<int, emu::SmemProbe::Site> sites; emu::SmemProbe::Site gather, gather_linear; size_t blocks = 0; };
 static SmemRun smem_profile_run(unsigned seed, int rotate) {
     const float dt = 1e-5f;
     Host H;
@@ -372,7 +372,20 @@ static SmemRun smem_profile_run(unsigned seed, int rotate) {
             k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, false>(C, N, ids.data(), H.work.data(), &H.dc, H.grid.data(), H.gd, H.sc, dt);
         });
         pr.on = false;
-        if (step == 2) out.gather = pr.sites[40];
+        if (step == 2) {
+            out.gather = pr.sites[40];
+            // the same gather on the experimental LINEAR tile (row stride 9, plane stride 73 float4), into a scratch copy
+            Host L = H;
+            Planes LC = L.planes(cur), LN = L.planes(cur ^ 1);
+            L.dc.work_b = 0;
+            pr.reset();
+            pr.on = true;
+            emu::launch(2, G2P_T, sizeof(G2PSmemLinear), [&] {
+                k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, false>(LC, LN, ids.data(), L.work.data(), &L.dc, L.grid.data(), L.gd, L.sc, dt);
+            });
+            pr.on = false;
+            out.gather_linear = pr.sites[40];
+        }
         cur ^= 1;
     }
     pr.reset();
@@ -410,6 +423,9 @@ static int smem_profile(unsigned seed) {
     const double g_model = (double)r.gather.wavefronts / (double)r.gather.requests, g_ncu = 270289023.0 / (67108864.0 * 64.0 / 32.0);
     std::printf("  gather LDS.128 of the tile: model %.2f wavefronts per request, ncu %.2f\n", g_model, g_ncu);
     check(std::fabs(g_model - g_ncu) < 0.15, "bank model: wavefronts per tile read of the gather match ncu");
+    const double gl_model = (double)r.gather_linear.wavefronts / (double)r.gather_linear.requests;
+    std::printf("  gather LDS.128 of the experimental LINEAR tile: model %.2f wavefronts per request\n", gl_model);
+    check(gl_model < 2.1, "linear gather tile: the padded layout is as conflict-free as the blocked tile");
     check(p1a - ideal_p1 > 0.7 * ncu_conf && p1a - ideal_p1 < 1.1 * ncu_conf, "bank model: the aligned walk's phase-1 conflicts account for 70-110 % of ncu's bank-conflict wavefronts");
     check(p1r <= 1.05 * ideal_p1, "rotated walk: phase 1 is conflict-free on the 8-per-cell layout");
     check(tr < 0.62 * ta, "rotated walk: >= 38 % fewer shared-memory wavefronts per block");
