@@ -30,8 +30,13 @@ def _run_gpu_suite(emu_lib, select, experimental=False, timeout=1500):
     env.pop("MPM_TEST_EXPERIMENTAL", None)
     if experimental:
         env["MPM_TEST_EXPERIMENTAL"] = "1"
+    try:                      # the emulated kernels are single-threaded: spread the selected tests over a few worker processes
+        import xdist          # noqa: F401
+        workers = ["-n", str(max(1, min(4, (os.cpu_count() or 2) // 2)))]
+    except ImportError:
+        workers = []
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-p", "no:cacheprovider", "-k", f"({select}) and {NEEDS_DEVICE}"],
+                        "-p", "no:cacheprovider", "-k", f"({select}) and {NEEDS_DEVICE}"] + workers,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env, cwd=ROOT)
     return r
 

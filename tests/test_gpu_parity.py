@@ -585,7 +585,7 @@ def _stiff_sweep_properties(grid, n, substeps, compare_baseline):
 
 
 def test_stiff_sweep_properties_small():
-    _stiff_sweep_properties(32, 4096, 80, compare_baseline=True)
+    _stiff_sweep_properties(32, 4096, 60, compare_baseline=True)
 
 
 def test_full_size_properties_config4_stiff_sweep():
