@@ -1059,7 +1059,7 @@ int mpm_grid_device_ptr(mpm_t* s, void** grid) {
 int mpm_substep_begin_peer(mpm_t* s, float dt, int phase) {
     NEED(s);
     if (!s->peer_connected) return fail(MPM_ERR_INVALID, "mpm_peer_connect first");
-    if (p2g_fupd(s) || s->prm.p2g_variant == 1) return fail(MPM_ERR_INVALID, "the peer-memory halo runs with the default tile P2G");
+    if (s->prm.p2g_variant == 1) return fail(MPM_ERR_INVALID, "the peer-memory halo needs the tile P2G kernel (p2g_variant != 1)");
     int* mine = (int*)(s->grid + 64 * (size_t)s->gd.n_gblocks);          // my flag words, written by the neighbours
     // my lower neighbour sees me as ITS upper neighbour: I write its flags [1] / [3]; my upper neighbour's [0] / [2]
     if (phase == 0) {
@@ -1075,10 +1075,11 @@ int mpm_substep_begin_peer(mpm_t* s, float dt, int phase) {
     } else if (phase == 1) {
         k_peer_wait<<<1, 1, 0, s->stream>>>(s->peer.dn ? mine + 0 : nullptr, s->peer.up ? mine + 1 : nullptr, s->peer_epoch, s->dc);
         CKLAUNCH(); s->stats.kernel_launches++;
+        const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<P2G_FUSED>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
-                                       s->num_sms, (int)s->n_bound, s->stream, false, nullptr, &s->peer)));
+                                       s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), p2g_fupd(s) ? &nxt : nullptr, &s->peer)));
         s->stats.kernel_launches++;
-        s->fupd_pending = false;
+        s->fupd_pending = p2g_fupd(s);
         k_peer_signal<<<1, 1, 0, s->stream>>>(s->peer_flags_dn ? s->peer_flags_dn + 3 : nullptr, s->peer_flags_up ? s->peer_flags_up + 2 : nullptr, s->peer_epoch);
         CKLAUNCH(); s->stats.kernel_launches++;
     } else if (phase == 2) {

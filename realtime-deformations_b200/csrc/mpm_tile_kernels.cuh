@@ -640,7 +640,8 @@ inline cudaError_t tile_kernels_init_experimental() {
 #define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
     MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>), P2GSmem);
     MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, false, true>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, false, true>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true, true>), P2GSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
@@ -656,8 +657,12 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const Planes Nx = fupd_target ? *fupd_target : P;
-    if (peer && MODE == P2G_FUSED) {              // experimental peer-memory halo: plain accumulation loop, F-update in its own kernel
-        k_p2g_tile<P2G_FUSED, false, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
+    if (peer && MODE == P2G_FUSED) {              // experimental peer-memory halo, with or without the other experimental options
+        const bool fu = fupd_target != nullptr;
+        if (packed && fu) k_p2g_tile<P2G_FUSED, true, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
+        else if (packed) k_p2g_tile<P2G_FUSED, true, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
+        else if (fu) k_p2g_tile<P2G_FUSED, false, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
+        else k_p2g_tile<P2G_FUSED, false, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
         return cudaGetLastError();
     }
     if (fupd_target && MODE == P2G_FUSED) {       // only the fused substep moves the F-update into P2G

@@ -444,7 +444,8 @@ def test_p2g_rotated_record_walk_on_eight_per_cell_slab(monkeypatch):
 
 @pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1" and __import__("os").environ.get("MPM_B200_ALLOW_EMULATION") != "1",
                     reason="experimental path, opt-in on hardware until validated there (always on in the CPU emulation run)")
-def test_peer_memory_halo_two_slabs_in_one_process():
+@pytest.mark.parametrize("slab_variants", [(0, 0), (4, 4)])       # default kernels; every experimental option at once
+def test_peer_memory_halo_two_slabs_in_one_process(slab_variants):
     """EXPERIMENTAL peer-memory halo (mpm_substep_begin_peer): P2G adds the tile nodes of a shared block layer to the local
     grid AND to the neighbour slab's grid, device-side flags replace the halo messages. Two slab handles in ONE process
     (neighbour grids connected by pointer, migration buffers handed over directly) against the same scene in one domain,
@@ -466,7 +467,7 @@ def test_peer_memory_halo_two_slabs_in_one_process():
     parts, base = [], 0
     for lo, hi in ((0, mid), (mid, n_layers)):
         sel = np.flatnonzero((layer >= lo) & (layer < hi))
-        sim = mpm_b200.Sim(grid, grid, grid, len(sel), params(), slab=(lo, hi), capacity=n + 1024)
+        sim = mpm_b200.Sim(grid, grid, grid, len(sel), params(slab_variants), slab=(lo, hi), capacity=n + 1024)
         sim.set_pid_base(base)
         sim.upload(sc["pos"][sel], sc["vel"][sel], sc["mass"][sel])
         sim.set_migrate_capacity(4096)
