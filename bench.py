@@ -254,7 +254,9 @@ def main():
 
     from importlib import import_module
     multi = import_module("realtime-deformations_b200.multi")
-    runner = multi.SlabRunner(args.grid, args.particles, rank, world, torch)
+    # development only: MPM_B200_VARIANTS="p2g:g2p" selects experimental kernel variants for A/B runs (default 0:0)
+    variants = tuple(int(x) for x in os.environ.get("MPM_B200_VARIANTS", "0:0").split(":"))
+    runner = multi.SlabRunner(args.grid, args.particles, rank, world, torch, variants=variants)
     stream = runner.stream
 
     def barrier():
@@ -349,6 +351,7 @@ def main():
                        "decomposition": f"{world} slab(s) along i" + ("" if world == 1 else (", ghost layer reduced by P2G over peer memory (experimental)"
                                                                                    if getattr(runner, "peer_halo", False) else ", halo over NCCL send/recv")), "l2_policy": "inputs (22 GB particle state) >> 126 MB L2, no flush needed",
                        "timing": "CUDA events on the library stream, max over ranks",
+                       "kernel_variants": {"p2g": variants[0], "g2p": variants[1]},
                        "p2g_record_walk": "aligned (MPM_B200_P2G_ROTATE=0)" if os.environ.get("MPM_B200_P2G_ROTATE") == "0" else "rotated (default)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
