@@ -459,7 +459,7 @@ __global__ void k_stress(Planes P, const DevCounters* __restrict__ dc, SimConst 
 // updateDeformationGradient (cpp:306-330) + next substep's stress, one thread per sorted slot. It touches only
 // B (read), FE/FP/V0 (read) and FE/FP/tau (write), i.e. planes disjoint from what the gather kernel writes, so in the
 // re-sorting fused path the two kernels split the particle record between them at no extra HBM traffic.
-template <bool REORDER>
+template <bool REORDER, bool PK = false>
 __global__ void __launch_bounds__(256)
 k_fupdate(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc, SimConst sc, float dt) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,7 +471,7 @@ k_fupdate(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounter
     float FE[9] = { a6.z, a6.w, a7.x, a7.y, a7.z, a7.w, a8.x, a8.y, a8.z };
     float FP[9] = { a8.w, a9.x, a9.y, a9.z, a9.w, a10.x, a10.y, a10.z, a10.w };
     float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
-    if (!f_update_rn(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+    if (!f_update_rn<PK>(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
     tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
     const Planes& D = REORDER ? nxt : cur;
     const int q = REORDER ? j : p;

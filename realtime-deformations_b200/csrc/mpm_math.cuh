@@ -23,6 +23,44 @@ MPM_DI float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 MPM_DI float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 MPM_DI float rcp_rn(float a) { return __frcp_rn(a); }      // correctly rounded 1/a == IEEE 1.0f / a
 
+// packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
+// {x, x} operand into a scalar broadcast). Used only by the experimental kernel variants below.
+#ifndef MPM_HOST_EMU
+typedef unsigned long long f32x2_t;
+MPM_DI f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+MPM_DI float lo2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+MPM_DI float hi2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }   // c += a * b, in place
+MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#else   // host emulation of the kernels (tests/emu): same per-component IEEE operations
+typedef unsigned long long f32x2_t;
+MPM_DI f32x2_t pack2(float lo, float hi) { float v[2] = { lo, hi }; f32x2_t r; memcpy(&r, v, 8); return r; }
+MPM_DI float lo2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[0]; }
+MPM_DI float hi2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[1]; }
+MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) { return pack2(fmaf(lo2(a), lo2(b), lo2(c)), fmaf(hi2(a), hi2(b), hi2(c))); }
+MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { c = ffma2(a, b, c); }
+MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { return pack2(__fadd_rn(lo2(a), lo2(b)), __fadd_rn(hi2(a), hi2(b))); }
+MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { return pack2(__fmul_rn(lo2(a), lo2(b)), __fmul_rn(hi2(a), hi2(b))); }
+#endif
+
+// (x', y') = (c*x + s*y, -s*x + c*y), every product and every sum rounded once: the Jacobi rotation of Eigen's
+// applyOnTheLeft / applyOnTheRight. PK issues it as two packed multiplies and one packed add (mul.rn.f32x2 / add.rn.f32x2:
+// IEEE rounding per component, so the bits are those of the scalar form).
+template <bool PK>
+MPM_DI void rot_pair_rn(float c, float s, float x, float y, float& xo, float& yo) {
+    if (PK) {
+        const f32x2_t r = fadd2(fmul2(pack2(c, -s), pack2(x, x)), fmul2(pack2(s, c), pack2(y, y)));
+        xo = lo2(r); yo = hi2(r);
+    } else {
+        xo = add_rn(mul_rn(c, x), mul_rn(s, y));
+        yo = add_rn(mul_rn(-s, x), mul_rn(c, y));
+    }
+}
+
 // ---- reference weightNx, material_point_method.hpp:20-31 ----
 // The reference evaluates the polynomial in fp64 and rounds to fp32 (weight_nx_exact reproduces that bit for bit).
 // The hot kernels use the fp32/FMA form below: it differs from the exact value by <= 1 ulp (6e-8 relative), far
@@ -101,6 +139,24 @@ MPM_DI void m3_mul_rn(float* R, const float* A, const float* B) {   // R may not
         for (int r = 0; r < 3; ++r)
             R[c * 3 + r] = dot3_rn(A[0 + r], B[c * 3 + 0], A[3 + r], B[c * 3 + 1], A[6 + r], B[c * 3 + 2]);
 }
+// the same nine dot3_rn (same products, same order of the two additions) issued as packed pairs: rows 0,1 of every column
+// together, row 2 of columns 0,1 together, the last entry alone -- 25 instructions instead of 45
+MPM_DI f32x2_t dot3_rn2(f32x2_t a0, f32x2_t b0, f32x2_t a1, f32x2_t b1, f32x2_t a2, f32x2_t b2) {
+    return fadd2(fadd2(fmul2(a0, b0), fmul2(a1, b1)), fmul2(a2, b2));
+}
+template <bool PK>
+MPM_DI void m3_mul_rn_t(float* R, const float* A, const float* B) {
+    if (!PK) { m3_mul_rn(R, A, B); return; }
+    const f32x2_t A0 = pack2(A[0], A[1]), A1 = pack2(A[3], A[4]), A2 = pack2(A[6], A[7]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const f32x2_t v = dot3_rn2(A0, pack2(B[c * 3 + 0], B[c * 3 + 0]), A1, pack2(B[c * 3 + 1], B[c * 3 + 1]), A2, pack2(B[c * 3 + 2], B[c * 3 + 2]));
+        R[c * 3 + 0] = lo2(v); R[c * 3 + 1] = hi2(v);
+    }
+    const f32x2_t w = dot3_rn2(pack2(A[2], A[2]), pack2(B[0], B[3]), pack2(A[5], A[5]), pack2(B[1], B[4]), pack2(A[8], A[8]), pack2(B[2], B[5]));
+    R[2] = lo2(w); R[5] = hi2(w);
+    R[8] = dot3_rn(A[2], B[6], A[5], B[7], A[8], B[8]);
+}
 #define MG(m, c, r) ((m)[(c) * 3 + (r)])
 MPM_DI float m3_det_rn(const float* m) {
     const float t0 = mul_rn(MG(m,0,0), sub_rn(mul_rn(MG(m,1,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,1,2))));
@@ -131,7 +187,7 @@ MPM_DI void m3_transpose(float* R, const float* A) {
 // Control flow, sweep order (1,0),(2,0),(2,1), 2x2 kernel, sign fix-up and selection sort follow
 // external/Eigen/src/SVD/JacobiSVD.h:689-817, misc/RealSvd2x2.h:21-51, Jacobi/Jacobi.h:96-126,326-337
 // (restated in oracle/mpm_oracle.c: oracle_svd3). Arrays are ROW-major here (a[r*3+c] == Eigen m(r,c)).
-template <int P, int Q>
+template <int P, int Q, bool PK>
 MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxDiag, bool& finished) {
     const float pm = mul_rn(2.0f * FLT_EPSILON, maxDiag);
     const float threshold = (FLT_MIN < pm) ? pm : FLT_MIN;
@@ -147,8 +203,9 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
         s1 = rcp_rn(tmp); c1 = div_rn(u, tmp);
     }
     if (!(c1 == 1.0f && s1 == 0.0f)) {
-        const float a0 = add_rn(mul_rn(c1, m00), mul_rn(s1, m10)), b0 = add_rn(mul_rn(-s1, m00), mul_rn(c1, m10));
-        const float a1 = add_rn(mul_rn(c1, m01), mul_rn(s1, m11)), b1 = add_rn(mul_rn(-s1, m01), mul_rn(c1, m11));
+        float a0, b0, a1, b1;
+        rot_pair_rn<PK>(c1, s1, m00, m10, a0, b0);
+        rot_pair_rn<PK>(c1, s1, m01, m11, a1, b1);
         m00 = a0; m10 = b0; m01 = a1; m11 = b1;
     }
     float cr, sr;
@@ -169,27 +226,19 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
     if (!(cl == 1.0f && sl == 0.0f)) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {       // W.applyOnTheLeft(p,q,j_left)
-            const float x = W[P * 3 + c], y = W[Q * 3 + c];
-            W[P * 3 + c] = add_rn(mul_rn(cl, x), mul_rn(sl, y));
-            W[Q * 3 + c] = add_rn(mul_rn(-sl, x), mul_rn(cl, y));
+            rot_pair_rn<PK>(cl, sl, W[P * 3 + c], W[Q * 3 + c], W[P * 3 + c], W[Q * 3 + c]);
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {       // U.applyOnTheRight(p,q,j_left.transpose())
-            const float x = U[r * 3 + P], y = U[r * 3 + Q];
-            U[r * 3 + P] = add_rn(mul_rn(cl, x), mul_rn(sl, y));
-            U[r * 3 + Q] = add_rn(mul_rn(-sl, x), mul_rn(cl, y));
+            rot_pair_rn<PK>(cl, sl, U[r * 3 + P], U[r * 3 + Q], U[r * 3 + P], U[r * 3 + Q]);
         }
     }
     const float s = -sr;
     if (!(cr == 1.0f && s == 0.0f)) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {       // W.applyOnTheRight(p,q,j_right); V.applyOnTheRight(p,q,j_right)
-            const float x = W[r * 3 + P], y = W[r * 3 + Q];
-            W[r * 3 + P] = add_rn(mul_rn(cr, x), mul_rn(s, y));
-            W[r * 3 + Q] = add_rn(mul_rn(-s, x), mul_rn(cr, y));
-            const float vx = V[r * 3 + P], vy = V[r * 3 + Q];
-            V[r * 3 + P] = add_rn(mul_rn(cr, vx), mul_rn(s, vy));
-            V[r * 3 + Q] = add_rn(mul_rn(-s, vx), mul_rn(cr, vy));
+            rot_pair_rn<PK>(cr, s, W[r * 3 + P], W[r * 3 + Q], W[r * 3 + P], W[r * 3 + Q]);
+            rot_pair_rn<PK>(cr, s, V[r * 3 + P], V[r * 3 + Q], V[r * 3 + P], V[r * 3 + Q]);
         }
     }
     const float dm = fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q]));
@@ -198,6 +247,7 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
 
 // returns false on non-finite input (Eigen: InvalidInput). MAX_SWEEPS only guards the GPU against a hang;
 // Eigen itself has no cap and converges in 3-5 sweeps on finite input.
+template <bool PK = false>
 MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
     float W[9];
     float scale = 0.0f;
@@ -215,9 +265,9 @@ MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float 
     constexpr int MAX_SWEEPS = 64;
     for (int sweep = 0; sweep < MAX_SWEEPS && !finished; ++sweep) {
         finished = true;
-        jacobi_pair<1, 0>(W, U, V, maxDiag, finished);
-        jacobi_pair<2, 0>(W, U, V, maxDiag, finished);
-        jacobi_pair<2, 1>(W, U, V, maxDiag, finished);
+        jacobi_pair<1, 0, PK>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 0, PK>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 1, PK>(W, U, V, maxDiag, finished);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -249,6 +299,9 @@ MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float 
 // ---- F-update of one particle, material_point_method.cpp:306-330 (bit-faithful) ----
 // in: B (previous substep's APIC matrix), FE, FP; out: FE, FP overwritten, factors of the new FE for the stress.
 // Ug/Sg: FE_new = Ug * diag(Sg) * Vg^T as glm matrices (Ug is the glm view of Eigen's U, see utils.h:25-33).
+// PK (EXPERIMENTAL, with the packed-pair kernel variants): the 3x3 products and the Jacobi rotations issued as packed
+// unfused pairs -- the same IEEE operations, bit for bit (the reference's F-update KATs run through both forms).
+template <bool PK = false>
 MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], float dinv, float dt, float clamp_lo,
                         float clamp_hi, float (&Ug)[9], float (&Sg)[3]) {
     float T0[9], T1[9], T[9], FPinv[9], Fh[9], Vg[9];
@@ -257,11 +310,11 @@ MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], flo
         const float v = mul_rn(mul_rn(B[i], dinv), dt);
         T0[i] = add_rn((i % 4 == 0) ? 1.0f : 0.0f, v);
     }
-    m3_mul_rn(T1, T0, FE);
-    m3_mul_rn(T, T1, FP);                   // FPn1
+    m3_mul_rn_t<PK>(T1, T0, FE);
+    m3_mul_rn_t<PK>(T, T1, FP);             // FPn1
     m3_inverse_rn(FPinv, FP);
-    m3_mul_rn(Fh, T, FPinv);                // FEpKryshka
-    if (!svd3_eigen(Fh, Ug, Sg, Vg)) return false;
+    m3_mul_rn_t<PK>(Fh, T, FPinv);          // FEpKryshka
+    if (!svd3_eigen<PK>(Fh, Ug, Sg, Vg)) return false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { float s = Sg[k]; if (s < clamp_lo) s = clamp_lo; if (clamp_hi < s) s = clamp_hi; Sg[k] = s; }
     float US[9], Vt[9], FEinv[9];
@@ -270,9 +323,9 @@ MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], flo
 #pragma unroll
         for (int r = 0; r < 3; ++r) US[c * 3 + r] = mul_rn(Ug[c * 3 + r], Sg[c]);   // U * S (S diagonal)
     m3_transpose(Vt, Vg);
-    m3_mul_rn(FE, US, Vt);                  // U * S * transpose(V)
+    m3_mul_rn_t<PK>(FE, US, Vt);            // U * S * transpose(V)
     m3_inverse_rn(FEinv, FE);
-    m3_mul_rn(FP, FEinv, T);
+    m3_mul_rn_t<PK>(FP, FEinv, T);
     return true;
 }
 

@@ -35,30 +35,7 @@ namespace mpm {
 #define MPM_SMEM_EPOCH() emu::smem_epoch()
 #endif
 
-// packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
-// {x, x} operand into a scalar broadcast). Used only by the experimental kernel variants below.
-#ifndef MPM_HOST_EMU
-typedef unsigned long long f32x2_t;
-MPM_DI f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-MPM_DI float lo2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-MPM_DI float hi2(f32x2_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
-    f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }   // c += a * b, in place
-MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-#else   // host emulation of the kernels (tests/emu): same per-component IEEE operations
-typedef unsigned long long f32x2_t;
-MPM_DI f32x2_t pack2(float lo, float hi) { float v[2] = { lo, hi }; f32x2_t r; memcpy(&r, v, 8); return r; }
-MPM_DI float lo2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[0]; }
-MPM_DI float hi2(f32x2_t v) { float f[2]; memcpy(f, &v, 8); return f[1]; }
-MPM_DI f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) { return pack2(fmaf(lo2(a), lo2(b), lo2(c)), fmaf(hi2(a), hi2(b), hi2(c))); }
-MPM_DI void ffma2_acc(f32x2_t& c, f32x2_t a, f32x2_t b) { c = ffma2(a, b, c); }
-MPM_DI f32x2_t fadd2(f32x2_t a, f32x2_t b) { return pack2(__fadd_rn(lo2(a), lo2(b)), __fadd_rn(hi2(a), hi2(b))); }
-MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { return pack2(__fmul_rn(lo2(a), lo2(b)), __fmul_rn(hi2(a), hi2(b))); }
-#endif
-
+// (the packed fp32 pair helpers pack2 / lo2 / hi2 / ffma2 / fadd2 / fmul2 live in mpm_math.cuh)
 constexpr int P2G_T = 256;         // threads per CTA = 64 cells x 4 x-slabs
 constexpr int P2G_PPT = 2;         // particles derived per thread per chunk
 constexpr int P2G_CH = P2G_T * P2G_PPT;   // particles per chunk (a full 8-ppc block is one chunk)
@@ -91,12 +68,13 @@ MPM_DI FUpdIn fupd_load(const Planes& cur, int p) {
     r.a6 = cur.p[6][p]; r.a7 = cur.p[7][p]; r.a8 = cur.p[8][p]; r.a9 = cur.p[9][p]; r.a10 = cur.p[10][p];
     return r;
 }
+template <bool PK>
 MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCounters* dc, const SimConst& sc, float dt) {
     float B[9] = { in.a1.x, in.a1.y, in.a1.z, in.a1.w, in.a2.x, in.a2.y, in.a2.z, in.a2.w, in.a3.x };
     float FE[9] = { in.a6.z, in.a6.w, in.a7.x, in.a7.y, in.a7.z, in.a7.w, in.a8.x, in.a8.y, in.a8.z };
     float FP[9] = { in.a8.w, in.a9.x, in.a9.y, in.a9.z, in.a9.w, in.a10.x, in.a10.y, in.a10.z, in.a10.w };
     float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
-    if (!f_update_rn(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+    if (!f_update_rn<PK>(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
     tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), in.a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
     D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
     D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
@@ -379,8 +357,8 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 const int p0 = sorted_ids[j0], p1 = two ? sorted_ids[j1] : p0;
                 const FUpdIn in0 = fupd_load(P, p0);
                 const FUpdIn in1 = fupd_load(P, p1);
-                fupd_compute_store(in0, Nx, j0, dc, sc, dt);
-                if (two) fupd_compute_store(in1, Nx, j1, dc, sc, dt);
+                fupd_compute_store<PACKED>(in0, Nx, j0, dc, sc, dt);
+                if (two) fupd_compute_store<PACKED>(in1, Nx, j1, dc, sc, dt);
             }
         }
     }
@@ -693,7 +671,8 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
             if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
             fs = side->stream;
         }
-        k_fupdate<(FLAGS & G2P_REORDER) != 0><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
+        if (packed) k_fupdate<(FLAGS & G2P_REORDER) != 0, true><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
+        else k_fupdate<(FLAGS & G2P_REORDER) != 0><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (!overlap && side && side->mid && (FLAGS & G2P_GATHER)) {      // per-kernel timing: F-update | gather
             if ((e = cudaEventRecord(side->mid, st)) != cudaSuccess) return e;

@@ -45,7 +45,7 @@ def test_device_code_reproduces_reference_kats_on_the_host(tmp_path):
         np.ascontiguousarray(np.concatenate([raw[:, 13:29], raw[:, 0:3], raw[:, 10:13]], 1), np.float32).tofile(str(tmp_path / (n + ".f32")))
     r = subprocess.run([_build("emu_kat"), str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "all emulated known-answer tests passed" in r.stdout, r.stdout[-4000:]
-    assert r.stdout.count("ok  ") == 6
+    assert r.stdout.count("ok  ") == 7
 
 
 @pytest.mark.parametrize("seed,fast_div", [(1, 1), (7, 0)])
