@@ -87,7 +87,7 @@ def test_gather_kernel_contract(kernels, flags):
 
 
 def test_fupdate_kernel_contract(kernels):
-    k = _one(kernels, "k_fupdateILb1")
+    k = _one(kernels, "k_fupdateILb1ELb0E")
     assert k["regs"] <= 64, "4 CTAs of 256 threads per SM"
     assert _count(k, "LDG.E.128") >= 7 and _count(k, "STG.E.128") == 7, "eight planes in, seven planes out, all float4"
     assert not any(o.startswith(("LDS", "STS", "BAR")) for o in k["ops"])
@@ -97,6 +97,8 @@ def test_packed_variants_use_ffma2(kernels):
     p2g = _one(kernels, "k_p2g_tileILi2ELb1ELb0ELb0E")
     g2p = _one(kernels, "k_g2p_tileILi14ELb0ELb1")
     assert _count(p2g, "FFMA2") >= 40 and _count(g2p, "FFMA2") >= 200
+    fu, fu_pk = _one(kernels, "k_fupdateILb1ELb0E"), _one(kernels, "k_fupdateILb1ELb1E")
+    assert _count(fu_pk, "FMUL2") + _count(fu_pk, "FFMA2") >= 100 and len(fu_pk["ops"]) < 0.9 * len(fu["ops"]) and fu_pk["regs"] <= 64
 
 
 def test_peer_halo_p2g_issues_remote_vector_reds(kernels):
