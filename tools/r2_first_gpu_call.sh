@@ -15,7 +15,7 @@ for rot in 0 1; do
     --log-file gpurun_out/ncu_p2g_rotate_${rot}.csv python tools/profile_step.py 512 67108864 2 > gpurun_out/ncu_p2g_rotate_${rot}.log 2>&1
 done
 # 3b. one full ncu capture of the three top kernels of the default path (source-level counters: compile has -lineinfo)
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_p2g_tile|k_g2p_tile|k_fupdate' -s 9 -c 3 \
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_p2g_tile|k_g2p_tile|k_fupdate' -s 4 -c 3 \
   -o gpurun_out/ncu_r2_top_kernels_64M python tools/profile_step.py 512 67108864 3 > gpurun_out/ncu_full.log 2>&1
 # 4. experimental kernels: parity, then A/B timing
 timeout 900 env MPM_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q --maxfail=20 > gpurun_out/exp_tests.log 2>&1
