@@ -1,5 +1,5 @@
 """Host emulation of the CUDA tile kernels (tests/emu): the kernel sources under csrc/ are compiled by g++ against a
-shim (threads = OS threads, real barriers, emulated bulk copies with byte accounting) and the kernel VARIANTS are
+shim (threads = fibers resumed in seeded random order, real barriers, emulated bulk copies with byte accounting) and the kernel VARIANTS are
 checked against each other -- in particular the experimental ones (linear gather tile, packed fp32 pairs, F-update
 inside P2G) against the default kernels that the GPU tests validate against the oracle and the reference.
 Test infrastructure only: nothing in the package can reach this code."""
