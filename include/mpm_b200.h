@@ -44,6 +44,8 @@ typedef struct MpmParams {
     float gravity[3];     /*                         material_point_method.cpp:260  (0,-9.8,0) */
     float friction_mu;    /*                         material_point_method.cpp:288  (0.5)    */
     int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline),
+                             9 = deterministic debug mode: one thread adds the contributions in ascending particle-id order
+                             without atomics, so a run is bitwise reproducible (small scenes; single-domain handles),
                              experimental (not validated on hardware yet): 2 = tile kernel with packed
                              fp32 pairs (FFMA2) in the accumulation loop, 3 = the fused substep runs the F-update
                              inside the P2G kernel, 4 = both */

@@ -78,6 +78,7 @@ struct mpm_sim {
     void* ipc_mig_dn = nullptr; void* ipc_mig_up = nullptr;
     bool peer_mig_connected = false;
     int peer_mig_epoch = 0;
+    int* slot_of_pid = nullptr; // p2g_variant 9 (deterministic debug mode): binned slot of every particle id
     bool fupd_pending = false;  // experimental p2g_variant 3/4: P2G has put the F-update results into the idle buffer (until substep_end)
     int num_sms = 148;
     cudaEvent_t ev[8];
@@ -260,7 +261,7 @@ int mpm_destroy(mpm_t* s) {
     for (int b = 0; b < 2; ++b) { cudaFree(s->buf[b]); cudaFree(s->out_buf[b]); }
     cudaFree(s->key); cudaFree(s->sorted_ids); cudaFree(s->blk_count); cudaFree(s->blk_start); cudaFree(s->blk_cursor);
     cudaFree(s->pblock_list); cudaFree(s->gflag); cudaFree(s->gblock_list); cudaFree(s->partial);
-    cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc);
+    cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc); cudaFree(s->slot_of_pid);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
@@ -545,6 +546,17 @@ static int launch_p2g(mpm_sim* s, float4* target, float dt) {
     if (s->prm.p2g_variant == 1) {
         k_p2g_atomic<MODE><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, target, s->gd, s->sc, dt);
         CKLAUNCH();
+    } else if (s->prm.p2g_variant == 9) {
+        // deterministic debug mode: one thread, ascending particle id, plain additions (bitwise reproducible run to run)
+        const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+        if (slab) return fail(MPM_ERR_INVALID, "p2g_variant 9 (deterministic debug mode) is for single-domain handles");
+        const int n_pid = (int)s->n_uploaded;
+        if (!s->slot_of_pid) CK(cudaMalloc(&s->slot_of_pid, sizeof(int) * (size_t)std::max<int64_t>(s->capacity, 1)));
+        CK(cudaMemsetAsync(s->slot_of_pid, 0xff, sizeof(int) * (size_t)std::max(n_pid, 1), s->stream));       // -1: not binned
+        k_slot_of_pid<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->key, s->dc, s->gd, s->slot_of_pid, n_pid);
+        CKLAUNCH();
+        k_p2g_serial<MODE><<<1, 1, 0, s->stream>>>(s->planes(s->cur), s->slot_of_pid, n_pid, target, s->gd, s->sc, dt);
+        CKLAUNCH(); s->stats.kernel_launches++;
     } else if (MODE == P2G_FUSED && p2g_fupd(s)) {
         const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,

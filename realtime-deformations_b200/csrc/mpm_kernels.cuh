@@ -520,6 +520,52 @@ MPM_DI void advect_rn(ParticleRegs& r, const SimConst& sc, float dt) {   // cpp:
 }
 
 // ------------------------------------------------------------------------------------------------------
+// P2G, variant 9 (deterministic debug mode, SURVEY section 7 hard part 3): ONE thread adds the particles' contributions in
+// ascending particle-id order with plain (non-atomic) additions, so the grid -- and with it the whole substep, whose other
+// stages are pure per-particle / per-node functions -- is bitwise reproducible from run to run. Same per-node arithmetic
+// as k_p2g_atomic. Minutes per substep at millions of particles: for bisecting differences on small scenes only.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_slot_of_pid(Planes P, const int* __restrict__ key, const DevCounters* __restrict__ dc, GridDims gd,
+                              int* __restrict__ slot_of_pid, int n_pid) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= dc->n_slots) return;
+    const int k = key[slot];
+    const int pid = __float_as_int(P.p[6][slot].y);
+    if (k >= 0 && k < gd.n_pblocks && pid >= 0 && pid < n_pid) slot_of_pid[pid] = slot;      // binned particles only
+}
+template <int MODE>
+__global__ void k_p2g_serial(Planes P, const int* __restrict__ slot_of_pid, int n_pid, float4* __restrict__ grid, GridDims gd,
+                             SimConst sc, float dt) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int pid = 0; pid < n_pid; ++pid) {
+        const int p = slot_of_pid[pid];
+        if (p < 0) continue;
+        float4 xm; float mch, a0[3], A[9];
+        p2g_coeffs<MODE>(P, p, sc.dinv, dt, xm, mch, a0, A);
+        const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
+        float wx[4], wy[4], wz[4];
+        axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
+        for (int a = 0; a < 4; ++a) {
+            const float dx = (float)(cx - 1 + a) * sc.h - xm.x;
+            for (int b = 0; b < 4; ++b) {
+                const float dy = (float)(cy - 1 + b) * sc.h - xm.y;
+                const float wxy = wx[a] * wy[b];
+                for (int c = 0; c < 4; ++c) {
+                    const float dz = (float)(cz - 1 + c) * sc.h - xm.z;
+                    const float w = wxy * wz[c];
+                    if (w == 0.0f) continue;
+                    float4& g = grid[node_index(gd, cx - 1 + a, cy - 1 + b, cz - 1 + c)];
+                    g.x += w * mch;
+                    g.y += w * (a0[0] + A[0] * dx + A[1] * dy + A[2] * dz);
+                    g.z += w * (a0[1] + A[3] * dx + A[4] * dy + A[5] * dz);
+                    g.w += w * (a0[2] + A[6] * dx + A[7] * dy + A[8] * dz);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // G2P, variant 1 (baseline / debug / staged API): one thread per sorted slot, nodes read straight from global
 // ------------------------------------------------------------------------------------------------------
 template <int FLAGS>

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 # the full-size configs and the 2-GPU test need the real device; graphs are refused by the fake runtime (the C++ adapter
 # binary runs against the emulated build through LD_LIBRARY_PATH)
 NEEDS_DEVICE = "not full_size and not two_gpus and not graph"
-QUICK = "binning or stage_level or fupdate_kat or moving or volumes or staged_and_fused or parked or render or error_paths or ragged or empty_handle or rotated or adapter or peer_memory or stiff_sweep"
+QUICK = "binning or stage_level or fupdate_kat or moving or volumes or staged_and_fused or parked or render or error_paths or ragged or empty_handle or rotated or adapter or peer_memory or stiff_sweep or deterministic"
 
 
 @pytest.fixture(scope="module")
