@@ -5,6 +5,15 @@
 #include "mpm_kernels.cuh"
 #include "mpm_tile_kernels.cuh"
 
+#ifndef MPM_HOST_EMU
+#include <nvtx3/nvToolsExt.h>        // header-only; no-ops unless a profiler (nsys / ncu --nvtx) is attached
+#define MPM_NVTX_PUSH(name) nvtxRangePushA(name)
+#define MPM_NVTX_POP() nvtxRangePop()
+#else
+#define MPM_NVTX_PUSH(name)
+#define MPM_NVTX_POP()
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -666,21 +675,26 @@ int mpm_update_particle_positions(mpm_t* s, float dt) {        // cpp:344-350
 
 // ---- fused fast path --------------------------------------------------------------------------------------------
 #define EV(i) do { if (!s->capturing) CK(cudaEventRecord(s->ev[i], s->stream)); } while (0)   // timing events are not graph nodes
+// NVTX ranges name the phases of a substep for nsys / ncu --nvtx (tracing); the ranges cover the host-side
+// enqueue, the per-phase device times are in MpmStats::last_ms
+struct NvtxRange { explicit NvtxRange(const char* n) { MPM_NVTX_PUSH(n); (void)n; } ~NvtxRange() { MPM_NVTX_POP(); } };
 int mpm_substep_begin(mpm_t* s, float dt) {
     NEED(s);
+    NvtxRange r("mpm_substep_begin: bin/sort, clear, P2G");
     EV(0);
     TRY(ensure_tau(s));
-    TRY(do_binning(s));
+    { NvtxRange r1("bin/sort"); TRY(do_binning(s)); }
     EV(1);
     TRY(launch_clear(s));
     EV(2);
-    TRY((launch_p2g<P2G_FUSED>(s, s->grid, dt)));
+    { NvtxRange r2("P2G"); TRY((launch_p2g<P2G_FUSED>(s, s->grid, dt))); }
     s->fupd_pending = p2g_fupd(s);
     EV(3);
     return MPM_OK;
 }
 int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
     NEED(s);
+    NvtxRange r("mpm_substep_end: grid update, F-update, G2P");
     TRY(set_colliders(s, c, n));
     EV(4);
     TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
