@@ -22,6 +22,13 @@ timeout 900 env MPM_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q --maxfa
 echo "experimental gpu tests: exit $?" | tee -a gpurun_out/exp_tests.log
 timeout 300 python tools/perf_probe.py 256 8388608 20 slab 0:0,0:2,0:3,0:4,2:0,3:0,4:4 > gpurun_out/ab_8M.log 2>&1
 timeout 480 python tools/perf_probe.py 512 67108864 10 slab 0:0,4:4,3:0,2:0,0:4 > gpurun_out/ab_64M.log 2>&1
+# 4b. compute-sanitizer on the small case: default kernels (changed after round 1's sanitizer run) and all options on
+for v in "0 0" "4 4"; do
+  for tool in memcheck racecheck; do
+    echo "== $tool, variants $v" >> gpurun_out/sanitizer_r2.txt
+    timeout 600 compute-sanitizer --tool $tool --print-limit 5 python tools/sanitize_case.py $v 2>&1 | grep -v "^=========     \|^=========$" | tail -8 >> gpurun_out/sanitizer_r2.txt
+  done
+done
 # 5. (needs `gpurun --gpus 2`) peer-memory halo: the single-process protocol test is part of step 4; then 2 ranks with
 #    CUDA IPC against one domain, with and without MPM_B200_PEER_HALO, every multi-rank command under `timeout`
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
