@@ -343,7 +343,10 @@ def main():
     roof = roofline_block(ms_per_step, n_total, n_active, world, phase_ms, args.grid, args.particles)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(mpm_b200)
+        try:
+            cpu = cpu_baseline(mpm_b200)
+        except Exception as exc:      # the GPU measurement above must not be lost to a failing CPU arm
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"cpu baseline failed: {exc}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
