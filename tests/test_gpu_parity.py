@@ -617,6 +617,49 @@ def test_full_size_properties_config4_stiff_sweep():
     _stiff_sweep_properties(256, 1 << 22, 60, compare_baseline=True)
 
 
+def _slab_properties(grid, n, substeps=4):
+    """BASELINE config 5 (the benchmark scene: snow slab, 8 per cell, gravity tilted towards +i) through size-independent
+    properties: cell indices bit-exact against int(pos / h), binning sorted and a permutation, mass conserved by the
+    transfer, upload order kept by the re-sorting substeps, nothing lost or non-finite."""
+    sc = mpm_b200.scenes.snow_slab(grid=grid, n=n)
+    assert sc["n"] == n
+    sim, cols, nc = sim_from_scene(sc)
+    st = sim.stats()
+    assert st.n_particles == n and st.n_out_of_grid == 0
+    cells, key, ids = sim.binning()
+    assert (cells == (sc["pos"] / np.float32(sc["h"])).astype(np.int32)).all(), "cell = int(pos/h), bit-exact"
+    assert (np.bincount(ids, minlength=n) == 1).all() and (np.diff(key[ids]) >= 0).all()
+    del cells, key, ids
+    g = sim.grid()
+    m_p = float(sc["mass"].astype(np.float64).sum())
+    assert abs(float(g[:, 0].astype(np.float64).sum()) - m_p) <= 1e-5 * m_p, "grid mass != particle mass"
+    assert st.n_active_nodes == int((g[:, 0] != 0).sum())
+    # a resting slab of 8 per cell touches every node of its bounding box of cells, one layer below and two above
+    lo = (sc["pos"].min(0) / np.float32(sc["h"])).astype(np.int64) - 1
+    hi = (sc["pos"].max(0) / np.float32(sc["h"])).astype(np.int64) + 2
+    assert st.n_active_nodes <= int(np.prod(hi - lo + 1)) and st.n_active_nodes >= 0.95 * int(np.prod(hi - lo + 1) - (hi - lo + 1)[1:].prod() * 4)
+    del g
+    xyzs, _ = sim.render_buffers()
+    assert np.array_equal(xyzs[:, :3].view(np.uint32), sc["pos"].view(np.uint32)), "render buffer rows are in upload order"
+    sim.substep(float(sc["dt"]), cols, nc, substeps)
+    xyzs, _ = sim.render_buffers()
+    st = sim.stats()
+    assert np.isfinite(xyzs).all() and st.svd_failed == 0 and st.n_particles == n and st.n_out_of_grid == 0
+    # at rest under gravity: |v| <= g * substeps * dt, far below one ulp-scale step of the positions
+    assert float(np.abs(xyzs[:, :3] - sc["pos"]).max()) <= 1e-5, "a resting slab must not move in a few substeps"
+    assert st.substeps_done == substeps
+    sim.close()
+
+
+def test_slab_scene_properties_small():
+    _slab_properties(32, 8192)
+
+
+def test_full_size_properties_config5_slab():
+    """BASELINE config 5 at full size: 64 Mi particles, 512^3 (the scene bench.py times)."""
+    _slab_properties(512, 1 << 26)
+
+
 @pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1",
                     reason="experimental paths (CUDA-graph substeps, linear-tile gather) are opt-in until validated on hardware")
 def test_experimental_graph_substeps_match_plain_path(monkeypatch):

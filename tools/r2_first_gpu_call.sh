@@ -4,7 +4,7 @@
 # Everything is wrapped in `timeout`; outputs land in gpurun_out/.
 mkdir -p gpurun_out
 # 1. parity suite: default path (rotated P2G record walk, single-quotient weights, block coordinates in the work items)
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/gpu_tests.log 2>&1
 echo "default gpu tests: exit $?" | tee -a gpurun_out/gpu_tests.log
 # 2. A/B of the rotated record walk at 64 Mi (third field 0 = the aligned walk measured in round 1); one process, one scene
 timeout 420 python tools/perf_probe.py 512 67108864 10 slab 0:0:0,0:0:1 > gpurun_out/rotate_64M.log 2>&1
