@@ -226,8 +226,8 @@ WORKLOAD_NAME = "snow_slab_512: 64Mi-particle snow slab avalanche, 512^3 grid (B
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)           # >= 50 timed substeps after >= 10 warm-up
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=512)            # overrides are for development runs only
     ap.add_argument("--particles", type=int, default=1 << 26)
