@@ -135,7 +135,28 @@ def run_oracle_port(sc, steps, threads=1):
     return sc["n"] * steps / sec, sec
 
 
+def port_openmp_sample(mpm_b200, steps=3, grid=128, n=1 << 20):
+    """the CPU restatement (oracle/mpm_oracle.c) single-threaded and with OpenMP on all host cores, on a
+    1 Mi-particle / 128^3 sample of the slab workload (the reference's own class cannot allocate this size). Reported next to
+    the reference's number, never used as the baseline value."""
+    sc = mpm_b200.scenes.snow_slab(grid=grid, n=n)
+    out = {"sample": f"snow_slab sample: {sc['n']} particles, {grid}^3 grid, {steps} substeps", "unit": UNIT}
+    for name, th in (("single_thread", 1), ("openmp_all_cores", os.cpu_count() or 1)):
+        v, sec = run_oracle_port(sc, steps, th)
+        out[name] = {"value": v, "threads": th, "seconds": sec}
+    return out
+
+
 def cpu_baseline(mpm_b200, budget_steps=150):
+    out = cpu_baseline_reference(mpm_b200, budget_steps)
+    try:
+        out["port"] = port_openmp_sample(mpm_b200)
+    except Exception as e:
+        out["port"] = {"error": str(e)}
+    return out
+
+
+def cpu_baseline_reference(mpm_b200, budget_steps=150):
     sc = cpu_sample_scene(mpm_b200)
     sample = f"snow_slab sample: {sc['n']} particles, 32^3 grid, 8 ppc, {budget_steps} substeps, default gravity"
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_mpm")

@@ -50,3 +50,14 @@ def test_roofline_block_assembly():
     # 8 GPUs: per-GPU achieved against a per-GPU peak
     r8 = bench.roofline_block(2.0, n, a, 8, [0.1, 0.01, 0.55, 0.4, 0.65, 0.3, 1.7, 0.3], 512, 1 << 26)
     assert abs(r8["achieved"] - (272 * n + 80 * a) / 2.0e-3 / 1e9 / 8) < 1.0
+
+
+def test_port_openmp_sample_block():
+    """cpu_baseline.port: the restatement single-threaded and with OpenMP on all host cores (SURVEY 8d ii), here on a miniature."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import mpm_b200
+    out = bench.port_openmp_sample(mpm_b200, steps=2, grid=32, n=8192)
+    assert out["unit"] == bench.UNIT and "8192 particles" in out["sample"]
+    assert out["single_thread"]["threads"] == 1 and out["single_thread"]["value"] > 0
+    assert out["openmp_all_cores"]["threads"] >= 1 and out["openmp_all_cores"]["value"] > 0
