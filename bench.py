@@ -107,7 +107,10 @@ def run_reference_binary(sc, steps, nproc):
     cmd = [ref, "--grid", str(I), str(J), str(K), "--n", str(sc["n"]), "--load", d + "/p.f32", "--colliders", d + "/c.f32",
            "--steps", str(steps), "--quiet", "--bench"]
     t0 = time.time()
-    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(nproc)]
+    # the class's constructor also cudaMallocs its (dead) weight table (hpp:149-156; failure is non-fatal there): hide the GPU
+    # so that a replica per host core does not open a CUDA context per core -- this is the CPU path that is being timed
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for _ in range(nproc)]
     outs = [p.communicate()[0] for p in procs]
     wall = time.time() - t0
     secs = []
@@ -183,6 +186,13 @@ def reference_arm(args):
     sc = cpu_sample_scene(mpm_b200)
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_mpm")
     kind = "reference" if os.path.exists(ref) else "port"
+    if kind == "reference":
+        # every replica of the real class holds its I*J*K*N-float weight table (1.07 GB for the sample): stay inside host memory
+        try:
+            avail_kb = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+            cores = max(1, min(cores, int(0.5 * avail_kb * 1024 / (4.0 * sc["dims"][0] * sc["dims"][1] * sc["dims"][2] * sc["n"] + 2e8))))
+        except Exception:
+            pass
     per_step = []
     # one "step" = one substep of the bounded sample on every core; W warm-up + K timed, as one run of W+K substeps
     # per process is what the binary exposes, the warm-up run is a separate short launch
