@@ -343,7 +343,9 @@ def test_full_size_properties_config2():
     sv = np.linalg.svd(a[::64, 8:17].reshape(-1, 3, 3).astype(np.float64), compute_uv=False)
     assert sv.max() <= 1.005 + 1e-5 and sv.min() >= 0.975 - 1e-5
     e = traj_errors(a, b)
-    assert e[0] <= 1e-6 and e[1] <= 5e-3 and e[2] <= 1e-5, f"tile vs baseline kernels at 1 Mi particles: {e}"
+    # noise floor of this scene, measured on the CPU (oracle with vs without FMA contraction, same 6 substeps at full size):
+    # 4.8e-7 m / 3.9e-3 m/s / 2.7e-6; the two kernel families differ the same way (summation order), bound = 4 x floor
+    assert e[0] <= 2e-6 and e[1] <= 1.6e-2 and e[2] <= 1.1e-5, f"tile vs baseline kernels at 1 Mi particles: {e}"
     st = sim.stats()
     assert st.n_particles == n and st.reserved[0] == 1, "pos/h shortcut must pass its exhaustive check for h = 0.05"
 
