@@ -628,6 +628,9 @@ def _slab_properties(grid, n, substeps=4):
     sim, cols, nc = sim_from_scene(sc)
     st = sim.stats()
     assert st.n_particles == n and st.n_out_of_grid == 0
+    # the 3-FMA pos/h quotient passes its exhaustive check for h = 0.05 up to 512 cells per axis (IEEE operations only: the
+    # host-emulated check gives the same verdict), so the benchmark scene runs on the fast path
+    assert st.reserved[0] == 1
     cells, key, ids = sim.binning()
     assert (cells == (sc["pos"] / np.float32(sc["h"])).astype(np.int32)).all(), "cell = int(pos/h), bit-exact"
     assert (np.bincount(ids, minlength=n) == 1).all() and (np.diff(key[ids]) >= 0).all()
