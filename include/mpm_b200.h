@@ -52,7 +52,12 @@ typedef struct MpmParams {
     int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline),
                              experimental (none validated on hardware yet): 2 = linear-tile gather,
                              3 = packed fp32 pairs (FFMA2) in the separable gather, 4 = both */
-    int   reserved[6];
+    int   fupdate_exact;  /* F-update (cpp:306-330) inside the fused mpm_substep: 0 = tolerance form (FMA contraction, MUFU
+                             reciprocals / square roots, F^ = (I + dt C) FE taken directly; same Eigen Jacobi control flow;
+                             held to 4x the reference's own FMA-contraction noise floor by the trajectory tests),
+                             1 = the bit-faithful form everywhere, 2 = the tolerance form everywhere (tests). With 0 the staged
+                             mpm_update_deformation_gradient stays bit-faithful. */
+    int   reserved[5];
 } MpmParams;
 
 /* Box collider = MeshCollider (hpp:74-93) reduced to what its sdf lambda uses (hpp:80-85):

@@ -133,6 +133,7 @@ static void fill_consts(mpm_sim* s) {
     c.h = p.h; c.dinv = dp_inverse_scalar(p.h); c.E = p.youngs_modulus; c.nu = p.poisson_ratio; c.xi = p.hardening_xi;
     c.clamp_lo = (float)(1.0 - (double)p.theta_c); c.clamp_hi = (float)(1.0 + (double)p.theta_s);   // cpp:320
     c.friction = p.friction_mu;
+    c.mu0 = c.E / (2.0f * (1.0f + c.nu)); c.lambda0 = (c.E * c.nu) / ((1.0f + c.nu) * (1.0f - 2.0f * c.nu));   // cpp:237-238 (same float divisions as lame())
     for (int a = 0; a < 3; ++a) c.g[a] = p.gravity[a];
     c.pos_lo = (float)(3 * p.h);                                                                     // cpp:383
     c.pos_hi[0] = (float)((s->gd.I - 3) * p.h); c.pos_hi[1] = (float)((s->gd.J - 3) * p.h); c.pos_hi[2] = (float)((s->gd.K - 3) * p.h);
@@ -569,7 +570,7 @@ static int launch_p2g(mpm_sim* s, float4* target, float dt) {
     } else if (MODE == P2G_FUSED && p2g_fupd(s)) {
         const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
-                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), &nxt)));
+                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), &nxt, s->prm.fupdate_exact != 1)));
     } else {
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
                                   s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s))));
@@ -593,7 +594,8 @@ static int launch_g2p(mpm_sim* s, float dt) {
     } else {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream, &s->side,
-                                   s->prm.g2p_variant == 2 || s->prm.g2p_variant == 4, s->prm.g2p_variant == 3 || s->prm.g2p_variant == 4)));
+                                   s->prm.g2p_variant == 2 || s->prm.g2p_variant == 4, s->prm.g2p_variant == 3 || s->prm.g2p_variant == 4,
+                                   s->prm.fupdate_exact == 2 || ((FLAGS & G2P_REORDER) && s->prm.fupdate_exact == 0))));      // tolerance-form F-update: fused substep (or forced)
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {
@@ -1103,7 +1105,7 @@ int mpm_substep_begin_peer(mpm_t* s, float dt, int phase) {
         CKLAUNCH(); s->stats.kernel_launches++;
         const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<P2G_FUSED>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
-                                       s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), p2g_fupd(s) ? &nxt : nullptr, &s->peer)));
+                                       s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), p2g_fupd(s) ? &nxt : nullptr, s->prm.fupdate_exact != 1, &s->peer)));
         s->stats.kernel_launches++;
         s->fupd_pending = p2g_fupd(s);
         k_peer_signal<<<1, 1, 0, s->stream>>>(s->peer_flags_dn ? s->peer_flags_dn + 3 : nullptr, s->peer_flags_up ? s->peer_flags_up + 2 : nullptr, s->peer_epoch);

@@ -31,6 +31,7 @@ struct GridDims {
 
 struct SimConst {
     float h, dinv, E, nu, xi, clamp_lo, clamp_hi, friction;
+    float mu0, lambda0;        // E / (2 (1 + nu)), E nu / ((1 + nu)(1 - 2 nu)): cpp:237-238, hoisted for the tolerance-form F-update
     float g[3];
     float pos_lo, pos_hi[3];   // clampPosition bounds (cpp:381-388)
     int p2g_rotate;            // k_p2g_tile: start each cell's record walk at a different record (bank-conflict fix), 0 = off
@@ -459,29 +460,44 @@ __global__ void k_stress(Planes P, const DevCounters* __restrict__ dc, SimConst 
 // updateDeformationGradient (cpp:306-330) + next substep's stress, one thread per sorted slot. It touches only
 // B (read), FE/FP/V0 (read) and FE/FP/tau (write), i.e. planes disjoint from what the gather kernel writes, so in the
 // re-sorting fused path the two kernels split the particle record between them at no extra HBM traffic.
-template <bool REORDER, bool PK = false>
+// The F-update + next substep's stress of one particle from its loaded planes (1..3: B, 6..10: V0, pid, FE, FP); results to
+// planes 4..10 of D at slot q. FAST = tolerance form (f_update_fast, the fused substep's default), else bit-faithful.
+struct FUpdIn { float4 a1, a2, a3, a6, a7, a8, a9, a10; };
+MPM_DI FUpdIn fupd_load(const Planes& cur, int p) {
+    FUpdIn r;
+    r.a1 = cur.p[1][p]; r.a2 = cur.p[2][p]; r.a3 = cur.p[3][p];
+    r.a6 = cur.p[6][p]; r.a7 = cur.p[7][p]; r.a8 = cur.p[8][p]; r.a9 = cur.p[9][p]; r.a10 = cur.p[10][p];
+    return r;
+}
+template <bool FAST>
+MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCounters* dc, const SimConst& sc, float dt) {
+    float B[9] = { in.a1.x, in.a1.y, in.a1.z, in.a1.w, in.a2.x, in.a2.y, in.a2.z, in.a2.w, in.a3.x };
+    float FE[9] = { in.a6.z, in.a6.w, in.a7.x, in.a7.y, in.a7.z, in.a7.w, in.a8.x, in.a8.y, in.a8.z };
+    float FP[9] = { in.a8.w, in.a9.x, in.a9.y, in.a9.z, in.a9.w, in.a10.x, in.a10.y, in.a10.z, in.a10.w };
+    float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
+    if (FAST) {
+        if (!f_update_fast(B, FE, FP, sc.dinv * dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+        tau_from_factors_fast(Ug, Sg, m3_det_fast(FE), m3_det_fast(FP), in.a6.x, sc.dinv, sc.mu0, sc.lambda0, sc.xi, tau);
+    } else {
+        if (!f_update_rn(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
+        tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), in.a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
+    }
+    D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
+    D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
+    D.p[6][q] = make_float4(in.a6.x, in.a6.y, FE[0], FE[1]);
+    D.p[7][q] = make_float4(FE[2], FE[3], FE[4], FE[5]);
+    D.p[8][q] = make_float4(FE[6], FE[7], FE[8], FP[0]);
+    D.p[9][q] = make_float4(FP[1], FP[2], FP[3], FP[4]);
+    D.p[10][q] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+}
+template <bool REORDER, bool FAST = false>
 __global__ void __launch_bounds__(256)
 k_fupdate(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc, SimConst sc, float dt) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dc->n_binned) return;
     const int p = sorted_ids[j];
-    const float4 a1 = cur.p[1][p], a2 = cur.p[2][p], a3 = cur.p[3][p];
-    const float4 a6 = cur.p[6][p], a7 = cur.p[7][p], a8 = cur.p[8][p], a9 = cur.p[9][p], a10 = cur.p[10][p];
-    float B[9] = { a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x };
-    float FE[9] = { a6.z, a6.w, a7.x, a7.y, a7.z, a7.w, a8.x, a8.y, a8.z };
-    float FP[9] = { a8.w, a9.x, a9.y, a9.z, a9.w, a10.x, a10.y, a10.z, a10.w };
-    float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
-    if (!f_update_rn<PK>(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
-    tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
-    const Planes& D = REORDER ? nxt : cur;
-    const int q = REORDER ? j : p;
-    D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
-    D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
-    D.p[6][q] = make_float4(a6.x, a6.y, FE[0], FE[1]);
-    D.p[7][q] = make_float4(FE[2], FE[3], FE[4], FE[5]);
-    D.p[8][q] = make_float4(FE[6], FE[7], FE[8], FP[0]);
-    D.p[9][q] = make_float4(FP[1], FP[2], FP[3], FP[4]);
-    D.p[10][q] = make_float4(FP[5], FP[6], FP[7], FP[8]);
+    const FUpdIn in = fupd_load(cur, p);
+    fupd_compute_store<FAST>(in, REORDER ? nxt : cur, REORDER ? j : p, dc, sc, dt);
 }
 
 // computeParticleVolumesAndDensities (cpp:131-142): density = sum m_i w_ip / h^3, V0 = m / density

@@ -48,17 +48,12 @@ MPM_DI f32x2_t fmul2(f32x2_t a, f32x2_t b) { return pack2(__fmul_rn(lo2(a), lo2(
 #endif
 
 // (x', y') = (c*x + s*y, -s*x + c*y), every product and every sum rounded once: the Jacobi rotation of Eigen's
-// applyOnTheLeft / applyOnTheRight. PK issues it as two packed multiplies and one packed add (mul.rn.f32x2 / add.rn.f32x2:
-// IEEE rounding per component, so the bits are those of the scalar form).
-template <bool PK>
+// applyOnTheLeft / applyOnTheRight. (A packed mul.rn.f32x2 / add.rn.f32x2 form of this was tried in round 1 and is gone:
+// on hardware it did NOT reproduce the scalar bits -- 36512 of 38646 F-update KAT values differed, profiles/r2_ab_64M.md.)
 MPM_DI void rot_pair_rn(float c, float s, float x, float y, float& xo, float& yo) {
-    if (PK) {
-        const f32x2_t r = fadd2(fmul2(pack2(c, -s), pack2(x, x)), fmul2(pack2(s, c), pack2(y, y)));
-        xo = lo2(r); yo = hi2(r);
-    } else {
-        xo = add_rn(mul_rn(c, x), mul_rn(s, y));
-        yo = add_rn(mul_rn(-s, x), mul_rn(c, y));
-    }
+    const float a = add_rn(mul_rn(c, x), mul_rn(s, y));
+    const float b = add_rn(mul_rn(-s, x), mul_rn(c, y));
+    xo = a; yo = b;
 }
 
 // ---- reference weightNx, material_point_method.hpp:20-31 ----
@@ -139,24 +134,6 @@ MPM_DI void m3_mul_rn(float* R, const float* A, const float* B) {   // R may not
         for (int r = 0; r < 3; ++r)
             R[c * 3 + r] = dot3_rn(A[0 + r], B[c * 3 + 0], A[3 + r], B[c * 3 + 1], A[6 + r], B[c * 3 + 2]);
 }
-// the same nine dot3_rn (same products, same order of the two additions) issued as packed pairs: rows 0,1 of every column
-// together, row 2 of columns 0,1 together, the last entry alone -- 25 instructions instead of 45
-MPM_DI f32x2_t dot3_rn2(f32x2_t a0, f32x2_t b0, f32x2_t a1, f32x2_t b1, f32x2_t a2, f32x2_t b2) {
-    return fadd2(fadd2(fmul2(a0, b0), fmul2(a1, b1)), fmul2(a2, b2));
-}
-template <bool PK>
-MPM_DI void m3_mul_rn_t(float* R, const float* A, const float* B) {
-    if (!PK) { m3_mul_rn(R, A, B); return; }
-    const f32x2_t A0 = pack2(A[0], A[1]), A1 = pack2(A[3], A[4]), A2 = pack2(A[6], A[7]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const f32x2_t v = dot3_rn2(A0, pack2(B[c * 3 + 0], B[c * 3 + 0]), A1, pack2(B[c * 3 + 1], B[c * 3 + 1]), A2, pack2(B[c * 3 + 2], B[c * 3 + 2]));
-        R[c * 3 + 0] = lo2(v); R[c * 3 + 1] = hi2(v);
-    }
-    const f32x2_t w = dot3_rn2(pack2(A[2], A[2]), pack2(B[0], B[3]), pack2(A[5], A[5]), pack2(B[1], B[4]), pack2(A[8], A[8]), pack2(B[2], B[5]));
-    R[2] = lo2(w); R[5] = hi2(w);
-    R[8] = dot3_rn(A[2], B[6], A[5], B[7], A[8], B[8]);
-}
 #define MG(m, c, r) ((m)[(c) * 3 + (r)])
 MPM_DI float m3_det_rn(const float* m) {
     const float t0 = mul_rn(MG(m,0,0), sub_rn(mul_rn(MG(m,1,1), MG(m,2,2)), mul_rn(MG(m,2,1), MG(m,1,2))));
@@ -187,7 +164,7 @@ MPM_DI void m3_transpose(float* R, const float* A) {
 // Control flow, sweep order (1,0),(2,0),(2,1), 2x2 kernel, sign fix-up and selection sort follow
 // external/Eigen/src/SVD/JacobiSVD.h:689-817, misc/RealSvd2x2.h:21-51, Jacobi/Jacobi.h:96-126,326-337
 // (restated in oracle/mpm_oracle.c: oracle_svd3). Arrays are ROW-major here (a[r*3+c] == Eigen m(r,c)).
-template <int P, int Q, bool PK>
+template <int P, int Q>
 MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxDiag, bool& finished) {
     const float pm = mul_rn(2.0f * FLT_EPSILON, maxDiag);
     const float threshold = (FLT_MIN < pm) ? pm : FLT_MIN;
@@ -204,8 +181,8 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
     }
     if (!(c1 == 1.0f && s1 == 0.0f)) {
         float a0, b0, a1, b1;
-        rot_pair_rn<PK>(c1, s1, m00, m10, a0, b0);
-        rot_pair_rn<PK>(c1, s1, m01, m11, a1, b1);
+        rot_pair_rn(c1, s1, m00, m10, a0, b0);
+        rot_pair_rn(c1, s1, m01, m11, a1, b1);
         m00 = a0; m10 = b0; m01 = a1; m11 = b1;
     }
     float cr, sr;
@@ -226,19 +203,19 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
     if (!(cl == 1.0f && sl == 0.0f)) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {       // W.applyOnTheLeft(p,q,j_left)
-            rot_pair_rn<PK>(cl, sl, W[P * 3 + c], W[Q * 3 + c], W[P * 3 + c], W[Q * 3 + c]);
+            rot_pair_rn(cl, sl, W[P * 3 + c], W[Q * 3 + c], W[P * 3 + c], W[Q * 3 + c]);
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {       // U.applyOnTheRight(p,q,j_left.transpose())
-            rot_pair_rn<PK>(cl, sl, U[r * 3 + P], U[r * 3 + Q], U[r * 3 + P], U[r * 3 + Q]);
+            rot_pair_rn(cl, sl, U[r * 3 + P], U[r * 3 + Q], U[r * 3 + P], U[r * 3 + Q]);
         }
     }
     const float s = -sr;
     if (!(cr == 1.0f && s == 0.0f)) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {       // W.applyOnTheRight(p,q,j_right); V.applyOnTheRight(p,q,j_right)
-            rot_pair_rn<PK>(cr, s, W[r * 3 + P], W[r * 3 + Q], W[r * 3 + P], W[r * 3 + Q]);
-            rot_pair_rn<PK>(cr, s, V[r * 3 + P], V[r * 3 + Q], V[r * 3 + P], V[r * 3 + Q]);
+            rot_pair_rn(cr, s, W[r * 3 + P], W[r * 3 + Q], W[r * 3 + P], W[r * 3 + Q]);
+            rot_pair_rn(cr, s, V[r * 3 + P], V[r * 3 + Q], V[r * 3 + P], V[r * 3 + Q]);
         }
     }
     const float dm = fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q]));
@@ -247,7 +224,6 @@ MPM_DI void jacobi_pair(float (&W)[9], float (&U)[9], float (&V)[9], float& maxD
 
 // returns false on non-finite input (Eigen: InvalidInput). MAX_SWEEPS only guards the GPU against a hang;
 // Eigen itself has no cap and converges in 3-5 sweeps on finite input.
-template <bool PK = false>
 MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
     float W[9];
     float scale = 0.0f;
@@ -265,9 +241,9 @@ MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float 
     constexpr int MAX_SWEEPS = 64;
     for (int sweep = 0; sweep < MAX_SWEEPS && !finished; ++sweep) {
         finished = true;
-        jacobi_pair<1, 0, PK>(W, U, V, maxDiag, finished);
-        jacobi_pair<2, 0, PK>(W, U, V, maxDiag, finished);
-        jacobi_pair<2, 1, PK>(W, U, V, maxDiag, finished);
+        jacobi_pair<1, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair<2, 1>(W, U, V, maxDiag, finished);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -299,9 +275,6 @@ MPM_DI bool svd3_eigen(const float (&A)[9], float (&U)[9], float (&S)[3], float 
 // ---- F-update of one particle, material_point_method.cpp:306-330 (bit-faithful) ----
 // in: B (previous substep's APIC matrix), FE, FP; out: FE, FP overwritten, factors of the new FE for the stress.
 // Ug/Sg: FE_new = Ug * diag(Sg) * Vg^T as glm matrices (Ug is the glm view of Eigen's U, see utils.h:25-33).
-// PK (EXPERIMENTAL, with the packed-pair kernel variants): the 3x3 products and the Jacobi rotations issued as packed
-// unfused pairs -- the same IEEE operations, bit for bit (the reference's F-update KATs run through both forms).
-template <bool PK = false>
 MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], float dinv, float dt, float clamp_lo,
                         float clamp_hi, float (&Ug)[9], float (&Sg)[3]) {
     float T0[9], T1[9], T[9], FPinv[9], Fh[9], Vg[9];
@@ -310,11 +283,11 @@ MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], flo
         const float v = mul_rn(mul_rn(B[i], dinv), dt);
         T0[i] = add_rn((i % 4 == 0) ? 1.0f : 0.0f, v);
     }
-    m3_mul_rn_t<PK>(T1, T0, FE);
-    m3_mul_rn_t<PK>(T, T1, FP);             // FPn1
+    m3_mul_rn(T1, T0, FE);
+    m3_mul_rn(T, T1, FP);             // FPn1
     m3_inverse_rn(FPinv, FP);
-    m3_mul_rn_t<PK>(Fh, T, FPinv);          // FEpKryshka
-    if (!svd3_eigen<PK>(Fh, Ug, Sg, Vg)) return false;
+    m3_mul_rn(Fh, T, FPinv);          // FEpKryshka
+    if (!svd3_eigen(Fh, Ug, Sg, Vg)) return false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { float s = Sg[k]; if (s < clamp_lo) s = clamp_lo; if (clamp_hi < s) s = clamp_hi; Sg[k] = s; }
     float US[9], Vt[9], FEinv[9];
@@ -323,9 +296,160 @@ MPM_DI bool f_update_rn(const float (&B)[9], float (&FE)[9], float (&FP)[9], flo
 #pragma unroll
         for (int r = 0; r < 3; ++r) US[c * 3 + r] = mul_rn(Ug[c * 3 + r], Sg[c]);   // U * S (S diagonal)
     m3_transpose(Vt, Vg);
-    m3_mul_rn_t<PK>(FE, US, Vt);            // U * S * transpose(V)
+    m3_mul_rn(FE, US, Vt);            // U * S * transpose(V)
     m3_inverse_rn(FEinv, FE);
-    m3_mul_rn_t<PK>(FP, FEinv, T);
+    m3_mul_rn(FP, FEinv, T);
+    return true;
+}
+
+// ---- F-update, tolerance form (the fused substep's default; the staged API and fupdate_exact keep f_update_rn) ----
+// Same algorithm and control flow as f_update_rn / svd3_eigen above (Eigen's two-sided Jacobi sweeps in the order
+// (1,0),(2,0),(2,1), its 2x2 kernel, threshold, sign fix-up and descending selection sort; the reference's transposed
+// re-assembly), but with the freedoms a floating-point tolerance gives: products and sums contract into FMAs, divisions
+// and square roots are single MUFU approximations (<= 2 ulp), the max|a| pre-scaling is dropped (it only guards Eigen
+// against overflow; F is O(1) here) and F^ = (I + dt C) FE is taken directly instead of ((I + dt C) FE FP) FP^-1
+// (cpp:309-311 multiplies by FP and by its inverse again). About 350 instead of 1050 instructions per particle at rest.
+// Differences to the bit-faithful form are of the size of the reference's own sensitivity to FMA contraction (SURVEY
+// App. C): the trajectory tests hold this path to 4x that noise floor.
+#ifndef MPM_HOST_EMU
+MPM_DI float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MPM_DI float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MPM_DI float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MPM_DI float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+MPM_DI float fast_rcp(float x) { return 1.0f / x; }
+MPM_DI float fast_rsqrt(float x) { return 1.0f / std::sqrt(x); }
+MPM_DI float fast_sqrt(float x) { return std::sqrt(x); }
+MPM_DI float fast_ex2(float x) { return std::exp2(x); }
+#endif
+MPM_DI void rot_pair_fast(float c, float s, float x, float y, float& xo, float& yo) {
+    const float a = fmaf(c, x, s * y), b = fmaf(c, y, -s * x);
+    xo = a; yo = b;
+}
+MPM_DI void m3_mul_fast(float* R, const float* A, const float* B) {   // R may not alias A or B
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            R[c * 3 + r] = fmaf(A[6 + r], B[c * 3 + 2], fmaf(A[3 + r], B[c * 3 + 1], A[0 + r] * B[c * 3 + 0]));
+}
+MPM_DI float m3_det_fast(const float* m) {
+    return MG(m,0,0) * (MG(m,1,1) * MG(m,2,2) - MG(m,2,1) * MG(m,1,2))
+         - MG(m,1,0) * (MG(m,0,1) * MG(m,2,2) - MG(m,2,1) * MG(m,0,2))
+         + MG(m,2,0) * (MG(m,0,1) * MG(m,1,2) - MG(m,1,1) * MG(m,0,2));
+}
+MPM_DI void m3_inverse_fast(float* R, const float* m) {             // R may not alias m; adjugate / det
+    const float c00 = MG(m,1,1) * MG(m,2,2) - MG(m,2,1) * MG(m,1,2);
+    const float c01 = MG(m,2,1) * MG(m,0,2) - MG(m,0,1) * MG(m,2,2);
+    const float c02 = MG(m,0,1) * MG(m,1,2) - MG(m,1,1) * MG(m,0,2);
+    const float ood = fast_rcp(fmaf(MG(m,2,0), c02, fmaf(MG(m,1,0), c01, MG(m,0,0) * c00)));
+    MG(R,0,0) = c00 * ood; MG(R,0,1) = c01 * ood; MG(R,0,2) = c02 * ood;
+    MG(R,1,0) = (MG(m,2,0) * MG(m,1,2) - MG(m,1,0) * MG(m,2,2)) * ood;
+    MG(R,1,1) = (MG(m,0,0) * MG(m,2,2) - MG(m,2,0) * MG(m,0,2)) * ood;
+    MG(R,1,2) = (MG(m,1,0) * MG(m,0,2) - MG(m,0,0) * MG(m,1,2)) * ood;
+    MG(R,2,0) = (MG(m,1,0) * MG(m,2,1) - MG(m,2,0) * MG(m,1,1)) * ood;
+    MG(R,2,1) = (MG(m,2,0) * MG(m,0,1) - MG(m,0,0) * MG(m,2,1)) * ood;
+    MG(R,2,2) = (MG(m,0,0) * MG(m,1,1) - MG(m,1,0) * MG(m,0,1)) * ood;
+}
+template <int P, int Q>
+MPM_DI void jacobi_pair_fast(float (&W)[9], float (&U)[9], float (&V)[9], float& maxDiag, bool& finished) {
+    const float threshold = fmaxf(FLT_MIN, (2.0f * FLT_EPSILON) * maxDiag);
+    if (!(fabsf(W[P * 3 + Q]) > threshold || fabsf(W[Q * 3 + P]) > threshold)) return;
+    finished = false;
+    float m00 = W[P * 3 + P], m01 = W[P * 3 + Q], m10 = W[Q * 3 + P], m11 = W[Q * 3 + Q];
+    float c1 = 1.0f, s1 = 0.0f;
+    const float t = m00 + m11, d = m10 - m01;
+    const float n2 = fmaf(t, t, d * d);
+    if (!(fabsf(d) < FLT_MIN) && n2 >= FLT_MIN) {       // u = t/d; s = 1/sqrt(1+u^2) = |d|/sqrt(t^2+d^2); c = u*s
+        const float rs = fast_rsqrt(n2);
+        s1 = fabsf(d) * rs; c1 = copysignf(t * rs, t * d);
+        rot_pair_fast(c1, s1, m00, m10, m00, m10);
+        rot_pair_fast(c1, s1, m01, m11, m01, m11);
+    }
+    float cr = 1.0f, sr = 0.0f;
+    const float deno = 2.0f * fabsf(m01);
+    if (!(deno < FLT_MIN)) {
+        const float tau = (m00 - m11) * fast_rcp(deno);
+        const float w = fast_sqrt(fmaf(tau, tau, 1.0f));
+        const float tt = fast_rcp(tau > 0.0f ? tau + w : tau - w);
+        const float nn = fast_rsqrt(fmaf(tt, tt, 1.0f));
+        sr = copysignf(1.0f, m01) * -tt * nn;
+        cr = nn;
+    }
+    const float cl = fmaf(c1, cr, s1 * sr);              // j_left = rot1 * j_right^T
+    const float sl = fmaf(s1, cr, -c1 * sr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rot_pair_fast(cl, sl, W[P * 3 + c], W[Q * 3 + c], W[P * 3 + c], W[Q * 3 + c]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) rot_pair_fast(cl, sl, U[r * 3 + P], U[r * 3 + Q], U[r * 3 + P], U[r * 3 + Q]);
+    const float s = -sr;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        rot_pair_fast(cr, s, W[r * 3 + P], W[r * 3 + Q], W[r * 3 + P], W[r * 3 + Q]);
+        rot_pair_fast(cr, s, V[r * 3 + P], V[r * 3 + Q], V[r * 3 + P], V[r * 3 + Q]);
+    }
+    maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q])));
+}
+MPM_DI bool svd3_fast(const float (&A)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
+    float W[9];
+    float chk = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { W[i] = A[i]; chk += fabsf(A[i]); U[i] = (i % 4 == 0) ? 1.0f : 0.0f; V[i] = U[i]; }
+    if (!isfinite(chk)) return false;                    // Eigen: InvalidInput
+    float maxDiag = fmaxf(fmaxf(fabsf(W[0]), fabsf(W[4])), fabsf(W[8]));
+    bool finished = false;
+    constexpr int MAX_SWEEPS = 64;
+    for (int sweep = 0; sweep < MAX_SWEEPS && !finished; ++sweep) {
+        finished = true;
+        jacobi_pair_fast<1, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair_fast<2, 0>(W, U, V, maxDiag, finished);
+        jacobi_pair_fast<2, 1>(W, U, V, maxDiag, finished);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = W[i * 3 + i];
+        S[i] = fabsf(a);
+        if (a < 0.0f) { U[0 + i] = -U[0 + i]; U[3 + i] = -U[3 + i]; U[6 + i] = -U[6 + i]; }
+    }
+#define MPM_SWAPCOL(i, j)                                                          \
+    do {                                                                           \
+        float t_ = S[i]; S[i] = S[j]; S[j] = t_;                                   \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r) {                            \
+            t_ = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + j]; U[r * 3 + j] = t_;     \
+            t_ = V[r * 3 + i]; V[r * 3 + i] = V[r * 3 + j]; V[r * 3 + j] = t_;     \
+        }                                                                          \
+    } while (0)
+    {
+        int pos = 0;
+        if (S[1] > S[pos]) pos = 1;
+        if (S[2] > S[pos]) pos = 2;
+        if (S[pos] == 0.0f) return true;
+        if (pos == 1) MPM_SWAPCOL(0, 1); else if (pos == 2) MPM_SWAPCOL(0, 2);
+        if (S[2] > S[1]) { MPM_SWAPCOL(1, 2); }
+    }
+#undef MPM_SWAPCOL
+    return true;
+}
+// s = dinv * dt. Outputs as f_update_rn.
+MPM_DI bool f_update_fast(const float (&B)[9], float (&FE)[9], float (&FP)[9], float s, float clamp_lo, float clamp_hi,
+                          float (&Ug)[9], float (&Sg)[3]) {
+    float T0[9], Fh[9], T[9], Vg[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T0[i] = fmaf(B[i], s, (i % 4 == 0) ? 1.0f : 0.0f);
+    m3_mul_fast(Fh, T0, FE);
+    m3_mul_fast(T, Fh, FP);
+    if (!svd3_fast(Fh, Ug, Sg, Vg)) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Sg[k] = fminf(fmaxf(Sg[k], clamp_lo), clamp_hi);
+    float US[9], Vt[9], FEinv[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) US[c * 3 + r] = Ug[c * 3 + r] * Sg[c];
+    m3_transpose(Vt, Vg);
+    m3_mul_fast(FE, US, Vt);
+    m3_inverse_fast(FEinv, FE);
+    m3_mul_fast(FP, FEinv, T);
     return true;
 }
 
@@ -351,6 +475,24 @@ MPM_DI void tau_from_factors(const float (&Ug)[9], const float (&Sg)[3], float J
     tau[0] = MPM_SYM(0, 0); tau[1] = MPM_SYM(1, 1); tau[2] = MPM_SYM(2, 2);
     tau[3] = MPM_SYM(0, 1); tau[4] = MPM_SYM(0, 2); tau[5] = MPM_SYM(1, 2);
 #undef MPM_SYM
+}
+// tolerance form for the fused path: Lame parameters of the undeformed material precomputed on the host (mu0, lambda0:
+// the same IEEE divisions), exp through one ex2.approx
+MPM_DI void tau_from_factors_fast(const float (&Ug)[9], const float (&Sg)[3], float J, float detFP, float V0, float dinv,
+                                  float mu0, float lambda0, float xi, float (&tau)[6]) {
+    const float e = fast_ex2(xi * (1.0f - detFP) * 1.4426950408889634f);
+    const float vol = V0 * dinv, two_mu = 2.0f * mu0 * e;
+    const float iso = lambda0 * e * (J - 1.0f) * J;
+    float Ud[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dk = vol * fmaf(two_mu * Sg[k], Sg[k] - 1.0f, iso);
+        Ud[k * 3 + 0] = Ug[k * 3 + 0] * dk; Ud[k * 3 + 1] = Ug[k * 3 + 1] * dk; Ud[k * 3 + 2] = Ug[k * 3 + 2] * dk;
+    }
+#define MPM_SYMF(r, s) fmaf(Ud[6 + r], Ug[6 + s], fmaf(Ud[3 + r], Ug[3 + s], Ud[0 + r] * Ug[0 + s]))
+    tau[0] = MPM_SYMF(0, 0); tau[1] = MPM_SYMF(1, 1); tau[2] = MPM_SYMF(2, 2);
+    tau[3] = MPM_SYMF(0, 1); tau[4] = MPM_SYMF(0, 2); tau[5] = MPM_SYMF(1, 2);
+#undef MPM_SYMF
 }
 // general FE (after an upload): rotation by Newton iteration R <- (R + R^-T)/2, quadratically convergent
 MPM_DI void tau_general(const float (&FE)[9], float detFP, float V0, float dinv, float E, float nu, float xi,

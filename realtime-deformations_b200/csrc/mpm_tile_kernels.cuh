@@ -59,32 +59,6 @@ struct P2GSmem {
 };
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
-// The F-update of one particle, split into its loads and its compute + stores so that a thread can have the loads of
-// two particles in flight (same arithmetic and plane layout as k_fupdate<true> in mpm_kernels.cuh).
-struct FUpdIn { float4 a1, a2, a3, a6, a7, a8, a9, a10; };
-MPM_DI FUpdIn fupd_load(const Planes& cur, int p) {
-    FUpdIn r;
-    r.a1 = cur.p[1][p]; r.a2 = cur.p[2][p]; r.a3 = cur.p[3][p];
-    r.a6 = cur.p[6][p]; r.a7 = cur.p[7][p]; r.a8 = cur.p[8][p]; r.a9 = cur.p[9][p]; r.a10 = cur.p[10][p];
-    return r;
-}
-template <bool PK>
-MPM_DI void fupd_compute_store(const FUpdIn& in, const Planes& D, int q, DevCounters* dc, const SimConst& sc, float dt) {
-    float B[9] = { in.a1.x, in.a1.y, in.a1.z, in.a1.w, in.a2.x, in.a2.y, in.a2.z, in.a2.w, in.a3.x };
-    float FE[9] = { in.a6.z, in.a6.w, in.a7.x, in.a7.y, in.a7.z, in.a7.w, in.a8.x, in.a8.y, in.a8.z };
-    float FP[9] = { in.a8.w, in.a9.x, in.a9.y, in.a9.z, in.a9.w, in.a10.x, in.a10.y, in.a10.z, in.a10.w };
-    float Ug[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, Sg[3] = { 1, 1, 1 }, tau[6];
-    if (!f_update_rn<PK>(B, FE, FP, sc.dinv, dt, sc.clamp_lo, sc.clamp_hi, Ug, Sg)) { dc->svd_failed = 1; }
-    tau_from_factors(Ug, Sg, m3_det_rn(FE), m3_det_rn(FP), in.a6.x, sc.dinv, sc.E, sc.nu, sc.xi, tau);
-    D.p[4][q] = make_float4(tau[0], tau[1], tau[2], tau[3]);
-    D.p[5][q] = make_float4(tau[4], tau[5], 0.0f, 0.0f);
-    D.p[6][q] = make_float4(in.a6.x, in.a6.y, FE[0], FE[1]);
-    D.p[7][q] = make_float4(FE[2], FE[3], FE[4], FE[5]);
-    D.p[8][q] = make_float4(FE[6], FE[7], FE[8], FP[0]);
-    D.p[9][q] = make_float4(FP[1], FP[2], FP[3], FP[4]);
-    D.p[10][q] = make_float4(FP[5], FP[6], FP[7], FP[8]);
-}
-
 // FUPD (p2g_variant = 3 / 4, EXPERIMENTAL, fused substep only, not yet validated on hardware): after a block's tile has
 // been written back, the same CTA runs the F-update (cpp:306-330) of the block's particles: it depends only on particle
 // state of the START of the substep (B of the previous gather, FE, FP), never on the grid, so it can run anywhere
@@ -107,7 +81,7 @@ struct PeerLayers { float4* dn; float4* up; };      // lower neighbour's ghost l
 // alternate between the front and the back of the list -- so that the NVLink traffic overlaps the interior blocks and the
 // neighbours' waits end early.
 MPM_DI int peer_work_order(int ticket, int n_work) { return (ticket & 1) ? n_work - 1 - (ticket >> 1) : (ticket >> 1); }
-template <int MODE, bool PACKED = false, bool FUPD = false, bool PEER = false>
+template <int MODE, bool PACKED = false, int FUPD = 0 /* 0 none, 1 bit-faithful, 2 tolerance form */, bool PEER = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx, PeerLayers peer = PeerLayers{ nullptr, nullptr }) {
@@ -357,8 +331,8 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 const int p0 = sorted_ids[j0], p1 = two ? sorted_ids[j1] : p0;
                 const FUpdIn in0 = fupd_load(P, p0);
                 const FUpdIn in1 = fupd_load(P, p1);
-                fupd_compute_store<PACKED>(in0, Nx, j0, dc, sc, dt);
-                if (two) fupd_compute_store<PACKED>(in1, Nx, j1, dc, sc, dt);
+                fupd_compute_store<FUPD == 2>(in0, Nx, j0, dc, sc, dt);
+                if (two) fupd_compute_store<FUPD == 2>(in1, Nx, j1, dc, sc, dt);
             }
         }
     }
@@ -603,53 +577,46 @@ __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ so
 #if !defined(MPM_HOST_EMU) || defined(MPM_HOST_EMU_API)        // host launch code (nvcc; or the whole-library emulation build of tests/emu)
 inline cudaError_t tile_kernels_init() {
     cudaError_t e;
-#define MPM_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem))) != cudaSuccess) return e
-    MPM_SET_SMEM(k_p2g_tile<P2G_MOMENTUM>); MPM_SET_SMEM(k_p2g_tile<P2G_FORCE>); MPM_SET_SMEM(k_p2g_tile<P2G_FUSED>);
-#undef MPM_SET_SMEM
-#define MPM_SET_SMEM2(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2PSmem))) != cudaSuccess) return e
-    MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER>); MPM_SET_SMEM2(k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>);
-#undef MPM_SET_SMEM2
-    return cudaSuccess;
-}
-// the experimental variants are set up only when a handle selects one of them (p2g_variant >= 2 / g2p_variant >= 2), so
-// that the default path issues exactly the CUDA calls it was validated with
-inline cudaError_t tile_kernels_init_experimental() {
-    cudaError_t e;
 #define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
-    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, false, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, false, true>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, false, true, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, true, true, true>), P2GSmem);
+#define MPM_SET_P2G(MODE, PK) MPM_SET_SMEM((k_p2g_tile<MODE, PK>), P2GSmem)
+    MPM_SET_P2G(P2G_MOMENTUM, false); MPM_SET_P2G(P2G_FORCE, false); MPM_SET_P2G(P2G_FUSED, false);
+    MPM_SET_P2G(P2G_MOMENTUM, true); MPM_SET_P2G(P2G_FORCE, true); MPM_SET_P2G(P2G_FUSED, true);
+#define MPM_SET_P2G_F(PK, FU, PE) MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, PK, FU, PE>), P2GSmem)
+    MPM_SET_P2G_F(false, 1, false); MPM_SET_P2G_F(false, 2, false); MPM_SET_P2G_F(true, 1, false); MPM_SET_P2G_F(true, 2, false);
+    MPM_SET_P2G_F(false, 0, true); MPM_SET_P2G_F(false, 1, true); MPM_SET_P2G_F(false, 2, true);
+    MPM_SET_P2G_F(true, 0, true); MPM_SET_P2G_F(true, 1, true); MPM_SET_P2G_F(true, 2, true);
+#undef MPM_SET_P2G_F
+#undef MPM_SET_P2G
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>), G2PSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
 #undef MPM_SET_SMEM
     return cudaSuccess;
 }
+inline cudaError_t tile_kernels_init_experimental() { return cudaSuccess; }
 
 template <int MODE>
 cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            bool packed = false, const Planes* fupd_target = nullptr, const PeerLayers* peer = nullptr) {
+                            bool packed = false, const Planes* fupd_target = nullptr, bool fupd_fast = false, const PeerLayers* peer = nullptr) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const Planes Nx = fupd_target ? *fupd_target : P;
-    if (peer && MODE == P2G_FUSED) {              // experimental peer-memory halo, with or without the other experimental options
-        const bool fu = fupd_target != nullptr;
-        if (packed && fu) k_p2g_tile<P2G_FUSED, true, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
-        else if (packed) k_p2g_tile<P2G_FUSED, true, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
-        else if (fu) k_p2g_tile<P2G_FUSED, false, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
-        else k_p2g_tile<P2G_FUSED, false, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, *peer);
-        return cudaGetLastError();
+    const PeerLayers pl = peer ? *peer : PeerLayers{ nullptr, nullptr };
+    const int fu = (fupd_target && MODE == P2G_FUSED) ? (fupd_fast ? 2 : 1) : 0;      // only the fused substep moves the F-update into P2G
+    const bool pe = peer && MODE == P2G_FUSED;
+#define MPM_P2G_LAUNCH(PK, FU, PE) k_p2g_tile<MODE, PK, FU, PE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
+#define MPM_P2G_FU(PK, PE) do { if (fu == 2) MPM_P2G_LAUNCH(PK, 2, PE); else if (fu == 1) MPM_P2G_LAUNCH(PK, 1, PE); else MPM_P2G_LAUNCH(PK, 0, PE); } while (0)
+    if (MODE == P2G_FUSED) {
+        if (pe) { if (packed) MPM_P2G_FU(true, true); else MPM_P2G_FU(false, true); }
+        else { if (packed) MPM_P2G_FU(true, false); else MPM_P2G_FU(false, false); }
+    } else {
+        if (packed) MPM_P2G_LAUNCH(true, 0, false); else MPM_P2G_LAUNCH(false, 0, false);
     }
-    if (fupd_target && MODE == P2G_FUSED) {       // only the fused substep moves the F-update into P2G
-        if (packed) k_p2g_tile<P2G_FUSED, true, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
-        else k_p2g_tile<P2G_FUSED, false, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
-    } else if (packed)
-        k_p2g_tile<MODE, true><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
-    else
-        k_p2g_tile<MODE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx);
+#undef MPM_P2G_FU
+#undef MPM_P2G_LAUNCH
     return cudaGetLastError();
 }
 
@@ -657,7 +624,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side, bool linear_tile = false, bool packed = false) {
+                            SideStream* side, bool linear_tile = false, bool packed = false, bool fupd_fast = false) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -671,7 +638,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
             if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
             fs = side->stream;
         }
-        if (packed) k_fupdate<(FLAGS & G2P_REORDER) != 0, true><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
+        if (fupd_fast) k_fupdate<(FLAGS & G2P_REORDER) != 0, true><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         else k_fupdate<(FLAGS & G2P_REORDER) != 0><<<n_bound > 0 ? (n_bound + 255) / 256 : 1, 256, 0, fs>>>(C, N, sorted_ids, dc, sc, dt);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (!overlap && side && side->mid && (FLAGS & G2P_GATHER)) {      // per-kernel timing: F-update | gather

@@ -63,7 +63,7 @@ static void build(Host& H, int dim, unsigned seed, bool fast_div) {
     gd.n_gblocks = (gd.hi - gd.lo + 1) * gd.nbj * gd.nbk;
     SimConst& c = H.sc;
     const float h = 0.05f;
-    c.h = h; c.dinv = 1.0f / ((1.0f / 3.0f) * h * h); c.E = 1.4e5f; c.nu = 0.2f; c.xi = 10.f;
+    c.h = h; c.dinv = 1.0f / ((1.0f / 3.0f) * h * h); c.E = 1.4e5f; c.nu = 0.2f; c.xi = 10.f; c.mu0 = c.E / (2.0f * (1.0f + c.nu)); c.lambda0 = (c.E * c.nu) / ((1.0f + c.nu) * (1.0f - 2.0f * c.nu));
     c.clamp_lo = (float)(1.0 - 2.5e-2); c.clamp_hi = (float)(1.0 + 5e-3); c.friction = 0.5f;
     c.g[0] = 0; c.g[1] = -9.8f; c.g[2] = 0;
     c.pos_lo = 3 * h; c.pos_hi[0] = c.pos_hi[1] = c.pos_hi[2] = (dim - 3) * h;

@@ -23,7 +23,8 @@ def run(grid, n, steps, pv, gv, scene="slab", rotate=None):
         _scene_cache[key] = mpm_b200.scenes.snow_slab(grid=grid, n=n) if scene == "slab" else mpm_b200.scenes.snowball_drop(grid=grid, n=n)
     sc = _scene_cache[key]
     tg = time.time() - t0
-    p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv)
+    fx = int(os.environ.get("MPM_PROBE_FUPDATE_EXACT", "0"))
+    p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv, fupdate_exact=fx)
     if "gravity" in sc: p.gravity[:] = [float(x) for x in sc["gravity"]]
     sim = mpm_b200.Sim(grid, grid, grid, sc["n"], p)
     t0 = time.time(); sim.upload(sc["pos"], sc["vel"], sc["mass"]); tu = time.time() - t0
@@ -33,7 +34,7 @@ def run(grid, n, steps, pv, gv, scene="slab", rotate=None):
     t0 = time.time(); sim.substep(1e-5, cols, nc, steps); sim.synchronize(); dt = (time.time() - t0) / steps
     st = sim.stats()
     ms = list(st.last_ms)
-    print(f"{scene} grid={grid} n={sc['n']} variants=({pv},{gv}) rotate={'default' if rotate is None else rotate} gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
+    print(f"{scene} grid={grid} n={sc['n']} fexact={fx} variants=({pv},{gv}) rotate={'default' if rotate is None else rotate} gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
           f"{sc['n']/dt/1e9:.3f} G upd/s  bin={ms[0]:.3f} clear={ms[1]:.3f} p2g={ms[2]:.3f} grid={ms[3]:.3f} g2p={ms[4]:.3f} (fupdate={ms[7]:.3f}) total={ms[6]:.3f} "
           f"active_nodes={st.n_active_nodes} pblocks={st.n_particle_blocks} gblocks={st.n_grid_blocks}", flush=True)
     sim.close()
