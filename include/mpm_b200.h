@@ -247,6 +247,14 @@ int mpm_migrate_peer(mpm_t* s, int phase);
  * 35-float rows (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) with their ids. */
 int mpm_set_pid_base(mpm_t* s, int64_t pid_base);
 int mpm_download_live_particles(mpm_t* s, int64_t capacity, int64_t* n_out, float* state35, int32_t* pid);
+/* Conserved quantities of this handle's live particles, reduced on the device (the reference's own self-check is the momentum
+ * balance it prints, cpp:122-128): fsum5 = { sum m, sum m vx, sum m vy, sum m vz, sum m y } in fp64,
+ * isum3 = { count, sum id, sum splitmix64(id) } mod 2^64 (ids = upload indices + pid base: a lost or duplicated particle
+ * changes the checksums). Summing the arrays over the slabs of a decomposed run gives the single-domain values. */
+int mpm_reduce_invariants(mpm_t* s, double* fsum5, uint64_t* isum3);
+/* Tuning aid: clock64 ticks per phase of the block-tile P2G kernel summed over its CTAs; all zero unless the library was
+ * built with -DMPM_P2G_PROFILE (tools/p2g_phase_profile.py). */
+int mpm_debug_p2g_profile(mpm_t* s, int64_t* ticks8, int reset);
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,7 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
            "mpm_box_transform_flip_velocity", "mpm_fill_ball", "mpm_peer_export", "mpm_peer_connect", "mpm_peer_connect_ptr",
            "mpm_grid_device_ptr", "mpm_substep_begin_peer", "mpm_peer_export_migration", "mpm_peer_connect_migration",
-           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer"]
+           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer", "mpm_reduce_invariants", "mpm_debug_p2g_profile"]
 
 _lib = None
 
@@ -113,6 +113,8 @@ def lib():
     L.mpm_sync_counts.argtypes = [vp]
     L.mpm_set_pid_base.argtypes = [vp, i64]
     L.mpm_download_live_particles.argtypes = [vp, i64, C.POINTER(i64), fp, vp]
+    L.mpm_debug_p2g_profile.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
+    L.mpm_reduce_invariants.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.mpm_box_collider_from_transform.argtypes = [C.POINTER(MpmBoxTransform), C.POINTER(MpmBoxCollider)]
     L.mpm_box_transform_move.argtypes = [C.POINTER(MpmBoxTransform), C.c_float]
     L.mpm_box_transform_flip_velocity.argtypes = [C.POINTER(MpmBoxTransform)]
@@ -433,6 +435,13 @@ class Sim:
         st = np.empty((capacity, 35), np.float32); pid = np.empty(capacity, np.int32); n = C.c_int64()
         _ck(self.L.mpm_download_live_particles(self.h, capacity, C.byref(n), _fp(st), pid.ctypes.data))
         return st[:n.value], pid[:n.value]
+
+    def invariants(self):
+        """{count, id_sum, id_hash} (exact integers mod 2^64) and {mass, momentum[3], mass_y} (fp64 sums) of the live particles."""
+        f = (C.c_double * 5)(); i = (C.c_uint64 * 3)()
+        _ck(self.L.mpm_reduce_invariants(self.h, f, i))
+        return {"count": int(i[0]), "id_sum": int(i[1]), "id_hash": int(i[2]), "mass": float(f[0]),
+                "momentum": [float(f[1]), float(f[2]), float(f[3])], "mass_y": float(f[4])}
 
     def set_params(self, params):
         self.params = params

@@ -77,6 +77,8 @@ struct mpm_sim {
     ColliderSet graph_cols;
     void* pinned = nullptr; size_t pinned_bytes = 0;
     bool tau_valid = false, binned = false;
+    bool hist_valid = false;   // key[] and blk_count[] already describe the current buffer (written by the fused substep's gather)
+    bool hist_fuse = true;     // MPM_B200_FUSE_HIST=0 restores the separate k_bin_count pass (A/B)
     // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
     PeerLayers peer = { nullptr, nullptr };
     int* peer_flags_dn = nullptr; int* peer_flags_up = nullptr;      // the neighbours' flag words (peer-mapped)
@@ -239,6 +241,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     for (auto& e : s->ev) CK(cudaEventCreate(&e));
     s->ev_ok = true;
     { const char* g = getenv("MPM_B200_GRAPH"); s->graph_enabled = g && atoi(g) > 0; }
+    { const char* f = getenv("MPM_B200_FUSE_HIST"); s->hist_fuse = !(f && atoi(f) == 0); }
     {
         // Running the F-update on a side stream next to the gather was measured at <= 1.5 % (the gather's persistent CTAs
         // own the register file), so it is opt-in; the default keeps the two kernels back to back and times them apart.
@@ -364,7 +367,7 @@ static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
     CK(cudaMemcpyAsync(&s->dc->n_slots, &ni, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->n_uploaded = n; s->n_bound = n;
-    s->tau_valid = false; s->binned = false;
+    s->tau_valid = false; s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 
@@ -504,11 +507,14 @@ int mpm_wait_render_buffers(mpm_t* s) {
 // ---- binning / sort -----------------------------------------------------------------------------------------
 static int do_binning(mpm_sim* s) {
     const GridDims& g = s->gd;
-    CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
     const int nb = grid_for(s->n_bound, BIN_T * BIN_E);
     Planes C = s->planes(s->cur);
-    k_bin_count<<<nb, BIN_T, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.pd, s->key, s->blk_count);
-    CKLAUNCH();
+    if (!s->hist_valid) {      // (the fused substep's gather has already written next substep's keys and histogram)
+        CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
+        k_bin_count<<<nb, BIN_T, 0, s->stream>>>(C.p[0], (int)s->n_bound, s->dc, g, s->sc.pd, s->key, s->blk_count);
+        CKLAUNCH(); s->stats.kernel_launches++;
+    }
+    s->hist_valid = false;
     k_scan_reduce<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial);
     CKLAUNCH();
     k_scan_partials<<<1, 1024, 0, s->stream>>>(s->partial, s->n_chunks, s->dc);
@@ -518,7 +524,7 @@ static int do_binning(mpm_sim* s) {
     CKLAUNCH();
     k_fix_counts<<<1, 1, 0, s->stream>>>(s->blk_count, g.n_pblocks, s->dc);
     CKLAUNCH();
-    s->stats.kernel_launches += 5;
+    s->stats.kernel_launches += 4;
     const int layer_threads = g.nbj * g.nbk;
     if (g.lo > 0) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(0, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
     if (g.hi < g.npbi_global) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(g.hi - g.lo, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
@@ -588,6 +594,12 @@ static int launch_grid_update(mpm_sim* s, float dt) {
 template <int FLAGS>
 static int launch_g2p(mpm_sim* s, float dt) {
     Planes C = s->planes(s->cur), N = s->planes(s->cur ^ 1);
+    // next substep's keys + histogram inside the gather: single-domain handles only (a slab's migration changes the particle
+    // set between the gather and the next binning)
+    const bool slab_handle = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
+    const bool fuse_hist = s->hist_fuse && !slab_handle && s->prm.g2p_variant != 1 && (FLAGS & G2P_REORDER) && (FLAGS & G2P_ADVECT) && (FLAGS & G2P_GATHER);
+    if ((FLAGS & G2P_ADVECT) && !fuse_hist) s->hist_valid = false;       // positions change without new keys
+    if (fuse_hist) CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
     if (s->prm.g2p_variant == 1 || !(FLAGS & (G2P_GATHER | G2P_F))) {
         k_g2p_direct<FLAGS><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->grid, s->gd, s->sc, dt);
         CKLAUNCH();
@@ -595,7 +607,8 @@ static int launch_g2p(mpm_sim* s, float dt) {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream, &s->side,
                                    s->prm.g2p_variant == 2 || s->prm.g2p_variant == 4, s->prm.g2p_variant == 3 || s->prm.g2p_variant == 4,
-                                   s->prm.fupdate_exact == 2 || ((FLAGS & G2P_REORDER) && s->prm.fupdate_exact == 0))));      // tolerance-form F-update: fused substep (or forced)
+                                   s->prm.fupdate_exact == 2 || ((FLAGS & G2P_REORDER) && s->prm.fupdate_exact == 0),      // tolerance-form F-update: fused substep (or forced)
+                                   fuse_hist ? s->key : nullptr, fuse_hist ? s->blk_count : nullptr)));
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {
@@ -603,6 +616,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
         CKLAUNCH(); s->stats.kernel_launches++;
         s->cur ^= 1;
         s->binned = false;      // sorted_ids referred to the old buffer
+        s->hist_valid = fuse_hist;
     }
     return MPM_OK;
 }
@@ -718,6 +732,7 @@ static int graph_prepare(mpm_sim* s, float dt, const MpmBoxCollider* c, int n) {
     if (same) return MPM_OK;
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     TRY(ensure_tau(s));                                     // the one lazily launched kernel stays outside the capture
+    s->hist_valid = false;                                  // the captured pair starts with a full binning, whatever ran before
     const int64_t launches0 = s->stats.kernel_launches, steps0 = s->stats.substeps_done;
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
@@ -750,7 +765,7 @@ int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* c, int n, int n_subste
         for (int i = 0; i < pairs; ++i) CK(cudaGraphLaunch(s->graph_exec, s->stream));
         s->stats.substeps_done += 2 * pairs;
         s->stats.kernel_launches += (int64_t)s->graph_launches * pairs;
-        s->tau_valid = true; s->binned = false;
+        s->tau_valid = true; s->binned = false; s->hist_valid = false;
         n_substeps -= 2 * pairs;                            // an odd leftover runs through the plain path below
     }
     for (int i = 0; i < n_substeps; ++i) {
@@ -1133,7 +1148,7 @@ int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** 
     *n_down = h.n_mig[0]; *n_up = h.n_mig[1];
     *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
     s->n_bound = h.n_slots;          // exact after the sync
-    s->binned = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
@@ -1144,7 +1159,7 @@ int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
     k_append_incoming<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, (int)s->n_bound, (int)n);
     CKLAUNCH(); s->stats.kernel_launches++;
     s->n_bound += n;
-    s->binned = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 static int64_t default_migrate_capacity(const mpm_sim* s) { return std::min<int64_t>(std::max<int64_t>(1 << 14, s->capacity / 128), 1 << 18); }
@@ -1174,7 +1189,7 @@ int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up) {
     k_mark_outgoing_hdr<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
     *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
-    s->binned = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
@@ -1187,7 +1202,7 @@ int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
     k_bump_slots<<<1, 1, 0, s->stream>>>(s->dc, (const float4*)dev_buf, cap, (int)s->capacity);
     CKLAUNCH(); s->stats.kernel_launches += 2;
     s->n_bound = std::min<int64_t>(s->capacity, s->n_bound + cap);      // upper bound; mpm_sync_counts tightens it
-    s->binned = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 // EXPERIMENTAL peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own
@@ -1264,6 +1279,32 @@ int mpm_set_pid_base(mpm_t* s, int64_t pid_base) {
     NEED(s);
     if (pid_base < 0 || pid_base >= ((int64_t)1 << 31)) return fail(MPM_ERR_INVALID, "pid_base out of range");
     s->pid_base = pid_base;
+    return MPM_OK;
+}
+int mpm_debug_p2g_profile(mpm_t* s, int64_t* ticks8, int reset) {      /* profiling builds (-DMPM_P2G_PROFILE): per-phase clock64 sums */
+    NEED(s);
+    CK(cudaStreamSynchronize(s->stream));
+    if (ticks8) CK(cudaMemcpy(ticks8, s->dc->prof, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(s->dc->prof, 0, sizeof(long long) * 8));
+    return MPM_OK;
+}
+int mpm_reduce_invariants(mpm_t* s, double* fsum5, uint64_t* isum3) {
+    NEED(s);
+    if (!fsum5 || !isum3) return fail(MPM_ERR_INVALID, "bad argument");
+    unsigned char* d = nullptr;
+    CK(cudaMalloc(&d, 64));
+    cudaError_t e = cudaMemsetAsync(d, 0, 64, s->stream);
+    if (e == cudaSuccess) {
+        k_invariants<<<s->num_sms * 4, 256, 0, s->stream>>>(s->planes(s->cur), s->dc, reinterpret_cast<double*>(d), reinterpret_cast<unsigned long long*>(d + 40));
+        e = cudaGetLastError();
+    }
+    unsigned char h[64];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "reduce_invariants: %s", cudaGetErrorString(e));
+    memcpy(fsum5, h, 40); memcpy(isum3, h + 40, 24);
     return MPM_OK;
 }
 int mpm_download_live_particles(mpm_t* s, int64_t capacity, int64_t* n_out, float* state35, int32_t* pid) {

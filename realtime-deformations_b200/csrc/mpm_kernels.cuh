@@ -55,6 +55,7 @@ struct DevCounters {
     int mig_overflow;
     int peer_timeout;       // experimental peer-memory halo: a neighbour's flag did not arrive (k_peer_wait gave up)
     int pad[2];
+    long long prof[8];      // MPM_P2G_PROFILE builds only: clock64 ticks per P2G phase, summed over CTAs (thread 0)
 };
 
 enum { KEY_DEAD = -2 };
@@ -338,18 +339,28 @@ enum { P2G_MOMENTUM = 0, P2G_FORCE = 1, P2G_FUSED = 2 };
 
 // affine scatter coefficients of one particle: contribution to node x_i is
 //   w * (mass_ch, a0 + A * (x_i - x_p))      with A row-major here: A[r*3+c]
+struct P2GInG { float4 xm, b0, b1, b2, t0, t1; };      // the six planes P2G reads of one particle
 template <int MODE>
-MPM_DI void p2g_coeffs(const Planes& P, int p, float dinv, float dt, float4& xm, float& mass_ch, float (&a0)[3], float (&A)[9]) {
-    xm = P.p[0][p];
-    const float m = xm.w;
+MPM_DI P2GInG p2g_load_planes(const Planes& P, int gid) {
+    P2GInG r;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.xm = P.p[0][gid];
+    r.b0 = r.b1 = r.b2 = r.t0 = r.t1 = z;
+    if (MODE != P2G_FORCE) { r.b0 = P.p[1][gid]; r.b1 = P.p[2][gid]; r.b2 = P.p[3][gid]; }
+    if (MODE != P2G_MOMENTUM) { r.t0 = P.p[4][gid]; r.t1 = P.p[5][gid]; }
+    return r;
+}
+template <int MODE, class In>
+MPM_DI void p2g_coeffs(const In& in, float dinv, float dt, float& mass_ch, float (&a0)[3], float (&A)[9]) {
+    const float m = in.xm.w;
     float Bm[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 }, v[3] = { 0, 0, 0 }, tau[6] = { 0, 0, 0, 0, 0, 0 };
     if (MODE != P2G_FORCE) {
-        const float4 b0 = P.p[1][p], b1 = P.p[2][p], b2 = P.p[3][p];
+        const float4 b0 = in.b0, b1 = in.b1, b2 = in.b2;
         Bm[0] = b0.x; Bm[1] = b0.y; Bm[2] = b0.z; Bm[3] = b0.w; Bm[4] = b1.x; Bm[5] = b1.y; Bm[6] = b1.z; Bm[7] = b1.w; Bm[8] = b2.x;
         v[0] = b2.y; v[1] = b2.z; v[2] = b2.w;
     }
     if (MODE != P2G_MOMENTUM) {
-        const float4 t0 = P.p[4][p], t1 = P.p[5][p];
+        const float4 t0 = in.t0, t1 = in.t1;
         tau[0] = t0.x; tau[1] = t0.y; tau[2] = t0.z; tau[3] = t0.w; tau[4] = t1.x; tau[5] = t1.y;
     }
     const float md = m * dinv;
@@ -373,8 +384,10 @@ __global__ void k_p2g_atomic(Planes P, const int* __restrict__ sorted_ids, const
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dc->n_binned) return;
     const int p = sorted_ids[j];
-    float4 xm; float mch, a0[3], A[9];
-    p2g_coeffs<MODE>(P, p, sc.dinv, dt, xm, mch, a0, A);
+    float mch, a0[3], A[9];
+    const P2GInG in = p2g_load_planes<MODE>(P, p);
+    const float4 xm = in.xm;
+    p2g_coeffs<MODE>(in, sc.dinv, dt, mch, a0, A);
     const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
     float wx[4], wy[4], wz[4];
     axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
@@ -523,7 +536,7 @@ __global__ void k_volumes(Planes P, const int* __restrict__ sorted_ids, const De
     P.p[6][p] = a6;
 }
 
-enum { G2P_F = 1, G2P_GATHER = 2, G2P_ADVECT = 4, G2P_REORDER = 8 };
+enum { G2P_F = 1, G2P_GATHER = 2, G2P_ADVECT = 4, G2P_REORDER = 8, G2P_HIST = 16 };
 
 MPM_DI void advect_rn(ParticleRegs& r, const SimConst& sc, float dt) {   // cpp:344-350, 381-388
 #pragma unroll
@@ -556,8 +569,10 @@ __global__ void k_p2g_serial(Planes P, const int* __restrict__ slot_of_pid, int 
     for (int pid = 0; pid < n_pid; ++pid) {
         const int p = slot_of_pid[pid];
         if (p < 0) continue;
-        float4 xm; float mch, a0[3], A[9];
-        p2g_coeffs<MODE>(P, p, sc.dinv, dt, xm, mch, a0, A);
+        float mch, a0[3], A[9];
+        const P2GInG in = p2g_load_planes<MODE>(P, p);
+        const float4 xm = in.xm;
+        p2g_coeffs<MODE>(in, sc.dinv, dt, mch, a0, A);
         const int cx = cell_of(xm.x, sc.pd), cy = cell_of(xm.y, sc.pd), cz = cell_of(xm.z, sc.pd);
         float wx[4], wy[4], wz[4];
         axis_weights(xm.x, sc.pd, cx, wx); axis_weights(xm.y, sc.pd, cy, wy); axis_weights(xm.z, sc.pd, cz, wz);
@@ -749,6 +764,43 @@ __global__ void k_export_live(Planes cur, const DevCounters* __restrict__ dc, fl
 #pragma unroll
     for (int q = 0; q < 9; ++q) { o[8 + q] = r.FE[q]; o[17 + q] = r.FP[q]; o[26 + q] = r.B[q]; }
     pid_out[i] = r.pid;
+}
+
+// conserved quantities of the live particles, for run-time correctness checks (bench.py prints them at every GPU count):
+// fsum = { sum m, sum m vx, sum m vy, sum m vz, sum m y } in fp64, isum = { count, sum pid, sum hash(pid) } mod 2^64
+MPM_DI unsigned long long pid_hash(unsigned long long pid) {          // splitmix64 finaliser
+    unsigned long long z = pid + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+k_invariants(Planes cur, const DevCounters* __restrict__ dc, double* __restrict__ fsum, unsigned long long* __restrict__ isum) {
+    double f[5] = { 0, 0, 0, 0, 0 };
+    unsigned long long c[3] = { 0, 0, 0 };
+    const int n = dc->n_slots;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float4 a0 = cur.p[0][p];
+        if (a0.w < 0.0f) continue;
+        const float4 a3 = cur.p[3][p];
+        const unsigned long long pid = (unsigned long long)(unsigned)__float_as_int(cur.p[6][p].y);
+        const double m = (double)a0.w;
+        f[0] += m; f[1] += m * (double)a3.y; f[2] += m * (double)a3.z; f[3] += m * (double)a3.w; f[4] += m * (double)a0.y;
+        c[0] += 1ull; c[1] += pid; c[2] += pid_hash(pid);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) f[k] += __shfl_down_sync(0xffffffffu, f[k], o);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c[k] += __shfl_down_sync(0xffffffffu, c[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(&fsum[k], f[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(&isum[k], c[k]);
+    }
 }
 
 // blocked <-> linear grid (download_grid / upload_grid, tests only)

@@ -47,16 +47,23 @@ struct P2GSmem {
             float4 qc[P2G_CH];            // (mass channel, c0.x, c0.y, c0.z)
             float4 hA0[P2G_CH], hA1[P2G_CH];   // h*A row-major entries 0..3, 4..7
             float hA8[P2G_CH];
-            int gid[P2G_CH];
             unsigned short order[P2G_CH];
         } c;
         float4 t1[4][4][4][42];           // phase 2: z-folded partial sums [cx][cy][a][b*7 + k]; the a-stride is padded
                                           // from 28 to 42 float4 (= 2 mod 8 slots) so that a quarter-warp's stores
                                           // (a = 0..3, two consecutive k) land in 8 different 16-byte bank groups
     } u;
-    int cell_cnt[64], cell_start[65];
+    int cell_cnt[64];
     int4 work;
 };
+typedef P2GInG P2GIn;
+// first-chunk ids of a work item (chunks interleave the block's segment: slot q of chunk 0 is rank start + q * n_chunks)
+MPM_DI void p2g_first_chunk_ids(const int4& wk, const int* __restrict__ sorted_ids, int t, int (&gid)[P2G_PPT], int& nch0) {
+    const int nck0 = (wk.z + P2G_CH - 1) / P2G_CH;
+    nch0 = wk.x < 0 ? 0 : (nck0 <= 1 ? wk.z : (wk.z + nck0 - 1) / nck0);      // (one chunk: no division by a variable)
+#pragma unroll
+    for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid[u] = q < nch0 ? sorted_ids[wk.y + q * nck0] : 0; }
+}
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
 // FUPD (p2g_variant = 3 / 4, EXPERIMENTAL, fused substep only, not yet validated on hardware): after a block's tile has
@@ -97,23 +104,26 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
     // block's first chunk during phase 2.
     int w_ticket = 0;
     int4 wk_reg = make_int4(-1, 0, 0, 0);
+    const int4 no_work = make_int4(-1, 0, 0, 0);
     if (t == 0) {
         const int w0 = atomicAdd(&dc->work_a, 1);
-        S.work = w0 < n_work ? pblock_list[PEER ? peer_work_order(w0, n_work) : w0] : make_int4(-1, 0, 0, 0);
+        S.work = w0 < n_work ? pblock_list[PEER ? peer_work_order(w0, n_work) : w0] : no_work;
         w_ticket = atomicAdd(&dc->work_a, 1);
     }
     __syncthreads();
     int gid_pref[P2G_PPT];
-    {
-        const int4 wk0 = S.work;
-        const int nck0 = (wk0.z + P2G_CH - 1) / P2G_CH, nch0 = nck0 <= 1 ? wk0.z : (wk0.z + nck0 - 1) / nck0;     // (one chunk: no division by a variable)
-#pragma unroll
-        for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wk0.x >= 0 && q < nch0) ? sorted_ids[wk0.y + q * nck0] : 0; }
-    }
+    { int nch0; p2g_first_chunk_ids(S.work, sorted_ids, t, gid_pref, nch0); }
+#ifdef MPM_P2G_PROFILE
+    long long prof_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, prof_c = clock64();
+#define MPM_PROF(i) do { const long long c_ = clock64(); prof_t[i] += c_ - prof_c; prof_c = c_; } while (0)
+#else
+#define MPM_PROF(i)
+#endif
     for (;;) {
         const int4 wk = S.work;
         if (t < 64) S.cell_cnt[t] = 0;
         __syncthreads();          // also: everyone has read S.work, and phase 2b of the previous block is done with t1
+        MPM_PROF(0);              // top barrier
         if (wk.x < 0) break;
         const int start = wk.y, cnt = wk.z;
         const int pbk = wk.w & (PB_COORD_MAX - 1), pbj = (wk.w >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (wk.w >> (2 * PB_COORD_BITS)) + gd.lo;   // global block coords
@@ -135,14 +145,17 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 __syncthreads();
             }
             // ---- derive per-particle data (P2G_PPT particles per thread, loads of both issued back to back) ----
-            int cell_rank[P2G_PPT];          // cell (low 8 bits) and rank inside the cell: the counting atomic's return value
+            int cell_rank[P2G_PPT], gids[P2G_PPT];   // cell (low 8 bits) and rank inside the cell: the counting atomic's return value
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
+                cell_rank[u] = 0; gids[u] = 0;
                 if (q < nch) {
                     const int gid = ck == 0 ? gid_pref[u] : sorted_ids[start + ck + q * n_chunks];
-                    float4 xm; float mch, a0[3], A[9];
-                    p2g_coeffs<MODE>(P, gid, sc.dinv, dt, xm, mch, a0, A);
+                    const P2GIn in = p2g_load_planes<MODE>(P, gid);
+                    const float4 xm = in.xm;
+                    float mch, a0[3], A[9];
+                    p2g_coeffs<MODE>(in, sc.dinv, dt, mch, a0, A);
                     float wx[4], wy[4], wz[4];
                     // cell index and weights from ONE pos/h quotient per axis (the same operations as cell_of + axis_weights,
                     // which form the quotient twice: identical bits, 68 fewer instructions per particle)
@@ -157,43 +170,42 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     S.u.c.hA0[q] = make_float4(A[0] * sc.h, A[1] * sc.h, A[2] * sc.h, A[3] * sc.h);
                     S.u.c.hA1[q] = make_float4(A[4] * sc.h, A[5] * sc.h, A[6] * sc.h, A[7] * sc.h);
                     S.u.c.hA8[q] = A[8] * sc.h;
-                    S.u.c.gid[q] = gid;
+                    gids[u] = gid;
                     const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
                     cell_rank[u] = lc | (atomicAdd(&S.cell_cnt[lc], 1) << 8);
                 }
             }
             __syncthreads();
-            // ---- counting sort of the chunk by cell (64 bins) ----
-            if (t < 32) {
-                const int c0 = S.cell_cnt[2 * t], c1 = S.cell_cnt[2 * t + 1];
-                int inc = c0 + c1;
+            MPM_PROF(1);          // derive (+ barrier)
+            // ---- counting sort of the chunk by cell (64 bins): EVERY warp scans the 64 counts in its own registers (two bins
+            // per lane, five shuffles), so no warp waits for a scanning warp and no barrier separates the scan from its use ----
+            const int c0 = S.cell_cnt[2 * lane], c1 = S.cell_cnt[2 * lane + 1];
+            int inc = c0 + c1;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += v; }
-                const int ex = inc - (c0 + c1);
-                S.cell_start[2 * t] = ex; S.cell_start[2 * t + 1] = ex + c0;
-                if (t == 31) S.cell_start[64] = inc;
-            }
-            __syncthreads();
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            const int ex = inc - (c0 + c1);          // exclusive prefix of bin 2*lane; bin 2*lane+1 starts at ex + c0
 #pragma unroll
             for (int u = 0; u < P2G_PPT; ++u) {
                 const int q = t + u * P2G_T;
+                const int c = cell_rank[u] & 255;
+                const int e = __shfl_sync(0xffffffffu, ex, c >> 1), f = __shfl_sync(0xffffffffu, c0, c >> 1);
                 if (q < nch) {           // sorted slot = start of my cell + my rank in it (no second round of atomics)
-                    const int slot = S.cell_start[cell_rank[u] & 255] + (cell_rank[u] >> 8);
+                    const int slot = e + ((c & 1) ? f : 0) + (cell_rank[u] >> 8);
                     MPM_SMEM_PROBE(5, u, &S.u.c.order[slot], 2);
                     S.u.c.order[slot] = (unsigned short)q;
+                    // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
+                    // cells (smem broadcasts) and the re-sorted particle buffer stays cell-coherent for the next substep
+                    sorted_ids[start + ck + slot * n_chunks] = gids[u];
                 }
+            }
+            int i0, i1;
+            {
+                const int e = __shfl_sync(0xffffffffu, ex, my_cell >> 1), f = __shfl_sync(0xffffffffu, c0, my_cell >> 1), g = __shfl_sync(0xffffffffu, c1, my_cell >> 1);
+                i0 = e + ((my_cell & 1) ? f : 0);
+                i1 = i0 + ((my_cell & 1) ? g : f);
             }
             __syncthreads();
-            // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
-            // cells (smem broadcasts) and the re-sorted particle buffer stays cell-coherent for the next substep
-#pragma unroll
-            for (int u = 0; u < P2G_PPT; ++u) {
-                const int q = t + u * P2G_T;
-                if (q < nch) {
-                    MPM_SMEM_PROBE(6, u, &S.u.c.gid[S.u.c.order[q]], 4);
-                    sorted_ids[start + ck + q * n_chunks] = S.u.c.gid[S.u.c.order[q]];
-                }
-            }
+            MPM_PROF(2);          // counting sort + id rewrite
             // ---- phase 1: register accumulation over the particles of my cell ----
             // The 8 cells of a warp read 8 different records per iteration; a record's 16-byte bank group is its slot
             // mod 8. Once the ids are cell-ordered (after the first substep) a cell's records sit in consecutive slots, and
@@ -202,13 +214,12 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             // 1-2; 2.4 k of the 2.9 k bank-conflict wavefronts per block ncu counted at 64 Mi, profiles/r1_analysis.md).
             // So cell c starts its (cyclic) walk at record c mod 8: with runs of 8 the reads of an iteration then hit 8
             // different bank groups, and ragged runs are no worse off than before. Only the summation order changes.
-            const int i0 = S.cell_start[my_cell], i1 = S.cell_start[my_cell + 1];
             int i = i0;
             if (sc.p2g_rotate && i1 - i0 > 1) i += (my_cell & 7) % (i1 - i0);
+            int pi = i1 > i0 ? S.u.c.order[i] : 0;          // record index, fetched one iteration ahead of its record
 #pragma unroll 1
             for (int k = 0; k < i1 - i0; ++k) {
                 MPM_SMEM_PROBE(10, k, &S.u.c.order[i], 2);
-                const int pi = S.u.c.order[i];
                 i = (i + 1 == i1) ? i0 : i + 1;
                 MPM_SMEM_PROBE(11, k, &reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a], 4);
                 MPM_SMEM_PROBE(12, k, &S.u.c.wy[pi], 16); MPM_SMEM_PROBE(13, k, &S.u.c.wz[pi], 16); MPM_SMEM_PROBE(14, k, &S.u.c.qc[pi], 16);
@@ -216,6 +227,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 const float wxa = reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a];
                 const float4 wy = S.u.c.wy[pi], wz = S.u.c.wz[pi], qc = S.u.c.qc[pi], h0 = S.u.c.hA0[pi], h1 = S.u.c.hA1[pi];
                 const float h8 = S.u.c.hA8[pi];
+                pi = S.u.c.order[i];                       // (slot i is inside the cell's run, possibly wrapped: always valid)
                 // value(a,b,c)_r = c0_r + a*hA[r][0] + b*hA[r][1] + c*hA[r][2]
                 const float bx = qc.y + fa * h0.x, by = qc.z + fa * h0.w, bz = qc.w + fa * h1.z;
                 const float wyv[4] = { wy.x, wy.y, wy.z, wy.w }, wzv[4] = { wz.x, wz.y, wz.z, wz.w };
@@ -253,7 +265,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     }
                 }
             }
+            MPM_PROF(3);          // accumulation loop
             __syncthreads();
+            MPM_PROF(4);          // barrier after the accumulation
         }
         if (PACKED) {
 #pragma unroll
@@ -262,7 +276,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 acc[2 * i + 1] = make_float4(hi2(AM[i]), hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
             }
         }
-        if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[PEER ? peer_work_order(w_ticket, n_work) : w_ticket] : make_int4(-1, 0, 0, 0);   // issued here, stored below
+        if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[PEER ? peer_work_order(w_ticket, n_work) : w_ticket] : no_work;   // issued here, stored below
         // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
         // node k = cz + c; this lane ends up owning k = cz (slot 0) and k = cz + 4 (slot 1, cz <= 2)
         float4 s0[4], s1[4];
@@ -292,24 +306,28 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         }
         if (t == 0) { S.work = wk_reg; w_ticket = atomicAdd(&dc->work_a, 1); }
         __syncthreads();
-        {   // ids of the next block's first chunk: in flight while this block's tile is reduced and written back
-            const int4 wn = S.work;
-            const int nckn = (wn.z + P2G_CH - 1) / P2G_CH, nchn = nckn <= 1 ? wn.z : (wn.z + nckn - 1) / nckn;
-#pragma unroll
-            for (int u = 0; u < P2G_PPT; ++u) { const int q = t + u * P2G_T; gid_pref[u] = (wn.x >= 0 && q < nchn) ? sorted_ids[wn.y + q * nckn] : 0; }
-        }
+        MPM_PROF(5);              // z-fold (shuffles) + patch stores + barrier
+        { int nchn; p2g_first_chunk_ids(S.work, sorted_ids, t, gid_pref, nchn); }       // ids of the next block's first chunk: in flight while this block's tile is reduced and written back
         // ---- phase 2b: fold x and y from smem (<= 16 terms per tile node), one vector red per node ----
         // (visiting the nodes sorted by fold length to even out the trip counts was measured SLOWER than natural order:
         // the contiguous k-runs of natural order matter more to the smem pipe than the divergence costs)
         for (int n = t; n < 343; n += P2G_T) {
             const int ni = n / 49, nj = (n / 7) % 7, nk = n % 7;
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int cx = max(0, ni - 3); cx <= min(3, ni); ++cx)
-                for (int cy = max(0, nj - 3); cy <= min(3, nj); ++cy) {
-                    MPM_SMEM_PROBE(30, ((n / P2G_T) * 4 + (cx - max(0, ni - 3))) * 4 + (cy - max(0, nj - 3)), &S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk], 16);
-                    const float4 v = S.u.t1[cx][cy][ni - cx][(nj - cy) * 7 + nk];
-                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            // the <= 4 x 4 patches that cover this node, as a fixed, fully unrolled walk with predicated loads: all loads of a
+            // node are in flight together (the bounded loops this replaces waited for one shared-memory round trip per term)
+            float4 v[16];
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+                for (int dy = 0; dy < 4; ++dy) {
+                    const int cx = ni - dx, cy = nj - dy;          // patch of cell (cx, cy, .), its local node (dx, dy, nk)
+                    const bool ok = cx >= 0 && cx <= 3 && cy >= 0 && cy <= 3;
+                    MPM_SMEM_PROBE(30, ((n / P2G_T) * 4 + dx) * 4 + dy, &S.u.t1[ok ? cx : 0][ok ? cy : 0][dx][dy * 7 + nk], 16);
+                    v[dx * 4 + dy] = ok ? S.u.t1[cx][cy][dx][dy * 7 + nk] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { sum.x += v[i].x; sum.y += v[i].y; sum.z += v[i].z; sum.w += v[i].w; }
             if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) {
                 const size_t idx = node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk);
                 atomicAdd(&grid[idx], sum);
@@ -321,6 +339,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 }
             }
         }
+        MPM_PROF(6);              // x/y fold + reds
         if (FUPD) {
             // F-update of this block's particles, two per thread and round with both particles' loads issued first.
             // sorted_ids[start .. start+cnt) is final here (the cell-ordering writes above are behind CTA barriers).
@@ -334,8 +353,13 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 fupd_compute_store<FUPD == 2>(in0, Nx, j0, dc, sc, dt);
                 if (two) fupd_compute_store<FUPD == 2>(in1, Nx, j1, dc, sc, dt);
             }
+            MPM_PROF(7);          // in-kernel F-update
         }
     }
+#ifdef MPM_P2G_PROFILE
+    if (t == 0) for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&dc->prof[i]), (unsigned long long)prof_t[i]);
+#endif
+#undef MPM_PROF
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -400,7 +424,7 @@ struct G2PSmemLinear {
 template <int FLAGS, bool LINEAR = false, bool PACKED = false>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
-           const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt) {
+           const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr) {
     MPM_DYN_SMEM(g2p_smem_raw, 128);
     using Smem = typename std::conditional<LINEAR, G2PSmemLinear, G2PSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(g2p_smem_raw);
@@ -463,6 +487,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
             p = p_nn;
             a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
             p_nn = (base + 64 + lane < cnt) ? sorted_ids[j + 64] : -1;
+            float4 xm_new = make_float4(0.f, 0.f, 0.f, -1.f);      // (G2P_HIST) the advected position, for next substep's key
             if (active) {
                 struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
                 r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
@@ -556,9 +581,19 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 const Planes& D = (FLAGS & G2P_REORDER) ? nxt : cur;
                 const int q = (FLAGS & G2P_REORDER) ? j : p_cur;
                 if (FLAGS & (G2P_ADVECT | G2P_REORDER)) D.p[0][q] = make_float4(r.x[0], r.x[1], r.x[2], r.m);
+                xm_new = make_float4(r.x[0], r.x[1], r.x[2], r.m);
                 D.p[1][q] = make_float4(r.B[0], r.B[1], r.B[2], r.B[3]);
                 D.p[2][q] = make_float4(r.B[4], r.B[5], r.B[6], r.B[7]);
                 D.p[3][q] = make_float4(r.B[8], r.v[0], r.v[1], r.v[2]);
+            }
+            if (FLAGS & G2P_HIST) {
+                // next substep's binning, first half, done here where the new position is in registers: block key of slot j of
+                // the re-sorted buffer + warp-aggregated histogram (what k_bin_count would re-read P0 for)
+                int cells[3];
+                const int k = active ? particle_key(xm_new, gd, sc.pd, cells) : KEY_DEAD;
+                if (active) key_out[j] = k;
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                if (k >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&blk_count[k], __popc(peers));
             }
         }
         __syncwarp();     // every lane is done with the tile before the next bulk copy overwrites it
@@ -566,12 +601,14 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
 }
 
 // parked (out-of-grid) particles ride along unchanged through a re-sorting G2P
-__global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const DevCounters* __restrict__ dc) {
+__global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const DevCounters* __restrict__ dc,
+                              int parked_key, int* __restrict__ key_out, int* __restrict__ blk_count) {
     const int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dc->n_sorted) return;
     const int p = sorted_ids[j];
 #pragma unroll
     for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
+    if (key_out) { key_out[j] = parked_key; atomicAdd(&blk_count[parked_key], 1); }      // (fused histogram) still parked next substep
 }
 
 #if !defined(MPM_HOST_EMU) || defined(MPM_HOST_EMU_API)        // host launch code (nvcc; or the whole-library emulation build of tests/emu)
@@ -588,6 +625,8 @@ inline cudaError_t tile_kernels_init() {
 #undef MPM_SET_P2G_F
 #undef MPM_SET_P2G
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, true>), G2PSmemLinear);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, false, true>), G2PSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
@@ -609,7 +648,7 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
     const bool pe = peer && MODE == P2G_FUSED;
 #define MPM_P2G_LAUNCH(PK, FU, PE) k_p2g_tile<MODE, PK, FU, PE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
 #define MPM_P2G_FU(PK, PE) do { if (fu == 2) MPM_P2G_LAUNCH(PK, 2, PE); else if (fu == 1) MPM_P2G_LAUNCH(PK, 1, PE); else MPM_P2G_LAUNCH(PK, 0, PE); } while (0)
-    if (MODE == P2G_FUSED) {
+    if constexpr (MODE == P2G_FUSED) {
         if (pe) { if (packed) MPM_P2G_FU(true, true); else MPM_P2G_FU(false, true); }
         else { if (packed) MPM_P2G_FU(true, false); else MPM_P2G_FU(false, false); }
     } else {
@@ -624,7 +663,8 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side, bool linear_tile = false, bool packed = false, bool fupd_fast = false) {
+                            SideStream* side, bool linear_tile = false, bool packed = false, bool fupd_fast = false,
+                            int* key_out = nullptr, int* blk_count = nullptr) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -648,14 +688,21 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
     }
     if (FLAGS & G2P_GATHER) {
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
-        if (linear_tile && packed)
-            k_g2p_tile<FLAGS & ~G2P_F, true, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmemLinear), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
-        else if (linear_tile)
-            k_g2p_tile<FLAGS & ~G2P_F, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmemLinear), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
-        else if (packed)
-            k_g2p_tile<FLAGS & ~G2P_F, false, true><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
-        else
-            k_g2p_tile<FLAGS & ~G2P_F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt);
+        constexpr int GF = FLAGS & ~G2P_F;
+        constexpr bool CAN_HIST = (GF & G2P_REORDER) != 0 && (GF & G2P_ADVECT) != 0;       // the fused substep's gather
+#define MPM_G2P_LAUNCH(F, LIN, PK, SM) k_g2p_tile<F, LIN, PK><<<num_sms * per_sm, G2P_T, sizeof(SM), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count)
+        if (CAN_HIST && key_out) {
+            if (linear_tile && packed) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), true, true, G2PSmemLinear);
+            else if (linear_tile) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), true, false, G2PSmemLinear);
+            else if (packed) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), false, true, G2PSmem);
+            else MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), false, false, G2PSmem);
+        } else {
+            if (linear_tile && packed) MPM_G2P_LAUNCH(GF, true, true, G2PSmemLinear);
+            else if (linear_tile) MPM_G2P_LAUNCH(GF, true, false, G2PSmemLinear);
+            else if (packed) MPM_G2P_LAUNCH(GF, false, true, G2PSmem);
+            else MPM_G2P_LAUNCH(GF, false, false, G2PSmem);
+        }
+#undef MPM_G2P_LAUNCH
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (overlap) {
@@ -663,7 +710,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_REORDER) {
-        k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc);     // parked particles are few; 16 K slots per launch wave
+        k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc, gd.n_pblocks, key_out, blk_count);     // parked particles are few; 16 K slots per launch wave
         e = cudaGetLastError();
     }
     return e;

@@ -426,6 +426,16 @@ inline float atomicAdd(float* p, float v) {
         if (__atomic_compare_exchange_n(u, &o, n, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return f;
     }
 }
+inline double atomicAdd(double* p, double v) {
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(p);
+    for (;;) {
+        unsigned long long o = __atomic_load_n(u, __ATOMIC_RELAXED);
+        double f; std::memcpy(&f, &o, 8);
+        const double nf = f + v;
+        unsigned long long n; std::memcpy(&n, &nf, 8);
+        if (__atomic_compare_exchange_n(u, &o, n, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return f;
+    }
+}
 inline float4 atomicAdd(float4* p, float4 v) {       // red.global.add.v4.f32: four independent fp32 additions
     float4 o;
     o.x = atomicAdd(&p->x, v.x); o.y = atomicAdd(&p->y, v.y); o.z = atomicAdd(&p->z, v.z); o.w = atomicAdd(&p->w, v.w);

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=realtime-deformations_b200
+for lib in libmpm_b200_prof.so libmpm_b200_prof_pf.so; do
+  for v in 0:4 2:4 4:4; do
+    MPM_B200_LIB=$L/$lib timeout 300 python tools/p2g_phase_profile.py run 512 67108864 $v >> gpurun_out/c4_phase.log 2>&1
+  done
+done
+timeout 600 python tools/perf_probe.py 512 67108864 10 slab 0:0,2:4,4:4 > gpurun_out/c4_ab_64M.log 2>&1
+MPM_B200_FUSE_HIST=0 timeout 600 python tools/perf_probe.py 512 67108864 10 slab 2:4,4:4 >> gpurun_out/c4_ab_64M.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/c4_gpu_tests.log 2>&1
+cat gpurun_out/c4_phase.log gpurun_out/c4_ab_64M.log; tail -3 gpurun_out/c4_gpu_tests.log
