@@ -43,15 +43,13 @@ typedef struct MpmParams {
     float theta_s;        /* critical stretch        material_point_method.cpp:320  (5.0e-3) */
     float gravity[3];     /*                         material_point_method.cpp:260  (0,-9.8,0) */
     float friction_mu;    /*                         material_point_method.cpp:288  (0.5)    */
-    int   p2g_variant;    /* 0 = auto (block-tile kernel), 1 = per-particle global atomics (debug/baseline),
-                             9 = deterministic debug mode: one thread adds the contributions in ascending particle-id order
-                             without atomics, so a run is bitwise reproducible (small scenes; single-domain handles),
-                             experimental (not validated on hardware yet): 2 = tile kernel with packed
-                             fp32 pairs (FFMA2) in the accumulation loop, 3 = the fused substep runs the F-update
-                             inside the P2G kernel, 4 = both */
-    int   g2p_variant;    /* 0 = auto (TMA-staged tile kernel), 1 = direct global gathers (debug/baseline),
-                             experimental (none validated on hardware yet): 2 = linear-tile gather,
-                             3 = packed fp32 pairs (FFMA2) in the separable gather, 4 = both */
+    int   p2g_variant;    /* 0 = auto: block-tile kernel (packed fp32 pairs); inside the fused mpm_substep it also runs the F-update,
+                             1 = per-particle global atomics (debug / baseline), 2 = block-tile kernel with the F-update as a
+                             kernel of its own (A/B), 9 = deterministic debug mode: one thread adds the contributions in
+                             ascending particle-id order without atomics, so a run is bitwise reproducible (small scenes;
+                             single-domain handles) */
+    int   g2p_variant;    /* 0 = auto: warp-per-block gather from a TMA-staged linear tile with packed fp32 pairs,
+                             1 = direct global gathers (debug / baseline) */
     int   fupdate_exact;  /* F-update (cpp:306-330) inside the fused mpm_substep: 0 = tolerance form (FMA contraction, MUFU
                              reciprocals / square roots, F^ = (I + dt C) FE taken directly; same Eigen Jacobi control flow;
                              held to 4x the reference's own FMA-contraction noise floor by the trajectory tests),

@@ -90,7 +90,7 @@ struct mpm_sim {
     bool peer_mig_connected = false;
     int peer_mig_epoch = 0;
     int* slot_of_pid = nullptr; // p2g_variant 9 (deterministic debug mode): binned slot of every particle id
-    bool fupd_pending = false;  // experimental p2g_variant 3/4: P2G has put the F-update results into the idle buffer (until substep_end)
+    bool fupd_pending = false;  // P2G has put the F-update results into the idle buffer (until substep_end)
     int num_sms = 148;
     cudaEvent_t ev[8];
     bool ev_ok = false;
@@ -171,6 +171,10 @@ static int validate_pos_div(mpm_sim* s) {
     return MPM_OK;
 }
 
+static bool valid_variants(const MpmParams& p) {
+    return (p.p2g_variant == 0 || p.p2g_variant == 1 || p.p2g_variant == 2 || p.p2g_variant == 9) && (p.g2p_variant == 0 || p.g2p_variant == 1) &&
+           p.fupdate_exact >= 0 && p.fupdate_exact <= 2;
+}
 static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
 static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k, int block_lo, int block_hi,
@@ -214,6 +218,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     if (g.hi - g.lo > PB_COORD_MAX || g.npbj > PB_COORD_MAX || g.npbk > PB_COORD_MAX)       // work items carry 10-bit block coordinates
         return fail(MPM_ERR_INVALID, "grid too large: at most %d particle blocks (%d nodes) per axis and slab", PB_COORD_MAX, 4 * PB_COORD_MAX);
     g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
+    if (!valid_variants(s->prm)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9 and g2p_variant 0 or 1");
     fill_consts(s);
     s->capacity = std::max<int64_t>(capacity, 1);
     s->n_uploaded = n_particles; s->n_bound = n_particles;
@@ -258,7 +263,6 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
-    if (s->prm.p2g_variant >= 2 || s->prm.g2p_variant >= 2) CK(tile_kernels_init_experimental());
     CK(cudaStreamSynchronize(s->stream));
     { int rc = validate_pos_div(s); if (rc) return rc; }
     return MPM_OK;
@@ -301,7 +305,7 @@ int mpm_set_stream(mpm_t* s, void* st) {
 int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
     if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
-    if (p->p2g_variant >= 2 || p->g2p_variant >= 2) CK(tile_kernels_init_experimental());
+    if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9 and g2p_variant 0 or 1");
     s->prm = *p;
     const int fast = s->sc.pd.fast;
     fill_consts(s);
@@ -554,9 +558,9 @@ static int launch_clear(mpm_sim* s) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
-// p2g_variant: 2 = packed pairs, 3 = F-update inside the fused substep's P2G, 4 = both (all experimental)
-static bool p2g_packed(const mpm_sim* s) { return s->prm.p2g_variant == 2 || s->prm.p2g_variant == 4; }
-static bool p2g_fupd(const mpm_sim* s) { return s->prm.p2g_variant == 3 || s->prm.p2g_variant == 4; }
+// p2g_variant 0 (auto): the fused substep runs the F-update inside the P2G kernel; 2: as a kernel of its own (k_fupdate), which is
+// also what the side-stream overlap (MPM_B200_OVERLAP) needs
+static bool p2g_fupd(const mpm_sim* s) { return s->prm.p2g_variant == 0 && s->prm.g2p_variant == 0 && !s->side.stream; }
 template <int MODE>
 static int launch_p2g(mpm_sim* s, float4* target, float dt) {
     if (s->prm.p2g_variant == 1) {
@@ -576,10 +580,10 @@ static int launch_p2g(mpm_sim* s, float4* target, float dt) {
     } else if (MODE == P2G_FUSED && p2g_fupd(s)) {
         const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
-                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), &nxt, s->prm.fupdate_exact != 1)));
+                                  s->num_sms, (int)s->n_bound, s->stream, &nxt, s->prm.fupdate_exact != 1)));
     } else {
         CK((launch_p2g_tile<MODE>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, target, s->gd, s->sc, dt,
-                                  s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s))));
+                                  s->num_sms, (int)s->n_bound, s->stream)));
     }
     s->stats.kernel_launches++;
     return MPM_OK;
@@ -606,7 +610,6 @@ static int launch_g2p(mpm_sim* s, float dt) {
     } else {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream, &s->side,
-                                   s->prm.g2p_variant == 2 || s->prm.g2p_variant == 4, s->prm.g2p_variant == 3 || s->prm.g2p_variant == 4,
                                    s->prm.fupdate_exact == 2 || ((FLAGS & G2P_REORDER) && s->prm.fupdate_exact == 0),      // tolerance-form F-update: fused substep (or forced)
                                    fuse_hist ? s->key : nullptr, fuse_hist ? s->blk_count : nullptr)));
     }
@@ -1079,7 +1082,6 @@ int mpm_peer_connect_ptr(mpm_t* s, void* lower_grid, int lower_layers, void* upp
     s->peer_flags_dn = lower_grid ? (int*)((float4*)lower_grid + (size_t)(lower_layers + 1) * layer_nodes) : nullptr;
     s->peer.up = upper_grid ? (float4*)upper_grid : nullptr;                                                // its first layer == my ghost layer
     s->peer_flags_up = upper_grid ? (int*)((float4*)upper_grid + (size_t)(upper_layers + 1) * layer_nodes) : nullptr;
-    CK(tile_kernels_init_experimental());
     s->peer_connected = true;
     s->peer_epoch = 0;
     return MPM_OK;
@@ -1120,7 +1122,7 @@ int mpm_substep_begin_peer(mpm_t* s, float dt, int phase) {
         CKLAUNCH(); s->stats.kernel_launches++;
         const Planes nxt = s->planes(s->cur ^ 1);
         CK((launch_p2g_tile<P2G_FUSED>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
-                                       s->num_sms, (int)s->n_bound, s->stream, p2g_packed(s), p2g_fupd(s) ? &nxt : nullptr, s->prm.fupdate_exact != 1, &s->peer)));
+                                       s->num_sms, (int)s->n_bound, s->stream, p2g_fupd(s) ? &nxt : nullptr, s->prm.fupdate_exact != 1, &s->peer)));
         s->stats.kernel_launches++;
         s->fupd_pending = p2g_fupd(s);
         k_peer_signal<<<1, 1, 0, s->stream>>>(s->peer_flags_dn ? s->peer_flags_dn + 3 : nullptr, s->peer_flags_up ? s->peer_flags_up + 2 : nullptr, s->peer_epoch);

@@ -19,7 +19,6 @@
 //   (the physical re-sort that keeps the next substep's loads coalesced).
 #pragma once
 #include "mpm_kernels.cuh"
-#include <type_traits>
 
 namespace mpm {
 
@@ -66,17 +65,12 @@ MPM_DI void p2g_first_chunk_ids(const int4& wk, const int* __restrict__ sorted_i
 }
 
 // Thread t = cell*4 + a with cell = (cx*4 + cy)*4 + cz: within a warp the four cells of a z-column sit at lane stride 4.
-// FUPD (p2g_variant = 3 / 4, EXPERIMENTAL, fused substep only, not yet validated on hardware): after a block's tile has
-// been written back, the same CTA runs the F-update (cpp:306-330) of the block's particles: it depends only on particle
-// state of the START of the substep (B of the previous gather, FE, FP), never on the grid, so it can run anywhere
-// between two gathers. Inside P2G its HBM streaming (240 B/particle, 2.4 ms as a kernel of its own) overlaps the
-// smem-bound accumulation of the SM's other CTA, and B is read once per substep instead of twice. Results go to
-// planes 4..10 of the OTHER buffer at the particle's sorted rank, exactly where k_fupdate<true> puts them; the gather
-// then runs without its F-update launch.
-// PACKED (p2g_variant = 2, EXPERIMENTAL, not the default, not yet validated on hardware): phase 1 accumulates each channel
-// of two consecutive z-nodes as one fp32 pair: per node pair 1 FMUL2 + 7 FFMA2 instead of 2 FMUL + 8 FFMA + 6 FADD.
-// The affine value at node c is formed as fma(c, step, v0) instead of c repeated additions (one rounding instead
-// of c: an fp32 re-association like the tile kernel's own summation order, covered by the trajectory tolerances).
+// FUPD (the fused substep's default): after a block's tile has been written back, the same CTA runs the F-update
+// (cpp:306-330) of the block's particles: it depends only on particle state of the START of the substep (B of the previous
+// gather, FE, FP), never on the grid, so it can run anywhere between two gathers. Inside P2G its HBM streaming
+// (240 B/particle, 2.4 ms as a kernel of its own) shares the SM with the other CTA's accumulation. Results go to planes
+// 4..10 of the OTHER buffer at the particle's sorted rank, exactly where k_fupdate<true> puts them; the gather then runs
+// without an F-update launch. Measured at 64 Mi (profiles/r2_ab_64M.md): P2G 3.53 + k_fupdate 2.37 -> 5.08 ms.
 // PEER (EXPERIMENTAL, opt-in through mpm_substep_begin_peer, not yet run on hardware): the ghost-layer reduction of the slab
 // decomposition done by this kernel itself. A tile node that lies in a block layer shared with a neighbouring slab (my
 // ghost layer = the upper neighbour's first layer; my first layer = the lower neighbour's ghost layer) is added to the
@@ -88,7 +82,7 @@ struct PeerLayers { float4* dn; float4* up; };      // lower neighbour's ghost l
 // alternate between the front and the back of the list -- so that the NVLink traffic overlaps the interior blocks and the
 // neighbours' waits end early.
 MPM_DI int peer_work_order(int ticket, int n_work) { return (ticket & 1) ? n_work - 1 - (ticket >> 1) : (ticket >> 1); }
-template <int MODE, bool PACKED = false, int FUPD = 0 /* 0 none, 1 bit-faithful, 2 tolerance form */, bool PEER = false>
+template <int MODE, int FUPD = 0 /* 0 none, 1 bit-faithful, 2 tolerance form */, bool PEER = false>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx, PeerLayers peer = PeerLayers{ nullptr, nullptr }) {
@@ -127,10 +121,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
         if (wk.x < 0) break;
         const int start = wk.y, cnt = wk.z;
         const int pbk = wk.w & (PB_COORD_MAX - 1), pbj = (wk.w >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (wk.w >> (2 * PB_COORD_BITS)) + gd.lo;   // global block coords
-        float4 acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        f32x2_t AM[8], AX[8], AY[8], AZ[8];     // PACKED only: channel-major pairs over (c, c+1)
+        f32x2_t AM[8], AX[8], AY[8], AZ[8];     // 16 stencil nodes x (mass, momentum): channel-major fp32 pairs over the z-nodes (c, c+1)
 #pragma unroll
         for (int i = 0; i < 8; ++i) AM[i] = AX[i] = AY[i] = AZ[i] = 0ull;
 
@@ -230,38 +221,26 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 pi = S.u.c.order[i];                       // (slot i is inside the cell's run, possibly wrapped: always valid)
                 // value(a,b,c)_r = c0_r + a*hA[r][0] + b*hA[r][1] + c*hA[r][2]
                 const float bx = qc.y + fa * h0.x, by = qc.z + fa * h0.w, bz = qc.w + fa * h1.z;
-                const float wyv[4] = { wy.x, wy.y, wy.z, wy.w }, wzv[4] = { wz.x, wz.y, wz.z, wz.w };
-                if (PACKED) {
-                    // pairs over two consecutive z-nodes (c, c+1): weights W = wab * (wz_c, wz_c+1) straight from the aligned
-                    // halves of the wz record, channel values v0 + (c, c+1) * step by one FFMA2 with broadcast operands
-                    const f32x2_t wzp[2] = { pack2(wz.x, wz.y), pack2(wz.z, wz.w) };
-                    const f32x2_t cp2[2] = { pack2(0.f, 1.f), pack2(2.f, 3.f) };
-                    const f32x2_t mm = pack2(qc.x, qc.x), sx = pack2(h0.z, h0.z), sy = pack2(h1.y, h1.y), sz = pack2(h8, h8);
-#pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) {
-                        const float wab = wxa * wyv[bb];
-                        const float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
-                        const f32x2_t wab2 = pack2(wab, wab), vx2 = pack2(vx, vx), vy2 = pack2(vy, vy), vz2 = pack2(vz, vz);
-#pragma unroll
-                        for (int cp = 0; cp < 2; ++cp) {
-                            const f32x2_t W = fmul2(wzp[cp], wab2);
-                            ffma2_acc(AM[bb * 2 + cp], W, mm);
-                            ffma2_acc(AX[bb * 2 + cp], W, ffma2(cp2[cp], sx, vx2));
-                            ffma2_acc(AY[bb * 2 + cp], W, ffma2(cp2[cp], sy, vy2));
-                            ffma2_acc(AZ[bb * 2 + cp], W, ffma2(cp2[cp], sz, vz2));
-                        }
-                    }
-                } else
+                const float wyv[4] = { wy.x, wy.y, wy.z, wy.w };
+                // pairs over two consecutive z-nodes (c, c+1): weights W = wab * (wz_c, wz_c+1) straight from the aligned
+                // halves of the wz record, channel values v0 + (c, c+1) * step by one FFMA2 with broadcast operands. The affine
+                // value at node c is fma(c, step, v0) (one rounding). Per node pair 1 FMUL2 + 7 FFMA2 where scalar code needs
+                // 2 FMUL + 8 FFMA + 6 FADD (measured 3.87 -> 3.60 ms at 64 Mi; the scalar form is gone).
+                const f32x2_t wzp[2] = { pack2(wz.x, wz.y), pack2(wz.z, wz.w) };
+                const f32x2_t cp2[2] = { pack2(0.f, 1.f), pack2(2.f, 3.f) };
+                const f32x2_t mm = pack2(qc.x, qc.x), sx = pack2(h0.z, h0.z), sy = pack2(h1.y, h1.y), sz = pack2(h8, h8);
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) {
                     const float wab = wxa * wyv[bb];
-                    float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
+                    const float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
+                    const f32x2_t wab2 = pack2(wab, wab), vx2 = pack2(vx, vx), vy2 = pack2(vy, vy), vz2 = pack2(vz, vz);
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const float wgt = wab * wzv[cc];
-                        float4& a4 = acc[bb * 4 + cc];
-                        a4.x += wgt * qc.x; a4.y += wgt * vx; a4.z += wgt * vy; a4.w += wgt * vz;
-                        vx += h0.z; vy += h1.y; vz += h8;
+                    for (int cp = 0; cp < 2; ++cp) {
+                        const f32x2_t W = fmul2(wzp[cp], wab2);
+                        ffma2_acc(AM[bb * 2 + cp], W, mm);
+                        ffma2_acc(AX[bb * 2 + cp], W, ffma2(cp2[cp], sx, vx2));
+                        ffma2_acc(AY[bb * 2 + cp], W, ffma2(cp2[cp], sy, vy2));
+                        ffma2_acc(AZ[bb * 2 + cp], W, ffma2(cp2[cp], sz, vz2));
                     }
                 }
             }
@@ -269,12 +248,11 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             __syncthreads();
             MPM_PROF(4);          // barrier after the accumulation
         }
-        if (PACKED) {
+        float4 acc[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc[2 * i] = make_float4(lo2(AM[i]), lo2(AX[i]), lo2(AY[i]), lo2(AZ[i]));
-                acc[2 * i + 1] = make_float4(hi2(AM[i]), hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
-            }
+        for (int i = 0; i < 8; ++i) {
+            acc[2 * i] = make_float4(lo2(AM[i]), lo2(AX[i]), lo2(AY[i]), lo2(AZ[i]));
+            acc[2 * i + 1] = make_float4(hi2(AM[i]), hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
         }
         if (t == 0) wk_reg = w_ticket < n_work ? pblock_list[PEER ? peer_work_order(w_ticket, n_work) : w_ticket] : no_work;   // issued here, stored below
         // ---- phase 2a: fold the four cells of a z-column with warp shuffles (lanes at stride 4) ----
@@ -397,37 +375,31 @@ MPM_DI void mbar_fence_init() {}
 #define G2P_MIN_CTAS 2
 #endif
 constexpr int G2P_WARPS = 8, G2P_T = G2P_WARPS * 32;
-struct G2PSmem {
-    float4 tile[G2P_WARPS][512];         // one 2x2x2-grid-block tile (8 x 1 KB) per warp
-    unsigned long long bar[G2P_WARPS];
-};
-
-// EXPERIMENTAL (g2p_variant = 2, not the default, not yet validated on hardware): the tile re-laid out LINEARLY in
-// smem, slot(ti,tj,tk) = ti*73 + tj*9 + tk (rows padded 8->9, planes 72->73 so that the bank group is (ti+tj+tk) mod 8).
-// The 64 stencil reads of a particle then are LDS.128 [base + immediate] with no per-node address arithmetic
-// (the blocked tile costs ~190 integer instructions per particle, 17 % of the gather loop). The re-layout is done by
-// the copy engine: 128 bulk copies of 64 B (one 4-node k-row each), 4 per lane.
+// The 2x2x2-grid-block tile of a particle block, re-laid out LINEARLY in shared memory: slot(ti,tj,tk) = ti*73 + tj*9 + tk
+// (rows padded 8 -> 9, planes 72 -> 73, so the 16-byte bank group of a node is (ti+tj+tk) mod 8). The 64 stencil reads of a
+// particle then are LDS.128 [base + immediate] with no per-node address arithmetic (the blocked tile of round 1 spent ~190
+// integer instructions per particle on addresses). The re-layout is done by the copy engine: 128 bulk copies of 64 B
+// (one 4-node k-row each), 4 per lane, completing on the warp's own mbarrier.
 constexpr int G2P_LIN_ROW = 9, G2P_LIN_PLANE = 73, G2P_LIN_SLOTS = 8 * G2P_LIN_PLANE;
-struct G2PSmemLinear {
+struct G2PSmem {
     float4 tile[G2P_WARPS][G2P_LIN_SLOTS];
     unsigned long long bar[G2P_WARPS];
 };
 
-// EXPERIMENTAL (g2p_variant = 3 / 4, not the default, not yet validated on hardware): the separable gather issued as
-// packed fp32 pairs. sm_100a has FFMA2 (PTX fma.rn.f32x2): two IEEE fma.rn per lane per instruction, and ptxas folds a
-// duplicated {x, x} operand into a scalar broadcast, so (s0, s1) += (wz, wz*dz) * n needs ONE instruction instead of
-// two. Same operations in the same order on every component -> results identical to the scalar code (up to the sign
-// of an exact zero); 576 FFMA per particle become 240 FFMA2 + 84 FFMA.
-// Warp-per-block gather: every warp owns a whole particle block at a time (its own TMA-loaded tile, its own
-// mbarrier), so there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
-// FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER (the F-update runs in k_fupdate).
-template <int FLAGS, bool LINEAR = false, bool PACKED = false>
+// Warp-per-block gather: every warp owns a whole particle block at a time (its own TMA-loaded tile, its own mbarrier), so
+// there is no CTA-wide barrier and no ragged-tail idling beyond the last 32-particle slice of a block.
+// The separable gather is issued as packed fp32 pairs: sm_100a has FFMA2 (PTX fma.rn.f32x2), two IEEE fma.rn per lane per
+// instruction, and ptxas folds a duplicated {x, x} operand into a scalar broadcast, so (s0, s1) += (wz, wz*dz) * n needs ONE
+// instruction instead of two: 576 FFMA per particle become 252 FFMA2 + 84 FFMA.
+// Measured at 64 Mi particles (profiles/r2_ab_64M.md): blocked tile + scalar FMA 2.40 ms, linear tile 2.22, packed pairs
+// 2.19, both 1.99 -> only this form is kept.
+// FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER, G2P_HIST (the F-update runs in P2G or in k_fupdate).
+template <int FLAGS>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr) {
     MPM_DYN_SMEM(g2p_smem_raw, 128);
-    using Smem = typename std::conditional<LINEAR, G2PSmemLinear, G2PSmem>::type;
-    Smem& S = *reinterpret_cast<Smem*>(g2p_smem_raw);
+    G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_work = dc->n_active_pblocks;
     float4* __restrict__ tile = S.tile[wid];
@@ -445,15 +417,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
             if (w < n_work) {
                 const int4 wk = pblock_list[w];
                 bc = wk.w; start = wk.y; cnt = wk.z;
-                const int pbk0 = bc & (PB_COORD_MAX - 1), pbj0 = (bc >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi_l = bc >> (2 * PB_COORD_BITS);
                 mbar_expect_tx(bar, 8 * 1024);
-                if (!LINEAR) {
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        const size_t gb = ((size_t)(pbi_l + (d >> 2)) * gd.nbj + pbj0 + ((d >> 1) & 1)) * gd.nbk + pbk0 + (d & 1);
-                        tma_load_1d(&tile[d * 64], grid + gb * 64, 1024, bar);
-                    }
-                }
             }
         }
         w = __shfl_sync(0xffffffffu, w, 0);
@@ -461,7 +425,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
         bc = __shfl_sync(0xffffffffu, bc, 0); start = __shfl_sync(0xffffffffu, start, 0); cnt = __shfl_sync(0xffffffffu, cnt, 0);
         const int pbk = bc & (PB_COORD_MAX - 1), pbj = (bc >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (bc >> (2 * PB_COORD_BITS)) + gd.lo;
         MPM_SMEM_EPOCH();
-        if (LINEAR) {
+        {
             // lane 0 has armed the barrier with the byte count (ordered before the copies by the shuffles above);
             // every lane issues 4 of the 128 row copies: row = lane & 15 of grid blocks d = (lane >> 4) + 2m
             const int row = lane & 15, li = row >> 2, lj = row & 3;
@@ -496,78 +460,47 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                     // one pos/h quotient per axis feeds the cell index and the weights (same bits as cell_of + axis_weights)
                     const int cx = cell_and_weights(r.x[0], sc.pd, wx), cy = cell_and_weights(r.x[1], sc.pd, wy), cz = cell_and_weights(r.x[2], sc.pd, wz);
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
-                    int offx[4], offy[4], offz[4];
-                    float wxd[4], wyd[4], wzd[4];
-                    const float4* __restrict__ lin = tile + (LINEAR ? ox * G2P_LIN_PLANE + oy * G2P_LIN_ROW + oz : 0);
+                    const float4* __restrict__ lin = tile + (ox * G2P_LIN_PLANE + oy * G2P_LIN_ROW + oz);
+                    // pairs: S = (s0, s1) <- (wz, wz dz) * n ;  T = (t0, t1y) <- (wy, wy dy) * s0 ;  V = (v, Bx) <- (wx, wx dx) * t0
+                    f32x2_t WX[4], WY[4], WZ[4], V[3] = { 0ull, 0ull, 0ull };
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        offx[a] = LINEAR ? 0 : ((ox + a) >> 2) * 256 + ((ox + a) & 3) * 16;
-                        offy[a] = LINEAR ? 0 : ((oy + a) >> 2) * 128 + ((oy + a) & 3) * 4;
-                        offz[a] = LINEAR ? 0 : ((oz + a) >> 2) * 64 + ((oz + a) & 3);
-                        wxd[a] = wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]);
-                        wyd[a] = wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]);
-                        wzd[a] = wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]);
+                        WX[a] = pack2(wx[a], wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]));
+                        WY[a] = pack2(wy[a], wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]));
+                        WZ[a] = pack2(wz[a], wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]));
                     }
-                    float v[3] = { 0, 0, 0 }, Bx[3] = { 0, 0, 0 }, By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
-                    if (PACKED) {
-                        // pairs: S = (s0, s1) <- (wz, wz dz) * n ;  T = (t0, t1y) <- (wy, wy dy) * s0 ;  V = (v, Bx) <- (wx, wx dx) * t0
-                        f32x2_t WX[4], WY[4], WZ[4], V[3] = { 0ull, 0ull, 0ull };
+                    float By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) { WX[a] = pack2(wx[a], wxd[a]); WY[a] = pack2(wy[a], wyd[a]); WZ[a] = pack2(wz[a], wzd[a]); }
+                    for (int a = 0; a < 4; ++a) {
+                        f32x2_t T[3] = { 0ull, 0ull, 0ull };
+                        float t1z[3] = { 0, 0, 0 };
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            f32x2_t T[3] = { 0ull, 0ull, 0ull };
-                            float t1z[3] = { 0, 0, 0 };
+                        for (int bb = 0; bb < 4; ++bb) {
+                            f32x2_t Sx[3] = { 0ull, 0ull, 0ull };
 #pragma unroll
-                            for (int bb = 0; bb < 4; ++bb) {
-                                f32x2_t S[3] = { 0ull, 0ull, 0ull };
-                                const int oab = offx[a] + offy[bb];
-#pragma unroll
-                                for (int cc = 0; cc < 4; ++cc) {
-                                    const float4 n = LINEAR ? lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : tile[oab + offz[cc]];
-                                    S[0] = ffma2(WZ[cc], pack2(n.y, n.y), S[0]);
-                                    S[1] = ffma2(WZ[cc], pack2(n.z, n.z), S[1]);
-                                    S[2] = ffma2(WZ[cc], pack2(n.w, n.w), S[2]);
-                                }
-#pragma unroll
-                                for (int q = 0; q < 3; ++q) {
-                                    const float s0q = lo2(S[q]);
-                                    T[q] = ffma2(WY[bb], pack2(s0q, s0q), T[q]);
-                                    t1z[q] += lo2(WY[bb]) * hi2(S[q]);
-                                }
+                            for (int cc = 0; cc < 4; ++cc) {
+                                MPM_SMEM_PROBE(40, (base / 32) * 64 + (a * 4 + bb) * 4 + cc, &lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc], 16);
+                                const float4 n = lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc];
+                                Sx[0] = ffma2(WZ[cc], pack2(n.y, n.y), Sx[0]);
+                                Sx[1] = ffma2(WZ[cc], pack2(n.z, n.z), Sx[1]);
+                                Sx[2] = ffma2(WZ[cc], pack2(n.w, n.w), Sx[2]);
                             }
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
-                                const float t0q = lo2(T[q]);
-                                V[q] = ffma2(WX[a], pack2(t0q, t0q), V[q]);
-                                By[q] += lo2(WX[a]) * hi2(T[q]); Bz[q] += lo2(WX[a]) * t1z[q];
+                                const float s0q = lo2(Sx[q]);
+                                T[q] = ffma2(WY[bb], pack2(s0q, s0q), T[q]);
+                                t1z[q] += lo2(WY[bb]) * hi2(Sx[q]);
                             }
                         }
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) { v[q] = lo2(V[q]); Bx[q] = hi2(V[q]); }
-                    } else
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        float t0[3] = { 0, 0, 0 }, t1y[3] = { 0, 0, 0 }, t1z[3] = { 0, 0, 0 };
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) {
-                            float s0[3] = { 0, 0, 0 }, s1[3] = { 0, 0, 0 };
-                            const int oab = offx[a] + offy[bb];
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                MPM_SMEM_PROBE(40, (base / 32) * 64 + (a * 4 + bb) * 4 + cc, LINEAR ? &lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : &tile[oab + offz[cc]], 16);
-                                const float4 n = LINEAR ? lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc] : tile[oab + offz[cc]];
-                                s0[0] += wz[cc] * n.y; s0[1] += wz[cc] * n.z; s0[2] += wz[cc] * n.w;
-                                s1[0] += wzd[cc] * n.y; s1[1] += wzd[cc] * n.z; s1[2] += wzd[cc] * n.w;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) { t0[q] += wy[bb] * s0[q]; t1y[q] += wyd[bb] * s0[q]; t1z[q] += wy[bb] * s1[q]; }
+                        for (int q = 0; q < 3; ++q) {
+                            const float t0q = lo2(T[q]);
+                            V[q] = ffma2(WX[a], pack2(t0q, t0q), V[q]);
+                            By[q] += lo2(WX[a]) * hi2(T[q]); Bz[q] += lo2(WX[a]) * t1z[q];
                         }
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) { v[q] += wx[a] * t0[q]; Bx[q] += wxd[a] * t0[q]; By[q] += wx[a] * t1y[q]; Bz[q] += wx[a] * t1z[q]; }
                     }
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) { r.v[q] = v[q]; r.B[q] = Bx[q]; r.B[3 + q] = By[q]; r.B[6 + q] = Bz[q]; }
+                    for (int q = 0; q < 3; ++q) { r.v[q] = lo2(V[q]); r.B[q] = hi2(V[q]); r.B[3 + q] = By[q]; r.B[6 + q] = Bz[q]; }
                 }
                 if (FLAGS & G2P_ADVECT) {
 #pragma unroll
@@ -615,30 +548,19 @@ __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ so
 inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
-#define MPM_SET_P2G(MODE, PK) MPM_SET_SMEM((k_p2g_tile<MODE, PK>), P2GSmem)
-    MPM_SET_P2G(P2G_MOMENTUM, false); MPM_SET_P2G(P2G_FORCE, false); MPM_SET_P2G(P2G_FUSED, false);
-    MPM_SET_P2G(P2G_MOMENTUM, true); MPM_SET_P2G(P2G_FORCE, true); MPM_SET_P2G(P2G_FUSED, true);
-#define MPM_SET_P2G_F(PK, FU, PE) MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, PK, FU, PE>), P2GSmem)
-    MPM_SET_P2G_F(false, 1, false); MPM_SET_P2G_F(false, 2, false); MPM_SET_P2G_F(true, 1, false); MPM_SET_P2G_F(true, 2, false);
-    MPM_SET_P2G_F(false, 0, true); MPM_SET_P2G_F(false, 1, true); MPM_SET_P2G_F(false, 2, true);
-    MPM_SET_P2G_F(true, 0, true); MPM_SET_P2G_F(true, 1, true); MPM_SET_P2G_F(true, 2, true);
-#undef MPM_SET_P2G_F
-#undef MPM_SET_P2G
+    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 1>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 0, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 1, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2, true>), P2GSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>), G2PSmem);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, true>), G2PSmemLinear);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, false, true>), G2PSmem);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true>), G2PSmemLinear);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, true, true>), G2PSmemLinear); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, true, true>), G2PSmemLinear);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, false, true>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, false, true>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST>), G2PSmem);
 #undef MPM_SET_SMEM
     return cudaSuccess;
 }
-inline cudaError_t tile_kernels_init_experimental() { return cudaSuccess; }
 
 template <int MODE>
 cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            bool packed = false, const Planes* fupd_target = nullptr, bool fupd_fast = false, const PeerLayers* peer = nullptr) {
+                            const Planes* fupd_target = nullptr, bool fupd_fast = false, const PeerLayers* peer = nullptr) {
     (void)n_bound;
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
@@ -646,15 +568,13 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
     const PeerLayers pl = peer ? *peer : PeerLayers{ nullptr, nullptr };
     const int fu = (fupd_target && MODE == P2G_FUSED) ? (fupd_fast ? 2 : 1) : 0;      // only the fused substep moves the F-update into P2G
     const bool pe = peer && MODE == P2G_FUSED;
-#define MPM_P2G_LAUNCH(PK, FU, PE) k_p2g_tile<MODE, PK, FU, PE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
-#define MPM_P2G_FU(PK, PE) do { if (fu == 2) MPM_P2G_LAUNCH(PK, 2, PE); else if (fu == 1) MPM_P2G_LAUNCH(PK, 1, PE); else MPM_P2G_LAUNCH(PK, 0, PE); } while (0)
+#define MPM_P2G_LAUNCH(FU, PE) k_p2g_tile<MODE, FU, PE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
     if constexpr (MODE == P2G_FUSED) {
-        if (pe) { if (packed) MPM_P2G_FU(true, true); else MPM_P2G_FU(false, true); }
-        else { if (packed) MPM_P2G_FU(true, false); else MPM_P2G_FU(false, false); }
+        if (pe) { if (fu == 2) MPM_P2G_LAUNCH(2, true); else if (fu == 1) MPM_P2G_LAUNCH(1, true); else MPM_P2G_LAUNCH(0, true); }
+        else { if (fu == 2) MPM_P2G_LAUNCH(2, false); else if (fu == 1) MPM_P2G_LAUNCH(1, false); else MPM_P2G_LAUNCH(0, false); }
     } else {
-        if (packed) MPM_P2G_LAUNCH(true, 0, false); else MPM_P2G_LAUNCH(false, 0, false);
+        MPM_P2G_LAUNCH(0, false);
     }
-#undef MPM_P2G_FU
 #undef MPM_P2G_LAUNCH
     return cudaGetLastError();
 }
@@ -663,8 +583,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side, bool linear_tile = false, bool packed = false, bool fupd_fast = false,
-                            int* key_out = nullptr, int* blk_count = nullptr) {
+                            SideStream* side, bool fupd_fast = false, int* key_out = nullptr, int* blk_count = nullptr) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -690,18 +609,9 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
         constexpr int GF = FLAGS & ~G2P_F;
         constexpr bool CAN_HIST = (GF & G2P_REORDER) != 0 && (GF & G2P_ADVECT) != 0;       // the fused substep's gather
-#define MPM_G2P_LAUNCH(F, LIN, PK, SM) k_g2p_tile<F, LIN, PK><<<num_sms * per_sm, G2P_T, sizeof(SM), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count)
-        if (CAN_HIST && key_out) {
-            if (linear_tile && packed) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), true, true, G2PSmemLinear);
-            else if (linear_tile) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), true, false, G2PSmemLinear);
-            else if (packed) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), false, true, G2PSmem);
-            else MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0), false, false, G2PSmem);
-        } else {
-            if (linear_tile && packed) MPM_G2P_LAUNCH(GF, true, true, G2PSmemLinear);
-            else if (linear_tile) MPM_G2P_LAUNCH(GF, true, false, G2PSmemLinear);
-            else if (packed) MPM_G2P_LAUNCH(GF, false, true, G2PSmem);
-            else MPM_G2P_LAUNCH(GF, false, false, G2PSmem);
-        }
+#define MPM_G2P_LAUNCH(F) k_g2p_tile<F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count)
+        if (CAN_HIST && key_out) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0));
+        else MPM_G2P_LAUNCH(GF);
 #undef MPM_G2P_LAUNCH
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -18,7 +18,7 @@ import oracle_py as op                                                # noqa: E4
 from helpers import assert_traj_close_calibrated                      # noqa: E402
 from scene_util import oracle_from_scene                              # noqa: E402
 
-VARIANTS = [(0, 0), (1, 1), (0, 2), (2, 3), (0, 4), (3, 0), (4, 4), (1, 0), (0, 1)]
+VARIANTS = [(0, 0), (1, 1), (2, 0), (1, 0), (0, 1)]
 
 
 def random_scene(rng):

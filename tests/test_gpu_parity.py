@@ -473,11 +473,9 @@ def test_p2g_rotated_record_walk_on_eight_per_cell_slab(monkeypatch):
     assert rot.stats().n_particles == ali.stats().n_particles == sc["n"]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1" and __import__("os").environ.get("MPM_B200_ALLOW_EMULATION") != "1",
-                    reason="experimental path, opt-in on hardware until validated there (always on in the CPU emulation run)")
-@pytest.mark.parametrize("slab_variants", [(0, 0), (4, 4)])       # default kernels; every experimental option at once
+@pytest.mark.parametrize("slab_variants", [(0, 0), (2, 0)])       # F-update inside P2G; as a kernel of its own
 def test_peer_memory_halo_two_slabs_in_one_process(slab_variants):
-    """EXPERIMENTAL peer-memory halo (mpm_substep_begin_peer): P2G adds the tile nodes of a shared block layer to the local
+    """Peer-memory halo (mpm_substep_begin_peer): P2G adds the tile nodes of a shared block layer to the local
     grid AND to the neighbour slab's grid, device-side flags replace the halo messages. Two slab handles in ONE process
     (neighbour grids connected by pointer, migration buffers handed over directly) against the same scene in one domain,
     with the tile-vs-baseline difference of the single domain as the noise floor."""
@@ -694,9 +692,7 @@ def test_full_size_properties_config5_slab():
     _slab_properties(512, 1 << 26)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MPM_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental paths (CUDA-graph substeps, linear-tile gather) are opt-in until validated on hardware")
-def test_experimental_graph_substeps_match_plain_path(monkeypatch):
+def test_graph_substeps_match_plain_path(monkeypatch):
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0)
     plain, cols, nc = sim_from_scene(sc)
     monkeypatch.setenv("MPM_B200_GRAPH", "1")
