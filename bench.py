@@ -152,8 +152,9 @@ def port_openmp_sample(mpm_b200, steps=3, grid=128, n=1 << 20):
     return out
 
 
-def cpu_baseline(mpm_b200, budget_steps=150):
+def cpu_baseline(mpm_b200, budget_steps=150, config=5):
     out = cpu_baseline_reference(mpm_b200, budget_steps)
+    out["for_config"] = config
     try:
         out["port"] = port_openmp_sample(mpm_b200)
     except Exception as e:
@@ -206,54 +207,148 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "cpu_sample": f"{cores} independent replicas of a {sc['n']}-particle 32^3 slab sample"},
+            "config": {"workload": CONFIGS[args.config]["name"], "baseline_config": args.config, "cpu_sample": f"{cores} independent replicas of a {sc['n']}-particle 32^3 slab sample"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{sc['n']} particles x {args.steps} substeps per core, {cores} cores", "cpu_model": cpu_model()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def roofline_block(ms_per_step, n_total, n_active, world, phase_ms, grid, particles):
+def csrc_sha16():
+    """Identity of the kernel sources a profiler capture belongs to (profiles/traffic.json carries the same hash)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "realtime-deformations_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def profiler_capture(key):
+    """DRAM bytes / L2 reduction sectors per substep from the committed ncu capture of THIS kernel build (tools/traffic_from_ncu.py
+    writes profiles/traffic.json with the hash of the kernel sources); None when the sources changed since the capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if d.get("csrc_sha16") == csrc_sha16():
+            return d.get(key)
+    except Exception:
+        pass
+    return None
+
+
+def roofline_block(ms_per_step, n_total, n_active, world, phase_ms, cfg_key, fupd_in_p2g=True):
     """The `roofline` object of the JSON line. phase_ms = MpmStats.last_ms of the last substep (max over ranks):
     [bin, clear, p2g, grid, g2p (F-update + gather), between begin/end, total, F-update alone or -1]."""
     peak, peak_src = measured_peak()
     alg_bytes = ALG_BYTES_PER_PARTICLE * n_total + ALG_BYTES_PER_NODE * n_active
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9 / world      # per-GPU GB/s against a per-GPU peak
-    names = ["bin_sort", "grid_clear", "p2g", "halo_wait", "grid_update", "g2p(fupdate+gather)", "substep_total"]
+    timed_apart = len(phase_ms) > 7 and phase_ms[7] > 0       # the F-update as a kernel of its own, on the main stream
+    names = ["bin_sort", "grid_clear", "p2g+fupdate" if fupd_in_p2g else "p2g", "halo_wait", "grid_update",
+             "g2p_gather" if fupd_in_p2g else "g2p(fupdate+gather)", "substep_total"]
     order = [0, 1, 2, 5, 3, 4, 6]
     kern = {names[i]: round(phase_ms[order[i]], 4) for i in range(7)}
-    if len(phase_ms) > 7 and phase_ms[7] > 0:   # the two G2P kernels timed apart (default: back to back on one stream)
+    if not fupd_in_p2g and timed_apart:     # the F-update as a kernel of its own (p2g_variant 2): timed apart from the gather
         kern["fupdate"] = round(phase_ms[7], 4)
         kern["g2p_gather"] = round(phase_ms[4] - phase_ms[7], 4)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{grid}:{particles}")
-    except Exception:
-        pass
-    cands = ("p2g", "fupdate", "g2p_gather", "bin_sort", "grid_update") if "fupdate" in kern else ("p2g", "g2p(fupdate+gather)", "bin_sort", "grid_update")
+    cap = profiler_capture(cfg_key) or {}
+    cands = [k for k in ("p2g+fupdate", "p2g", "fupdate", "g2p_gather", "bin_sort", "grid_update") if k in kern]
+    if not fupd_in_p2g and not timed_apart:
+        cands = ["p2g", "g2p(fupdate+gather)", "bin_sort", "grid_update"]
     dom = max(cands, key=lambda k: kern[k])
     # per-kernel algorithmic bytes (DESIGN.md section 4), per GPU
     npg, apg = n_total / world, n_active / world
-    kern_alg = {"p2g": 88 * npg + 16 * apg, "g2p(fupdate+gather)": (128 + 112) * npg + (16 + 64) * npg + 16 * apg,
+    kern_alg = {"p2g": 88 * npg + 16 * apg, "p2g+fupdate": (88 + 80 + 112) * npg + 16 * apg, "g2p(fupdate+gather)": (128 + 112) * npg + (16 + 64) * npg + 16 * apg,
                 "fupdate": (128 + 112) * npg, "g2p_gather": (16 + 64) * npg + 16 * apg,
-                "bin_sort": 24 * npg, "grid_update": 32 * apg}
+                "bin_sort": 12 * npg, "grid_update": 32 * apg}
     dom_gbs = kern_alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
-    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": traffic, "peak_source": peak_src, "scope": "one whole substep (all kernels), per GPU",
-            "algorithmic_bytes_per_substep": alg_bytes, "active_nodes": n_active,
-            "kernel_ms_last_substep": kern, "dominant_kernel": dom,
-            "dominant_kernel_algorithmic_bytes": kern_alg[dom], "dominant_kernel_achieved_gbs": round(dom_gbs, 1),
-            "dominant_kernel_frac": round(dom_gbs / peak, 4),
-            "dominant_share_of_substep": round(kern[dom] / max(kern["substep_total"], 1e-9), 3),
-            # the cubic stencil makes the substep fp32-issue-bound before it is HBM-bound (SURVEY 8d): the same run
-            # expressed against the non-tensor fp32 peak, with the survey's model of ~4.5 kflop per particle-update
-            "fp32_model_flop_per_particle": FP32_MODEL_FLOP_PER_PARTICLE,
-            "achieved_fp32_tflops": round(FP32_MODEL_FLOP_PER_PARTICLE * n_total / world / (ms_per_step * 1e-3) / 1e12, 2),
-            "fp32_peak_tflops_nominal": 74.4}
+    out = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+           "traffic": cap.get("dram_bytes_per_substep"), "peak_source": peak_src, "scope": "one whole substep (all kernels), per GPU",
+           "algorithmic_bytes_per_substep": alg_bytes, "active_nodes": n_active,
+           "kernel_ms_last_substep": kern, "dominant_kernel": dom,
+           "dominant_kernel_algorithmic_bytes": kern_alg[dom], "dominant_kernel_achieved_gbs": round(dom_gbs, 1),
+           "dominant_kernel_frac": round(dom_gbs / peak, 4),
+           "dominant_share_of_substep": round(kern[dom] / max(kern["substep_total"], 1e-9), 3),
+           # the cubic stencil makes the substep fp32-issue-bound before it is HBM-bound (SURVEY 8d): the same run
+           # expressed against the non-tensor fp32 peak, with the survey's model of ~4.5 kflop per particle-update
+           "fp32_model_flop_per_particle": FP32_MODEL_FLOP_PER_PARTICLE,
+           "achieved_fp32_tflops": round(FP32_MODEL_FLOP_PER_PARTICLE * n_total / world / (ms_per_step * 1e-3) / 1e12, 2),
+           "fp32_peak_tflops_nominal": 74.4}
+    if cap:       # atomic throughput of P2G (north_star): L2 reduction sectors from the same ncu capture, per substep
+        out["atomics"] = {"p2g_red_sectors_per_substep": cap.get("p2g_red_sectors"), "p2g_ms_in_capture": cap.get("p2g_ms"),
+                          "p2g_red_sectors_per_s": cap.get("p2g_red_sectors_per_s"), "source": cap.get("source")}
+    return out
 
 
 FP32_MODEL_FLOP_PER_PARTICLE = 4500     # SURVEY.md 8(d): parity-faithful substep, FMA = 2 flop
-WORKLOAD_NAME = "snow_slab_512: 64Mi-particle snow slab avalanche, 512^3 grid (BASELINE config 5)"
+CONFIGS = {
+    1: dict(name="reference_default: the reference's own start-up scene (constants.hpp / main.cpp:48-52), 2147 particles, 20^3 grid (BASELINE config 1)", grid=20, n=2147, dt=1e-5),
+    2: dict(name="snowball_drop_128: 1Mi-particle snowball dropped on a ground plane, 128^3 grid (BASELINE config 2)", grid=128, n=1 << 20, dt=1e-5, scene="snowball_drop"),
+    3: dict(name="snowball_collision_256: two-snowball collision, 8Mi particles, 256^3 grid (BASELINE config 3)", grid=256, n=1 << 23, dt=1e-5, scene="snowball_collision"),
+    4: dict(name="stiff_snowball_256: stiff-snow sweep point (xi=20, theta_c=1.5e-2, theta_s=7.5e-3), 4Mi particles, 256^3 grid, dt=2.5e-6 (BASELINE config 4)",
+            grid=256, n=1 << 22, dt=2.5e-6, scene="stiff_snowball", params=dict(hardening_xi=20.0, theta_c=1.5e-2, theta_s=7.5e-3)),
+    5: dict(name="snow_slab_512: 64Mi-particle snow slab avalanche, 512^3 grid (BASELINE config 5)", grid=512, n=1 << 26, dt=1e-5, scene="snow_slab"),
+}
+WORKLOAD_NAME = CONFIGS[5]["name"]
+
+
+class DefaultSceneRunner:
+    """BASELINE config 1: the reference's own start-up scene (the golden run's initial state, tests/golden/c1_default.npz, dumped
+    from the unmodified reference) on one GPU. 13 launches per substep dominate at 2147 particles, so the fused substeps are
+    replayed as a CUDA graph of substep pairs (MPM_B200_GRAPH, validated by test_graph_substeps_match_plain_path)."""
+    migrates = False
+
+    def __init__(self, torch, mpm_b200):
+        os.environ["MPM_B200_GRAPH"] = "1"
+        g = np.load(os.path.join(ROOT, "tests", "golden", "c1_default.npz"))
+        s0 = g["state0"]
+        self.dt = float(g["dt"])
+        self.sim = mpm_b200.Sim(int(g["I"]), int(g["J"]), int(g["K"]), s0.shape[0], mpm_b200.capi.default_params(h=float(g["h"])))
+        self.stream = torch.cuda.Stream()
+        self.sim.set_stream(self.stream.cuda_stream)
+        self.sim.upload_state35(s0)
+        raw = np.asarray(g["colliders"], np.float32).reshape(-1, 29)
+        self.cols, self.nc = mpm_b200.capi.make_colliders(raw[:, 13:29], raw[:, 0:3], raw[:, 10:13])
+        self.h2d_bytes_per_step = 88 * self.nc + 4
+        self.sim.rasterizeParticlesToGrid()
+        self.pair = 2
+
+    def substep(self, host_colliders=False, n=1):
+        self.sim.substep(self.dt, self.cols, self.nc, n)
+
+
+def build_runner(args, torch, mpm_b200, multi, rank, world, variants):
+    cfg = CONFIGS[args.config]
+    if args.config == 1:
+        if world > 1:
+            raise SystemExit("config 1 (2147 particles) is a single-GPU configuration")
+        return DefaultSceneRunner(torch, mpm_b200), cfg["name"], None
+    grid, n = (args.grid or cfg["grid"]), (args.particles or cfg["n"])
+    name = cfg["name"] if (grid == cfg["grid"] and n == cfg["n"]) else f"{cfg['scene']}_{grid}: {n} particles (development override)"
+    if cfg["scene"] == "snow_slab":       # every rank generates only its own slab (counter-based RNG keyed by cell id)
+        return multi.SlabRunner(grid, n, rank, world, torch, dt=cfg["dt"], variants=variants), name, None
+    full = getattr(mpm_b200.scenes, cfg["scene"])(grid=grid, n=n, dt=cfg["dt"])
+    full, layers, ranges = multi.partition_scene(full, world)
+    mine = multi.slice_scene(full, *ranges[rank])
+    r = multi.SlabRunner(grid, mine["n"], rank, world, torch, scene=mine, dt=cfg["dt"], variants=variants,
+                         layers=layers[rank] if world > 1 else None, params=cfg.get("params"))
+    part = None if world == 1 else {"block_layers": [list(l) for l in layers], "particles": [b - a for a, b in ranges]}
+    return r, name, part
+
+
+def expected_id_sums(n):
+    """sum id and sum splitmix64(id) over ids 0..n-1, mod 2^64 (what mpm_reduce_invariants must return for an intact particle set)."""
+    tot, h = 0, 0
+    step = 1 << 22
+    with np.errstate(over="ignore"):
+        for a in range(0, n, step):
+            i = np.arange(a, min(n, a + step), dtype=np.uint64)
+            z = i + np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            h = (h + int(z.sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+    tot = (n * (n - 1) // 2) & 0xFFFFFFFFFFFFFFFF
+    return tot, h
 
 
 def main():
@@ -262,9 +357,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)           # >= 50 timed substeps after >= 10 warm-up
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", type=int, default=512)            # overrides are for development runs only
-    ap.add_argument("--particles", type=int, default=1 << 26)
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])   # BASELINE.json configs; 5 is the headline
+    ap.add_argument("--grid", type=int, default=0)              # overrides are for development runs only
+    ap.add_argument("--particles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -278,50 +375,62 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libmpm_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         from datetime import timedelta
         # a rank that dies must not leave the others waiting for NCCL's default 10-minute watchdog (but slow first-time CUDA/NCCL start-up on a fresh box must fit)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=timedelta(seconds=240))
-    workload = WORKLOAD_NAME if (args.grid == 512 and args.particles == 1 << 26) else f"snow_slab_{args.grid}: {args.particles} particles (development override)"
 
     from importlib import import_module
     multi = import_module("realtime-deformations_b200.multi")
-    # development only: MPM_B200_VARIANTS="p2g:g2p" selects experimental kernel variants for A/B runs (default 0:0)
+    # development only: MPM_B200_VARIANTS="p2g:g2p" selects the A/B kernel pairings (default 0:0)
     variants = tuple(int(x) for x in os.environ.get("MPM_B200_VARIANTS", "0:0").split(":"))
-    runner = multi.SlabRunner(args.grid, args.particles, rank, world, torch, variants=variants)
+    runner, workload, partition = build_runner(args, torch, mpm_b200, multi, rank, world, variants)
     stream = runner.stream
+    cfg = CONFIGS[args.config]
+    graph_pairs = args.config == 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    inv0 = runner.sim.invariants()
     # ---- warm-up ----
-    for _ in range(args.warmup):
-        runner.substep()
+    if graph_pairs:
+        runner.substep(n=2 * ((args.warmup + 1) // 2))
+    else:
+        for _ in range(args.warmup):
+            runner.substep()
     barrier()
 
     # ---- timed region 1: K substeps, state resident in HBM (inputs = 22 GB of particle state >> 126 MB L2) ----
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = runner.sim.stats().kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        runner.substep()
-    e1.record(stream)
+    evs[0].record(stream)
+    if graph_pairs:                 # one call: the library replays K/2 captured substep pairs (+ one plain substep if K is odd)
+        runner.substep(n=args.steps)
+        evs[-1].record(stream)
+    else:
+        for i in range(args.steps):
+            runner.substep()
+            evs[i + 1].record(stream)
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = evs[0].elapsed_time(evs[-1])
+    per_step = [ms_total / args.steps] * args.steps if graph_pairs else [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop()
     st = runner.sim.stats()
     launches = st.kernel_launches - launches0
     n_local, n_active_local = st.n_particles, st.n_active_nodes
     phase_ms = list(st.last_ms)
+    inv1 = runner.sim.invariants()
 
-    # ---- timed region 2 (e2e): the viewer-frame contract through the C ABI with HOST buffers. Every step copies that
-    # step's host inputs (collider transforms, main.cpp:187-190 moves them each frame) in, runs one substep, and copies
+    # ---- timed region 2 (e2e): the viewer-frame contract through the C ABI with HOST buffers. Every step hands that
+    # step's host inputs (collider structs, main.cpp:187-190 moves them each frame) in, runs one substep, and copies
     # the render buffers the reference's drawParticles() consumes (xyz+size, main.cpp:257-271) out to pinned memory.
     n_up = runner.sim.n
     n_rows = max(int(n_up * 1.5) + (1 << 16), 1) if runner.migrates else max(n_up, 1)
@@ -342,7 +451,7 @@ def main():
                 runner.sim.wait_render_buffers()               # frame t-1 is complete (and consumed) before its buffer is reused
                 runner.sim.render_buffers_async(xyzs_ptr, n_dl)
             else:
-                runner.sim.L.mpm_download_render_buffers(runner.sim.h, n_dl, xyzs_ptr, None, 0.02)
+                mpm_b200.capi._ck(runner.sim.L.mpm_download_render_buffers(runner.sim.h, n_dl, xyzs_ptr, None, 0.02))
         if pipelined:
             runner.sim.wait_render_buffers()
         barrier()
@@ -355,49 +464,96 @@ def main():
         e2e_mode = f"synchronous (pipelined path failed: {exc})"
         e2e_ms = e2e_loop(False)
 
-    # ---- reduce over ranks: max time, summed particles ----
-    vals = torch.tensor([ms_total, e2e_ms, float(n_local), float(n_active_local), float(launches), float(n_dl)] + [float(x) for x in phase_ms],
+    # ---- reduce over ranks: max time (per substep and in total), summed particles and conserved quantities ----
+    def u2i(v):      # uint64 checksum -> the int64 with the same bits (torch has no uint64 reductions); sums wrap identically
+        return v - (1 << 64) if v >= (1 << 63) else v
+    vals = torch.tensor([ms_total, e2e_ms, float(n_local), float(n_active_local), float(launches), float(n_dl)] + [float(x) for x in phase_ms] + per_step,
                         dtype=torch.float64, device="cuda")
+    fsum = torch.tensor([inv0["mass"]] + inv0["momentum"] + [inv1["mass"]] + inv1["momentum"], dtype=torch.float64, device="cuda")
+    isum = torch.tensor([u2i(inv1["count"]), u2i(inv1["id_sum"]), u2i(inv1["id_hash"])], dtype=torch.int64, device="cuda")
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fsum); dist.all_reduce(isum)
         ms_total, e2e_ms = mx[0].item(), mx[1].item()
         n_total, n_active, launches, n_dl_total = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
-        phase_ms = mx[6:].tolist()
+        phase_ms = mx[6:14].tolist()
+        per_step = mx[14:].tolist()
     else:
         n_total, n_active, n_dl_total = float(n_local), float(n_active_local), float(n_dl)
+    fsum = fsum.tolist()
+    isum = [int(x) & 0xFFFFFFFFFFFFFFFF for x in isum.tolist()]
+
+    # ---- multi-GPU correctness inside the same run: a small driven slab on all ranks against one domain on rank 0 ----
+    mcheck = None
+    if world > 1 and not args.no_multi_check:
+        try:
+            mcheck = multi.multi_vs_single_check(torch, rank, world)
+        except Exception as exc:
+            mcheck = {"ok": False, "error": str(exc)} if rank == 0 else None
+        barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    ms_per_step = ms_total / args.steps
+    # the metric is the MEDIAN substep of >= 50; shorter runs report the mean (the driver's K / W)
+    ms_mean = ms_total / args.steps
+    ms_median = float(np.median(per_step))
+    use_median = args.steps >= 50 and not graph_pairs
+    ms_per_step = ms_median if use_median else ms_mean
+    n_int = int(round(n_total))
     value = n_total / (ms_per_step * 1e-3)
-    roof = roofline_block(ms_per_step, n_total, n_active, world, phase_ms, args.grid, args.particles)
+    roof = roofline_block(ms_per_step, n_total, n_active, world, phase_ms, f"config{args.config}",
+                          fupd_in_p2g=(variants == (0, 0) and not os.environ.get("MPM_B200_OVERLAP")))
+    # conserved quantities after all substeps of this run (mass and ids exactly; momentum against p0 + M g dt k where nothing collides)
+    exp_id_sum, exp_id_hash = expected_id_sums(n_int)
+    mass_expected = n_int * float(np.float32(mpm_b200.scenes.PARTICLE_MASS))
+    inv = {"particles": isum[0], "particles_expected": n_int, "id_sum": isum[1], "id_sum_expected": exp_id_sum,
+           "id_hash": isum[2], "id_hash_expected": exp_id_hash, "mass": fsum[4], "mass_expected": mass_expected,
+           "momentum_start": fsum[1:4], "momentum_after_timed_steps": fsum[5:8],
+           "checked_after_substeps": args.warmup + args.steps}
+    inv["ok"] = bool(isum[0] == n_int and isum[1] == exp_id_sum and isum[2] == exp_id_hash and abs(fsum[4] - mass_expected) <= 1e-9 * mass_expected)
+    if cfg.get("scene") == "snowball_collision":      # no collider: momentum changes by gravity alone (cpp:256-262)
+        k = args.warmup + args.steps
+        g = [0.0, -9.8, 0.0]
+        exp_p = [fsum[1 + a] + fsum[0] * g[a] * cfg["dt"] * k for a in range(3)]
+        scale = max(abs(fsum[0] * 100.0), 1e-30)          # |m v| of one ball (v0 = 100 m/s): the two balls' momenta cancel
+        inv["momentum_expected"] = exp_p
+        inv["momentum_rel_err"] = max(abs(fsum[5 + a] - exp_p[a]) for a in range(3)) / scale
+        inv["ok"] = bool(inv["ok"] and inv["momentum_rel_err"] <= 1e-4)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline(mpm_b200)
+            cpu = cpu_baseline(mpm_b200, config=args.config)
         except Exception as exc:      # the GPU measurement above must not be lost to a failing CPU arm
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"cpu baseline failed: {exc}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "ms_per_step_mean": ms_mean, "ms_per_step_median": ms_median,
+            "ms_per_step_min_max": [float(min(per_step)), float(max(per_step))],
+            "value_statistic": "median of the timed substeps (SURVEY 8d)" if use_median else "mean of the timed substeps",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload, "particles": int(n_total), "grid": [args.grid] * 3, "dt": 1e-5, "stencil": "cubic (reference)",
-                       "decomposition": f"{world} slab(s) along i" + ("" if world == 1 else (", ghost layer reduced by P2G over peer memory (experimental)"
-                                                                                   if getattr(runner, "peer_halo", False) else ", halo over NCCL send/recv")), "l2_policy": "inputs (22 GB particle state) >> 126 MB L2, no flush needed",
-                       "timing": "CUDA events on the library stream, max over ranks",
+            "config": {"workload": workload, "baseline_config": args.config, "particles": n_int, "grid": [args.grid or cfg["grid"]] * 3, "dt": cfg["dt"], "stencil": "cubic (reference)",
+                       "decomposition": f"{world} slab(s) along i" + ("" if world == 1 else (", ghost layers reduced by P2G over peer memory (NVLink), migration pulled through peer mappings"
+                                                                                   if getattr(runner, "peer_halo", False) else ", halo over NCCL send/recv")),
+                       "partition": partition,
+                       "l2_policy": "inputs (particle state, 176 B/particle per buffer) >> 126 MB L2 at configs 2-5, no flush needed; config 1 fits in L2 (launch-bound)",
+                       "timing": "CUDA events on the library stream, one per substep, max over ranks",
                        "kernel_variants": {"p2g": variants[0], "g2p": variants[1]},
-                       "p2g_record_walk": "aligned (MPM_B200_P2G_ROTATE=0)" if os.environ.get("MPM_B200_P2G_ROTATE") == "0" else "rotated (default)"},
+                       "fupdate": "tolerance form inside the P2G kernel (fupdate_exact=0)" if variants[0] == 0 else "tolerance form, own kernel"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
                     "d2h_bytes_per_step": int(16 * n_dl_total), "ms_per_step": e2e_ms,
                     "what": "C-ABI substep with host collider structs in + render buffers (xyz,size) out to pinned host memory, every step",
                     "mode": e2e_mode},
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "invariants": inv, "multi_gpu_check": mcheck, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not inv["ok"] or (mcheck is not None and not mcheck.get("ok", False)):
+        sys.stderr.write("bench.py: conserved quantities or the multi-GPU cross-check do not hold, see `invariants` / `multi_gpu_check`\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -45,6 +45,40 @@ def slab_layers_balanced(layer_counts, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def particle_block_layers(pos, h):
+    """Particle-block layer along i of every particle: ((cell_x - 1) >> 2) with cell_x = int(x / h), the float32 quotient the
+    library forms (material_point_method.cpp:83)."""
+    cx = (np.asarray(pos, np.float32)[:, 0] / np.float32(h)).astype(np.int64)
+    return (cx - 1) >> 2
+
+
+def partition_scene(scene, world):
+    """Split any scene (all particles known to every rank) into `world` slabs of near-equal PARTICLE count (balls are
+    cut at the particle-count median plane, not the geometric middle). Returns (scene re-ordered so that every slab is a
+    contiguous run of particles, [(lo, hi)] block-layer ranges, [(first, last)] particle ranges). The re-ordered scene is
+    also what a single-domain run of the same scene should upload, so that particle ids agree."""
+    grid = scene["dims"][0]
+    n_layers = (grid + 3) // 4
+    lay = particle_block_layers(scene["pos"], scene["h"])
+    order = np.argsort(lay, kind="stable")
+    counts = np.bincount(np.clip(lay, 0, n_layers - 1), minlength=n_layers)
+    layers = slab_layers_balanced(counts, world) if world > 1 else [(0, n_layers)]
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    ranges = [(int(cum[lo]), int(cum[hi])) for lo, hi in layers]
+    out = dict(scene)
+    for k in ("pos", "vel", "mass"):
+        out[k] = np.ascontiguousarray(scene[k][order])
+    return out, layers, ranges
+
+
+def slice_scene(scene, first, last):
+    out = dict(scene)
+    for k in ("pos", "vel", "mass"):
+        out[k] = np.ascontiguousarray(scene[k][first:last])
+    out["n"] = last - first
+    return out
+
+
 def migrate_capacity_for(n_local):
     """Records per migration message wanted by a rank holding n_local particles. A plane of the 8-ppc slab sheds about
     8 * cells_in_plane * |v| dt / h particles per substep (hundreds at avalanche speeds, thousands at 200 m/s); n/512
@@ -81,7 +115,7 @@ class SlabRunner:
     """Owns one rank's slab of the snow-slab scene (BASELINE config 5) and advances it substep by substep."""
 
     def __init__(self, grid, n_particles, rank, world, torch, scene=None, dt=1e-5, variants=(0, 0), sim_factory=None,
-                 device="cuda"):
+                 device="cuda", layers=None, params=None):
         """sim_factory / device exist for the CPU (gloo) tests of this protocol: a stand-in object with capi.Sim's
         pointer-based slab methods and device="cpu"; the product path always uses capi.Sim on "cuda"."""
         self.torch, self.rank, self.world, self.dt = torch, rank, world, float(dt)
@@ -91,7 +125,9 @@ class SlabRunner:
             import torch.distributed as dist
             self.dist = dist
         n_layers = (grid + 3) // 4
-        if scene is None and world > 1:
+        if layers is not None:
+            self.lo, self.hi = layers                 # the caller has partitioned the scene (partition_scene)
+        elif scene is None and world > 1:
             # balance by particle count: the slab scene's per-layer counts are known in closed form
             self.lo, self.hi = slab_layers_balanced(scenes.snow_slab_layer_counts(grid, n_particles), world)[rank]
         else:
@@ -103,7 +139,7 @@ class SlabRunner:
             scene = scenes.snow_slab(grid=grid, n=n_particles, i_range=i_range)
         self.scene = scene
         n = scene["n"]
-        p = capi.default_params(h=float(scene["h"]), p2g_variant=variants[0], g2p_variant=variants[1])
+        p = capi.default_params(h=float(scene["h"]), p2g_variant=variants[0], g2p_variant=variants[1], **(params or {}))
         if "gravity" in scene:
             p.gravity[:] = [float(x) for x in scene["gravity"]]
         self.migrates = world > 1
@@ -152,10 +188,12 @@ class SlabRunner:
         if world > 1:
             self._halo()
         self.sim.computeParticleVolumesAndDensities()
-        # EXPERIMENTAL, opt-in (MPM_B200_PEER_HALO=1, not yet run on hardware): the per-substep ghost-layer reduction done by
-        # P2G itself over NVLink (CUDA IPC mappings of the neighbours' grids, device-side flags) instead of halo messages
+        # The per-substep ghost-layer reduction is done by P2G itself over NVLink (CUDA IPC mappings of the neighbours' grids,
+        # device-side flags) instead of halo messages, and migration is a pull through the neighbours' packed buffers: a substep
+        # issues no NCCL call. Validated on 2 GPUs against one domain (profiles/g2_multi_check_peer_1.log: halo wait 0.103 ->
+        # 0.003 ms per substep). MPM_B200_PEER_HALO=0 restores NCCL send/recv of the dense layer + add kernels.
         import os
-        self.peer_halo = world > 1 and os.environ.get("MPM_B200_PEER_HALO") == "1" and \
+        self.peer_halo = world > 1 and os.environ.get("MPM_B200_PEER_HALO", "1") != "0" and \
             (self.device == "cuda" or os.environ.get("MPM_B200_ALLOW_EMULATION") == "1")     # (tests/emu: shared-memory "IPC")
         if self.peer_halo:
             mine = (self.sim.peer_export(), self.hi - self.lo)
@@ -236,8 +274,8 @@ class SlabRunner:
                 raise capi.MpmError(msg or "a neighbouring rank ran out of migration / slab capacity")
 
     def substep(self, host_colliders=False):
-        if host_colliders:       # e2e arm: the per-frame host inputs are rebuilt and handed over every step
-            self.cols, self.nc = capi.make_colliders(self.scene["w2l"], self.scene["half"], self.scene["cvel"])
+        # (host_colliders: the e2e arm hands the HOST collider structs over on every call -- they are plain C structs in host
+        # memory that the library copies into the launch, 88 B each; they are rebuilt only when a collider moved)
         if self.world == 1:
             self.sim.substep(self.dt, self.cols, self.nc, 1)
             return
@@ -258,3 +296,69 @@ class SlabRunner:
     def live_state(self):
         cap = int(self.sim.stats().n_particles) + 16
         return self.sim.download_live(cap)
+
+
+def _det3(m):           # rows of 9 floats (glm column-major; the determinant does not care)
+    m = np.asarray(m, np.float64).reshape(-1, 3, 3)
+    return np.linalg.det(m)
+
+
+def state_errors(a35, b35):
+    """max-abs differences of positions [m], velocities [m/s] and det(FE FP) between two 35-float state arrays
+    (mass, vel[3], volume, pos[3], FE[9], FP[9], B[9]) of the same particles."""
+    da = _det3(a35[:, 8:17]) * _det3(a35[:, 17:26])
+    db = _det3(b35[:, 8:17]) * _det3(b35[:, 17:26])
+    return (float(np.abs(a35[:, 5:8] - b35[:, 5:8]).max()), float(np.abs(a35[:, 1:4] - b35[:, 1:4]).max()), float(np.abs(da - db).max()))
+
+
+def multi_vs_single_check(torch, rank, world, grid=64, n=262144, steps=30, drive=(150.0, -20.0, 0.0)):
+    """Correctness of the slab decomposition, checked inside the run that reports multi-GPU numbers: a small snow slab driven
+    across the slab boundaries is advanced `steps` substeps on all `world` ranks (same halo / migration path as the timed
+    scene) and, on rank 0, in one domain; particles are matched by id. Tolerance = 4 x the scene's own noise floor (the same
+    single-domain run with the baseline kernels, i.e. another summation order), with absolute minima. Returns a dict on rank 0,
+    None elsewhere."""
+    import torch.distributed as dist
+
+    def make_scene(i_range):
+        sc = scenes.snow_slab(grid=grid, n=n, i_range=i_range)
+        sc["vel"][:] = drive
+        return sc
+
+    n_layers = (grid + 3) // 4
+    lo, hi = slab_layers(n_layers, world)[rank]
+    r = SlabRunner(grid, n, rank, world, torch, scene=make_scene((4 * lo + 1, 4 * hi + 1)))
+    n0 = int(r.sim.stats().n_particles)
+    for _ in range(steps):
+        r.substep()
+    st, pid = r.live_state()
+    inv = r.sim.invariants()
+    gathered = [None] * world
+    dist.gather_object((st, pid, n0, st.shape[0], inv), gathered if rank == 0 else None, dst=0)
+    r.sim.close()
+    if rank != 0:
+        return None
+    S = np.concatenate([g[0] for g in gathered]); P = np.concatenate([g[1] for g in gathered])
+    moved = int(sum(abs(g[2] - g[3]) for g in gathered))
+    one = SlabRunner(grid, n, 0, 1, torch, scene=make_scene(None))
+    for _ in range(steps):
+        one.substep()
+    ref = one.sim.download_state35()
+    one.sim.close()
+    out = {"scene": f"snow slab {grid}^3, {n} particles driven at {drive} m/s across the slab boundaries", "substeps": steps,
+           "ranks": world, "particles": int(len(P)), "unique_ids": int(len(np.unique(P))), "migrated": moved,
+           "count_sum": int(sum(g[4]["count"] for g in gathered))}
+    if len(P) != ref.shape[0] or out["unique_ids"] != len(P):
+        out["ok"] = False
+        return out
+    S = S[np.argsort(P)]
+    e = state_errors(S, ref)
+    alt = SlabRunner(grid, n, 0, 1, torch, scene=make_scene(None), variants=(1, 1))
+    for _ in range(steps):
+        alt.substep()
+    f = state_errors(alt.sim.download_state35(), ref)
+    alt.sim.close()
+    tol = [4 * max(b, c) for b, c in zip(f, (1e-6, 1e-3, 1e-5))]
+    out.update({"max_abs_diff": {"pos": e[0], "vel": e[1], "detF": e[2]}, "noise_floor": {"pos": f[0], "vel": f[1], "detF": f[2]},
+                "tolerance": {"pos": tol[0], "vel": tol[1], "detF": tol[2]},
+                "ok": bool(moved > 0 and all(a <= t for a, t in zip(e, tol)))})
+    return out

@@ -63,48 +63,50 @@ def test_no_kernel_spills_to_local_memory(kernels):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_p2g_tile_kernel_contract(kernels, mode):
-    k = _one(kernels, f"k_p2g_tileILi{mode}ELb0ELb0ELb0E")
+    k = _one(kernels, f"k_p2g_tileILi{mode}ELi0ELb0E")
     assert k["regs"] <= 128, "2 CTAs of 256 threads per SM need <= 128 registers"
     assert _count(k, "REDG.E.ADD.F32x4") == 1, "one vector red.global.add.v4.f32 per tile node"
     assert not any("CAST" in o for o in k["ops"]), "no shared-memory float atomics (ATOMS.CAST.SPIN loops)"
     assert _count(k, "ATOMS") <= 2, "the counting sort uses one round of integer shared atomics (two unrolled particles)"
     assert _count(k, "LDS.128") >= 5 and _count(k, "STS.128") >= 6, "records and fold buffers move as 128-bit accesses"
     assert _count(k, "LDG.E.128") >= (6, 6, 12)[mode], "particle planes are read as float4 (2 particles x 4 / 3 / 6 planes)"
-    assert _count(k, "SHFL.IDX") == 48, "z-fold: 3 rounds x 16 values by warp shuffles"
-    assert _count(k, "BAR.SYNC") <= 8
+    assert _count(k, "SHFL.IDX") >= 48, "z-fold: 3 rounds x 16 values by warp shuffles (+ the warp-local scan look-ups)"
+    assert _count(k, "BAR.SYNC") <= 7
+    assert _count(k, "FFMA2") >= 40, "the accumulation loop runs on packed fp32 pairs"
 
 
-@pytest.mark.parametrize("flags", [4, 14])
-def test_gather_kernel_contract(kernels, flags):
-    k = _one(kernels, f"k_g2p_tileILi{flags}ELb0ELb0")
-    assert k["regs"] <= 128
-    assert _count(k, "UBLKCP") == 8, "the 2x2x2 grid blocks of a tile arrive as eight 1 KB bulk copies (TMA)"
-    assert _count(k, "SYNCS.ARRIVE.TRANS64") == 1 and any("TRYWAIT" in o for o in k["ops"]), "mbarrier expect_tx + try_wait"
-    assert _count(k, "LDS.128") == 64, "64 stencil nodes, one LDS.128 each"
-    assert _count(k, "BAR.SYNC") == 0, "warp-per-block: no CTA barrier"
-    ffma = sum(o == "FFMA" or o.startswith("FFMA.") for o in k["ops"])
-    assert 576 <= ffma <= 700, f"separable gather: 576 FMA per particle in the loop, found {ffma} in the kernel"
+def test_gather_kernel_contract(kernels):
+    for flags in (2, 14, 30):           # staged gather; fused gather + advect + re-sort; + next substep's keys and histogram
+        k = _one(kernels, f"k_g2p_tileILi{flags}EE")
+        assert k["regs"] <= 128
+        assert _count(k, "UBLKCP") == 4, "the tile arrives as 128 row-wise 64-byte bulk copies (TMA), 4 per lane"
+        assert _count(k, "SYNCS.ARRIVE.TRANS64") == 1 and any("TRYWAIT" in o for o in k["ops"]), "mbarrier expect_tx + try_wait"
+        assert _count(k, "LDS.128") == 64, "64 stencil nodes, one LDS.128 [base + immediate] each"
+        assert _count(k, "BAR.SYNC") == 0, "warp-per-block: no CTA barrier"
+        assert _count(k, "FFMA2") >= 200, "separable gather on packed fp32 pairs (252 FFMA2 + 84 FFMA per particle)"
+    assert _count(_one(kernels, "k_g2p_tileILi30EE"), "MATCH.ANY") == 1, "warp-aggregated histogram of next substep's keys"
 
 
 def test_fupdate_kernel_contract(kernels):
-    k = _one(kernels, "k_fupdateILb1ELb0E")
-    assert k["regs"] <= 64, "4 CTAs of 256 threads per SM"
-    assert _count(k, "LDG.E.128") >= 7 and _count(k, "STG.E.128") == 7, "eight planes in, seven planes out, all float4"
-    assert not any(o.startswith(("LDS", "STS", "BAR")) for o in k["ops"])
+    exact, fast = _one(kernels, "k_fupdateILb1ELb0E"), _one(kernels, "k_fupdateILb1ELb1E")
+    for k in (exact, fast):
+        assert k["regs"] <= 64, "4 CTAs of 256 threads per SM"
+        assert _count(k, "LDG.E.128") >= 7 and _count(k, "STG.E.128") == 7, "eight planes in, seven planes out, all float4"
+        assert not any(o.startswith(("LDS", "STS", "BAR")) for o in k["ops"])
+    assert len(fast["ops"]) < 0.5 * len(exact["ops"]), "the tolerance form is less than half the bit-faithful one"
+    assert _count(fast, "MUFU") >= 4, "MUFU reciprocals / square roots instead of IEEE division sequences"
 
 
-def test_packed_variants_use_ffma2(kernels):
-    p2g = _one(kernels, "k_p2g_tileILi2ELb1ELb0ELb0E")
-    g2p = _one(kernels, "k_g2p_tileILi14ELb0ELb1")
-    assert _count(p2g, "FFMA2") >= 40 and _count(g2p, "FFMA2") >= 200
-    fu, fu_pk = _one(kernels, "k_fupdateILb1ELb0E"), _one(kernels, "k_fupdateILb1ELb1E")
-    assert _count(fu_pk, "FMUL2") + _count(fu_pk, "FFMA2") >= 100 and len(fu_pk["ops"]) < 0.9 * len(fu["ops"]) and fu_pk["regs"] <= 64
+def test_fused_substep_p2g_carries_the_f_update(kernels):
+    k = _one(kernels, "k_p2g_tileILi2ELi2ELb0E")
+    assert k["regs"] <= 128 and _count(k, "STG.E.128") >= 7 and _count(k, "REDG.E.ADD.F32x4") == 1
 
 
 def test_peer_halo_p2g_issues_remote_vector_reds(kernels):
-    k = _one(kernels, "k_p2g_tileILi2ELb0ELb0ELb1E")
-    assert _count(k, "REDG.E.ADD.F32x4") == 3, "local copy + the upper / lower neighbour's copy of a shared layer"
-    assert k["regs"] <= 128 and not any("CAST" in o for o in k["ops"])
+    for fu in (0, 1, 2):
+        k = _one(kernels, f"k_p2g_tileILi2ELi{fu}ELb1E")
+        assert _count(k, "REDG.E.ADD.F32x4") == 3, "local copy + the upper / lower neighbour's copy of a shared layer"
+        assert k["regs"] <= 128 and not any("CAST" in o for o in k["ops"])
 
 
 def test_binning_uses_warp_aggregated_atomics(kernels):
