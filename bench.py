@@ -502,7 +502,10 @@ def main():
     ms_median = float(np.median(per_step))
     use_median = args.steps >= 50 and not graph_pairs
     ms_per_step = ms_median if use_median else ms_mean
-    n_int = int(round(n_total))
+    # (n_total summed the ranks' SLOT counts, which include the slots of just-migrated particles until the next re-sort:
+    # the scene's particle count is what the metric and the conserved-quantity check are about)
+    n_int = int(args.particles or cfg["n"])
+    n_total = float(n_int)
     value = n_total / (ms_per_step * 1e-3)
     roof = roofline_block(ms_per_step, n_total, n_active, world, phase_ms, f"config{args.config}",
                           fupd_in_p2g=(variants == (0, 0) and not os.environ.get("MPM_B200_OVERLAP")))

@@ -91,7 +91,8 @@ typedef struct MpmStats {
     int32_t svd_failed;         /* 1 if the last F-update met a non-finite matrix */
     int32_t reserved[7];        /* [0] = 1 if the pos/h shortcut passed its exhaustive check for this h,
                                    [1] = 1 if a migration buffer overflowed (particles kept one more substep),
-                                   [2] = 1 if a peer-memory halo wait gave up (experimental mpm_substep_begin_peer) */
+                                   [2] = 1 if a peer-memory halo wait gave up (mpm_substep_begin_peer): FATAL for the run -- the flag stays set,
+                                       later waits return at once and mpm_sync_counts keeps failing with MPM_ERR_CUDA */
 } MpmStats;
 
 typedef struct mpm_sim mpm_t;

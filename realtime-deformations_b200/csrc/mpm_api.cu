@@ -79,6 +79,7 @@ struct mpm_sim {
     bool tau_valid = false, binned = false;
     bool hist_valid = false;   // key[] and blk_count[] already describe the current buffer (written by the fused substep's gather)
     bool hist_fuse = true;     // MPM_B200_FUSE_HIST=0 restores the separate k_bin_count pass (A/B)
+    bool mig_packed = false;   // slab handles: the gather of the last substep has already packed the leavers into out_buf (fused migration)
     // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
     PeerLayers peer = { nullptr, nullptr };
     int* peer_flags_dn = nullptr; int* peer_flags_up = nullptr;      // the neighbours' flag words (peer-mapped)
@@ -274,6 +275,7 @@ int mpm_create(const MpmParams* params, int max_i, int max_j, int max_k, int64_t
 
 int mpm_destroy(mpm_t* s) {
     if (!s) return MPM_OK;
+    cudaSetDevice(s->device);           // the handle's allocations live on the device it was created on
     cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) { cudaFree(s->buf[b]); cudaFree(s->out_buf[b]); }
     cudaFree(s->key); cudaFree(s->sorted_ids); cudaFree(s->blk_count); cudaFree(s->blk_start); cudaFree(s->blk_cursor);
@@ -295,10 +297,14 @@ int mpm_destroy(mpm_t* s) {
     return MPM_OK;
 }
 
+static void drop_graph(mpm_sim* s) {     // a captured substep pair bakes in the stream, SimConst and the kernel variants
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+}
 int mpm_set_stream(mpm_t* s, void* st) {
-    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    NEED(s);
     CK(cudaStreamSynchronize(s->stream));
     s->stream = st ? (cudaStream_t)st : s->own_stream;
+    drop_graph(s);
     return MPM_OK;
 }
 
@@ -307,6 +313,7 @@ int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
     if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9 and g2p_variant 0 or 1");
     s->prm = *p;
+    drop_graph(s);                  // material constants and kernel variants are baked into a captured substep pair
     const int fast = s->sc.pd.fast;
     fill_consts(s);
     s->sc.pd.fast = fast;           // h is unchanged, so the validation still holds
@@ -332,6 +339,7 @@ static const float ID9[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
 static const float Z9[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
+    NEED(s);
     if (n < 0 || n > s->capacity) return fail(MPM_ERR_CAPACITY, "n = %lld exceeds capacity %lld", (long long)n, (long long)s->capacity);
     if (n > 0 && (!f.pos || !f.vel || !f.mass)) return fail(MPM_ERR_INVALID, "pos, vel and mass are required");
     const int64_t CH = 1 << 20;
@@ -378,6 +386,7 @@ static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
 struct HostFieldPtrsW { char *mass, *vel, *vol, *pos, *FE, *FP, *B; size_t s_mass, s_vel, s_vol, s_pos, s_FE, s_FP, s_B; };
 
 static int download_common(mpm_sim* s, int64_t n, const HostFieldPtrsW& f) {
+    NEED(s);
     if (s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global)
         return fail(MPM_ERR_INVALID, "slab handles exchange particles: use mpm_download_live_particles");
     if (n != s->n_uploaded) return fail(MPM_ERR_INVALID, "download of %lld particles but %lld were uploaded", (long long)n, (long long)s->n_uploaded);
@@ -440,7 +449,7 @@ int mpm_download_particles_soa(mpm_t* s, int64_t n, float* pos, float* vel, floa
 }
 
 int mpm_download_render_buffers(mpm_t* s, int64_t n, float* xyzs, unsigned char* rgba, float size) {
-    if (!s) return fail(MPM_ERR_INVALID, "null handle");
+    NEED(s);
     const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
     if (!slab && n != s->n_uploaded) return fail(MPM_ERR_INVALID, "n mismatch");
     if (slab && (n < 0 || n > s->capacity)) return fail(MPM_ERR_INVALID, "n exceeds the slab capacity");
@@ -595,15 +604,35 @@ static int launch_grid_update(mpm_sim* s, float dt) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
+static int ensure_out_buffers(mpm_sim* s);
+__global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, DevCounters* dc);
 template <int FLAGS>
 static int launch_g2p(mpm_sim* s, float dt) {
     Planes C = s->planes(s->cur), N = s->planes(s->cur ^ 1);
-    // next substep's keys + histogram inside the gather: single-domain handles only (a slab's migration changes the particle
-    // set between the gather and the next binning)
+    // Next substep's keys + histogram are produced inside the gather, where the advected position is in registers. On a slab
+    // handle the same pass packs the particles that left the slab into the migration buffers and retires their slots, so
+    // that the particle set the histogram describes is the one the next binning sees (incoming particles add their own keys
+    // in k_append_incoming_hdr). Not with the side-stream F-update: a packed record needs this substep's planes 4..10.
     const bool slab_handle = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
-    const bool fuse_hist = s->hist_fuse && !slab_handle && s->prm.g2p_variant != 1 && (FLAGS & G2P_REORDER) && (FLAGS & G2P_ADVECT) && (FLAGS & G2P_GATHER);
+    const bool fuse_hist = s->hist_fuse && s->prm.g2p_variant != 1 && !(slab_handle && s->side.stream) &&
+                           (FLAGS & G2P_REORDER) && (FLAGS & G2P_ADVECT) && (FLAGS & G2P_GATHER);
     if ((FLAGS & G2P_ADVECT) && !fuse_hist) s->hist_valid = false;       // positions change without new keys
-    if (fuse_hist) CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
+    MigOut mo = { nullptr, nullptr, 0 };
+    if (fuse_hist) {
+        CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
+        if (slab_handle) {
+            TRY(ensure_out_buffers(s));
+            if (s->peer_mig_connected) {      // the neighbours must have consumed the buffers of the previous substep before they are refilled
+                int* mine = (int*)(s->grid + 64 * (size_t)s->gd.n_gblocks);
+                k_peer_wait<<<1, 1, 0, s->stream>>>(s->gd.lo > 0 ? mine + 6 : nullptr, s->gd.hi < s->gd.npbi_global ? mine + 7 : nullptr, s->peer_mig_epoch, s->dc);
+                CKLAUNCH(); s->stats.kernel_launches++;
+            }
+            for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(s->out_buf[d], 0, sizeof(float4), s->stream));
+            mo.dn = s->gd.lo > 0 ? s->out_buf[0] : nullptr;
+            mo.up = s->gd.hi < s->gd.npbi_global ? s->out_buf[1] : nullptr;
+            mo.cap = (int)s->out_cap;
+        }
+    }
     if (s->prm.g2p_variant == 1 || !(FLAGS & (G2P_GATHER | G2P_F))) {
         k_g2p_direct<FLAGS><<<grid_for(s->n_bound, 128), 128, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->grid, s->gd, s->sc, dt);
         CKLAUNCH();
@@ -611,7 +640,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
         CK((launch_g2p_tile<FLAGS>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt,
                                    s->num_sms, (int)s->n_bound, s->stream, &s->side,
                                    s->prm.fupdate_exact == 2 || ((FLAGS & G2P_REORDER) && s->prm.fupdate_exact == 0),      // tolerance-form F-update: fused substep (or forced)
-                                   fuse_hist ? s->key : nullptr, fuse_hist ? s->blk_count : nullptr)));
+                                   fuse_hist ? s->key : nullptr, fuse_hist ? s->blk_count : nullptr, mo)));
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {
@@ -620,6 +649,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
         s->cur ^= 1;
         s->binned = false;      // sorted_ids referred to the old buffer
         s->hist_valid = fuse_hist;
+        s->mig_packed = fuse_hist && slab_handle;
     }
     return MPM_OK;
 }
@@ -1141,6 +1171,19 @@ int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** 
     NEED(s);
     if (!n_down || !n_up || !dev_down || !dev_up) return fail(MPM_ERR_INVALID, "null argument");
     TRY(ensure_out_buffers(s));
+    if (s->mig_packed) {
+        // the last gather has packed the leavers already (header + records): hand those out, counts from the headers
+        int hdr[2] = { 0, 0 };
+        DevCounters h;
+        for (int d = 0; d < 2; ++d) CK(cudaMemcpyAsync(&hdr[d], s->out_buf[d], sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(&h, s->dc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        *n_down = std::min<int64_t>(hdr[0], s->out_cap); *n_up = std::min<int64_t>(hdr[1], s->out_cap);
+        *dev_down = s->out_buf[0] + 1; *dev_up = s->out_buf[1] + 1;
+        s->n_bound = h.n_slots;
+        s->mig_packed = false; s->binned = false;
+        return MPM_OK;
+    }
     CK(cudaMemsetAsync(s->dc->n_mig, 0, 3 * sizeof(int), s->stream));
     k_mark_outgoing<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
@@ -1150,7 +1193,7 @@ int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** 
     *n_down = h.n_mig[0]; *n_up = h.n_mig[1];
     *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
     s->n_bound = h.n_slots;          // exact after the sync
-    s->binned = false; s->hist_valid = false;
+    s->binned = false; s->hist_valid = false; s->mig_packed = false;
     return MPM_OK;
 }
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
@@ -1187,10 +1230,15 @@ int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up) {
     NEED(s);
     if (!dev_down || !dev_up) return fail(MPM_ERR_INVALID, "null argument");
     TRY(ensure_out_buffers(s));
+    *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
+    if (s->mig_packed) {                // the gather has packed the leavers already (and kept keys + histogram consistent)
+        s->mig_packed = false;
+        s->binned = false;
+        return MPM_OK;
+    }
     for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(s->out_buf[d], 0, sizeof(float4), s->stream));
     k_mark_outgoing_hdr<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
-    *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
     s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
@@ -1199,12 +1247,13 @@ int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
     if (!dev_buf) return fail(MPM_ERR_INVALID, "null buffer");
     TRY(ensure_out_buffers(s));
     const int cap = (int)s->out_cap;
-    k_append_incoming_hdr<<<grid_for(cap, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, cap, (int)s->capacity);
+    k_append_incoming_hdr<<<grid_for(cap, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, cap, (int)s->capacity,
+                                                                   s->gd, s->sc.pd, s->hist_valid ? s->key : nullptr, s->hist_valid ? s->blk_count : nullptr);
     CKLAUNCH();
     k_bump_slots<<<1, 1, 0, s->stream>>>(s->dc, (const float4*)dev_buf, cap, (int)s->capacity);
     CKLAUNCH(); s->stats.kernel_launches += 2;
     s->n_bound = std::min<int64_t>(s->capacity, s->n_bound + cap);      // upper bound; mpm_sync_counts tightens it
-    s->binned = false; s->hist_valid = false;
+    s->binned = false;          // (keys + histogram stay valid: the appended particles have added theirs)
     return MPM_OK;
 }
 // EXPERIMENTAL peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own
@@ -1247,8 +1296,10 @@ int mpm_migrate_peer(mpm_t* s, int phase) {
     const bool has_dn = s->gd.lo > 0, has_up = s->gd.hi < s->gd.npbi_global;
     if (phase == 0) {
         ++s->peer_mig_epoch;
-        k_peer_wait<<<1, 1, 0, s->stream>>>(has_dn ? mine + 6 : nullptr, has_up ? mine + 7 : nullptr, s->peer_mig_epoch - 1, s->dc);
-        CKLAUNCH(); s->stats.kernel_launches++;
+        if (!s->mig_packed) {           // (a gather that packed the leavers has waited for "consumed" itself, before refilling the buffers)
+            k_peer_wait<<<1, 1, 0, s->stream>>>(has_dn ? mine + 6 : nullptr, has_up ? mine + 7 : nullptr, s->peer_mig_epoch - 1, s->dc);
+            CKLAUNCH(); s->stats.kernel_launches++;
+        }
         const void *d0, *d1;
         TRY(mpm_migrate_pack(s, &d0, &d1));
         k_peer_signal<<<1, 1, 0, s->stream>>>(has_dn ? s->peer_flags_dn + 5 : nullptr, has_up ? s->peer_flags_up + 4 : nullptr, s->peer_mig_epoch);

@@ -95,6 +95,25 @@ MPM_DI int particle_key(float4 xm, const GridDims& gd, const PosDiv& pd, int* ce
     return ((pbi - gd.lo) * gd.npbj + pbj) * gd.npbk + pbk;
 }
 
+// Slab migration fused into the re-sorting gather: a particle whose new block layer left [lo, hi) (key n_pblocks+1 / +2) is
+// appended to the packed buffer for that neighbour -- one float4 header whose first int is the record count (it IS the atomic
+// cursor, so the receiver learns the count on the device), then 11 float4 per record -- and its slot is retired (m < 0,
+// key KEY_DEAD). If the buffer is full the particle simply stays (alive, in its "leaving" bucket, frozen like a parked one)
+// and is offered again by the next substep's k_copy_parked.
+struct MigOut { float4* dn; float4* up; int cap; };
+MPM_DI bool mig_try_pack(const MigOut& mo, bool upward, const Planes& D, int q, DevCounters* dc) {
+    float4* buf = upward ? mo.up : mo.dn;
+    if (!buf) return false;
+    const int idx = atomicAdd(reinterpret_cast<int*>(buf), 1);
+    if (idx >= mo.cap) { dc->mig_overflow = 1; return false; }      // header count may exceed cap; the receiver clamps it
+    float4* o = buf + 1 + (size_t)idx * NPLANES;
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) o[k] = D.p[k][q];
+    const float4 a0 = D.p[0][q];
+    D.p[0][q] = make_float4(a0.x, a0.y, a0.z, -1.0f);               // dead slot: skipped by the binning, dropped by the next re-sort
+    return true;
+}
+
 // Both binning kernels handle BIN_E elements per thread (warp-coalesced, stride = blockDim) so that several
 // position loads / atomic round trips are in flight per thread: they are latency-bound, not bandwidth-bound.
 constexpr int BIN_E = 4, BIN_T = 256;
@@ -239,7 +258,10 @@ __global__ void k_scan_apply(const int* __restrict__ blk_count, int n, int n_rea
         if (i < n) {
             blk_start[i] = ex.x; blk_cursor[i] = ex.x;
             if (i == n_real) dc->n_binned = ex.x;                 // start of the parked bucket
-            if (i == n_real + 1) dc->n_sorted = ex.x;             // end of the parked bucket
+            // what a re-sort keeps besides the binned particles: parked ones AND the two "leaving the slab" buckets. The latter
+            // are empty unless a migration buffer overflowed (k_mark_outgoing*: such a leaver stays alive here one more
+            // substep, frozen like a parked particle, and is offered to the neighbour again after the next gather)
+            if (i == n_real + 2) dc->n_sorted = ex.x + c[e];
             if (c[e] > 0 && i < n_real) {
                 const int pbk = i % gd.npbk, pbj = (i / gd.npbk) % gd.npbj, pbi = i / (gd.npbk * gd.npbj);
                 // work item: (block id, first sorted rank, count, slab-local block coordinates) -- the tile kernels read the
@@ -735,7 +757,8 @@ __global__ void k_mark_outgoing_hdr(Planes cur, DevCounters* dc, GridDims gd, Po
     for (int q = 0; q < NPLANES; ++q) o[q] = cur.p[q][p];
     cur.p[0][p] = make_float4(a0.x, a0.y, a0.z, -1.0f);
 }
-__global__ void k_append_incoming_hdr(Planes cur, const DevCounters* __restrict__ dc, const float4* __restrict__ in, int cap, int capacity) {
+__global__ void k_append_incoming_hdr(Planes cur, const DevCounters* __restrict__ dc, const float4* __restrict__ in, int cap, int capacity,
+                                      GridDims gd, PosDiv pd, int* __restrict__ key_out, int* __restrict__ blk_count) {
     const int n = min(*reinterpret_cast<const int*>(in), cap);
     const int base = dc->n_slots;          // advanced by k_bump_slots after this kernel
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -743,6 +766,12 @@ __global__ void k_append_incoming_hdr(Planes cur, const DevCounters* __restrict_
     const float4* r = in + 1 + (size_t)i * NPLANES;
 #pragma unroll
     for (int q = 0; q < NPLANES; ++q) cur.p[q][base + i] = r[q];
+    if (key_out) {                          // keep the gather's keys + histogram of the current buffer complete (fused binning)
+        int cells[3];
+        const int k = particle_key(r[0], gd, pd, cells);
+        key_out[base + i] = k;
+        if (k >= 0) atomicAdd(&blk_count[k], 1);
+    }
 }
 __global__ void k_bump_slots(DevCounters* dc, const float4* __restrict__ in, int cap, int capacity) {
     const int n = min(*reinterpret_cast<const int*>(in), cap);

@@ -397,7 +397,8 @@ struct G2PSmem {
 template <int FLAGS>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
-           const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr) {
+           const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr,
+           MigOut mo = MigOut{ nullptr, nullptr, 0 }) {
     MPM_DYN_SMEM(g2p_smem_raw, 128);
     G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -451,7 +452,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
             p = p_nn;
             a0 = (p >= 0) ? cur.p[0][p] : make_float4(0.f, 0.f, 0.f, 0.f);
             p_nn = (base + 64 + lane < cnt) ? sorted_ids[j + 64] : -1;
-            float4 xm_new = make_float4(0.f, 0.f, 0.f, -1.f);      // (G2P_HIST) the advected position, for next substep's key
+            int key_new = KEY_DEAD;                                 // (G2P_HIST) block key of the advected position
             if (active) {
                 struct { float x[3], m, v[3], B[9]; } r;     // the gather touches only x (in) and x, v, B (out)
                 r.x[0] = a_cur.x; r.x[1] = a_cur.y; r.x[2] = a_cur.z; r.m = a_cur.w;
@@ -514,19 +515,23 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 const Planes& D = (FLAGS & G2P_REORDER) ? nxt : cur;
                 const int q = (FLAGS & G2P_REORDER) ? j : p_cur;
                 if (FLAGS & (G2P_ADVECT | G2P_REORDER)) D.p[0][q] = make_float4(r.x[0], r.x[1], r.x[2], r.m);
-                xm_new = make_float4(r.x[0], r.x[1], r.x[2], r.m);
                 D.p[1][q] = make_float4(r.B[0], r.B[1], r.B[2], r.B[3]);
                 D.p[2][q] = make_float4(r.B[4], r.B[5], r.B[6], r.B[7]);
                 D.p[3][q] = make_float4(r.B[8], r.v[0], r.v[1], r.v[2]);
+                if (FLAGS & G2P_HIST) {
+                    // next substep's binning, first half, done here where the new position is in registers: block key of slot j
+                    // of the re-sorted buffer (what k_bin_count would re-read P0 for); a particle that left the slab goes
+                    // straight into the packed migration buffer (planes 4..10 of this slot were written by the F-update earlier
+                    // in the substep) and retires its slot
+                    int cells[3];
+                    key_new = particle_key(make_float4(r.x[0], r.x[1], r.x[2], r.m), gd, sc.pd, cells);
+                    if (key_new > gd.n_pblocks && mig_try_pack(mo, key_new == gd.n_pblocks + 2, D, q, dc)) key_new = KEY_DEAD;
+                    key_out[j] = key_new;
+                }
             }
-            if (FLAGS & G2P_HIST) {
-                // next substep's binning, first half, done here where the new position is in registers: block key of slot j of
-                // the re-sorted buffer + warp-aggregated histogram (what k_bin_count would re-read P0 for)
-                int cells[3];
-                const int k = active ? particle_key(xm_new, gd, sc.pd, cells) : KEY_DEAD;
-                if (active) key_out[j] = k;
-                const unsigned peers = __match_any_sync(0xffffffffu, k);
-                if (k >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&blk_count[k], __popc(peers));
+            if (FLAGS & G2P_HIST) {        // warp-aggregated histogram of the new keys
+                const unsigned peers = __match_any_sync(0xffffffffu, key_new);
+                if (key_new >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&blk_count[key_new], __popc(peers));
             }
         }
         __syncwarp();     // every lane is done with the tile before the next bulk copy overwrites it
@@ -534,14 +539,22 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
 }
 
 // parked (out-of-grid) particles ride along unchanged through a re-sorting G2P
-__global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const DevCounters* __restrict__ dc,
-                              int parked_key, int* __restrict__ key_out, int* __restrict__ blk_count) {
+__global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc,
+                              GridDims gd, PosDiv pd, int* __restrict__ key_out, int* __restrict__ blk_count, MigOut mo) {
     const int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dc->n_sorted) return;
     const int p = sorted_ids[j];
 #pragma unroll
     for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
-    if (key_out) { key_out[j] = parked_key; atomicAdd(&blk_count[parked_key], 1); }      // (fused histogram) still parked next substep
+    if (key_out) {
+        // (fused binning) these particles did not move: parked ones stay parked; a leaver that found the migration buffer full
+        // last substep is offered to the neighbour again
+        int cells[3];
+        int k = particle_key(nxt.p[0][j], gd, pd, cells);
+        if (k > gd.n_pblocks && mig_try_pack(mo, k == gd.n_pblocks + 2, nxt, j, dc)) k = KEY_DEAD;
+        key_out[j] = k;
+        if (k >= 0) atomicAdd(&blk_count[k], 1);
+    }
 }
 
 #if !defined(MPM_HOST_EMU) || defined(MPM_HOST_EMU_API)        // host launch code (nvcc; or the whole-library emulation build of tests/emu)
@@ -583,7 +596,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; int gather_ctas
 template <int FLAGS>
 cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, const float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
-                            SideStream* side, bool fupd_fast = false, int* key_out = nullptr, int* blk_count = nullptr) {
+                            SideStream* side, bool fupd_fast = false, int* key_out = nullptr, int* blk_count = nullptr, MigOut mo = MigOut{ nullptr, nullptr, 0 }) {
     cudaError_t e = cudaMemsetAsync(&dc->work_b, 0, sizeof(int), st);
     if (side) side->mid_recorded = false;
     if (e != cudaSuccess) return e;
@@ -609,7 +622,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
         constexpr int GF = FLAGS & ~G2P_F;
         constexpr bool CAN_HIST = (GF & G2P_REORDER) != 0 && (GF & G2P_ADVECT) != 0;       // the fused substep's gather
-#define MPM_G2P_LAUNCH(F) k_g2p_tile<F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count)
+#define MPM_G2P_LAUNCH(F) k_g2p_tile<F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count, mo)
         if (CAN_HIST && key_out) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0));
         else MPM_G2P_LAUNCH(GF);
 #undef MPM_G2P_LAUNCH
@@ -620,7 +633,7 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
     }
     if (FLAGS & G2P_REORDER) {
-        k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc, gd.n_pblocks, key_out, blk_count);     // parked particles are few; 16 K slots per launch wave
+        k_copy_parked<<<64, 256, 0, st>>>(C, N, sorted_ids, dc, gd, sc.pd, key_out, blk_count, mo);     // parked particles are few; 16 K slots per launch wave
         e = cudaGetLastError();
     }
     return e;

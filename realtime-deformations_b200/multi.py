@@ -186,6 +186,8 @@ class SlabRunner:
         # start-up of the reference (main.cpp:53-54): one P2G for the particle volumes; needs the halo as well
         self.sim.rasterizeParticlesToGrid()
         if world > 1:
+            # (the staged rasterisation has already normalised the shared layers' velocities; adding them is meaningless, but
+            # computeParticleVolumesAndDensities reads the MASS channel only, which is a plain sum -- cpp:131-142)
             self._halo()
         self.sim.computeParticleVolumesAndDensities()
         # The per-substep ghost-layer reduction is done by P2G itself over NVLink (CUDA IPC mappings of the neighbours' grids,
@@ -291,7 +293,7 @@ class SlabRunner:
 
     def download_positions(self, pinned_xyzs):
         n = min(pinned_xyzs.shape[0], int(self.sim.stats().n_particles))
-        self.sim.L.mpm_download_render_buffers(self.sim.h, n, pinned_xyzs.numpy().ctypes.data, None, 0.02)
+        capi._ck(self.sim.L.mpm_download_render_buffers(self.sim.h, n, pinned_xyzs.numpy().ctypes.data, None, 0.02))
 
     def live_state(self):
         cap = int(self.sim.stats().n_particles) + 16

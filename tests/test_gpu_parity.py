@@ -687,6 +687,35 @@ def test_slab_scene_properties_small():
     _slab_properties(32, 8192)
 
 
+def test_migration_overflow_keeps_every_particle():
+    """A slab whose migration buffer is far too small (8 records) while hundreds of particles leave it per substep: the
+    leavers that do not fit must stay alive on the handle (frozen, like parked particles) and be offered again after the next
+    gather -- live particles + migrated particles == uploaded particles after every substep, and the overflow is reported
+    (MpmStats.reserved[1]). Before the fix the re-sort dropped them (n_sorted ended at the parked bucket)."""
+    grid = 32
+    sc = mpm_b200.scenes.snow_slab(grid=grid, n=1 << 14)
+    sc["vel"][:] = (200.0, 0.0, 0.0)                     # towards +i: across the slab boundary at block layer 4
+    lay = ((sc["pos"][:, 0] / np.float32(sc["h"])).astype(np.int64) - 1) >> 2
+    sel = lay < 4
+    n = int(sel.sum())
+    p = mpm_b200.capi.default_params(h=float(sc["h"]))
+    sim = mpm_b200.Sim(grid, grid, grid, n, p, slab=(0, 4), capacity=n + 64)
+    sim.set_migrate_capacity(8)
+    sim.upload(sc["pos"][sel], sc["vel"][sel], sc["mass"][sel])
+    sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
+    cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
+    migrated, overflowed = 0, False
+    for step in range(40):
+        sim.substep_begin(float(sc["dt"])); sim.substep_end(float(sc["dt"]), cols, nc)
+        nd, nu, _, _ = sim.migrate_outgoing()
+        assert nd == 0 and 0 <= nu <= 8
+        migrated += nu
+        overflowed = overflowed or sim.stats().reserved[1] == 1
+        live = sim.invariants()["count"]
+        assert live + migrated == n, f"substep {step}: {live} live + {migrated} migrated != {n} uploaded"
+    assert overflowed and migrated > 0, "the scene must overflow the 8-record buffer"
+
+
 def test_full_size_properties_config5_slab():
     """BASELINE config 5 at full size: 64 Mi particles, 512^3 (the scene bench.py times)."""
     _slab_properties(512, 1 << 26)
