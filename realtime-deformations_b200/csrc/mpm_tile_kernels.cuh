@@ -186,6 +186,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     S.u.c.order[slot] = (unsigned short)q;
                     // keep the block's segment of sorted_ids (approximately) cell-ordered: the G2P lanes of a warp then share
                     // cells (smem broadcasts) and the re-sorted particle buffer stays cell-coherent for the next substep
+                    // (measured, profiles/r2_experiments.md: on cell-coherent order the rewrite costs nothing, on a shuffled upload
+                    // the gather runs 2.2x slower without it -- so it stays on in every substep. Moving the F-update into this
+                    // derive phase, which needs the ids left alone, was tried and was SLOWER: 5.32 vs 5.09 ms at 64 Mi.)
                     sorted_ids[start + ck + slot * n_chunks] = gids[u];
                 }
             }

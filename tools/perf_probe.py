@@ -27,6 +27,9 @@ def run(grid, n, steps, pv, gv, scene="slab", rotate=None):
     p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv, fupdate_exact=fx)
     if "gravity" in sc: p.gravity[:] = [float(x) for x in sc["gravity"]]
     sim = mpm_b200.Sim(grid, grid, grid, sc["n"], p)
+    if os.environ.get("MPM_PROBE_SHUFFLE") == "1":          # worst case for everything that relies on cell-coherent particle order
+        perm = np.random.default_rng(1).permutation(sc["n"])
+        sc = dict(sc, pos=sc["pos"][perm], vel=sc["vel"][perm], mass=sc["mass"][perm])
     t0 = time.time(); sim.upload(sc["pos"], sc["vel"], sc["mass"]); tu = time.time() - t0
     sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
     cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
