@@ -131,14 +131,15 @@ def stiff_snowball(grid=256, n=1 << 22, h=0.05, dt=2.5e-6, seed=SEED, gap_cells=
     return _scene(pos[:n], (0.0, -200.0, 0.0), dims, h, dt, [ground_collider(top, dims, h)], name=f"stiff_snowball_{grid}")
 
 
-def snowball_collision(grid=256, n=1 << 23, h=0.05, dt=1e-5, seed=SEED):
-    """Config 3: two snowballs colliding head-on along i, no ground."""
+def snowball_collision(grid=256, n=1 << 23, h=0.05, dt=1e-5, seed=SEED, gap_cells=3.6):
+    """Config 3: two snowballs colliding head-on along i, no ground. gap_cells = initial surface gap (3.6 cells: first contact
+    after ~90 substeps at 2 x 100 m/s; tests that must reach the contact inside a short window pass a smaller gap)."""
     dims = (grid, grid, grid)
     L = grid * h
     half_n = n // 2
     r_cells = (half_n / 8.0 * 3.0 / (4.0 * np.pi)) ** (1.0 / 3.0)
     radius = r_cells * h * 1.004
-    gap = 3.6 * h
+    gap = gap_cells * h
     c1 = (0.5 * L - radius - gap / 2, 0.5 * L, 0.5 * L)
     c2 = (0.5 * L + radius + gap / 2, 0.5 * L, 0.5 * L)
     while True:

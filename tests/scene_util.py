@@ -12,12 +12,12 @@ if os.environ.get("MPM_TEST_EXPERIMENTAL") == "1":
 TILE_VARIANTS = [v for v in VARIANTS if v != (1, 1)]     # the tile kernels only (edge cases of block occupancy)
 
 
-def oracle_from_scene(sc, fma=False, **prm):
+def oracle_from_scene(sc, fma=False, threads=1, **prm):
     I, J, K = sc["dims"]
     p = op.default_params(h=float(sc["h"]), **prm)
     if "gravity" in sc and "gravity" not in prm:
         p.gravity[:] = [float(x) for x in sc["gravity"]]
-    o = op.Oracle(I, J, K, sc["n"], p, fma=fma)
+    o = op.Oracle(I, J, K, sc["n"], p, threads=threads, fma=fma)
     s = op.initial_state(sc["pos"], sc["vel"], sc["mass"])
     o.set_state(s)
     o.rasterize(); o.volumes()

@@ -8,7 +8,7 @@ import pytest
 
 import mpm_b200
 import oracle_py as op
-from helpers import assert_bit_exact, assert_traj_close, assert_traj_close_calibrated, full_grid, traj_errors
+from helpers import assert_bit_exact, assert_traj_close, assert_traj_close_calibrated, det_F, full_grid, traj_errors
 from scene_util import TILE_VARIANTS, VARIANTS, gpu_colliders_from_ref_dump, oracle_from_scene, sim_from_scene, sim_from_state35
 
 pytestmark = pytest.mark.gpu
@@ -169,12 +169,12 @@ def test_default_scene_trajectory_vs_reference(golden_c1, variants):
     cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
     sim = sim_from_state35(g["state0"], (20, 20, 20), variants)
     done = 0
-    for n in (1, 20, 100, 200):
+    for n in (1, 20, 100, 200, 400):          # every trajectory point the unmodified reference dumped
         sim.substep(float(g["dt"]), cols, nc, n - done)
         done = n
         assert_traj_close(sim.download_state35(), g[f"state{n}"], max(n, 20), f"fused CUDA path {variants} vs reference")
     st = sim.stats()
-    assert st.svd_failed == 0 and st.substeps_done == 200 and st.n_particles == g["state0"].shape[0]
+    assert st.svd_failed == 0 and st.substeps_done == 400 and st.n_particles == g["state0"].shape[0]
 
 
 def test_staged_and_fused_paths_agree(golden_c1):
@@ -222,6 +222,80 @@ def test_synthetic_ball_vs_oracle(variants):
         of.substep(float(sc["dt"]), ocols, onc, n)
         sim.substep(float(sc["dt"]), cols, nc, n)
         assert_traj_close_calibrated(sim.download_state35(), o.state(), of.state(), f"CUDA {variants} vs oracle, synthetic ball")
+
+
+# Tolerance of the at-size tests, in units of the scene's own noise floor (max-abs and mean-abs of oracle vs oracle + FMA
+# contraction at the same step): 4 with the bit-faithful F-update -- whose arithmetic IS the oracle's, so only the scatter /
+# gather sums differ -- and 6 with the fused path's default tolerance-form F-update, which perturbs every stage like the FMA
+# build does but with 2-ulp MUFU reciprocals on top. Measured (tools/fupdate_mode_errors.py, profiles/r2_fupdate_modes.log):
+# 1.0-2.8 x the floor in general, 4.1-4.3 x for det F in the first substeps after an impact, 1.0-2.0 x for the bit-faithful form.
+AT_SIZE_FACTOR = {0: 6.0, 1: 4.0}
+
+
+def _at_size_vs_oracle(sc, steps_list, what, fupdate_exact=0, **prm):
+    """A benchmark configuration (or a 1/8-size member of its scene family) against the CPU oracle itself, not against the
+    CUDA path's own baseline kernels: the OpenMP oracle on all host cores, tolerance AT_SIZE_FACTOR x the scene's noise floor."""
+    import os as _os
+    th = min(_os.cpu_count() or 1, 32)
+    o, ocols, onc = oracle_from_scene(sc, threads=th, **prm)
+    of, _, _ = oracle_from_scene(sc, fma=True, threads=th, **prm)
+    gp = {{"xi": "hardening_xi"}.get(k, k): v for k, v in prm.items()}
+    sim, cols, nc = sim_from_scene(sc, fupdate_exact=fupdate_exact, **gp)
+    close_sum(sim.download_state35()[:, 4], o.state()[:, 4], f"{what}: initial volumes")
+    for n in steps_list:
+        o.substep(float(sc["dt"]), ocols, onc, n)
+        of.substep(float(sc["dt"]), ocols, onc, n)
+        sim.substep(float(sc["dt"]), cols, nc, n)
+        assert_traj_close_calibrated(sim.download_state35(), o.state(), of.state(), f"{what} (fupdate_exact={fupdate_exact})", factor=AT_SIZE_FACTOR[fupdate_exact])
+    st = sim.stats()
+    assert st.svd_failed == 0 and st.n_particles == sc["n"] and st.n_out_of_grid == 0
+    return sim, o
+
+
+def test_config2_full_size_vs_oracle():
+    """BASELINE config 2 at FULL size (1 Mi particles, 128^3) against the oracle: 12 substeps of free fall."""
+    _at_size_vs_oracle(mpm_b200.scenes.snowball_drop(grid=128, n=1 << 20), (4, 8), "config 2 (1 Mi, 128^3) CUDA vs oracle")
+
+
+@pytest.mark.parametrize("fupdate_exact", [0, 1])
+def test_config2_family_through_contact_vs_oracle(fupdate_exact):
+    """The config-2 scene family at 1/8 size with the ball started a quarter cell above the ground box, so that impact,
+    collision and plastic clamping happen inside the compared window (the full-size ball needs ~100 substeps of free fall)."""
+    sc = mpm_b200.scenes.stiff_snowball(grid=64, n=1 << 17, dt=1e-5, gap_cells=0.25)
+    sim, o = _at_size_vs_oracle(sc, (10, 20), "config 2 family (128 Ki, 64^3, through contact) CUDA vs oracle", fupdate_exact=fupdate_exact)
+    assert np.abs(det_F(o.state()) - 1.0).max() > 1e-3, "the window must include compression"
+
+
+def test_config3_eighth_vs_oracle():
+    """BASELINE config 3 (two-snowball collision) at 1/8 size (1 Mi particles, 128^3), surface gap 0.4 cells so that the balls
+    meet after ~10 substeps and the compared window holds the collision."""
+    sc = mpm_b200.scenes.snowball_collision(grid=128, n=1 << 20, gap_cells=0.4)
+    sim, o = _at_size_vs_oracle(sc, (10, 14), "config 3 (1/8: 1 Mi, 128^3) CUDA vs oracle")
+    assert np.abs(det_F(o.state()) - 1.0).max() > 1e-3, "the window must include the collision"
+
+
+def test_config4_eighth_vs_oracle():
+    """BASELINE config 4 (stiff snow, dt = 2.5e-6) at 1/8 size (512 Ki particles, 128^3), stiffest sweep point, through contact."""
+    sc = mpm_b200.scenes.stiff_snowball(grid=128, n=1 << 19)
+    _at_size_vs_oracle(sc, (20, 20), "config 4 (1/8: 512 Ki, 128^3, xi=20) CUDA vs oracle", xi=20.0, theta_c=1.5e-2, theta_s=7.5e-3)
+
+
+def test_invariants_reduction_matches_download(golden_c1):
+    """mpm_reduce_invariants (bench.py's conserved-quantity check) against the same sums formed on the host from a download."""
+    g = golden_c1
+    cols, nc = gpu_colliders_from_ref_dump(g["colliders"])
+    sim = sim_from_state35(g["state0"], (20, 20, 20))
+    sim.substep(float(g["dt"]), cols, nc, 30)
+    inv, s = sim.invariants(), sim.download_state35().astype(np.float64)
+    n = s.shape[0]
+    assert inv["count"] == n and inv["id_sum"] == n * (n - 1) // 2
+    assert abs(inv["mass"] - s[:, 0].sum()) <= 1e-12 * s[:, 0].sum()
+    mom = (s[:, 0:1] * s[:, 1:4]).sum(0)
+    assert np.allclose(inv["momentum"], mom, rtol=1e-9, atol=1e-12)
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    assert (inv["id_sum"], inv["id_hash"]) == bench.expected_id_sums(n)
 
 
 def test_material_sweep_vs_oracle():
