@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 #include <algorithm>
@@ -141,12 +142,39 @@ void LagrangeEulerView::gridBasedCollisions(ftype timeDelta, const std::vector<M
 void LagrangeEulerView::updateDeformationGradient(ftype timeDelta) { check(mpm_update_deformation_gradient(binding(this).sim, timeDelta), "updateDeformationGradient"); }
 void LagrangeEulerView::updateParticleVelocities() { check(mpm_update_particle_velocities(binding(this).sim), "updateParticleVelocities"); }
 
+// What is mirrored into the host std::vector<Particle> after every substep. getParticles() is an inline accessor of the
+// reference's header (hpp:181-183), so the adapter cannot know which fields its caller reads:
+//   full   (default)  all 35 floats per particle -- every observable of the reference class stays current (what the
+//                     golden-trajectory test of this adapter compares);
+//   render            MPM_B200_ADAPTER_MIRROR=render: only what the viewer reads each frame, pos (main.cpp:257-271; size and
+//                     rgba never change) -- 16 B instead of 140 B per particle over PCIe, through the library's pinned
+//                     render-buffer path. A caller that then wants everything calls mpm_b200_adapter_sync_full(view).
+static bool mirror_render_only() {
+    static const bool v = [] { const char* e = std::getenv("MPM_B200_ADAPTER_MIRROR"); return e && std::string(e) == "render"; }();
+    return v;
+}
 void LagrangeEulerView::updateParticlePositions(ftype timeDelta) {
     Binding& b = binding(this);
     check(mpm_update_particle_positions(b.sim, timeDelta), "updateParticlePositions");
     // getParticles() hands the viewer a pointer into `particles` (hpp:181-183, main.cpp:257-271): mirror the state
+    if (mirror_render_only()) {
+        static thread_local std::vector<float> xyzs;
+        xyzs.resize(4 * (size_t)std::max(nParticles, 1));
+        check(mpm_download_render_buffers(b.sim, nParticles, xyzs.data(), nullptr, 0.02f), "mpm_download_render_buffers");
+        for (int k = 0; k < nParticles; ++k) particles[k].pos = { xyzs[4 * (size_t)k], xyzs[4 * (size_t)k + 1], xyzs[4 * (size_t)k + 2] };
+        return;
+    }
     check(mpm_download_particles_aos(b.sim, particles.data(), nParticles, sizeof(Particle), OFF_MASS, OFF_VEL, OFF_VOL, OFF_POS, OFF_FE,
                                      OFF_FP, OFF_B), "mpm_download_particles_aos");
 }
 
 }  // namespace MaterialPointMethod
+
+// explicit full mirror for callers that run with MPM_B200_ADAPTER_MIRROR=render (declared by the caller as
+// `extern "C" void mpm_b200_adapter_sync_full(MaterialPointMethod::LagrangeEulerView*);`)
+extern "C" void mpm_b200_adapter_sync_full(MaterialPointMethod::LagrangeEulerView* v) {
+    using namespace MaterialPointMethod;
+    Binding& b = binding(v);
+    check(mpm_download_particles_aos(b.sim, v->getParticles(), v->getNumParticles(), sizeof(Particle), OFF_MASS, OFF_VEL, OFF_VOL, OFF_POS,
+                                     OFF_FE, OFF_FP, OFF_B), "mpm_b200_adapter_sync_full");
+}

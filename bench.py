@@ -214,6 +214,49 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def adapter_e2e(mpm_b200, config, steps):
+    """End-to-end time of the ZERO-CHANGE drop-in: the reference's own headless driver loop (oracle/ref_driver.cpp = main.cpp:192-218,
+    one call per stage) linked against adapter/lagrange_euler_view_b200.cpp instead of material_point_method.cpp, with host
+    std::vector<Particle> mirrored after every substep -- all 35 floats (default) or only what the viewer reads
+    (MPM_B200_ADAPTER_MIRROR=render) -- next to the unmodified reference binary on the same scene where its class can allocate it."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "adapter_mpm")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_mpm")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp()
+    if config == 1:
+        scene_args, n, what = [], 2147, "reference default scene (rand() fill, 2147 particles, 20^3)"
+    else:
+        sc = mpm_b200.scenes.snowball_drop(grid=128, n=1 << 20)
+        np.concatenate([sc["pos"], sc["vel"], sc["mass"][:, None]], 1).astype(np.float32).tofile(d + "/p.f32")
+        t = -sc["w2l"][0][12:15]
+        np.array([t[0], t[1], t[2], 0.0, *sc["half"][0]], np.float32).tofile(d + "/c.f32")
+        scene_args = ["--grid", "128", "128", "128", "--n", str(sc["n"]), "--load", d + "/p.f32", "--colliders", d + "/c.f32"]
+        n, what = sc["n"], "snowball_drop_128 (1 Mi particles, 128^3)"
+
+    def run(binary, env_extra):
+        r = subprocess.run([binary] + scene_args + ["--steps", str(steps), "--quiet", "--bench"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                           text=True, env=dict(os.environ, **env_extra), timeout=600)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)["seconds"]
+        raise RuntimeError(r.stdout[-300:])
+    out = {"scene": what, "substeps": steps, "unit": UNIT, "what": "reference driver loop + adapter (staged C-ABI calls) + host Particle mirror per substep"}
+    for mode in ("full", "render"):
+        try:
+            sec = run(exe, {"MPM_B200_ADAPTER_MIRROR": mode})
+            out[f"mirror_{mode}"] = {"ms_per_substep": sec * 1e3 / steps, "value": n * steps / sec}
+        except Exception as exc:
+            out[f"mirror_{mode}"] = {"error": str(exc)}
+    if config == 1 and os.path.exists(ref):
+        try:
+            sec = run(ref, {"CUDA_VISIBLE_DEVICES": ""})
+            out["unmodified_reference"] = {"ms_per_substep": sec * 1e3 / steps, "value": n * steps / sec, "cores": 1}
+        except Exception as exc:
+            out["unmodified_reference"] = {"error": str(exc)}
+    return out
+
+
 def csrc_sha16():
     """Identity of the kernel sources a profiler capture belongs to (profiles/traffic.json carries the same hash)."""
     import hashlib
@@ -531,6 +574,13 @@ def main():
             cpu = cpu_baseline(mpm_b200, config=args.config)
         except Exception as exc:      # the GPU measurement above must not be lost to a failing CPU arm
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"cpu baseline failed: {exc}"}
+    e2e_adapter = None
+    if world == 1 and args.config in (1, 2) and not args.no_cpu_baseline:
+        try:
+            runner.sim.close()           # the adapter's own process creates its handle on the same GPU
+            e2e_adapter = adapter_e2e(mpm_b200, args.config, 400 if args.config == 1 else 40)
+        except Exception as exc:
+            e2e_adapter = {"error": str(exc)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_step_mean": ms_mean, "ms_per_step_median": ms_median,
             "ms_per_step_min_max": [float(min(per_step)), float(max(per_step))],
@@ -550,6 +600,7 @@ def main():
                     "d2h_bytes_per_step": int(16 * n_dl_total), "ms_per_step": e2e_ms,
                     "what": "C-ABI substep with host collider structs in + render buffers (xyz,size) out to pinned host memory, every step",
                     "mode": e2e_mode},
+            "e2e_adapter": e2e_adapter,
             "roofline": roof, "invariants": inv, "multi_gpu_check": mcheck, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
