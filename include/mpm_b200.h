@@ -55,7 +55,10 @@ typedef struct MpmParams {
                              held to 4x the reference's own FMA-contraction noise floor by the trajectory tests),
                              1 = the bit-faithful form everywhere, 2 = the tolerance form everywhere (tests). With 0 the staged
                              mpm_update_deformation_gradient stays bit-faithful. */
-    int   reserved[5];
+    int   stencil;        /* 0 = cubic B-spline, the reference's (hpp:20-31; the parity default); 1 = quadratic B-spline: three nodes
+                             per axis instead of four, D = h^2/4 -- not reference behaviour, checked against
+                             the oracle's own quadratic mode; the tile kernels run W = 3 instantiations */
+    int   reserved[4];
 } MpmParams;
 
 /* Box collider = MeshCollider (hpp:74-93) reduced to what its sdf lambda uses (hpp:80-85):

@@ -107,12 +107,21 @@ float oracle_weight(float x) {
     return 0.0f;
 }
 
+/* quadratic B-spline (stencil = 1; not in the reference, same style: fp64 polynomial, float result):
+ * N(x) = 3/4 - x^2 (|x| < 1/2), (3/2 - |x|)^2 / 2 (|x| < 3/2), 0 otherwise */
+float oracle_weight_quadratic(float x) {
+    const float modx = fabsf(x);
+    if ((double)modx < 0.5) return (float)(0.75 - (double)modx * (double)modx);
+    if ((double)modx < 1.5) { const double a = 1.5 - (double)modx; return (float)(0.5 * a * a); }
+    return 0.0f;
+}
+
 /* per-axis weights of the 5 enumerated nodes cell-2..cell+2 (cpp:84-91, hpp:53-58) */
-static void axis_weights(float pos, float h, int cell, float w[5]) {
+static void axis_weights(float pos, float h, int cell, float w[5], int stencil) {
     for (int d = 0; d < 5; ++d) {
         const int idx = cell + d - 2;
         const float comp = pos / h - (float)idx;
-        w[d] = oracle_weight(comp);
+        w[d] = stencil == 1 ? oracle_weight_quadratic(comp) : oracle_weight(comp);
     }
 }
 
@@ -121,6 +130,7 @@ void oracle_default_params(OracleParams* p) {
     p->theta_c = 2.5f * 1e-2; p->theta_s = 5.0f * 1e-3;
     p->gravity[0] = 0.0f; p->gravity[1] = (float)-9.8; p->gravity[2] = 0.0f;
     p->friction = 0.5f;
+    p->stencil = 0;
 }
 
 Oracle* oracle_create(int I, int J, int K, int n, const OracleParams* prm) {
@@ -129,7 +139,7 @@ Oracle* oracle_create(int I, int J, int K, int n, const OracleParams* prm) {
     if (prm) o->prm = *prm; else oracle_default_params(&o->prm);
     /* hpp:177: inverse(mat3(1.0) * (1.0f/3.0f) * h * h) */
     float d[9];
-    m3scale(d, ID3, 1.0f / 3.0f); m3scale(d, d, o->prm.h); m3scale(d, d, o->prm.h);
+    m3scale(d, ID3, o->prm.stencil == 1 ? 1.0f / 4.0f : 1.0f / 3.0f); m3scale(d, d, o->prm.h); m3scale(d, d, o->prm.h);     /* (quadratic: D = h^2/4) */
     m3inverse(o->Dinv, d);
     o->p = (OParticle*)calloc((size_t)n, sizeof(OParticle));
     for (int i = 0; i < n; ++i) { memcpy(o->p[i].FE, ID3, sizeof ID3); memcpy(o->p[i].FP, ID3, sizeof ID3); }
@@ -183,9 +193,9 @@ static void cache_neighbourhood(Oracle* o) {   /* getParticleNeighs, cpp:80-93 *
         const OParticle* P_ = &(o)->p[pi];                                                            \
         const int* c_ = &(o)->cell[(pi) * 3];                                                         \
         float wx_[5], wy_[5], wz_[5];                                                                 \
-        axis_weights(P_->pos[0], (o)->prm.h, c_[0], wx_);                                             \
-        axis_weights(P_->pos[1], (o)->prm.h, c_[1], wy_);                                             \
-        axis_weights(P_->pos[2], (o)->prm.h, c_[2], wz_);                                             \
+        axis_weights(P_->pos[0], (o)->prm.h, c_[0], wx_, (o)->prm.stencil);                                             \
+        axis_weights(P_->pos[1], (o)->prm.h, c_[1], wy_, (o)->prm.stencil);                                             \
+        axis_weights(P_->pos[2], (o)->prm.h, c_[2], wz_, (o)->prm.stencil);                                             \
         for (int dx_ = 0; dx_ < 5; ++dx_) for (int dy_ = 0; dy_ < 5; ++dy_) for (int dz_ = 0; dz_ < 5; ++dz_) { \
             const float w = wx_[dx_] * wy_[dy_] * wz_[dz_];                                           \
             if (w == 0.0f) continue;                                                                  \

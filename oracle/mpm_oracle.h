@@ -16,6 +16,8 @@ typedef struct {
     float theta_s;      /* critical stretch, :320 (5.0e-3) */
     float gravity[3];   /* :260 (0,-9.8,0) */
     float friction;     /* :288 (0.5) */
+    int stencil;        /* 0 = the reference's cubic B-spline (hpp:20-31); 1 = quadratic B-spline, NOT reference behaviour: the
+                           checker for MpmParams.stencil = 1 (same loops, other weight function and D = h^2/4) */
 } OracleParams;
 
 /* Same POD as MpmBoxCollider in include/mpm_b200.h. world_to_local is the glm column-major

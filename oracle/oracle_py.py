@@ -21,7 +21,7 @@ COL = dict(mass=slice(0, 1), vel=slice(1, 4), volume=slice(4, 5), pos=slice(5, 8
 class OracleParams(C.Structure):
     _fields_ = [("h", C.c_float), ("E", C.c_float), ("nu", C.c_float), ("xi", C.c_float),
                 ("theta_c", C.c_float), ("theta_s", C.c_float), ("gravity", C.c_float * 3),
-                ("friction", C.c_float)]
+                ("friction", C.c_float), ("stencil", C.c_int)]
 
 
 class BoxCollider(C.Structure):
@@ -103,6 +103,8 @@ def default_params(**kw):
             raise TypeError(f"unknown parameter {k!r}; fields are {sorted(known)}")
         if k == "gravity":
             p.gravity[:] = [float(x) for x in v]
+        elif k == "stencil":
+            p.stencil = int(v)
         else:
             setattr(p, k, float(v))
     return p

@@ -121,8 +121,9 @@ int mpm_device_count(void) {
 }
 
 // DpInverse exactly as the reference builds it (hpp:177): inverse(mat3(1) * (1.0f/3.0f) * h * h), glm formulas
-static float dp_inverse_scalar(float h) {
-    volatile float d = 1.0f * (1.0f / 3.0f); d = d * h; d = d * h;
+// (quadratic stencil: D = h^2/4, the same expression with 1/4)
+static float dp_inverse_scalar(float h, bool quadratic) {
+    volatile float d = 1.0f * (quadratic ? 1.0f / 4.0f : 1.0f / 3.0f); d = d * h; d = d * h;
     volatile float dd = d * d;                       // m11*m22 - 0*0
     volatile float det = d * dd;                     // + d*(dd - 0) - 0 + 0
     volatile float ood = 1.0f / det;
@@ -133,7 +134,7 @@ static float dp_inverse_scalar(float h) {
 static void fill_consts(mpm_sim* s) {
     const MpmParams& p = s->prm;
     SimConst& c = s->sc;
-    c.h = p.h; c.dinv = dp_inverse_scalar(p.h); c.E = p.youngs_modulus; c.nu = p.poisson_ratio; c.xi = p.hardening_xi;
+    c.h = p.h; c.dinv = dp_inverse_scalar(p.h, p.stencil == 1); c.E = p.youngs_modulus; c.nu = p.poisson_ratio; c.xi = p.hardening_xi;
     c.clamp_lo = (float)(1.0 - (double)p.theta_c); c.clamp_hi = (float)(1.0 + (double)p.theta_s);   // cpp:320
     c.friction = p.friction_mu;
     c.mu0 = c.E / (2.0f * (1.0f + c.nu)); c.lambda0 = (c.E * c.nu) / ((1.0f + c.nu) * (1.0f - 2.0f * c.nu));   // cpp:237-238 (same float divisions as lame())
@@ -143,7 +144,7 @@ static void fill_consts(mpm_sim* s) {
     // P2G accumulation loop: rotated record walk (see k_p2g_tile). On by default; MPM_B200_P2G_ROTATE=0 restores the
     // aligned walk of the round-1 measurements for A/B timing.
     { const char* r = getenv("MPM_B200_P2G_ROTATE"); c.p2g_rotate = (r && atoi(r) == 0) ? 0 : 1; }
-    c.pd.h = p.h; c.pd.rh = 1.0f / p.h;
+    c.pd.h = p.h; c.pd.rh = 1.0f / p.h; c.pd.quadratic = p.stencil == 1 ? 1 : 0;
     // the fast quotient is validated (validate_pos_div) on [2h, (max dim + 2) h]: every position whose particle is not
     // parked anyway lies in there (cell >= 2), see particle_key
     const int md = std::max(s->gd.I, std::max(s->gd.J, s->gd.K));
@@ -174,7 +175,7 @@ static int validate_pos_div(mpm_sim* s) {
 
 static bool valid_variants(const MpmParams& p) {
     return (p.p2g_variant == 0 || p.p2g_variant == 1 || p.p2g_variant == 2 || p.p2g_variant == 9) && (p.g2p_variant == 0 || p.g2p_variant == 1) &&
-           p.fupdate_exact >= 0 && p.fupdate_exact <= 2;
+           p.fupdate_exact >= 0 && p.fupdate_exact <= 2 && (p.stencil == 0 || p.stencil == 1);
 }
 static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
@@ -219,7 +220,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     if (g.hi - g.lo > PB_COORD_MAX || g.npbj > PB_COORD_MAX || g.npbk > PB_COORD_MAX)       // work items carry 10-bit block coordinates
         return fail(MPM_ERR_INVALID, "grid too large: at most %d particle blocks (%d nodes) per axis and slab", PB_COORD_MAX, 4 * PB_COORD_MAX);
     g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
-    if (!valid_variants(s->prm)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9 and g2p_variant 0 or 1");
+    if (!valid_variants(s->prm)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1");
     fill_consts(s);
     s->capacity = std::max<int64_t>(capacity, 1);
     s->n_uploaded = n_particles; s->n_bound = n_particles;
@@ -310,8 +311,8 @@ int mpm_set_stream(mpm_t* s, void* st) {
 
 int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
-    if (p->h != s->prm.h) return fail(MPM_ERR_INVALID, "h cannot change after creation");
-    if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9 and g2p_variant 0 or 1");
+    if (p->h != s->prm.h || p->stencil != s->prm.stencil) return fail(MPM_ERR_INVALID, "h and stencil cannot change after creation");
+    if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1");
     s->prm = *p;
     drop_graph(s);                  // material constants and kernel variants are baked into a captured substep pair
     const int fast = s->sc.pd.fast;

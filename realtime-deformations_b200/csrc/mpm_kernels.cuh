@@ -82,9 +82,10 @@ __global__ void k_validate_pos_div(PosDiv pd, unsigned lo_bits, unsigned hi_bits
 // ------------------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------------------
+template <int Q = 2>
 MPM_DI int particle_key(float4 xm, const GridDims& gd, const PosDiv& pd, int* cells /*3*/) {
     if (xm.w < 0.0f) return KEY_DEAD;
-    const int cx = cell_of(xm.x, pd), cy = cell_of(xm.y, pd), cz = cell_of(xm.z, pd);
+    const int cx = cell_of_t<Q>(xm.x, pd), cy = cell_of_t<Q>(xm.y, pd), cz = cell_of_t<Q>(xm.z, pd);
     cells[0] = cx; cells[1] = cy; cells[2] = cz;
     // the reference enumerates cell-2..cell+2 without bounds checks (cpp:84-91); outside that the particle is parked
     const bool ok = cx >= 2 && cy >= 2 && cz >= 2 && cx + 2 <= gd.I - 1 && cy + 2 <= gd.J - 1 && cz + 2 <= gd.K - 1;

@@ -83,7 +83,7 @@ MPM_DI float weight_nx_exact(float x) {
 // rh = RN(1/h): three dependent FMA-pipe ops instead of the ~10-instruction __fdiv_rn sequence. That shortcut is
 // only used on [lo, hi], where mpm_create has checked it EXHAUSTIVELY (every fp32 in the range) against __fdiv_rn
 // for this h; elsewhere, or if the check ever failed, the exact intrinsic runs.
-struct PosDiv { float h, rh, lo, hi; int fast; };
+struct PosDiv { float h, rh, lo, hi; int fast; int quadratic; };    // quadratic: MpmParams.stencil = 1 (see cell_of below)
 MPM_DI float pos_div(float x, const PosDiv& d) {
     if (d.fast && x >= d.lo && x <= d.hi) {
         const float q0 = mul_rn(x, d.rh);
@@ -93,21 +93,50 @@ MPM_DI float pos_div(float x, const PosDiv& d) {
 }
 // cell index and the four non-zero per-axis weights (nodes cell-1 .. cell+2).
 // material_point_method.cpp:83 (ivec3(pos / h): IEEE divide + truncation), hpp:53-58 (pos/h - idx).
-MPM_DI int cell_of(float x, const PosDiv& d) { return __float2int_rz(pos_div(x, d)); }
+// Stencil order (MpmParams.stencil): with the QUADRATIC B-spline -- not reference behaviour -- a particle
+// touches the three nodes base .. base+2 per axis, base = int(pos/h - 1/2). Every kernel addresses a particle's stencil as
+// "cell - 1 + a", a = 0..3, so the quadratic case simply reports the pseudo-cell base + 1 and a fourth weight of zero: block
+// keys, tiles, local cell numbers and node offsets need no second code path (the tile kernels additionally have W = 3
+// instantiations that skip the zero column).
+// Q selects the stencil at COMPILE time in the hot kernels (0 cubic, 1 quadratic) or at run time (2: d.quadratic), so that the
+// benchmark path (cubic) carries no trace of the switch.
+template <int Q>
+MPM_DI int cell_of_t(float x, const PosDiv& d) {
+    const float q = pos_div(x, d);
+    const bool quad = Q == 1 || (Q == 2 && d.quadratic);
+    return quad ? __float2int_rz(q - 0.5f) + 1 : __float2int_rz(q);
+}
+MPM_DI int cell_of(float x, const PosDiv& d) { return cell_of_t<2>(x, d); }
+// quadratic weights at offset t = q - (base + 1) in [-1/2, 1/2): N(t + 1), N(t), N(t - 1) with N(x) = 3/4 - x^2 (|x| < 1/2),
+// (3/2 - |x|)^2 / 2 (|x| < 3/2)
+MPM_DI void quadratic_weights(float t, float w[4]) {
+    const float a = 0.5f - t, b = 0.5f + t;
+    w[0] = 0.5f * a * a;
+    w[1] = fmaf(-t, t, 0.75f);
+    w[2] = 0.5f * b * b;
+    w[3] = 0.0f;
+}
 // The four stencil offsets are q-(cell-1) = fx+1, fx, fx-1, fx-2 with fx = q - cell in [0,1) (all exact in fp32), so
 // the reference's |x|<1 / |x|<2 branches are known statically: far, near, near, far. Branch-free, <= 1 ulp from
 // weight_nx_exact, partition of unity to fp32 rounding.
 MPM_DI void axis_weights(float x, const PosDiv& d, int cell, float w[4]) {
     const float fx = sub_rn(pos_div(x, d), (float)cell);
+    if (d.quadratic) { quadratic_weights(fx, w); return; }
     const float gx = 1.0f - fx;
     w[0] = 0.16666667163372040f * gx * gx * gx;
     w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
     w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
     w[3] = 0.16666667163372040f * fx * fx * fx;
 }
-// same as cell_of + axis_weights with the quotient formed once (used by the experimental kernel variants)
-MPM_DI int cell_and_weights(float x, const PosDiv& d, float w[4]) {
+// same as cell_of + axis_weights with the quotient formed once
+template <int Q>
+MPM_DI int cell_and_weights_t(float x, const PosDiv& d, float w[4]) {
     const float q = pos_div(x, d);
+    if (Q == 1 || (Q == 2 && d.quadratic)) {
+        const int cell = __float2int_rz(q - 0.5f) + 1;
+        quadratic_weights(sub_rn(q, (float)cell), w);
+        return cell;
+    }
     const int cell = __float2int_rz(q);
     const float fx = sub_rn(q, (float)cell);
     const float gx = 1.0f - fx;
@@ -117,6 +146,7 @@ MPM_DI int cell_and_weights(float x, const PosDiv& d, float w[4]) {
     w[3] = 0.16666667163372040f * fx * fx * fx;
     return cell;
 }
+MPM_DI int cell_and_weights(float x, const PosDiv& d, float w[4]) { return cell_and_weights_t<2>(x, d, w); }
 MPM_DI void axis_weights_exact(float x, const PosDiv& d, int cell, float w[4]) {
     const float q = pos_div(x, d);
 #pragma unroll

@@ -82,12 +82,14 @@ struct PeerLayers { float4* dn; float4* up; };      // lower neighbour's ghost l
 // alternate between the front and the back of the list -- so that the NVLink traffic overlaps the interior blocks and the
 // neighbours' waits end early.
 MPM_DI int peer_work_order(int ticket, int n_work) { return (ticket & 1) ? n_work - 1 - (ticket >> 1) : (ticket >> 1); }
-template <int MODE, int FUPD = 0 /* 0 none, 1 bit-faithful, 2 tolerance form */, bool PEER = false>
+template <int MODE, int FUPD = 0 /* 0 none, 1 bit-faithful, 2 tolerance form */, bool PEER = false, int W = 4 /* stencil: 4 = cubic (compile time), 3 = quadratic (compile time, zero column skipped), 0 = either (run time, 4-wide) */>
 __global__ void __launch_bounds__(P2G_T, 2)
 k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, Planes Nx, PeerLayers peer = PeerLayers{ nullptr, nullptr }) {
     MPM_DYN_SMEM(smem_raw, 16);
     P2GSmem& S = *reinterpret_cast<P2GSmem*>(smem_raw);
+    constexpr int SQ = W == 3 ? 1 : (W == 4 ? 0 : 2);      // stencil selection of the weight functions
+    constexpr int WN = W == 3 ? 3 : 4;                     // stencil nodes per axis that can carry weight
     const int t = threadIdx.x, lane = t & 31;
     const int my_cell = t >> 2, my_a = t & 3;
     const int my_cx = my_cell >> 4, my_cy = (my_cell >> 2) & 3, my_cz = my_cell & 3;
@@ -150,7 +152,7 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     float wx[4], wy[4], wz[4];
                     // cell index and weights from ONE pos/h quotient per axis (the same operations as cell_of + axis_weights,
                     // which form the quotient twice: identical bits, 68 fewer instructions per particle)
-                    const int cx = cell_and_weights(xm.x, sc.pd, wx), cy = cell_and_weights(xm.y, sc.pd, wy), cz = cell_and_weights(xm.z, sc.pd, wz);
+                    const int cx = cell_and_weights_t<SQ>(xm.x, sc.pd, wx), cy = cell_and_weights_t<SQ>(xm.y, sc.pd, wy), cz = cell_and_weights_t<SQ>(xm.z, sc.pd, wz);
                     const float d0 = (float)(cx - 1) * sc.h - xm.x, d1 = (float)(cy - 1) * sc.h - xm.y, d2 = (float)(cz - 1) * sc.h - xm.z;
                     MPM_SMEM_PROBE(1, u, &S.u.c.wx[q], 16); MPM_SMEM_PROBE(2, u, &S.u.c.hA8[q], 4);
                     S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
@@ -211,8 +213,11 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
             int i = i0;
             if (sc.p2g_rotate && i1 - i0 > 1) i += (my_cell & 7) % (i1 - i0);
             int pi = i1 > i0 ? S.u.c.order[i] : 0;          // record index, fetched one iteration ahead of its record
+            // (W = 3, quadratic stencil: the x-slab a = 3 and the y-row b = 3 carry zero weights and are skipped; the z pairs
+            // keep their zero fourth weight)
+            const int n_vis = (WN == 4 || my_a < WN) ? i1 - i0 : 0;
 #pragma unroll 1
-            for (int k = 0; k < i1 - i0; ++k) {
+            for (int k = 0; k < n_vis; ++k) {
                 MPM_SMEM_PROBE(10, k, &S.u.c.order[i], 2);
                 i = (i + 1 == i1) ? i0 : i + 1;
                 MPM_SMEM_PROBE(11, k, &reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a], 4);
@@ -233,17 +238,17 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                 const f32x2_t cp2[2] = { pack2(0.f, 1.f), pack2(2.f, 3.f) };
                 const f32x2_t mm = pack2(qc.x, qc.x), sx = pack2(h0.z, h0.z), sy = pack2(h1.y, h1.y), sz = pack2(h8, h8);
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
+                for (int bb = 0; bb < WN; ++bb) {
                     const float wab = wxa * wyv[bb];
                     const float vx = bx + (float)bb * h0.y, vy = by + (float)bb * h1.x, vz = bz + (float)bb * h1.w;
                     const f32x2_t wab2 = pack2(wab, wab), vx2 = pack2(vx, vx), vy2 = pack2(vy, vy), vz2 = pack2(vz, vz);
 #pragma unroll
                     for (int cp = 0; cp < 2; ++cp) {
-                        const f32x2_t W = fmul2(wzp[cp], wab2);
-                        ffma2_acc(AM[bb * 2 + cp], W, mm);
-                        ffma2_acc(AX[bb * 2 + cp], W, ffma2(cp2[cp], sx, vx2));
-                        ffma2_acc(AY[bb * 2 + cp], W, ffma2(cp2[cp], sy, vy2));
-                        ffma2_acc(AZ[bb * 2 + cp], W, ffma2(cp2[cp], sz, vz2));
+                        const f32x2_t Wg = fmul2(wzp[cp], wab2);
+                        ffma2_acc(AM[bb * 2 + cp], Wg, mm);
+                        ffma2_acc(AX[bb * 2 + cp], Wg, ffma2(cp2[cp], sx, vx2));
+                        ffma2_acc(AY[bb * 2 + cp], Wg, ffma2(cp2[cp], sy, vy2));
+                        ffma2_acc(AZ[bb * 2 + cp], Wg, ffma2(cp2[cp], sz, vz2));
                     }
                 }
             }
@@ -397,13 +402,14 @@ struct G2PSmem {
 // Measured at 64 Mi particles (profiles/r2_ab_64M.md): blocked tile + scalar FMA 2.40 ms, linear tile 2.22, packed pairs
 // 2.19, both 1.99 -> only this form is kept.
 // FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER, G2P_HIST (the F-update runs in P2G or in k_fupdate).
-template <int FLAGS>
+template <int FLAGS, int W = 4 /* stencil: 4 = cubic (compile time), 3 = quadratic (compile time: 27 tile reads instead of 64), 0 = either (run time) */>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr,
            MigOut mo = MigOut{ nullptr, nullptr, 0 }) {
     MPM_DYN_SMEM(g2p_smem_raw, 128);
     G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
+    constexpr int SQ = W == 3 ? 1 : (W == 4 ? 0 : 2), WN = W == 3 ? 3 : 4;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_work = dc->n_active_pblocks;
     float4* __restrict__ tile = S.tile[wid];
@@ -462,7 +468,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 {
                     float wx[4], wy[4], wz[4];
                     // one pos/h quotient per axis feeds the cell index and the weights (same bits as cell_of + axis_weights)
-                    const int cx = cell_and_weights(r.x[0], sc.pd, wx), cy = cell_and_weights(r.x[1], sc.pd, wy), cz = cell_and_weights(r.x[2], sc.pd, wz);
+                    const int cx = cell_and_weights_t<SQ>(r.x[0], sc.pd, wx), cy = cell_and_weights_t<SQ>(r.x[1], sc.pd, wy), cz = cell_and_weights_t<SQ>(r.x[2], sc.pd, wz);
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     const float4* __restrict__ lin = tile + (ox * G2P_LIN_PLANE + oy * G2P_LIN_ROW + oz);
                     // pairs: S = (s0, s1) <- (wz, wz dz) * n ;  T = (t0, t1y) <- (wy, wy dy) * s0 ;  V = (v, Bx) <- (wx, wx dx) * t0
@@ -475,14 +481,14 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                     }
                     float By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
+                    for (int a = 0; a < WN; ++a) {
                         f32x2_t T[3] = { 0ull, 0ull, 0ull };
                         float t1z[3] = { 0, 0, 0 };
 #pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) {
+                        for (int bb = 0; bb < WN; ++bb) {
                             f32x2_t Sx[3] = { 0ull, 0ull, 0ull };
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
+                            for (int cc = 0; cc < WN; ++cc) {
                                 MPM_SMEM_PROBE(40, (base / 32) * 64 + (a * 4 + bb) * 4 + cc, &lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc], 16);
                                 const float4 n = lin[a * G2P_LIN_PLANE + bb * G2P_LIN_ROW + cc];
                                 Sx[0] = ffma2(WZ[cc], pack2(n.y, n.y), Sx[0]);
@@ -527,7 +533,7 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                     // straight into the packed migration buffer (planes 4..10 of this slot were written by the F-update earlier
                     // in the substep) and retires its slot
                     int cells[3];
-                    key_new = particle_key(make_float4(r.x[0], r.x[1], r.x[2], r.m), gd, sc.pd, cells);
+                    key_new = particle_key<SQ>(make_float4(r.x[0], r.x[1], r.x[2], r.m), gd, sc.pd, cells);
                     if (key_new > gd.n_pblocks && mig_try_pack(mo, key_new == gd.n_pblocks + 2, D, q, dc)) key_new = KEY_DEAD;
                     key_out[j] = key_new;
                 }
@@ -564,11 +570,16 @@ __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ so
 inline cudaError_t tile_kernels_init() {
     cudaError_t e;
 #define MPM_SET_SMEM(K, T) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T))) != cudaSuccess) return e
-    MPM_SET_SMEM((k_p2g_tile<P2G_MOMENTUM>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FORCE>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 1>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2>), P2GSmem);
-    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 0, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 1, true>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2, true>), P2GSmem);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER>), G2PSmem);
-    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST>), G2PSmem);
+#define MPM_SET_P2G(MODE, FU, PE) MPM_SET_SMEM((k_p2g_tile<MODE, FU, PE, 4>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<MODE, FU, PE, 0>), P2GSmem)
+    MPM_SET_P2G(P2G_MOMENTUM, 0, false); MPM_SET_P2G(P2G_FORCE, 0, false); MPM_SET_P2G(P2G_FUSED, 1, false);
+    MPM_SET_P2G(P2G_FUSED, 0, true); MPM_SET_P2G(P2G_FUSED, 1, true); MPM_SET_P2G(P2G_FUSED, 2, true);
+#undef MPM_SET_P2G
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 0, false, 4>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2, false, 4>), P2GSmem);
+    MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 0, false, 3>), P2GSmem); MPM_SET_SMEM((k_p2g_tile<P2G_FUSED, 2, false, 3>), P2GSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, 4>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER, 0>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, 4>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, 0>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, 4>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, 3>), G2PSmem);
 #undef MPM_SET_SMEM
     return cudaSuccess;
 }
@@ -578,19 +589,26 @@ cudaError_t launch_p2g_tile(Planes P, int* sorted_ids, const int4* pblock_list,
                             DevCounters* dc, float4* grid, GridDims gd, SimConst sc, float dt, int num_sms, int n_bound, cudaStream_t st,
                             const Planes* fupd_target = nullptr, bool fupd_fast = false, const PeerLayers* peer = nullptr) {
     (void)n_bound;
+    const bool w3 = sc.pd.quadratic != 0;        // quadratic stencil: the fused substep's kernels have W = 3 instantiations
     cudaError_t e = cudaMemsetAsync(&dc->work_a, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const Planes Nx = fupd_target ? *fupd_target : P;
     const PeerLayers pl = peer ? *peer : PeerLayers{ nullptr, nullptr };
     const int fu = (fupd_target && MODE == P2G_FUSED) ? (fupd_fast ? 2 : 1) : 0;      // only the fused substep moves the F-update into P2G
     const bool pe = peer && MODE == P2G_FUSED;
-#define MPM_P2G_LAUNCH(FU, PE) k_p2g_tile<MODE, FU, PE><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
+    // stencil: the cubic (reference) path always runs W = 4 instantiations, which carry no trace of the switch; the quadratic
+    // stencil runs W = 3 for the fused substep's kernels and the generic W = 0 (4-wide, run-time weights) elsewhere
+#define MPM_P2G_LAUNCH_W(FU, PE, WW) k_p2g_tile<MODE, FU, PE, WW><<<num_sms * 2, P2G_T, sizeof(P2GSmem), st>>>(P, sorted_ids, pblock_list, dc, grid, gd, sc, dt, Nx, pl)
+#define MPM_P2G_LAUNCH(FU, PE) do { if (w3) MPM_P2G_LAUNCH_W(FU, PE, 0); else MPM_P2G_LAUNCH_W(FU, PE, 4); } while (0)
     if constexpr (MODE == P2G_FUSED) {
         if (pe) { if (fu == 2) MPM_P2G_LAUNCH(2, true); else if (fu == 1) MPM_P2G_LAUNCH(1, true); else MPM_P2G_LAUNCH(0, true); }
-        else { if (fu == 2) MPM_P2G_LAUNCH(2, false); else if (fu == 1) MPM_P2G_LAUNCH(1, false); else MPM_P2G_LAUNCH(0, false); }
+        else if (w3 && fu == 2) MPM_P2G_LAUNCH_W(2, false, 3);
+        else if (w3 && fu == 0) MPM_P2G_LAUNCH_W(0, false, 3);
+        else { if (fu == 2) MPM_P2G_LAUNCH_W(2, false, 4); else if (fu == 1) MPM_P2G_LAUNCH(1, false); else MPM_P2G_LAUNCH_W(0, false, 4); }
     } else {
         MPM_P2G_LAUNCH(0, false);
     }
+#undef MPM_P2G_LAUNCH_W
 #undef MPM_P2G_LAUNCH
     return cudaGetLastError();
 }
@@ -625,9 +643,14 @@ cudaError_t launch_g2p_tile(Planes C, Planes N, const int* sorted_ids, const int
         const int per_sm = overlap ? side->gather_ctas_per_sm : G2P_MIN_CTAS;
         constexpr int GF = FLAGS & ~G2P_F;
         constexpr bool CAN_HIST = (GF & G2P_REORDER) != 0 && (GF & G2P_ADVECT) != 0;       // the fused substep's gather
-#define MPM_G2P_LAUNCH(F) k_g2p_tile<F><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count, mo)
-        if (CAN_HIST && key_out) MPM_G2P_LAUNCH(GF | (CAN_HIST ? G2P_HIST : 0));
-        else MPM_G2P_LAUNCH(GF);
+#define MPM_G2P_LAUNCH_W(F, WW) k_g2p_tile<F, WW><<<num_sms * per_sm, G2P_T, sizeof(G2PSmem), st>>>(C, N, sorted_ids, pblock_list, dc, grid, gd, sc, dt, key_out, blk_count, mo)
+#define MPM_G2P_LAUNCH(F) do { if (sc.pd.quadratic) MPM_G2P_LAUNCH_W(F, 0); else MPM_G2P_LAUNCH_W(F, 4); } while (0)
+        if constexpr (CAN_HIST) {
+            if (key_out && sc.pd.quadratic) MPM_G2P_LAUNCH_W(GF | G2P_HIST, 3);       // quadratic stencil: W = 3 instantiation of the fused substep's gather
+            else if (key_out) MPM_G2P_LAUNCH_W(GF | G2P_HIST, 4);
+            else MPM_G2P_LAUNCH(GF);
+        } else MPM_G2P_LAUNCH(GF);
+#undef MPM_G2P_LAUNCH_W
 #undef MPM_G2P_LAUNCH
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -298,6 +298,35 @@ def test_invariants_reduction_matches_download(golden_c1):
     assert (inv["id_sum"], inv["id_hash"]) == bench.expected_id_sums(n)
 
 
+@pytest.mark.parametrize("variants", VARIANTS)
+def test_quadratic_stencil_vs_oracle(variants):
+    """MpmParams.stencil = 1 (quadratic B-spline, three nodes per axis, D = h^2/4: SURVEY 0.3 / 8b; not reference behaviour)
+    against the oracle's own quadratic mode -- the same loops as the reference restatement with the other weight function:
+    the scattered grid after one rasterisation, the initial volumes, and the trajectory through free fall, ground contact and
+    crushing, with the W = 3 tile kernels and with the baseline kernels (which see a zero fourth weight)."""
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=5.0)
+    o, ocols, onc = oracle_from_scene(sc, stencil=1)
+    of, _, _ = oracle_from_scene(sc, fma=True, stencil=1)
+    sim, cols, nc = sim_from_scene(sc, variants, stencil=1)
+    close_sum(sim.download_state35()[:, 4], o.state()[:, 4], "quadratic stencil: initial volumes")
+    # one staged rasterisation: grid mass and velocity (mass != 0 pattern identical: the same nodes are touched)
+    o.rasterize(); sim.rasterizeParticlesToGrid()
+    og, gg = o.grid(), sim.grid()
+    assert np.array_equal(og[:, 0] != 0, gg[:, 0] != 0), "quadratic stencil: used cells differ"
+    close_sum(gg[:, 0], og[:, 0], "quadratic stencil: grid mass")
+    close_sum(gg[:, 4:7], og[:, 4:7], "quadratic stencil: grid velocity")
+    # and the cubic grid of the same particles is a different one (the switch really changes the stencil)
+    simc, _, _ = sim_from_scene(sc, variants)
+    simc.rasterizeParticlesToGrid()
+    assert (simc.grid()[:, 0] != 0).sum() > (gg[:, 0] != 0).sum()
+    for n in (20, 60, 40):
+        o.substep(float(sc["dt"]), ocols, onc, n)
+        of.substep(float(sc["dt"]), ocols, onc, n)
+        sim.substep(float(sc["dt"]), cols, nc, n)
+        assert_traj_close_calibrated(sim.download_state35(), o.state(), of.state(), f"quadratic stencil, CUDA {variants} vs oracle", factor=6.0)
+    assert sim.stats().svd_failed == 0 and sim.stats().n_particles == sc["n"]
+
+
 def test_material_sweep_vs_oracle():
     # BASELINE config 4 in miniature: stiffer hardening, other clamp thresholds, smaller dt
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=4.0, dt=2.5e-6)

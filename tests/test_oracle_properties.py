@@ -93,3 +93,31 @@ def test_friction_quirk_is_reproduced():
             vn = vy                                            # normal ~ (0,1,0): vn = vy
             f = 1.0 + 0.5 * vn / 3.0
             assert abs(out[0] - 1.0 * f) < 1e-3 and abs(out[2] - 0.5 * f) < 1e-3 and abs(out[1]) < 1e-3
+
+
+def test_quadratic_stencil_mode_of_the_oracle():
+    """The oracle's quadratic mode (the checker for MpmParams.stencil = 1; not reference behaviour): partition of unity of the
+    three-node weights, D = h^2/4, and mass / momentum conservation of one rasterisation + gather round trip."""
+    import ctypes as C
+    L = op.lib()
+    L.oracle_weight_quadratic.restype = C.c_float
+    L.oracle_weight_quadratic.argtypes = [C.c_float]
+    for fx in np.linspace(-0.5, 0.499, 41):
+        w = [L.oracle_weight_quadratic(float(np.float32(fx) - d)) for d in (-1, 0, 1)]
+        assert abs(sum(w) - 1.0) < 2e-7 and min(w) >= 0.0
+        assert L.oracle_weight_quadratic(float(np.float32(fx) - 2)) == 0.0 and L.oracle_weight_quadratic(float(np.float32(fx) + 2)) == 0.0
+    rng = np.random.default_rng(5)
+    n = 500
+    pos = (rng.uniform(0.3, 0.7, (n, 3))).astype(np.float32)
+    vel = rng.normal(0, 3, (n, 3)).astype(np.float32)
+    o = op.Oracle(20, 20, 20, n, op.default_params(stencil=1))
+    o.set_state(op.initial_state(pos, vel, np.float32(6e-5)))
+    o.rasterize()
+    g = o.grid().astype(np.float64)
+    assert abs(g[:, 0].sum() - n * float(np.float32(6e-5))) < 1e-9
+    mom = (g[:, 0:1] * g[:, 4:7]).sum(0)
+    assert np.allclose(mom, (float(np.float32(6e-5)) * vel.astype(np.float64)).sum(0), rtol=1e-5, atol=1e-9)
+    oc = op.Oracle(20, 20, 20, n, op.default_params())
+    oc.set_state(op.initial_state(pos, vel, np.float32(6e-5)))
+    oc.rasterize()
+    assert (oc.grid()[:, 0] != 0).sum() > (g[:, 0] != 0).sum()          # fewer nodes touched than with the cubic stencil

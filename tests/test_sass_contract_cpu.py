@@ -63,7 +63,7 @@ def test_no_kernel_spills_to_local_memory(kernels):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_p2g_tile_kernel_contract(kernels, mode):
-    k = _one(kernels, f"k_p2g_tileILi{mode}ELi0ELb0E")
+    k = _one(kernels, f"k_p2g_tileILi{mode}ELi0ELb0ELi4E")
     assert k["regs"] <= 128, "2 CTAs of 256 threads per SM need <= 128 registers"
     assert _count(k, "REDG.E.ADD.F32x4") == 1, "one vector red.global.add.v4.f32 per tile node"
     assert not any("CAST" in o for o in k["ops"]), "no shared-memory float atomics (ATOMS.CAST.SPIN loops)"
@@ -77,14 +77,14 @@ def test_p2g_tile_kernel_contract(kernels, mode):
 
 def test_gather_kernel_contract(kernels):
     for flags in (2, 14, 30):           # staged gather; fused gather + advect + re-sort; + next substep's keys and histogram
-        k = _one(kernels, f"k_g2p_tileILi{flags}EE")
+        k = _one(kernels, f"k_g2p_tileILi{flags}ELi4EE")
         assert k["regs"] <= 128
         assert _count(k, "UBLKCP") == 4, "the tile arrives as 128 row-wise 64-byte bulk copies (TMA), 4 per lane"
         assert _count(k, "SYNCS.ARRIVE.TRANS64") == 1 and any("TRYWAIT" in o for o in k["ops"]), "mbarrier expect_tx + try_wait"
         assert _count(k, "LDS.128") == 64, "64 stencil nodes, one LDS.128 [base + immediate] each"
         assert _count(k, "BAR.SYNC") == 0, "warp-per-block: no CTA barrier"
         assert _count(k, "FFMA2") >= 200, "separable gather on packed fp32 pairs (252 FFMA2 + 84 FFMA per particle)"
-    assert _count(_one(kernels, "k_g2p_tileILi30EE"), "MATCH.ANY") == 1, "warp-aggregated histogram of next substep's keys"
+    assert _count(_one(kernels, "k_g2p_tileILi30ELi4EE"), "MATCH.ANY") == 1, "warp-aggregated histogram of next substep's keys"
 
 
 def test_fupdate_kernel_contract(kernels):
@@ -98,15 +98,25 @@ def test_fupdate_kernel_contract(kernels):
 
 
 def test_fused_substep_p2g_carries_the_f_update(kernels):
-    k = _one(kernels, "k_p2g_tileILi2ELi2ELb0E")
+    k = _one(kernels, "k_p2g_tileILi2ELi2ELb0ELi4E")
     assert k["regs"] <= 128 and _count(k, "STG.E.128") >= 7 and _count(k, "REDG.E.ADD.F32x4") == 1
 
 
 def test_peer_halo_p2g_issues_remote_vector_reds(kernels):
     for fu in (0, 1, 2):
-        k = _one(kernels, f"k_p2g_tileILi2ELi{fu}ELb1E")
+        k = _one(kernels, f"k_p2g_tileILi2ELi{fu}ELb1ELi4E")
         assert _count(k, "REDG.E.ADD.F32x4") == 3, "local copy + the upper / lower neighbour's copy of a shared layer"
         assert k["regs"] <= 128 and not any("CAST" in o for o in k["ops"])
+
+
+def test_quadratic_stencil_instantiations_skip_the_zero_column(kernels):
+    """MpmParams.stencil = 1: the fused substep's tile kernels have W = 3 instantiations -- 27 instead of 64 tile reads per
+    particle in the gather, 3 instead of 4 y-rows per visit in P2G's accumulation loop."""
+    g3, g4 = _one(kernels, "k_g2p_tileILi30ELi3EE"), _one(kernels, "k_g2p_tileILi30ELi4EE")
+    assert _count(g3, "LDS.128") == 27 and _count(g4, "LDS.128") == 64
+    assert _count(g3, "FFMA2") < 0.5 * _count(g4, "FFMA2")
+    p3, p4 = _one(kernels, "k_p2g_tileILi2ELi2ELb0ELi3E"), _one(kernels, "k_p2g_tileILi2ELi2ELb0ELi4E")
+    assert _count(p3, "FFMA2") < _count(p4, "FFMA2") and p3["regs"] <= 128
 
 
 def test_binning_uses_warp_aggregated_atomics(kernels):
