@@ -531,14 +531,12 @@ static int do_binning(mpm_sim* s) {
     s->hist_valid = false;
     k_scan_reduce<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial);
     CKLAUNCH();
-    k_scan_partials<<<1, 1024, 0, s->stream>>>(s->partial, s->n_chunks, s->dc);
+    k_scan_partials<<<1, 1024, 0, s->stream>>>(s->partial, s->n_chunks, s->dc, s->blk_count, g.n_pblocks);
     CKLAUNCH();
     k_scan_apply<<<s->n_chunks, SCAN_T, 0, s->stream>>>(s->blk_count, s->n_buckets, g.n_pblocks, s->partial, s->blk_start,
                                                       s->blk_cursor, s->pblock_list, s->gflag, s->gblock_list, s->dc, g);
     CKLAUNCH();
-    k_fix_counts<<<1, 1, 0, s->stream>>>(s->blk_count, g.n_pblocks, s->dc);
-    CKLAUNCH();
-    s->stats.kernel_launches += 4;
+    s->stats.kernel_launches += 3;
     const int layer_threads = g.nbj * g.nbk;
     if (g.lo > 0) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(0, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
     if (g.hi < g.npbi_global) { k_mark_layer<<<grid_for(layer_threads, 256), 256, 0, s->stream>>>(g.hi - g.lo, g, s->gflag, s->gblock_list, s->dc); CKLAUNCH(); s->stats.kernel_launches++; }
@@ -606,6 +604,7 @@ static int launch_grid_update(mpm_sim* s, float dt) {
     return MPM_OK;
 }
 static int ensure_out_buffers(mpm_sim* s);
+__global__ void k_after_reorder(DevCounters* dc) { dc->n_slots = dc->n_sorted; }      // baseline gather: the re-sorted buffer holds n_sorted contiguous slots
 __global__ void k_peer_wait(const int* flag_a, const int* flag_b, int epoch, DevCounters* dc);
 template <int FLAGS>
 static int launch_g2p(mpm_sim* s, float dt) {
@@ -645,8 +644,10 @@ static int launch_g2p(mpm_sim* s, float dt) {
     }
     s->stats.kernel_launches += (s->prm.g2p_variant == 1) ? 1 : ((FLAGS & G2P_F) ? 1 : 0) + ((FLAGS & G2P_GATHER) ? 1 : 0) + ((FLAGS & G2P_REORDER) ? 1 : 0);
     if (FLAGS & G2P_REORDER) {
-        k_after_reorder<<<1, 1, 0, s->stream>>>(s->dc);
-        CKLAUNCH(); s->stats.kernel_launches++;
+        if (s->prm.g2p_variant == 1) {      // (the tile path sets the slot count in k_copy_parked)
+            k_after_reorder<<<1, 1, 0, s->stream>>>(s->dc);
+            CKLAUNCH(); s->stats.kernel_launches++;
+        }
         s->cur ^= 1;
         s->binned = false;      // sorted_ids referred to the old buffer
         s->hist_valid = fuse_hist;

@@ -214,7 +214,7 @@ __global__ void k_scan_reduce(const int* __restrict__ blk_count, int n, int n_re
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 // pass 2: one CTA scans the chunk totals in place (exclusive)
-__global__ void k_scan_partials(int2* partial, int n_chunks, DevCounters* dc) {
+__global__ void k_scan_partials(int2* partial, int n_chunks, DevCounters* dc, const int* __restrict__ blk_count, int n_real) {
     __shared__ int2 sm[32];
     __shared__ int2 tot;
     int2 carry = make_int2(0, 0);
@@ -231,6 +231,10 @@ __global__ void k_scan_partials(int2* partial, int n_chunks, DevCounters* dc) {
         dc->n_active_gblocks = 0; dc->n_active_nodes = 0;
         dc->work_a = 0; dc->work_b = 0; dc->work_c = 0;
         dc->epoch += 1;
+        // bucket counts of the three special buckets (parked, leaving down, leaving up)
+        dc->n_out_of_grid = blk_count[n_real];
+        dc->n_out_down = blk_count[n_real + 1];
+        dc->n_out_up = blk_count[n_real + 2];
     }
 }
 // pass 3: write blk_start / blk_cursor, the occupied particle-block list, and mark the 2x2x2 grid blocks of
@@ -277,12 +281,6 @@ __global__ void k_scan_apply(const int* __restrict__ blk_count, int n, int n_rea
             ex.x += c[e]; ex.y += (c[e] > 0 && i < n_real) ? 1 : 0;
         }
     }
-}
-// bucket counts of the three special buckets (parked, leaving down, leaving up)
-__global__ void k_fix_counts(const int* __restrict__ blk_count, int n_real, DevCounters* dc) {
-    dc->n_out_of_grid = blk_count[n_real];
-    dc->n_out_down = blk_count[n_real + 1];
-    dc->n_out_up = blk_count[n_real + 2];
 }
 // slab exchange layers are always active (they are packed / added densely)
 __global__ void k_mark_layer(int layer, GridDims gd, int* __restrict__ gflag, int* __restrict__ gblock_list, DevCounters* dc) {
@@ -669,9 +667,6 @@ __global__ void k_g2p_direct(Planes cur, Planes nxt, const int* __restrict__ sor
     }
     store_particle((FLAGS & G2P_REORDER) ? nxt : cur, (FLAGS & G2P_REORDER) ? j : p, r);
 }
-
-// after a re-sorting G2P the new buffer holds n_sorted contiguous live particles
-__global__ void k_after_reorder(DevCounters* dc) { dc->n_slots = dc->n_sorted; }
 
 // ------------------------------------------------------------------------------------------------------
 // host <-> device format conversion

@@ -551,6 +551,8 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
 __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc,
                               GridDims gd, PosDiv pd, int* __restrict__ key_out, int* __restrict__ blk_count, MigOut mo) {
     const int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x;
+    // after this re-sort the new buffer holds n_sorted contiguous slots (nothing in this kernel reads n_slots)
+    if (blockIdx.x == 0 && threadIdx.x == 0) dc->n_slots = dc->n_sorted;
     if (j >= dc->n_sorted) return;
     const int p = sorted_ids[j];
 #pragma unroll
