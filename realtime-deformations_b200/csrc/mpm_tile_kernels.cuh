@@ -550,21 +550,22 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
 // parked (out-of-grid) particles ride along unchanged through a re-sorting G2P
 __global__ void k_copy_parked(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, DevCounters* dc,
                               GridDims gd, PosDiv pd, int* __restrict__ key_out, int* __restrict__ blk_count, MigOut mo) {
-    const int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x;
     // after this re-sort the new buffer holds n_sorted contiguous slots (nothing in this kernel reads n_slots)
     if (blockIdx.x == 0 && threadIdx.x == 0) dc->n_slots = dc->n_sorted;
-    if (j >= dc->n_sorted) return;
-    const int p = sorted_ids[j];
+    const int n_sorted = dc->n_sorted;
+    for (int j = dc->n_binned + blockIdx.x * blockDim.x + threadIdx.x; j < n_sorted; j += gridDim.x * blockDim.x) {      // (usually empty)
+        const int p = sorted_ids[j];
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
-    if (key_out) {
-        // (fused binning) these particles did not move: parked ones stay parked; a leaver that found the migration buffer full
-        // last substep is offered to the neighbour again
-        int cells[3];
-        int k = particle_key(nxt.p[0][j], gd, pd, cells);
-        if (k > gd.n_pblocks && mig_try_pack(mo, k == gd.n_pblocks + 2, nxt, j, dc)) k = KEY_DEAD;
-        key_out[j] = k;
-        if (k >= 0) atomicAdd(&blk_count[k], 1);
+        for (int k = 0; k < NPLANES; ++k) nxt.p[k][j] = cur.p[k][p];
+        if (key_out) {
+            // (fused binning) these particles did not move: parked ones stay parked; a leaver that found the migration buffer
+            // full last substep is offered to the neighbour again
+            int cells[3];
+            int k = particle_key(nxt.p[0][j], gd, pd, cells);
+            if (k > gd.n_pblocks && mig_try_pack(mo, k == gd.n_pblocks + 2, nxt, j, dc)) k = KEY_DEAD;
+            key_out[j] = k;
+            if (k >= 0) atomicAdd(&blk_count[k], 1);
+        }
     }
 }
 
