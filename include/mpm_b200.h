@@ -194,6 +194,18 @@ int mpm_synchronize(mpm_t* s);
 typedef int (*MpmRandFn)(void* user);
 int mpm_fill_ball(const float origin[3], float radius, float h, MpmRandFn rnd, void* user,
                   float* pos_xyz, int64_t capacity, int64_t* n_written, int64_t* n_missing);
+/* Bodies from triangle meshes (the reference ships common/objloader.hpp:4 loadOBJ and never calls it): mpm_load_obj reads the
+ * "v" / "f" records of a Wavefront OBJ into n_tri x 9 floats (malloc'ed: release with mpm_free; polygons are fanned);
+ * mpm_fill_mesh applies initializeParticles' fill rule (8 jittered sites per cell, the random stream of mpm_fill_ball) to the
+ * cells of the mesh's bounding box and keeps the candidates inside the CLOSED mesh (ray parity). */
+int mpm_load_obj(const char* path, float** tri_xyz, int64_t* n_tri);
+void mpm_free(void* p);
+int mpm_fill_mesh(const float* tri_xyz, int64_t n_tri, float h, MpmRandFn rnd, void* user,
+                  float* pos_xyz, int64_t capacity, int64_t* n_written, int64_t* n_missing);
+/* A second SDF shape through the same collider POD (MeshCollider::sdf is a std::function, hpp:87): sphere of `radius` about
+ * `centre`: world_to_local = translate(-centre), half_extent = (radius, -1, -1) -- a negative half_extent[1] marks the sphere;
+ * normal, friction rule and velocity handling are the reference's bodyCollision unchanged. */
+int mpm_sphere_collider(const float centre[3], float radius, const float velocity[3], MpmBoxCollider* out);
 int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out);
 int mpm_box_transform_move(MpmBoxTransform* t, float time_delta);
 int mpm_box_transform_flip_velocity(MpmBoxTransform* t);

@@ -359,6 +359,10 @@ float oracle_box_sdf(const OracleBoxCollider* c, const float pos[3]) {
     float p[3];
     for (int r = 0; r < 3; ++r)           /* detail/type_mat4x4.inl: (m0*x + m1*y) + (m2*z + m3*w), w = 1 */
         p[r] = (m[0 * 4 + r] * pos[0] + m[1 * 4 + r] * pos[1]) + (m[2 * 4 + r] * pos[2] + m[3 * 4 + r] * 1.0f);
+    if (c->half_extent[1] < 0.0f) {   /* sphere marker of mpm_sphere_collider (not a reference shape): |p_local| - radius */
+        const float s2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        return sqrtf(s2) - c->half_extent[0];
+    }
     const float qx = fabsf(p[0]) - c->half_extent[0], qy = fabsf(p[1]) - c->half_extent[1], qz = fabsf(p[2]) - c->half_extent[2];
     float mx = qx; if (mx < qy) mx = qy; if (mx < qz) mx = qz; if (mx < 0.0f) mx = 0.0f;   /* std::max({q.x,q.y,q.z,0}) */
     float in = qy < qz ? qz : qy; in = qx < in ? in : qx; in = 0.0f < in ? 0.0f : in;      /* std::min({max(..), 0}) */

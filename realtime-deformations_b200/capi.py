@@ -53,7 +53,7 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
            "mpm_box_transform_flip_velocity", "mpm_fill_ball", "mpm_peer_export", "mpm_peer_connect", "mpm_peer_connect_ptr",
            "mpm_grid_device_ptr", "mpm_substep_begin_peer", "mpm_peer_export_migration", "mpm_peer_connect_migration",
-           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer", "mpm_reduce_invariants", "mpm_debug_p2g_profile"]
+           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer", "mpm_reduce_invariants", "mpm_debug_p2g_profile", "mpm_load_obj", "mpm_free", "mpm_fill_mesh", "mpm_sphere_collider"]
 
 _lib = None
 
@@ -113,6 +113,11 @@ def lib():
     L.mpm_sync_counts.argtypes = [vp]
     L.mpm_set_pid_base.argtypes = [vp, i64]
     L.mpm_download_live_particles.argtypes = [vp, i64, C.POINTER(i64), fp, vp]
+    L.mpm_load_obj.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i64)]
+    L.mpm_free.argtypes = [vp]
+    L.mpm_free.restype = None
+    L.mpm_fill_mesh.argtypes = [C.POINTER(C.c_float), i64, C.c_float, vp, vp, fp, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.mpm_sphere_collider.argtypes = [fp, C.c_float, fp, C.POINTER(MpmBoxCollider)]
     L.mpm_debug_p2g_profile.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
     L.mpm_reduce_invariants.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.mpm_box_collider_from_transform.argtypes = [C.POINTER(MpmBoxTransform), C.POINTER(MpmBoxCollider)]
@@ -202,6 +207,30 @@ def colliders_from_transforms(transforms):
 
 def _fp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def load_obj(path):
+    """Triangles (n, 3, 3) of a Wavefront OBJ through mpm_load_obj."""
+    ptr, n = C.POINTER(C.c_float)(), C.c_int64()
+    _ck(lib().mpm_load_obj(str(path).encode(), C.byref(ptr), C.byref(n)))
+    tri = np.ctypeslib.as_array(ptr, shape=(n.value * 9,)).copy().reshape(n.value, 3, 3)
+    lib().mpm_free(ptr)
+    return tri
+
+
+def fill_mesh(tri, h, capacity):
+    """Particle positions inside a closed triangle mesh: initializeParticles' fill rule (libc rand()) through mpm_fill_mesh."""
+    tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+    pos = np.empty((capacity, 3), np.float32)
+    nw, nm = C.c_int64(), C.c_int64()
+    _ck(lib().mpm_fill_mesh(_fp(tri), tri.shape[0], float(h), None, None, _fp(pos), capacity, C.byref(nw), C.byref(nm)))
+    return pos[:nw.value].copy(), nm.value
+
+
+def sphere_collider(centre, radius, velocity=(0.0, 0.0, 0.0)):
+    c = MpmBoxCollider()
+    _ck(lib().mpm_sphere_collider(_fp(np.asarray(centre, np.float32)), float(radius), _fp(np.asarray(velocity, np.float32)), C.byref(c)))
+    return c
 
 
 def _f32(a, shape):

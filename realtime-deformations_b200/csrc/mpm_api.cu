@@ -934,6 +934,106 @@ int mpm_fill_ball(const float origin[3], float radius, float h, MpmRandFn rnd, v
     return MPM_OK;
 }
 
+// ---- bodies from triangle meshes (the reference ships common/objloader.hpp:4 loadOBJ but never calls it) ----
+// Minimal Wavefront OBJ reader: "v x y z" and "f a b c ..." (indices may carry /vt/vn, may be negative, polygons are fanned).
+int mpm_load_obj(const char* path, float** tri_xyz, int64_t* n_tri) {
+    if (!path || !tri_xyz || !n_tri) return fail(MPM_ERR_INVALID, "null argument");
+    *tri_xyz = nullptr; *n_tri = 0;
+    FILE* f = fopen(path, "r");
+    if (!f) return fail(MPM_ERR_INVALID, "cannot open %s", path);
+    std::vector<float> v, tri;
+    char line[1024];
+    while (fgets(line, sizeof line, f)) {
+        if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+            float x, y, z;
+            if (sscanf(line + 2, "%f %f %f", &x, &y, &z) == 3) { v.push_back(x); v.push_back(y); v.push_back(z); }
+        } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+            std::vector<long> idx;
+            for (char* tok = strtok(line + 2, " \t\r\n"); tok; tok = strtok(nullptr, " \t\r\n")) {
+                long i = strtol(tok, nullptr, 10);
+                const long nv = (long)(v.size() / 3);
+                if (i < 0) i = nv + 1 + i;
+                if (i < 1 || i > nv) { fclose(f); return fail(MPM_ERR_INVALID, "%s: face index %ld out of range", path, i); }
+                idx.push_back(i - 1);
+            }
+            for (size_t k = 2; k < idx.size(); ++k)
+                for (long i : { idx[0], idx[k - 1], idx[k] }) { tri.push_back(v[3 * i]); tri.push_back(v[3 * i + 1]); tri.push_back(v[3 * i + 2]); }
+        }
+    }
+    fclose(f);
+    if (tri.empty()) return fail(MPM_ERR_INVALID, "%s holds no faces", path);
+    float* out = (float*)malloc(tri.size() * sizeof(float));
+    if (!out) return fail(MPM_ERR_INVALID, "out of memory");
+    memcpy(out, tri.data(), tri.size() * sizeof(float));
+    *tri_xyz = out; *n_tri = (int64_t)(tri.size() / 9);
+    return MPM_OK;
+}
+void mpm_free(void* p) { free(p); }
+
+// point-in-closed-mesh by ray parity along +x (double precision; the ray is nudged off edges / vertices by an irrational offset)
+static bool inside_mesh(const float* tri, int64_t n_tri, const float p[3]) {
+    const double py = (double)p[1] + 1.2345678912e-7, pz = (double)p[2] + 2.7182818284e-7, px = p[0];
+    int crossings = 0;
+    for (int64_t t = 0; t < n_tri; ++t) {
+        const float* a = tri + 9 * t; const float* b = a + 3; const float* c = a + 6;
+        // barycentric test of (py, pz) in the triangle's yz projection
+        const double d = ((double)b[1] - a[1]) * ((double)c[2] - a[2]) - ((double)c[1] - a[1]) * ((double)b[2] - a[2]);
+        if (d == 0.0) continue;
+        const double u = ((py - a[1]) * ((double)c[2] - a[2]) - ((double)c[1] - a[1]) * (pz - a[2])) / d;
+        const double w = (((double)b[1] - a[1]) * (pz - a[2]) - (py - a[1]) * ((double)b[2] - a[2])) / d;
+        if (u < 0.0 || w < 0.0 || u + w > 1.0) continue;
+        const double x = a[0] + u * ((double)b[0] - a[0]) + w * ((double)c[0] - a[0]);
+        if (x > px) ++crossings;
+    }
+    return crossings & 1;
+}
+// initializeParticles' fill rule (cpp:29-54: 8 jittered sites per cell, the same random stream as mpm_fill_ball) over the
+// bounding box of a closed triangle mesh, a candidate being kept if it lies inside the mesh
+int mpm_fill_mesh(const float* tri_xyz, int64_t n_tri, float h, MpmRandFn rnd, void* user,
+                  float* pos_xyz, int64_t capacity, int64_t* n_written, int64_t* n_missing) {
+    if (!tri_xyz || n_tri < 1 || !(h > 0.0f) || capacity < 0 || (capacity > 0 && !pos_xyz)) return fail(MPM_ERR_INVALID, "bad argument");
+    using scene_fe::mm; using scene_fe::aa;
+    float lo[3] = { tri_xyz[0], tri_xyz[1], tri_xyz[2] }, hi[3] = { tri_xyz[0], tri_xyz[1], tri_xyz[2] };
+    for (int64_t i = 0; i < 3 * n_tri; ++i) for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], tri_xyz[3 * i + a]); hi[a] = std::max(hi[a], tri_xyz[3 * i + a]); }
+    int c0[3], c1[3];
+    for (int a = 0; a < 3; ++a) { c0[a] = (int)floorf(lo[a] / h) - 1; c1[a] = (int)floorf(hi[a] / h) + 2; }
+    static const float sites[8][3] = { {1, 1, 1}, {1, 1, 3}, {1, 3, 1}, {1, 3, 3}, {3, 1, 1}, {3, 1, 3}, {3, 3, 1}, {3, 3, 3} };
+    int64_t stored = 0, missing = 0;
+    for (int i = c0[0]; i < c1[0]; ++i)
+        for (int j = c0[1]; j < c1[1]; ++j)
+            for (int k = c0[2]; k < c1[2]; ++k)
+                for (int d = 0; d < 8; ++d) {
+                    const float phi = fe_rand_float(rnd, user, 0.0f, (float)(2.0 * 3.1415));          // utils.h:114-127, as in mpm_fill_ball
+                    volatile double costheta = (double)fe_rand_float(rnd, user, 0.0f, 2.0f) - 1.0;
+                    const float u = fe_rand_float(rnd, user, 0.0f, 1.0f);
+                    const double theta = acos(costheta);
+                    const float r = mm(0.25f, cbrtf(u));
+                    volatile double rs = (double)r * sin(theta);
+                    volatile double bx = rs * cos((double)phi), by = rs * sin((double)phi), bz = (double)r * cos(theta);
+                    const float ball[3] = { (float)bx, (float)by, (float)bz };
+                    const int cell[3] = { i, j, k };
+                    float cand[3];
+                    for (int a = 0; a < 3; ++a) cand[a] = mm(aa(aa((float)cell[a], mm(sites[d][a], 0.25f)), ball[a]), h);
+                    if (!inside_mesh(tri_xyz, n_tri, cand)) continue;
+                    if (stored == capacity) { ++missing; continue; }
+                    for (int a = 0; a < 3; ++a) pos_xyz[3 * stored + a] = cand[a];
+                    ++stored;
+                }
+    if (n_written) *n_written = stored;
+    if (n_missing) *n_missing = missing;
+    return MPM_OK;
+}
+// MeshCollider::sdf is a std::function (hpp:87): a host may install other shapes. A sphere travels through the same POD with
+// half_extent = (radius, -1, -1): world_to_local = translate(-centre), sdf = |p_local| - radius; everything after the sdf
+// (central-difference normal, friction rule, cpp:264-296) is the reference's bodyCollision unchanged.
+int mpm_sphere_collider(const float centre[3], float radius, const float velocity[3], MpmBoxCollider* out) {
+    if (!centre || !out || !(radius > 0.0f)) return fail(MPM_ERR_INVALID, "bad argument");
+    memset(out, 0, sizeof *out);
+    out->world_to_local[0] = out->world_to_local[5] = out->world_to_local[10] = out->world_to_local[15] = 1.0f;
+    for (int a = 0; a < 3; ++a) { out->world_to_local[12 + a] = -centre[a]; out->velocity[a] = velocity ? velocity[a] : 0.0f; }
+    out->half_extent[0] = radius; out->half_extent[1] = -1.0f; out->half_extent[2] = -1.0f;
+    return MPM_OK;
+}
 int mpm_box_collider_from_transform(const MpmBoxTransform* t, MpmBoxCollider* out) {
     if (!t || !out) return fail(MPM_ERR_INVALID, "null argument");
     using namespace scene_fe;

@@ -585,6 +585,8 @@ MPM_DI float box_sdf_rn(const BoxCollider& c, float px, float py, float pz) {
     for (int r = 0; r < 3; ++r)
         p[r] = add_rn(add_rn(mul_rn(c.w2l[0 + r], px), mul_rn(c.w2l[4 + r], py)),
                       add_rn(mul_rn(c.w2l[8 + r], pz), mul_rn(c.w2l[12 + r], 1.0f)));
+    if (c.half[1] < 0.0f)           // sphere (mpm_sphere_collider): |p_local| - radius, every operation rounded once like the oracle's
+        return sub_rn(__fsqrt_rn(add_rn(add_rn(mul_rn(p[0], p[0]), mul_rn(p[1], p[1])), mul_rn(p[2], p[2]))), c.half[0]);
     const float qx = sub_rn(fabsf(p[0]), c.half[0]), qy = sub_rn(fabsf(p[1]), c.half[1]), qz = sub_rn(fabsf(p[2]), c.half[2]);
     float mx = qx; if (mx < qy) mx = qy; if (mx < qz) mx = qz; if (mx < 0.0f) mx = 0.0f;
     float in = qy < qz ? qz : qy; in = qx < in ? in : qx; in = 0.0f < in ? 0.0f : in;

@@ -1,22 +1,24 @@
-// Block-tile P2G / G2P kernels: one CTA works on one occupied 4^3-cell particle block at a time
+// Block-tile P2G / G2P kernels: one CTA (P2G) or one warp (G2P) works on one occupied 4^3-cell particle block at a time
 // (persistent CTAs pulling blocks from a device-side work counter, so no host sync is needed to size the grid).
 //
 // P2G (k_p2g_tile):  no shared-memory float atomics at all (on sm_100a they are CAS loops, ATOMS.CAST.SPIN).
-//   chunk loop   : 256 particles at a time are loaded as coalesced float4 planes; each thread derives its
-//                  particle's 12 axis weights (fp64 polynomial, as the reference) and affine coefficients into smem,
-//                  and the chunk is counting-sorted by cell in smem (one round of integer atomics: the count's return
-//                  value is the particle's rank inside its cell).
-//   phase 1      : thread (cell, x-slab a) walks the particles of ITS cell and accumulates the 16 stencil nodes
-//                  (a, b, c) x (mass, momentum) in 64 registers -> the cross-particle reduction happens in
+//   derive       : 512 particles at a time (2 per thread) are loaded as coalesced float4 planes; each thread derives its
+//                  particles' 12 axis weights (branch-free fp32 form, <= 1 ulp from the reference's) and affine coefficients
+//                  into shared memory and draws its rank inside its cell with one shared integer atomic.
+//   sort         : every warp scans the 64 cell counts in its own registers (shuffles); the chunk's record indices and the
+//                  block's segment of sorted_ids come out in cell order.
+//   accumulate   : thread (cell, x-slab a) walks the particles of ITS cell and accumulates the 16 stencil nodes
+//                  (a, b, c) x (mass, momentum) in 32 packed fp32 pairs (FFMA2) -> the cross-particle reduction happens in
 //                  registers, never between lanes.
-//   phase 2      : per-cell 64-node patches go to smem with plain stores; each tile node then gathers the <= 64
-//                  patches that cover it (plain loads, fixed order -> deterministic within a block) and issues ONE
-//                  vector red.global.add.v4.f32 per tile node (7^3 = 343 per block instead of 64 per particle).
-// G2P (k_g2p_tile):  the 2x2x2 grid blocks of the tile are eight contiguous 1 KB chunks in HBM; one thread fetches
-//   them with cp.async.bulk (TMA, mbarrier completion), double-buffered against the previous block's compute. Each
-//   thread then owns one particle: bit-faithful F-update (Jacobi SVD in registers), separable gather of v and the
-//   APIC matrix from the smem tile, advection, and the write into the other particle buffer at its sorted rank
-//   (the physical re-sort that keeps the next substep's loads coalesced).
+//   fold         : the four cells of a z-column are folded with warp shuffles, x/y from a padded shared array; ONE vector
+//                  red.global.add.v4.f32 per tile node (7^3 = 343 per block instead of 64 per particle), also into the
+//                  neighbour slab's grid for nodes of a shared layer (PEER).
+//   F-update     : (fused substep) the block's particles, after the write-back, into planes 4..10 of the other buffer.
+// G2P (k_g2p_tile):  each warp fetches the 2x2x2 grid blocks of its block's tile with 128 row-wise cp.async.bulk copies (TMA,
+//   completion on the warp's own mbarrier) into a linear, padded layout; each lane then owns one particle: separable gather
+//   of v and the APIC matrix on packed pairs, advection, next substep's block key + histogram (and migration packing on slab
+//   handles), and the write into the other particle buffer at its sorted rank (the physical re-sort that keeps the next
+//   substep's loads coalesced).
 #pragma once
 #include "mpm_kernels.cuh"
 

@@ -138,3 +138,32 @@ def test_cxx_host_links_against_the_c_abi(tmp_path, L):
         pytest.skip("a GPU is present: the run itself is covered by the gpu tests")
     r = subprocess.run([exe, "32", "2", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+def test_mesh_bodies_and_sphere_collider_front_end(tmp_path):
+    """SURVEY 8(f2) remainder, host-only entry points: mpm_load_obj reads a Wavefront OBJ (quads fanned, negative and
+    v/vt/vn indices), mpm_fill_mesh applies initializeParticles' fill rule inside the closed mesh, mpm_sphere_collider fills
+    the collider POD with the sphere marker."""
+    import mpm_b200
+    capi = mpm_b200.capi
+    cube = tmp_path / "cube.obj"
+    cube.write_text("# unit test body\n" + "".join(f"v {x} {y} {z}\n" for z in (0.2, 0.6) for y in (0.2, 0.6) for x in (0.2, 0.6)) +
+                    "f 1 2 4 3\nf 5/1/1 7/2/1 8/3/1 6/4/1\nf 1 5 6 2\nf 2 6 8 4\nf 4 8 7 3\nf -6 -8 -4 -2\n")
+    tri = capi.load_obj(cube)
+    assert tri.shape == (12, 3, 3) and tri.min() == np.float32(0.2) and tri.max() == np.float32(0.6)
+    pos, missing = capi.fill_mesh(tri, 0.05, 10000)
+    assert len(pos) == 8 * 8 ** 3 and missing == 0                      # 8 sites in each of the 8^3 cells the cube covers
+    assert (pos > 0.2).all() and (pos < 0.6).all()
+    few, missing = capi.fill_mesh(tri, 0.05, 100)
+    assert len(few) == 100 and missing == 8 * 8 ** 3 - 100              # the reference's "k more!!!" count
+    tet = tmp_path / "tet.obj"
+    tet.write_text("v 0.1 0.1 0.1\nv 0.9 0.1 0.1\nv 0.1 0.9 0.1\nv 0.1 0.1 0.9\nf 1 3 2\nf 1 2 4\nf 1 4 3\nf 2 3 4\n")
+    tpos, _ = capi.fill_mesh(capi.load_obj(tet), 0.025, 200000)
+    expect = (0.8 ** 3 / 6.0) / 0.025 ** 3 * 8                           # volume / cell volume * 8 sites
+    assert abs(len(tpos) - expect) < 0.03 * expect
+    assert ((tpos - 0.1).sum(1) < 0.8 + 1e-6).all() and (tpos > 0.1 - 1e-6).all()
+    with pytest.raises(capi.MpmError):
+        capi.load_obj(tmp_path / "missing.obj")
+    c = capi.sphere_collider((0.5, 0.25, 0.5), 0.3, (1.0, 0.0, -2.0))
+    assert list(c.half_extent) == [np.float32(0.3), -1.0, -1.0] and list(c.velocity) == [1.0, 0.0, -2.0]
+    assert list(c.world_to_local)[12:15] == [-0.5, -0.25, -0.5] and list(c.world_to_local)[0:16:5] == [1.0, 1.0, 1.0, 1.0]

@@ -154,6 +154,55 @@ def test_collisions_with_moving_colliders_bit_exact(golden_kat):
     assert_bit_exact(sim.grid()[:, 4:7], ref, "gridBasedCollisions with moving colliders")
 
 
+def test_sphere_collider_bit_exact_vs_oracle_and_mesh_body_trajectory(tmp_path):
+    """SURVEY 8(f2) remainder: a second SDF shape (sphere, through the same collider POD) and a body filled from a triangle
+    mesh. gridBasedCollisions with a moving sphere on every node of a 20^3 grid must match the oracle -- the reference's
+    bodyCollision restated, with the sphere sdf in place of the box sdf -- bit for bit; then an octahedron of snow (OBJ ->
+    mpm_fill_mesh) dropped on the sphere follows the oracle within the scene's noise floor."""
+    capi = mpm_b200.capi
+    rng = np.random.default_rng(11)
+    n_nodes = 20 * 20 * 20
+    cols = (mpm_b200.capi.MpmBoxCollider * 2)()
+    cols[0] = capi.sphere_collider((0.5, 0.3, 0.5), 0.27, (3.0, -1.5, 0.75))
+    cols[1] = capi.sphere_collider((0.2, 0.7, 0.6), 0.15)
+    ocols = (op.BoxCollider * 2)()
+    for k in range(2):
+        ocols[k].world_to_local[:] = list(cols[k].world_to_local); ocols[k].half_extent[:] = list(cols[k].half_extent); ocols[k].velocity[:] = list(cols[k].velocity)
+    g = np.zeros((n_nodes, 7), np.float32)
+    g[:, 0] = 1.0
+    g[:, 4:7] = rng.normal(0, 5, (n_nodes, 3)).astype(np.float32)
+    sim = mpm_b200.Sim(20, 20, 20, 1)
+    sim.upload(np.full((1, 3), 0.5, np.float32), np.zeros((1, 3), np.float32), np.float32(6e-5))
+    sim.set_grid(g)
+    sim.gridBasedCollisions(1e-5, cols, 2)
+    o = op.Oracle(20, 20, 20, 1)
+    o.set_state(op.initial_state(np.full((1, 3), 0.5, np.float32), np.zeros((1, 3), np.float32), np.float32(6e-5)))
+    o.set_grid(g)
+    o.collisions(1e-5, ocols, 2)
+    assert_bit_exact(sim.grid()[:, 4:7], o.grid()[:, 4:7], "gridBasedCollisions with sphere colliders")
+    assert (sim.grid()[:, 4:7] != g[:, 4:7]).any(1).sum() > 300, "the spheres must cover a few hundred nodes"
+    # a mesh body: octahedron of radius 0.16 about (0.5, 0.75, 0.5), 0.06 above the sphere's top
+    obj = tmp_path / "octa.obj"
+    c, r = np.array([0.5, 0.75, 0.5]), 0.16
+    v = [c + r * np.array(d) for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))]
+    obj.write_text("".join(f"v {p[0]} {p[1]} {p[2]}\n" for p in v) + "f 1 3 5\nf 3 2 5\nf 2 4 5\nf 4 1 5\nf 3 1 6\nf 2 3 6\nf 4 2 6\nf 1 4 6\n")
+    pos, _ = capi.fill_mesh(capi.load_obj(obj), 0.05, 100000)
+    assert 600 < len(pos) < 1200 and (np.abs(pos - c).sum(1) < r + 1e-6).all()
+    n = len(pos)
+    vel = np.tile(np.array([0.0, -150.0, 0.0], np.float32), (n, 1))
+    one = (mpm_b200.capi.MpmBoxCollider * 1)(); one[0] = capi.sphere_collider((0.5, 0.3, 0.5), 0.27)
+    oone = (op.BoxCollider * 1)(); oone[0].world_to_local[:] = list(one[0].world_to_local); oone[0].half_extent[:] = list(one[0].half_extent)
+    sim2 = mpm_b200.Sim(20, 20, 20, n)
+    sim2.upload(pos, vel, np.float32(6e-5)); sim2.rasterizeParticlesToGrid(); sim2.computeParticleVolumesAndDensities()
+    oo, of = op.Oracle(20, 20, 20, n), op.Oracle(20, 20, 20, n, fma=True)
+    for x in (oo, of):
+        x.set_state(op.initial_state(pos, vel, np.float32(6e-5))); x.rasterize(); x.volumes()
+    for k in (20, 40):                     # contact with the sphere after ~13 substeps
+        sim2.substep(1e-5, one, 1, k); oo.substep(1e-5, oone, 1, k); of.substep(1e-5, oone, 1, k)
+        assert_traj_close_calibrated(sim2.download_state35(), oo.state(), of.state(), "mesh body on a sphere collider vs oracle", factor=6.0)
+    assert np.abs(det_F(oo.state()) - 1.0).max() > 1e-3, "the body must have hit the sphere"
+
+
 def test_volumes_match_reference(golden_c1):
     s0 = golden_c1["state0"].copy()
     ref = s0[:, 4].copy()
@@ -397,8 +446,19 @@ def test_render_buffers_written_to_device_memory():
         torch.cuda.synchronize()          # torch's fill kernels run on torch's stream, the library writes on its own
     sim.write_render_buffers_device(d_xyzs.data_ptr(), d_rgba.data_ptr(), size=0.03)
     sim.synchronize()
-    xyzs, rgba = sim.render_buffers(size=0.03)
-    assert np.array_equal(d_xyzs.cpu().numpy().view(np.uint32), xyzs.view(np.uint32)) and np.array_equal(d_rgba.cpu().numpy(), rgba)
+    # against what the reference's drawParticles() would copy out of getParticles() (main.cpp:257-271): Particle::pos in
+    # upload order, Particle::size, rgba = 255 (cpp:48-51) -- taken from the full particle download, and from the oracle
+    got = d_xyzs.cpu().numpy()
+    st = sim.download_state35()
+    assert np.array_equal(got[:, 0:3].view(np.uint32), st[:, 5:8].view(np.uint32)) and (got[:, 3] == np.float32(0.03)).all()
+    assert (d_rgba.cpu().numpy() == 255).all()
+    o, ocols, onc = oracle_from_scene(sc)
+    of, _, _ = oracle_from_scene(sc, fma=True)
+    o.substep(float(sc["dt"]), ocols, onc, 3); of.substep(float(sc["dt"]), ocols, onc, 3)
+    floor = np.abs(o.state()[:, 5:8] - of.state()[:, 5:8]).max()
+    assert np.abs(got[:, 0:3] - o.state()[:, 5:8]).max() <= max(4 * floor, 1e-6), "instance buffer positions vs the oracle's particles"
+    xyzs, rgba = sim.render_buffers(size=0.03)       # the host-copy entry point delivers the same bytes
+    assert np.array_equal(got.view(np.uint32), xyzs.view(np.uint32)) and np.array_equal(d_rgba.cpu().numpy(), rgba)
     sim.write_render_buffers_device(d_xyzs.data_ptr(), None, size=0.01)       # rgba is optional
     sim.synchronize()
     assert (d_xyzs[:, 3].cpu().numpy() == np.float32(0.01)).all()
