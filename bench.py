@@ -257,6 +257,25 @@ def adapter_e2e(mpm_b200, config, steps):
     return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated: the
+    per-frame render-buffer copies (e2e) then land in NUMA-local memory instead of all ranks sharing node 0's memory channels
+    and the inter-socket link. Returns the CPU list, or None if NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def csrc_sha16():
     """Identity of the kernel sources a profiler capture belongs to (profiles/traffic.json carries the same hash)."""
     import hashlib
@@ -418,6 +437,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libmpm_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("MPM_B200_NUMA_BIND", "1") != "0" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -599,7 +619,7 @@ def main():
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
                     "d2h_bytes_per_step": int(16 * n_dl_total), "ms_per_step": e2e_ms,
                     "what": "C-ABI substep with host collider structs in + render buffers (xyz,size) out to pinned host memory, every step",
-                    "mode": e2e_mode},
+                    "mode": e2e_mode, "host_numa_binding": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "none")},
             "e2e_adapter": e2e_adapter,
             "roofline": roof, "invariants": inv, "multi_gpu_check": mcheck, "cpu_baseline": cpu}
     print(json.dumps(line))
