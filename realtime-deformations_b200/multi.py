@@ -198,17 +198,44 @@ class SlabRunner:
         self.peer_halo = world > 1 and os.environ.get("MPM_B200_PEER_HALO", "1") != "0" and \
             (self.device == "cuda" or os.environ.get("MPM_B200_ALLOW_EMULATION") == "1")     # (tests/emu: shared-memory "IPC")
         if self.peer_halo:
-            mine = (self.sim.peer_export(), self.hi - self.lo)
+            # every collective below is entered by every rank whatever happens locally: a rank whose IPC export / mapping fails
+            # (no peer access between two GPUs, a container without CUDA IPC) reports it, and ALL ranks fall back to the
+            # NCCL-message path together
+            ok, why = 1, ""
+            try:
+                mine = (self.sim.peer_export(), self.hi - self.lo)
+            except capi.MpmError as exc:
+                mine, ok, why = (None, 0), 0, str(exc)
             everyone = [None] * world
             self.dist.all_gather_object(everyone, mine)
             lower = everyone[rank - 1] if rank > 0 else (None, 0)
             upper = everyone[rank + 1] if rank < world - 1 else (None, 0)
-            self.sim.peer_connect(lower[0], lower[1], upper[0], upper[1])
+            if ok and all(e[0] is not None for e in everyone):
+                try:
+                    self.sim.peer_connect(lower[0], lower[1], upper[0], upper[1])
+                except capi.MpmError as exc:
+                    ok, why = 0, str(exc)
+            else:
+                ok = 0
             # the migration the same way: neighbours READ the packed buffers through their mappings (pull), no message
+            try:
+                mig_mine = self.sim.peer_export_migration() if ok else None          # (down buffer, up buffer) handles
+            except capi.MpmError as exc:
+                mig_mine, ok, why = None, 0, str(exc)
             mig = [None] * world
-            self.dist.all_gather_object(mig, self.sim.peer_export_migration())          # (down buffer, up buffer) handles
-            self.sim.peer_connect_migration(mig[rank - 1][1] if rank > 0 else None, mig[rank + 1][0] if rank < world - 1 else None)
-            self.dist.barrier()            # every rank has mapped its neighbours before the first remote red
+            self.dist.all_gather_object(mig, mig_mine)
+            if ok and all(m is not None for m in mig):
+                try:
+                    self.sim.peer_connect_migration(mig[rank - 1][1] if rank > 0 else None, mig[rank + 1][0] if rank < world - 1 else None)
+                except capi.MpmError as exc:
+                    ok, why = 0, str(exc)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)      # (also: every rank has mapped its neighbours before the first remote red)
+            if int(flag.item()) == 0:
+                self.peer_halo = False
+                self.peer_fallback_reason = why or "a neighbouring rank could not map peer memory"
 
     # ghost-layer partial sums up, first-layer partial sums down, add on both sides
     def _halo(self):
