@@ -58,12 +58,7 @@ typedef struct MpmParams {
     int   stencil;        /* 0 = cubic B-spline, the reference's (hpp:20-31; the parity default); 1 = quadratic B-spline: three nodes
                              per axis instead of four, D = h^2/4 -- not reference behaviour, checked against
                              the oracle's own quadratic mode; the tile kernels run W = 3 instantiations */
-    int   substep_form;   /* mpm_substep on a single-domain handle with the default variants and the cubic stencil:
-                             0 = single pass: ONE kernel per substep gathers from grid(t), runs the F-update, advects, re-sorts
-                             and scatters into grid(t+1) (the stress never goes to memory; a second grid buffer is allocated),
-                             1 = two kernels (P2G + F-update | gather), which is also what every other handle / variant runs.
-                             Same arithmetic per particle; only the order of the grid's floating-point sums differs. */
-    int   reserved[3];
+    int   reserved[4];
 } MpmParams;
 
 /* Box collider = MeshCollider (hpp:74-93) reduced to what its sdf lambda uses (hpp:80-85):

@@ -21,7 +21,7 @@ class MpmParams(C.Structure):
     _fields_ = [("h", C.c_float), ("youngs_modulus", C.c_float), ("poisson_ratio", C.c_float),
                 ("hardening_xi", C.c_float), ("theta_c", C.c_float), ("theta_s", C.c_float),
                 ("gravity", C.c_float * 3), ("friction_mu", C.c_float), ("p2g_variant", C.c_int),
-                ("g2p_variant", C.c_int), ("fupdate_exact", C.c_int), ("stencil", C.c_int), ("substep_form", C.c_int), ("reserved", C.c_int * 3)]
+                ("g2p_variant", C.c_int), ("fupdate_exact", C.c_int), ("stencil", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class MpmBoxCollider(C.Structure):
@@ -151,7 +151,7 @@ def default_params(**kw):
             raise TypeError(f"unknown parameter {k!r}; fields are {sorted(known)}")
         if k == "gravity":
             p.gravity[:] = [float(x) for x in v]
-        elif k in ("p2g_variant", "g2p_variant", "fupdate_exact", "stencil", "substep_form"):
+        elif k in ("p2g_variant", "g2p_variant", "fupdate_exact", "stencil"):
             setattr(p, k, int(v))
         else:
             setattr(p, k, float(v))

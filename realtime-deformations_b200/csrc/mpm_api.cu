@@ -4,7 +4,6 @@
 #include "../../include/mpm_b200.h"
 #include "mpm_kernels.cuh"
 #include "mpm_tile_kernels.cuh"
-#include "mpm_g2p2g.cuh"
 
 #ifndef MPM_HOST_EMU
 #include <nvtx3/nvToolsExt.h>        // header-only; no-ops unless a profiler (nsys / ncu --nvtx) is attached
@@ -80,11 +79,6 @@ struct mpm_sim {
     bool tau_valid = false, binned = false;
     bool hist_valid = false;   // key[] and blk_count[] already describe the current buffer (written by the fused substep's gather)
     bool hist_fuse = true;     // MPM_B200_FUSE_HIST=0 restores the separate k_bin_count pass (A/B)
-    // single-pass substep (mpm_g2p2g.cuh): second grid, far-stray list; "ahead" = s->grid already holds the raw P2G sums of the
-    // CURRENT particle state, scattered with time step ahead_dt by the previous substep's kernel
-    float4* grid2 = nullptr; int* far_list = nullptr; int far_cap = 1 << 20;
-    bool single_pass_env = true, ahead = false, last_single_pass = false;
-    float ahead_dt = 0.0f;
     bool mig_packed = false;   // slab handles: the gather of the last substep has already packed the leavers into out_buf (fused migration)
     // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
     PeerLayers peer = { nullptr, nullptr };
@@ -181,7 +175,7 @@ static int validate_pos_div(mpm_sim* s) {
 
 static bool valid_variants(const MpmParams& p) {
     return (p.p2g_variant == 0 || p.p2g_variant == 1 || p.p2g_variant == 2 || p.p2g_variant == 9) && (p.g2p_variant == 0 || p.g2p_variant == 1) &&
-           p.fupdate_exact >= 0 && p.fupdate_exact <= 2 && (p.stencil == 0 || p.stencil == 1) && (p.substep_form == 0 || p.substep_form == 1);
+           p.fupdate_exact >= 0 && p.fupdate_exact <= 2 && (p.stencil == 0 || p.stencil == 1);
 }
 static int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
@@ -226,7 +220,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     if (g.hi - g.lo > PB_COORD_MAX || g.npbj > PB_COORD_MAX || g.npbk > PB_COORD_MAX)       // work items carry 10-bit block coordinates
         return fail(MPM_ERR_INVALID, "grid too large: at most %d particle blocks (%d nodes) per axis and slab", PB_COORD_MAX, 4 * PB_COORD_MAX);
     g.n_pblocks = (int)npb; g.n_gblocks = (int)ngb;
-    if (!valid_variants(s->prm)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1, substep_form 0 or 1");
+    if (!valid_variants(s->prm)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1");
     fill_consts(s);
     s->capacity = std::max<int64_t>(capacity, 1);
     s->n_uploaded = n_particles; s->n_bound = n_particles;
@@ -255,7 +249,6 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     s->ev_ok = true;
     { const char* g = getenv("MPM_B200_GRAPH"); s->graph_enabled = g && atoi(g) > 0; }
     { const char* f = getenv("MPM_B200_FUSE_HIST"); s->hist_fuse = !(f && atoi(f) == 0); }
-    { const char* f = getenv("MPM_B200_SINGLE_PASS"); s->single_pass_env = !(f && atoi(f) == 0); }
     {
         // Running the F-update on a side stream next to the gather was measured at <= 1.5 % (the gather's persistent CTAs
         // own the register file), so it is opt-in; the default keeps the two kernels back to back and times them apart.
@@ -272,7 +265,6 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
-    CK(g2p2g_init());
     CK(cudaStreamSynchronize(s->stream));
     { int rc = validate_pos_div(s); if (rc) return rc; }
     return MPM_OK;
@@ -289,7 +281,7 @@ int mpm_destroy(mpm_t* s) {
     for (int b = 0; b < 2; ++b) { cudaFree(s->buf[b]); cudaFree(s->out_buf[b]); }
     cudaFree(s->key); cudaFree(s->sorted_ids); cudaFree(s->blk_count); cudaFree(s->blk_start); cudaFree(s->blk_cursor);
     cudaFree(s->pblock_list); cudaFree(s->gflag); cudaFree(s->gblock_list); cudaFree(s->partial);
-    cudaFree(s->grid); cudaFree(s->grid2); cudaFree(s->far_list); cudaFree(s->gforce); cudaFree(s->dc); cudaFree(s->slot_of_pid);
+    cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc); cudaFree(s->slot_of_pid);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
@@ -320,14 +312,13 @@ int mpm_set_stream(mpm_t* s, void* st) {
 int mpm_set_params(mpm_t* s, const MpmParams* p) {
     if (!s || !p) return fail(MPM_ERR_INVALID, "null argument");
     if (p->h != s->prm.h || p->stencil != s->prm.stencil) return fail(MPM_ERR_INVALID, "h and stencil cannot change after creation");
-    if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1, substep_form 0 or 1");
+    if (!valid_variants(*p)) return fail(MPM_ERR_INVALID, "p2g_variant must be 0, 1, 2 or 9, g2p_variant 0 or 1, fupdate_exact 0..2, stencil 0 or 1");
     s->prm = *p;
     drop_graph(s);                  // material constants and kernel variants are baked into a captured substep pair
     const int fast = s->sc.pd.fast;
     fill_consts(s);
     s->sc.pd.fast = fast;           // h is unchanged, so the validation still holds
     s->tau_valid = false;
-    s->ahead = false;
     return MPM_OK;
 }
 
@@ -389,7 +380,7 @@ static int upload_common(mpm_sim* s, int64_t n, const HostFieldPtrs& f) {
     CK(cudaMemcpyAsync(&s->dc->n_slots, &ni, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->n_uploaded = n; s->n_bound = n;
-    s->tau_valid = false; s->binned = false; s->hist_valid = false; s->ahead = false;
+    s->tau_valid = false; s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 
@@ -530,7 +521,6 @@ int mpm_wait_render_buffers(mpm_t* s) {
 // ---- binning / sort -----------------------------------------------------------------------------------------
 static int do_binning(mpm_sim* s) {
     const GridDims& g = s->gd;
-    s->ahead = false;          // whoever bins is about to rebuild the grid (the single-pass substep reads the flag first)
     const int nb = grid_for(s->n_bound, BIN_T * BIN_E);
     Planes C = s->planes(s->cur);
     if (!s->hist_valid) {      // (the fused substep's gather has already written next substep's keys and histogram)
@@ -626,7 +616,7 @@ static int launch_g2p(mpm_sim* s, float dt) {
     const bool slab_handle = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
     const bool fuse_hist = s->hist_fuse && s->prm.g2p_variant != 1 && !(slab_handle && s->side.stream) &&
                            (FLAGS & G2P_REORDER) && (FLAGS & G2P_ADVECT) && (FLAGS & G2P_GATHER);
-    if ((FLAGS & G2P_ADVECT) && !fuse_hist) s->hist_valid = false; s->ahead = false;       // positions change without new keys
+    if ((FLAGS & G2P_ADVECT) && !fuse_hist) s->hist_valid = false;       // positions change without new keys
     MigOut mo = { nullptr, nullptr, 0 };
     if (fuse_hist) {
         CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
@@ -743,7 +733,6 @@ int mpm_substep_begin(mpm_t* s, float dt) {
     NEED(s);
     NvtxRange r("mpm_substep_begin: bin/sort, clear, P2G");
     EV(0);
-    s->last_single_pass = false;
     TRY(ensure_tau(s));
     { NvtxRange r1("bin/sort"); TRY(do_binning(s)); }
     EV(1);
@@ -766,68 +755,6 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
     s->fupd_pending = false;
     EV(6);
     s->tau_valid = true;
-    s->stats.substeps_done++;
-    return MPM_OK;
-}
-
-// ---- single-pass substep (mpm_g2p2g.cuh) ------------------------------------------------------------------------------------
-// Per substep: bin (keys + histogram come from the previous kernel) | grid update of grid(t) | active list of grid(t+1) = occupied
-// blocks dilated by one, cleared in the second grid | ONE kernel: gather(t), F-update, advect, re-sort, keys, P2G(t+1) | swap grids.
-// The first substep after anything else touched the handle (upload, a staged call, another dt) scatters grid(t) with the
-// plain block-tile P2G first. Single-domain handles with the default variants and the cubic stencil; everything else runs
-// the two-kernel form (mpm_substep_begin / mpm_substep_end).
-static bool single_pass_ok(const mpm_sim* s) {
-    const bool slab = s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global;
-    return s->single_pass_env && s->prm.substep_form == 0 && !slab && !s->peer_connected && !s->peer_mig_connected && s->prm.p2g_variant == 0 &&
-           s->prm.g2p_variant == 0 && s->prm.stencil == 0 && !s->side.stream && s->hist_fuse;
-}
-static int substep_single_pass(mpm_sim* s, float dt, const MpmBoxCollider* c, int n) {
-    NvtxRange r("mpm_substep (single pass): bin, grid update, G2P2G");
-    TRY(set_colliders(s, c, n));
-    const size_t grid_bytes = sizeof(float4) * 64 * (size_t)s->gd.n_gblocks;
-    if (!s->grid2) {
-        CK(cudaMalloc(&s->grid2, grid_bytes + PEER_FLAG_BYTES));      // same shape as the first one: the two swap roles every substep
-        CK(cudaMemsetAsync(s->grid2, 0, grid_bytes + PEER_FLAG_BYTES, s->stream));
-        CK(cudaMalloc(&s->far_list, sizeof(int) * (size_t)s->far_cap));
-    }
-    const bool ahead = s->ahead && s->ahead_dt == dt;
-    EV(0);
-    if (!ahead) TRY(ensure_tau(s));
-    TRY(do_binning(s));
-    if (!ahead) {      // grid(t) from scratch: plain block-tile P2G (momentum + dt * stress forces), no F-update
-        TRY(launch_clear(s));
-        CK((launch_p2g_tile<P2G_FUSED>(s->planes(s->cur), s->sorted_ids, s->pblock_list, s->dc, s->grid, s->gd, s->sc, dt, s->num_sms, (int)s->n_bound, s->stream)));
-        s->stats.kernel_launches++;
-    }
-    EV(1); EV(4);
-    TRY((launch_grid_update<GU_NORMALIZE | GU_GRAVITY | GU_COLLIDE | GU_COUNT>(s, dt)));
-    EV(5);
-    CK(cudaMemsetAsync(&s->dc->n_active_gblocks, 0, sizeof(int), s->stream));
-    k_mark_dilated<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->pblock_list, s->dc, s->gd, s->gflag, s->gblock_list);
-    CKLAUNCH();
-    k_grid_clear<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid2, nullptr);
-    CKLAUNCH();
-    EV(2);
-    CK(cudaMemsetAsync(s->blk_count, 0, sizeof(int) * (size_t)s->n_buckets, s->stream));
-    CK(cudaMemsetAsync(&s->dc->work_a, 0, sizeof(int), s->stream));
-    Planes C = s->planes(s->cur), N = s->planes(s->cur ^ 1);
-    if (s->prm.fupdate_exact == 1)
-        k_g2p2g<false><<<s->num_sms * 2, P2G_T, sizeof(G2P2GSmem), s->stream>>>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->grid2, s->gd, s->sc, dt, s->key, s->blk_count, s->far_list, s->far_cap);
-    else
-        k_g2p2g<true><<<s->num_sms * 2, P2G_T, sizeof(G2P2GSmem), s->stream>>>(C, N, s->sorted_ids, s->pblock_list, s->dc, s->grid, s->grid2, s->gd, s->sc, dt, s->key, s->blk_count, s->far_list, s->far_cap);
-    CKLAUNCH();
-    k_g2p2g_far<<<1, 256, 0, s->stream>>>(N, s->dc, s->far_list, s->far_cap, s->grid2, s->gd, s->sc, dt, s->gflag, s->gblock_list);
-    CKLAUNCH();
-    k_copy_parked<<<64, 256, 0, s->stream>>>(C, N, s->sorted_ids, s->dc, s->gd, s->sc.pd, s->key, s->blk_count, MigOut{ nullptr, nullptr, 0 });
-    CKLAUNCH();
-    EV(3); EV(6);
-    s->stats.kernel_launches += 6;
-    std::swap(s->grid, s->grid2);
-    s->cur ^= 1;
-    s->binned = false; s->hist_valid = true; s->mig_packed = false;
-    s->ahead = true; s->ahead_dt = dt;
-    s->tau_valid = true; s->fupd_pending = false;
-    s->last_single_pass = true;
     s->stats.substeps_done++;
     return MPM_OK;
 }
@@ -873,11 +800,10 @@ int mpm_substep(mpm_t* s, float dt, const MpmBoxCollider* c, int n, int n_subste
         for (int i = 0; i < pairs; ++i) CK(cudaGraphLaunch(s->graph_exec, s->stream));
         s->stats.substeps_done += 2 * pairs;
         s->stats.kernel_launches += (int64_t)s->graph_launches * pairs;
-        s->tau_valid = true; s->binned = false; s->hist_valid = false; s->ahead = false;
+        s->tau_valid = true; s->binned = false; s->hist_valid = false;
         n_substeps -= 2 * pairs;                            // an odd leftover runs through the plain path below
     }
     for (int i = 0; i < n_substeps; ++i) {
-        if (single_pass_ok(s)) { TRY(substep_single_pass(s, dt, c, n)); continue; }
         TRY(mpm_substep_begin(s, dt));
         TRY(mpm_substep_end(s, dt, c, n));
     }
@@ -1143,12 +1069,9 @@ int mpm_get_stats(mpm_t* s, MpmStats* out) {
     st.reserved[0] = s->sc.pd.fast;      // 1: the pos/h FMA shortcut passed its exhaustive check against __fdiv_rn
     st.reserved[1] = h.mig_overflow;
     st.reserved[2] = h.peer_timeout;     // experimental peer-memory halo: a neighbour's flag never arrived
-    st.reserved[3] = h.far_overflow;     // single-pass substep: more than far_cap particles moved over a cell in one substep
     if (st.substeps_done > 0) {
         float ms;
-        // (single-pass substep: bin [+ first P2G] | grid update | mark + clear | the kernel: "clear" runs after the grid update)
-        const bool sp = s->last_single_pass;      // there the kernel is reported in the P2G slot and the gather slot is empty
-        const int pairs[6][2] = { { 0, 1 }, { sp ? 5 : 1, 2 }, { 2, 3 }, { 4, 5 }, { sp ? 3 : 5, 6 }, { sp ? 1 : 3, 4 } };
+        const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 4, 5 }, { 5, 6 }, { 3, 4 } };
         for (int k = 0; k < 6; ++k) st.last_ms[k] = cudaEventElapsedTime(&ms, s->ev[pairs[k][0]], s->ev[pairs[k][1]]) == cudaSuccess ? ms : -1.0f;
         st.last_ms[6] = cudaEventElapsedTime(&ms, s->ev[0], s->ev[6]) == cudaSuccess ? ms : -1.0f;
         st.last_ms[7] = (s->side.mid_recorded && cudaEventElapsedTime(&ms, s->ev[5], s->side.mid) == cudaSuccess) ? ms : -1.0f;   // F-update alone
@@ -1177,7 +1100,6 @@ int mpm_upload_grid(mpm_t* s, const float* grid7) {
     NEED(s);
     if (!grid7) return fail(MPM_ERR_INVALID, "grid7 is NULL");
     TRY(ensure_gforce(s));
-    s->ahead = false;
     const size_t n = (size_t)s->gd.I * s->gd.J * s->gd.K;
     float* d = nullptr;
     CK(cudaMalloc(&d, n * 7 * sizeof(float)));
@@ -1373,7 +1295,7 @@ int mpm_migrate_outgoing(mpm_t* s, int64_t* n_down, int64_t* n_up, const void** 
     *n_down = h.n_mig[0]; *n_up = h.n_mig[1];
     *dev_down = s->out_buf[0]; *dev_up = s->out_buf[1];
     s->n_bound = h.n_slots;          // exact after the sync
-    s->binned = false; s->hist_valid = false; s->ahead = false; s->mig_packed = false;
+    s->binned = false; s->hist_valid = false; s->mig_packed = false;
     return MPM_OK;
 }
 int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
@@ -1384,7 +1306,7 @@ int mpm_migrate_append(mpm_t* s, const void* dev_buf, int64_t n) {
     k_append_incoming<<<grid_for(n, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, (const float4*)dev_buf, (int)s->n_bound, (int)n);
     CKLAUNCH(); s->stats.kernel_launches++;
     s->n_bound += n;
-    s->binned = false; s->hist_valid = false; s->ahead = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 static int64_t default_migrate_capacity(const mpm_sim* s) { return std::min<int64_t>(std::max<int64_t>(1 << 14, s->capacity / 128), 1 << 18); }
@@ -1419,7 +1341,7 @@ int mpm_migrate_pack(mpm_t* s, const void** dev_down, const void** dev_up) {
     for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(s->out_buf[d], 0, sizeof(float4), s->stream));
     k_mark_outgoing_hdr<<<grid_for(s->n_bound, 256), 256, 0, s->stream>>>(s->planes(s->cur), s->dc, s->gd, s->sc.pd, s->out_buf[0], s->out_buf[1], (int)s->out_cap);
     CKLAUNCH(); s->stats.kernel_launches++;
-    s->binned = false; s->hist_valid = false; s->ahead = false;
+    s->binned = false; s->hist_valid = false;
     return MPM_OK;
 }
 int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
@@ -1434,7 +1356,6 @@ int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
     CKLAUNCH(); s->stats.kernel_launches += 2;
     s->n_bound = std::min<int64_t>(s->capacity, s->n_bound + cap);      // upper bound; mpm_sync_counts tightens it
     s->binned = false;          // (keys + histogram stay valid: the appended particles have added theirs)
-    s->ahead = false;
     return MPM_OK;
 }
 // EXPERIMENTAL peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own

@@ -54,7 +54,7 @@ struct DevCounters {
     int n_mig[2];           // particles packed for the lower / upper slab neighbour by k_mark_outgoing
     int mig_overflow;
     int peer_timeout;       // experimental peer-memory halo: a neighbour's flag did not arrive (k_peer_wait gave up)
-    int n_far, far_overflow; // single-pass substep (mpm_g2p2g.cuh): particles that moved more than one cell, and whether their list overflowed
+    int pad[2];
     long long prof[8];      // MPM_P2G_PROFILE builds only: clock64 ticks per P2G phase, summed over CTAs (thread 0)
 };
 

@@ -25,8 +25,7 @@ def run(grid, n, steps, pv, gv, scene="slab", rotate=None):
     tg = time.time() - t0
     fx = int(os.environ.get("MPM_PROBE_FUPDATE_EXACT", "0"))
     stencil = int(os.environ.get("MPM_PROBE_STENCIL", "0"))          # 1 = quadratic B-spline (not the reference's stencil)
-    form = int(os.environ.get("MPM_PROBE_SUBSTEP_FORM", "0"))        # 1 = two kernels per substep instead of the single-pass kernel
-    p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv, fupdate_exact=fx, stencil=stencil, substep_form=form)
+    p = mpm_b200.capi.default_params(p2g_variant=pv, g2p_variant=gv, fupdate_exact=fx, stencil=stencil)
     if "gravity" in sc: p.gravity[:] = [float(x) for x in sc["gravity"]]
     sim = mpm_b200.Sim(grid, grid, grid, sc["n"], p)
     if os.environ.get("MPM_PROBE_SHUFFLE") == "1":          # worst case for everything that relies on cell-coherent particle order
@@ -39,7 +38,7 @@ def run(grid, n, steps, pv, gv, scene="slab", rotate=None):
     t0 = time.time(); sim.substep(1e-5, cols, nc, steps); sim.synchronize(); dt = (time.time() - t0) / steps
     st = sim.stats()
     ms = list(st.last_ms)
-    print(f"{scene} grid={grid} n={sc['n']} fexact={fx} stencil={stencil} form={form} variants=({pv},{gv}) rotate={'default' if rotate is None else rotate} gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
+    print(f"{scene} grid={grid} n={sc['n']} fexact={fx} stencil={stencil} variants=({pv},{gv}) rotate={'default' if rotate is None else rotate} gen={tg:.1f}s upload={tu:.1f}s  {dt*1e3:.3f} ms/substep  "
           f"{sc['n']/dt/1e9:.3f} G upd/s  bin={ms[0]:.3f} clear={ms[1]:.3f} p2g={ms[2]:.3f} grid={ms[3]:.3f} g2p={ms[4]:.3f} (fupdate={ms[7]:.3f}) total={ms[6]:.3f} "
           f"active_nodes={st.n_active_nodes} pblocks={st.n_particle_blocks} gblocks={st.n_grid_blocks}", flush=True)
     sim.close()
