@@ -589,3 +589,270 @@ void oracle_substep(Oracle* o, float dt, const OracleBoxCollider* c, int nc, int
         oracle_update_particle_positions(o, dt);
     }
 }
+
+/* =====================================================================================================
+ * Implicit (optimisation-based) time integration: material_point_method.cpp:160-233 + mathy.hpp:10-38 +
+ * the vendored mcloptlib (external/mcloptlib/include/MCL: LBFGS.hpp, Backtracking.hpp, Problem.hpp).
+ * The reference never calls timeIntegration (README.md:17 lists it as a TODO); its objective and its
+ * optimiser settings are restated here as written, including the placeholders mu0 = lambda0 = 1
+ * (hpp:212-214) and the hardening factor exp(xi*1 - det FP) (cpp:187-191).
+ * Not restated as written: the gradient. The library differentiates Energy by central differences with
+ * eps = 2.2204e-6 in float (Problem.hpp:87-107), which is below the resolution of a float velocity above
+ * 16 m/s and below the rounding noise of a float Energy everywhere, so the reference's own search
+ * direction is noise; gradient = 1 reproduces that rule for completeness, gradient = 0 (the checker for the
+ * CUDA path) is the analytic derivative of the same objective, evaluated in double.
+ * ===================================================================================================== */
+float oracle_weight_derivative(float x) {          /* hpp:32-52 */
+    const float modx = fabsf(x);
+    if (modx < 1.0f) {
+        if (x >= 0) return (float)(+3.0 / 2.0 * (double)x * (double)x - (double)(2 * x));
+        return (float)(-3.0 / 2.0 * (double)x * (double)x - (double)(2 * x));
+    } else if ((double)modx < 2.0) {
+        if (x >= 0) { const float a = 2 - x; return (float)(-0.5 * (double)a * (double)a); }
+        { const float a = 2 + x; return (float)(0.5 * (double)a * (double)a); }
+    }
+    return 0.0f;
+}
+void oracle_default_implicit_params(OracleImplicitParams* q) {
+    q->mu0 = 1.0f; q->lambda0 = 1.0f; q->xi = 10.0f;      /* hpp:212-214 */
+    q->hardening = 0;
+    q->max_iters = 50;                                    /* LBFGS.hpp:48 */
+    q->ls_decrease = 1e-4f; q->ls_tau = 0.7f; q->ls_max_iters = 100000;   /* Minimizer.hpp:62-63, Backtracking.hpp:46 */
+    q->tol_grad = 1e-2f; q->tol_step = 1e-2f;             /* mathy.hpp:31-35 */
+    q->gradient = 0;
+}
+void oracle_used_cells(const Oracle* o, int* idx) { memcpy(idx, o->used, (size_t)o->nused * sizeof(int)); }
+
+/* wipGrad, hpp:59-71: comp = (pos - idx*h)/h (NOT pos/h - idx as in wipHost) */
+static void wip_grad(const Oracle* o, const float pos[3], int ni, int nj, int nk, float g[3]) {
+    const float h = o->prm.h;
+    const float xc = (pos[0] - (float)ni * h) / h, yc = (pos[1] - (float)nj * h) / h, zc = (pos[2] - (float)nk * h) / h;
+    const float wx = oracle_weight(xc), wy = oracle_weight(yc), wz = oracle_weight(zc);
+    const double ih = 1.0 / (double)h;
+    g[0] = (float)(ih * (double)oracle_weight_derivative(xc) * (double)wy * (double)wz);
+    g[1] = (float)(ih * (double)wx * (double)oracle_weight_derivative(yc) * (double)wz);
+    g[2] = (float)(ih * (double)wx * (double)wy * (double)oracle_weight_derivative(zc));
+}
+static float hardening_factor(const OracleImplicitParams* q, float detFP) {
+    return q->hardening == 0 ? expf(q->xi * 1 - detFP) : expf(q->xi * (1 - detFP));
+}
+/* dense map node -> position in used_cells (or -1), built per call */
+static int* used_rank(const Oracle* o) {
+    const size_t N = (size_t)o->I * o->J * o->K;
+    int* r = (int*)malloc(N * sizeof(int));
+    for (size_t i = 0; i < N; ++i) r[i] = -1;
+    for (int u = 0; u < o->nused; ++u) r[o->used[u]] = u;
+    return r;
+}
+/* trial elastic deformation gradient of one particle, cpp:176-185: (I + sum_cells outer(v dt, wipGrad)) * FE.
+ * The reference sums over ALL used cells in lexicographic order; cells outside the 4^3 support add +-0. */
+static void trial_FE(const Oracle* o, const int* rank, int pi, const float* vel, float dt, float FEt[9]) {
+    const OParticle* P = &o->p[pi];
+    float A[9];
+    memcpy(A, ID3, sizeof A);
+    const int* c = &o->cell[pi * 3];
+    if (o->valid[pi])
+        for (int di = -2; di <= 2; ++di) for (int dj = -2; dj <= 2; ++dj) for (int dk = -2; dk <= 2; ++dk) {      /* lexicographic = used_cells order */
+            const int ni = c[0] + di, nj = c[1] + dj, nk = c[2] + dk;
+            const int u = rank[nidx(o, ni, nj, nk)];
+            if (u < 0) continue;
+            float g[3];
+            wip_grad(o, P->pos, ni, nj, nk, g);
+            const float vt[3] = { vel[u * 3 + 0] * dt, vel[u * 3 + 1] * dt, vel[u * 3 + 2] * dt };
+            for (int col = 0; col < 3; ++col) for (int r = 0; r < 3; ++r) A[col * 3 + r] += vt[r] * g[col];       /* outerProduct(c, r): m[col][row] = c[row] * r[col] */
+        }
+    m3mul(FEt, A, P->FE);
+}
+/* ElasticPlasticEnergyDensity, cpp:186-209 */
+static float energy_density(const OracleImplicitParams* q, const float FE[9], const float FP[9]) {
+    const float e = hardening_factor(q, m3det(FP));
+    const float mu = q->mu0 * e, lambda = q->lambda0 * e;
+    float R[9], D[9];
+    oracle_polar_rotation(FE, R);
+    m3sub(D, FE, R);
+    double val = 0.0;
+    for (int i = 0; i < 9; ++i) val += D[i] * D[i];
+    const float fn2 = (float)val;
+    const float JE = m3det(FE);
+    return mu * fn2 + lambda / 2 * (JE - 1) * (JE - 1);
+}
+float oracle_energy(Oracle* o, const float* vel, float dt, const OracleImplicitParams* q) {      /* cpp:160-185 */
+    double energy = 0.0;
+    for (int u = 0; u < o->nused; ++u) {
+        const OCell* c = &o->g[o->used[u]];
+        const float d[3] = { vel[u * 3] - c->vel[0], vel[u * 3 + 1] - c->vel[1], vel[u * 3 + 2] - c->vel[2] };
+        const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        energy += 0.5 * c->mass * n * n;
+    }
+    int* rank = used_rank(o);
+    float acc = 0.0f;
+    for (int i = 0; i < o->n; ++i) {
+        float FEt[9];
+        trial_FE(o, rank, i, vel, dt, FEt);
+        acc += o->p[i].volume * energy_density(q, FEt, o->p[i].FP);
+    }
+    free(rank);
+    energy += acc;
+    return (float)energy;
+}
+/* analytic gradient in double: dE/dv_i = m_i (v_i - v*_i) + dt sum_p V_p (2 mu (F - R) + lambda (J - 1) J F^-T) FE_p^T grad w_ip */
+void oracle_energy_gradient(Oracle* o, const float* vel, float dt, const OracleImplicitParams* q, double* grad) {
+    for (int u = 0; u < o->nused; ++u) {
+        const OCell* c = &o->g[o->used[u]];
+        for (int a = 0; a < 3; ++a) grad[u * 3 + a] = (double)c->mass * ((double)vel[u * 3 + a] - (double)c->vel[a]);
+    }
+    int* rank = used_rank(o);
+    for (int i = 0; i < o->n; ++i) {
+        if (!o->valid[i]) continue;
+        const OParticle* P = &o->p[i];
+        float FEt[9], R[9], Finv[9];
+        trial_FE(o, rank, i, vel, dt, FEt);
+        const double e = (double)hardening_factor(q, m3det(P->FP));
+        const double mu = q->mu0 * e, lambda = q->lambda0 * e;
+        oracle_polar_rotation(FEt, R);
+        m3inverse(Finv, FEt);
+        const double J = m3det(FEt);
+        double Pk[9], G[9];                                   /* column-major like everything else */
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+            Pk[c * 3 + r] = 2.0 * mu * ((double)FEt[c * 3 + r] - (double)R[c * 3 + r]) + lambda * (J - 1.0) * J * (double)Finv[r * 3 + c];   /* F^-T (r,c) = F^-1 (c,r) */
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) {                                                                           /* G = V Pk FE^T */
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += Pk[k * 3 + r] * (double)P->FE[k * 3 + c];
+            G[c * 3 + r] = (double)P->volume * s;
+        }
+        const int* c3 = &o->cell[i * 3];
+        for (int di = -2; di <= 2; ++di) for (int dj = -2; dj <= 2; ++dj) for (int dk = -2; dk <= 2; ++dk) {
+            const int ni = c3[0] + di, nj = c3[1] + dj, nk = c3[2] + dk;
+            const int u = rank[nidx(o, ni, nj, nk)];
+            if (u < 0) continue;
+            float g[3];
+            wip_grad(o, P->pos, ni, nj, nk, g);
+            for (int r = 0; r < 3; ++r) grad[u * 3 + r] += (double)dt * (G[0 + r] * g[0] + G[3 + r] * g[1] + G[6 + r] * g[2]);
+        }
+    }
+    free(rank);
+}
+/* Problem::gradient as the optimiser sees it: value + gradient (Problem.hpp:49-52, 87-107) */
+static float objective_gradient(Oracle* o, const float* x, float dt, const OracleImplicitParams* q, float* grad, int n, oracle_objective_fn fn, void* user) {
+    if (fn) return fn(user, x, grad, n);
+    if (q->gradient == 1) {
+        const float eps = 2.2204e-6f;
+        float* xx = (float*)malloc((size_t)n * sizeof(float));
+        for (int d = 0; d < n; ++d) {
+            memcpy(xx, x, (size_t)n * sizeof(float));
+            float gd = 0.0f;
+            xx[d] = x[d] + 1 * eps; gd += 1 * oracle_energy(o, xx, dt, q);
+            xx[d] = x[d] + -1 * eps; gd += -1 * oracle_energy(o, xx, dt, q);
+            grad[d] = gd / (2 * eps);
+        }
+        free(xx);
+    } else {
+        double* g = (double*)malloc((size_t)n * sizeof(double));
+        oracle_energy_gradient(o, x, dt, q, g);
+        for (int d = 0; d < n; ++d) grad[d] = (float)g[d];
+        free(g);
+    }
+    return oracle_energy(o, x, dt, q);
+}
+static float objective_value(Oracle* o, const float* x, float dt, const OracleImplicitParams* q, int n, oracle_objective_fn fn, void* user) {
+    if (fn) return fn(user, x, NULL, n);
+    return oracle_energy(o, x, dt, q);
+}
+static double vdot(const float* a, const float* b, int n) { double s = 0.0; for (int i = 0; i < n; ++i) s += (double)a[i] * (double)b[i]; return s; }
+/* mcl::optlib::LBFGS<float, Dynamic, 8>::minimize (LBFGS.hpp:52-152) with Backtracking::search (Backtracking.hpp:38-69) and
+ * Objective::converged (mathy.hpp:31-35). fn != NULL minimises a caller-supplied function instead of Energy (known-answer
+ * tests of the optimiser restatement against the vendored library). Returns the iteration count, -1 on line-search failure. */
+int oracle_lbfgs(Oracle* o, float* x, int n, float dt, const OracleImplicitParams* q, oracle_objective_fn fn, void* user, int* n_evals) {
+    enum { M = 8 };
+    float* s = (float*)calloc((size_t)n * M, sizeof(float));
+    float* y = (float*)calloc((size_t)n * M, sizeof(float));
+    float *grad = (float*)calloc(n, sizeof(float)), *qv = (float*)calloc(n, sizeof(float)), *grad_old = (float*)calloc(n, sizeof(float)),
+          *x_old = (float*)calloc(n, sizeof(float)), *x_last = (float*)calloc(n, sizeof(float)), *tmp = (float*)calloc(n, sizeof(float)),
+          *lsgrad = (float*)calloc(n, sizeof(float));
+    float alpha[M] = { 0 }, rho[M] = { 0 };
+    int evals = 0, result = 0;
+    objective_gradient(o, x, dt, q, grad, n, fn, user); ++evals;
+    float gamma_k = 1.0f;
+    float alpha_init = 1.0f;
+    int global_iter = 0, max_iters = q->max_iters;
+    for (int k = 0; k < max_iters; ++k) {
+        memcpy(x_old, x, (size_t)n * sizeof(float));
+        memcpy(grad_old, grad, (size_t)n * sizeof(float));
+        memcpy(qv, grad, (size_t)n * sizeof(float));
+        global_iter++;
+        const int iter = k < M ? k : M;
+        for (int i = iter - 1; i >= 0; --i) {
+            rho[i] = (float)(1.0 / vdot(s + (size_t)i * n, y + (size_t)i * n, n));
+            alpha[i] = rho[i] * (float)vdot(s + (size_t)i * n, qv, n);
+            for (int d = 0; d < n; ++d) qv[d] = qv[d] - alpha[i] * y[(size_t)i * n + d];
+        }
+        for (int d = 0; d < n; ++d) qv[d] = gamma_k * qv[d];
+        for (int i = 0; i < iter; ++i) {
+            const float beta = rho[i] * (float)vdot(qv, y + (size_t)i * n, n);
+            for (int d = 0; d < n; ++d) qv[d] = qv[d] + (alpha[i] - beta) * s[(size_t)i * n + d];
+        }
+        const float dir = (float)vdot(qv, grad, n);
+        if (dir <= 0) {
+            memcpy(qv, grad, (size_t)n * sizeof(float));
+            max_iters -= k;
+            k = 0;
+            float ginf = 0.0f;
+            for (int d = 0; d < n; ++d) ginf = fmaxf(ginf, fabsf(grad[d]));
+            alpha_init = (float)fmin(1.0, 1.0 / (double)ginf);
+        }
+        /* Backtracking::search(x, p = -q) */
+        float rate;
+        {
+            double pn = 0.0;
+            for (int d = 0; d < n; ++d) pn += (double)qv[d] * (double)qv[d];
+            if ((float)sqrt(pn) <= FLT_EPSILON) rate = q->ls_decrease;
+            else {
+                float a = alpha_init;
+                const float fx0 = objective_gradient(o, x, dt, q, lsgrad, n, fn, user); ++evals;
+                const float gtp = -(float)vdot(lsgrad, qv, n);
+                int it = 0;
+                for (; it < q->ls_max_iters; ++it) {
+                    for (int d = 0; d < n; ++d) tmp[d] = x[d] + a * -qv[d];
+                    const float fxa = objective_value(o, tmp, dt, q, n, fn, user); ++evals;
+                    const float bound = fx0 + a * q->ls_decrease * gtp;
+                    if (fxa <= bound) break;
+                    a *= q->ls_tau;
+                }
+                rate = it >= q->ls_max_iters ? -1.0f : a;
+            }
+        }
+        if (rate <= 0) { result = -1; break; }
+        memcpy(x_last, x, (size_t)n * sizeof(float));
+        for (int d = 0; d < n; ++d) x[d] -= rate * qv[d];
+        {   /* Objective::converged(x_last, x, grad) */
+            double gn = 0.0, sn = 0.0;
+            for (int d = 0; d < n; ++d) { gn += (double)grad[d] * grad[d]; const double dd = (double)x_last[d] - (double)x[d]; sn += dd * dd; }
+            if ((float)sqrt(gn) < q->tol_grad || (float)sqrt(sn) < q->tol_step) { result = global_iter; break; }
+        }
+        objective_gradient(o, x, dt, q, grad, n, fn, user); ++evals;
+        float *st = s + (size_t)(k < M ? k : M - 1) * n, *yt = y + (size_t)(k < M ? k : M - 1) * n;
+        if (k >= M) {
+            memmove(s, s + n, (size_t)n * (M - 1) * sizeof(float));
+            memmove(y, y + n, (size_t)n * (M - 1) * sizeof(float));
+        }
+        for (int d = 0; d < n; ++d) { st[d] = x[d] - x_old[d]; yt[d] = grad[d] - grad_old[d]; }
+        const float denom = (float)vdot(yt, yt, n);
+        if (fabsf(denom) <= 0) { result = global_iter; break; }
+        gamma_k = (float)vdot(st, yt, n) / denom;
+        alpha_init = 1.0f;
+        result = global_iter;
+    }
+    if (n_evals) *n_evals = evals;
+    free(s); free(y); free(grad); free(qv); free(grad_old); free(x_old); free(x_last); free(tmp); free(lsgrad);
+    return result;
+}
+/* timeIntegration, cpp:211-233: minimise Energy over the velocities of the used cells, starting from the grid's */
+int oracle_time_integration(Oracle* o, float dt, const OracleImplicitParams* q, int* n_evals) {
+    const int n = o->nused * 3;
+    float* x = (float*)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+    for (int u = 0; u < o->nused; ++u) for (int a = 0; a < 3; ++a) x[u * 3 + a] = o->g[o->used[u]].vel[a];
+    const int it = oracle_lbfgs(o, x, n, dt, q, NULL, NULL, n_evals);
+    for (int u = 0; u < o->nused; ++u) for (int a = 0; a < 3; ++a) o->g[o->used[u]].vel[a] = x[u * 3 + a];
+    free(x);
+    return it;
+}

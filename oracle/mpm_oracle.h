@@ -68,6 +68,27 @@ float oracle_box_sdf(const OracleBoxCollider* c, const float pos[3]);     /* hpp
 void  oracle_body_collision(const float pos[3], const float vel[3], const OracleBoxCollider* c, int nc,
                             float friction, float out[3]);      /* cpp:264-296 */
 
+/* ---- implicit (optimisation-based) time integration: material_point_method.cpp:160-233, mathy.hpp:10-38, vendored
+ * mcloptlib (LBFGS.hpp, Backtracking.hpp, Problem.hpp). Dead code in the reference (never called); see mpm_oracle.c. ---- */
+typedef struct {
+    float mu0, lambda0, xi;   /* hpp:212-214: 1, 10, 1 (placeholders in the reference) */
+    int hardening;            /* 0 = exp(xi*1 - det FP) as written (cpp:187-191); 1 = exp(xi*(1 - det FP)) like the explicit forces (cpp:240) */
+    int max_iters;            /* 50 (LBFGS.hpp:48) */
+    float ls_decrease, ls_tau; int ls_max_iters;   /* 1e-4, 0.7, 100000 (Minimizer.hpp:62-63, Backtracking.hpp:46) */
+    float tol_grad, tol_step; /* 1e-2 each (mathy.hpp:31-35) */
+    int gradient;             /* 0 = analytic derivative (double); 1 = the library's float central differences, eps 2.2204e-6 */
+} OracleImplicitParams;
+void  oracle_default_implicit_params(OracleImplicitParams* q);
+float oracle_weight_derivative(float x);                              /* hpp:32-52 */
+void  oracle_used_cells(const Oracle* o, int* node_index);            /* used_cells (cpp:105-110) as i*J*K + j*K + k */
+/* vel: 3 floats per used cell in used_cells order */
+float oracle_energy(Oracle* o, const float* vel, float dt, const OracleImplicitParams* q);                     /* cpp:160-209 */
+void  oracle_energy_gradient(Oracle* o, const float* vel, float dt, const OracleImplicitParams* q, double* grad);
+/* value (and gradient when grad != NULL) of a caller-supplied objective, for known-answer tests of the optimiser */
+typedef float (*oracle_objective_fn)(void* user, const float* x, float* grad, int n);
+int   oracle_lbfgs(Oracle* o, float* x, int n, float dt, const OracleImplicitParams* q, oracle_objective_fn fn, void* user, int* n_evals);
+int   oracle_time_integration(Oracle* o, float dt, const OracleImplicitParams* q, int* n_evals);              /* cpp:211-233 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,16 @@ class OracleParams(C.Structure):
                 ("friction", C.c_float), ("stencil", C.c_int)]
 
 
+class ImplicitParams(C.Structure):
+    """OracleImplicitParams (mpm_oracle.h): the objective's constants and the vendored optimiser's settings."""
+    _fields_ = [("mu0", C.c_float), ("lambda0", C.c_float), ("xi", C.c_float), ("hardening", C.c_int), ("max_iters", C.c_int),
+                ("ls_decrease", C.c_float), ("ls_tau", C.c_float), ("ls_max_iters", C.c_int), ("tol_grad", C.c_float),
+                ("tol_step", C.c_float), ("gradient", C.c_int)]
+
+
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_float, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int)
+
+
 class BoxCollider(C.Structure):
     _fields_ = [("world_to_local", C.c_float * 16), ("half_extent", C.c_float * 3), ("velocity", C.c_float * 3)]
 
@@ -87,6 +97,18 @@ def _bind(L):
         L.oracle_box_sdf.argtypes = [C.POINTER(BoxCollider), fp]
         L.oracle_box_sdf.restype = C.c_float
         L.oracle_body_collision.argtypes = [fp, fp, C.POINTER(BoxCollider), C.c_int, C.c_float, fp]
+        ip = C.POINTER(ImplicitParams)
+        L.oracle_default_implicit_params.argtypes = [ip]
+        L.oracle_weight_derivative.argtypes = [C.c_float]
+        L.oracle_weight_derivative.restype = C.c_float
+        L.oracle_used_cells.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.oracle_energy.argtypes = [C.c_void_p, fp, C.c_float, ip]
+        L.oracle_energy.restype = C.c_float
+        L.oracle_energy_gradient.argtypes = [C.c_void_p, fp, C.c_float, ip, C.POINTER(C.c_double)]
+        L.oracle_lbfgs.argtypes = [C.c_void_p, fp, C.c_int, C.c_float, ip, OBJECTIVE_FN, C.c_void_p, C.POINTER(C.c_int)]
+        L.oracle_lbfgs.restype = C.c_int
+        L.oracle_time_integration.argtypes = [C.c_void_p, C.c_float, ip, C.POINTER(C.c_int)]
+        L.oracle_time_integration.restype = C.c_int
     return L
 
 
@@ -204,6 +226,57 @@ class Oracle:
 
     def substep(self, dt, colliders, nc, nsteps=1):
         self.L.oracle_substep(self.h, dt, colliders, nc, nsteps)
+
+    # ---- implicit time integration (cpp:160-233; dead code in the reference) ----
+    def used_cells(self):
+        u = np.empty(self.num_used(), np.int32)
+        self.L.oracle_used_cells(self.h, u.ctypes.data_as(C.POINTER(C.c_int)))
+        return u
+
+    def energy(self, vel_used, dt, q=None):
+        q = q if q is not None else default_implicit_params()
+        v = np.ascontiguousarray(vel_used, np.float32).reshape(-1)
+        assert v.size == 3 * self.num_used()
+        return float(self.L.oracle_energy(self.h, _fp(v), dt, C.byref(q)))
+
+    def energy_gradient(self, vel_used, dt, q=None):
+        q = q if q is not None else default_implicit_params()
+        v = np.ascontiguousarray(vel_used, np.float32).reshape(-1)
+        g = np.empty(v.size, np.float64)
+        self.L.oracle_energy_gradient(self.h, _fp(v), dt, C.byref(q), g.ctypes.data_as(C.POINTER(C.c_double)))
+        return g.reshape(-1, 3)
+
+    def time_integration(self, dt, q=None):
+        q = q if q is not None else default_implicit_params()
+        evals = C.c_int(0)
+        it = self.L.oracle_time_integration(self.h, dt, C.byref(q), C.byref(evals))
+        return it, evals.value
+
+
+def default_implicit_params(**kw):
+    q = ImplicitParams()
+    lib().oracle_default_implicit_params(C.byref(q))
+    for k, v in kw.items():
+        if k not in {f[0] for f in ImplicitParams._fields_}:
+            raise TypeError(f"unknown implicit parameter {k!r}")
+        setattr(q, k, v)
+    return q
+
+
+def lbfgs(x0, fn, params=None):
+    """The optimiser restatement on a caller-supplied objective fn(x) -> (value, grad): (iterations, x, evaluations)."""
+    q = params if params is not None else default_implicit_params()
+    x = np.ascontiguousarray(x0, np.float32).copy()
+
+    def cb(_user, xp, gp, n):
+        xv = np.ctypeslib.as_array(xp, shape=(n,))
+        val, grad = fn(xv)
+        if gp:
+            np.ctypeslib.as_array(gp, shape=(n,))[:] = grad
+        return float(val)
+    evals = C.c_int(0)
+    it = lib().oracle_lbfgs(None, _fp(x), x.size, 0.0, C.byref(q), OBJECTIVE_FN(cb), None, C.byref(evals))
+    return it, x, evals.value
 
 
 def initial_state(pos, vel, mass):

@@ -34,6 +34,9 @@
 #include "material_point_method.hpp"
 #undef private
 #undef protected
+#ifndef DRIVER_NO_KAT
+#include "mathy.hpp"       // Optimizer / Objective and the vendored mcloptlib (implicit-integration known-answer modes)
+#endif
 
 // ---- stand-ins for what the GL viewer would have linked -------------------------------------
 static void GLAPIENTRY noopGenBuffers(GLsizei n, GLuint* b) { for (GLsizei i = 0; i < n; ++i) b[i] = 0; }
@@ -141,6 +144,9 @@ int main(int argc, char** argv) {
         else if (is("--kat-polar")) { katMode = "polar"; katIn = argv[++a]; katOut = argv[++a]; }
         else if (is("--kat-collide")) { katMode = "collide"; katIn = argv[++a]; katOut = argv[++a]; }
         else if (is("--kat-fupdate")) { katMode = "fupdate"; katOut = argv[++a]; }   // needs --load-full
+        else if (is("--kat-energy")) { katMode = "energy"; katIn = argv[++a]; katOut = argv[++a]; }    // in: I*J*K x 3 velocity perturbation
+        else if (is("--kat-implicit")) { katMode = "implicit"; katOut = argv[++a]; }
+        else if (is("--kat-lbfgs")) { katMode = "lbfgs"; katIn = argv[++a]; katOut = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
 
@@ -191,6 +197,65 @@ int main(int argc, char** argv) {
         }
         writeFile(katOut, out); return 0;
     }
+#ifndef DRIVER_NO_KAT
+    if (katMode == "lbfgs") {
+        // the vendored optimiser exactly as mathy.hpp:10-19 configures it (LBFGS<float, Dynamic>, Backtracking) with the
+        // convergence rule of mathy.hpp:31-35, on a smooth test function with an analytic gradient:
+        //   f(x) = sum_i 0.5 a_i (x_i - t_i)^2 + 0.25 sum_i (x_i - x_{i+1})^4        in: n, a[n], t[n], x0[n]
+        const std::vector<float> in = readFile(katIn);
+        const int dim = (int)in[0];
+        struct Fn : public mcl::optlib::Problem<ftype, Eigen::Dynamic> {
+            const float *a, *t; int n;
+            ftype value(const Eigen::VectorXf& x) override {
+                float f = 0.0f;
+                for (int i = 0; i < n; ++i) { const float d = x[i] - t[i]; f += 0.5f * a[i] * d * d; }
+                for (int i = 0; i + 1 < n; ++i) { const float d = x[i] - x[i + 1]; f += 0.25f * d * d * d * d; }
+                return f;
+            }
+            ftype gradient(const Eigen::VectorXf& x, Eigen::VectorXf& g) override {
+                for (int i = 0; i < n; ++i) g[i] = a[i] * (x[i] - t[i]);
+                for (int i = 0; i + 1 < n; ++i) { const float d = x[i] - x[i + 1]; g[i] += d * d * d; g[i + 1] -= d * d * d; }
+                return value(x);
+            }
+            bool converged(const Eigen::VectorXf& x0, const Eigen::VectorXf& x1, const Eigen::VectorXf& grad) override {
+                if (grad.norm() < 1e-2) { return true; }
+                if ((x0 - x1).norm() < 1e-2) { return true; }
+                return false;
+            }
+        } fn;
+        fn.a = &in[1]; fn.t = &in[1 + dim]; fn.n = dim;
+        Eigen::VectorXf x(dim);
+        for (int i = 0; i < dim; ++i) x[i] = in[1 + 2 * dim + i];
+        mcl::optlib::LBFGS<ftype, Eigen::Dynamic> opt;
+        opt.m_settings.ls_method = mcl::optlib::LSMethod::Backtracking;
+        const int iters = opt.minimize(fn, x);
+        std::vector<float> out(dim + 2);
+        out[0] = (float)iters; out[1] = fn.value(x);
+        for (int i = 0; i < dim; ++i) out[2 + i] = x[i];
+        writeFile(katOut, out); return 0;
+    }
+    if (katMode == "energy" || katMode == "implicit") {
+        // material_point_method.cpp:160-233 on the loaded state: rasterize (used_cells, grid velocities), then either
+        // Energy(grid velocities + perturbation, dt) or the whole timeIntegration(dt)
+        sim.rasterizeParticlesToGrid();
+        if (loadFullPath.empty()) sim.computeParticleVolumesAndDensities();
+        const int nu = (int)sim.used_cells.size();
+        if (katMode == "energy") {
+            const std::vector<float> pert = readFile(katIn);
+            Eigen::VectorXf v(nu * 3);
+            int q = 0;
+            for (const auto& c : sim.used_cells) {
+                const size_t node = ((size_t)c.x * J + c.y) * K + c.z;
+                const auto gv = sim.grid(c.x, c.y, c.z).velocity;
+                for (int a2 = 0; a2 < 3; ++a2) v[q++] = gv[a2] + pert[node * 3 + a2];
+            }
+            std::vector<float> out = { sim.Energy(v, dt), sim.ElasticPotential(v, dt), (float)nu };
+            writeFile(katOut, out); return 0;
+        }
+        sim.timeIntegration(dt);
+        dumpGrid(sim, katOut); return 0;
+    }
+#endif
     if (katMode == "fupdate") {       // material_point_method.cpp:306-330 on the loaded state
         sim.updateDeformationGradient(dt);
         dumpParticles(sim, katOut); return 0;
