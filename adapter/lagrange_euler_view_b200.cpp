@@ -123,7 +123,14 @@ void LagrangeEulerView::computeParticleVolumesAndDensities() {
 
 void LagrangeEulerView::computeExplicitGridForces() { check(mpm_compute_explicit_grid_forces(binding(this).sim), "computeExplicitGridForces"); }
 void LagrangeEulerView::gridVelocitiesUpdate(ftype timeDelta) { check(mpm_grid_velocities_update(binding(this).sim, timeDelta), "gridVelocitiesUpdate"); }
-void LagrangeEulerView::timeIntegration(ftype) { logger.log(Logger::LogLevel::WARNING, "timeIntegration: the implicit integrator is not part of the live path"); }
+// cpp:211-233 (never called by the reference's main loop): the library minimises the same Energy with the same optimiser
+// settings; mu0 / lambda0 / xi are the members the reference's Energy reads (hpp:212-214)
+void LagrangeEulerView::timeIntegration(ftype timeDelta) {
+    MpmImplicitParams q;
+    mpm_default_implicit_params(&q);
+    q.mu0 = mu0; q.lambda0 = lambda0; q.xi = xi;
+    check(mpm_time_integration(binding(this).sim, timeDelta, &q, nullptr), "timeIntegration");
+}
 
 void LagrangeEulerView::gridBasedCollisions(ftype timeDelta, const std::vector<MeshCollider>& objects) {
     std::vector<MpmBoxCollider> boxes(objects.size());

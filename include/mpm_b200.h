@@ -160,6 +160,41 @@ int mpm_update_deformation_gradient(mpm_t* s, float dt);         /* updateDeform
 int mpm_update_particle_velocities(mpm_t* s);                    /* updateParticleVelocities        cpp:332-342 */
 int mpm_update_particle_positions(mpm_t* s, float dt);           /* updateParticlePositions         cpp:344-350 */
 
+/* ---- implicit (optimisation-based) time integration ----
+ * LagrangeEulerView::timeIntegration (material_point_method.cpp:211-233): between mpm_grid_velocities_update and
+ * mpm_grid_based_collisions, replace the grid velocities v* of the used cells by the minimiser of
+ *     Energy(v) = sum_i 1/2 m_i |v_i - v*_i|^2 + sum_p V_p psi((I + dt sum_i v_i grad w_ip^T) FE_p, FP_p)      cpp:160-209
+ * found by the optimiser mathy.hpp:10-38 configures (external/mcloptlib: L-BFGS, history 8, <= 50 iterations, Armijo
+ * backtracking 0.7 / 1e-4, stop when |grad| < 1e-2 or |step| < 1e-2). The reference never calls this path
+ * (README.md:17: TODO) and its defaults are placeholders (mu0 = lambda0 = 1, hardening exp(xi*1 - det FP)): they are the
+ * defaults here too, for parity of the objective; pass E/(2(1+nu)), E nu/((1+nu)(1-2nu)) and hardening = 1 for the
+ * material of the explicit path. Deviation: the reference differentiates its float objective by central differences of
+ * 2.2e-6 (rounding noise; Problem.hpp:87-107); this library uses the analytic gradient of the same objective.
+ * Single-domain handles, cubic stencil; needs a binned handle (mpm_rasterize_particles_to_grid). */
+typedef struct MpmImplicitParams {
+    float mu0, lambda0, xi;   /* material_point_method.hpp:212-214  (1, 1, 10) */
+    int   hardening;          /* 0 = exp(xi*1 - det FP) as written (cpp:187-191); 1 = exp(xi*(1 - det FP)) as the explicit forces (cpp:240) */
+    int   max_iters;          /* LBFGS.hpp:48 (50) */
+    float ls_decrease, ls_tau; /* Minimizer.hpp:63 (1e-4), Backtracking.hpp:46 (0.7) */
+    int   ls_max_iters;       /* Minimizer.hpp:62 (100000) */
+    float tol_grad, tol_step; /* mathy.hpp:31-35 (1e-2, 1e-2) */
+    int   reserved[4];
+} MpmImplicitParams;
+typedef struct MpmImplicitStats {
+    int    iterations;        /* what LBFGS::minimize returns; -1 = line-search failure */
+    int    evaluations;       /* objective evaluations (each one pass over the particles) */
+    double energy_start, energy_end, grad_norm_end;
+    int    reserved[4];
+} MpmImplicitStats;
+void mpm_default_implicit_params(MpmImplicitParams* q);
+int mpm_time_integration(mpm_t* s, float dt, const MpmImplicitParams* q, MpmImplicitStats* stats /* may be NULL */);
+/* Diagnostics (parity checks): Energy / its gradient at a trial velocity field given as a dense host array of
+ * I*J*K x 3 floats in node order i*J*K + j*K + k (NULL = the grid's own velocities); relative != 0: the array is added to
+ * the grid's velocities. energy = the whole objective, elastic (may be NULL) = the ElasticPotential part (cpp:173-185).
+ * Parked (out-of-grid) particles are not part of the sums. gradient: I*J*K x 3 floats out, zero at nodes without mass. */
+int mpm_energy(mpm_t* s, float dt, const MpmImplicitParams* q, const float* trial_velocity, int relative, double* energy, double* elastic);
+int mpm_energy_gradient(mpm_t* s, float dt, const MpmImplicitParams* q, const float* trial_velocity, int relative, float* gradient);
+
 /* The fused fast path: n_substeps repetitions of the seven stages above in main.cpp's order, as
  * bin/sort -> clear -> P2G (mass + APIC momentum + stress) -> grid update (velocity solve, gravity, collisions)
  * -> G2P (F-update with the previous B, plasticity, gather, advect, re-sort). */

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmpm_b200.so")
 SRC = [os.path.join(HERE, "csrc", f) for f in ("mpm_api.cu",)]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("mpm_api.cu", "mpm_kernels.cuh", "mpm_tile_kernels.cuh", "mpm_math.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("mpm_api.cu", "mpm_kernels.cuh", "mpm_tile_kernels.cuh", "mpm_implicit.cuh", "mpm_math.cuh")] + \
        [os.path.join(HERE, "..", "include", "mpm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]

@@ -33,6 +33,17 @@ class MpmBoxTransform(C.Structure):
                 ("velocity", C.c_float * 3)]
 
 
+class MpmImplicitParams(C.Structure):
+    _fields_ = [("mu0", C.c_float), ("lambda0", C.c_float), ("xi", C.c_float), ("hardening", C.c_int), ("max_iters", C.c_int),
+                ("ls_decrease", C.c_float), ("ls_tau", C.c_float), ("ls_max_iters", C.c_int), ("tol_grad", C.c_float),
+                ("tol_step", C.c_float), ("reserved", C.c_int * 4)]
+
+
+class MpmImplicitStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("evaluations", C.c_int), ("energy_start", C.c_double), ("energy_end", C.c_double),
+                ("grad_norm_end", C.c_double), ("reserved", C.c_int * 4)]
+
+
 class MpmStats(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("n_out_of_grid", C.c_int64), ("n_active_nodes", C.c_int64),
                 ("n_particle_blocks", C.c_int64), ("n_grid_blocks", C.c_int64), ("substeps_done", C.c_int64),
@@ -53,7 +64,8 @@ EXPORTS = ["mpm_default_params", "mpm_last_error", "mpm_device_count", "mpm_crea
            "mpm_wait_render_buffers", "mpm_box_collider_from_transform", "mpm_box_transform_move",
            "mpm_box_transform_flip_velocity", "mpm_fill_ball", "mpm_peer_export", "mpm_peer_connect", "mpm_peer_connect_ptr",
            "mpm_grid_device_ptr", "mpm_substep_begin_peer", "mpm_peer_export_migration", "mpm_peer_connect_migration",
-           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer", "mpm_reduce_invariants", "mpm_debug_p2g_profile", "mpm_load_obj", "mpm_free", "mpm_fill_mesh", "mpm_sphere_collider"]
+           "mpm_peer_connect_migration_ptr", "mpm_migrate_peer", "mpm_reduce_invariants", "mpm_debug_p2g_profile", "mpm_load_obj", "mpm_free", "mpm_fill_mesh", "mpm_sphere_collider",
+           "mpm_default_implicit_params", "mpm_time_integration", "mpm_energy", "mpm_energy_gradient"]
 
 _lib = None
 
@@ -93,6 +105,11 @@ def lib():
               "mpm_substep_begin"):
         getattr(L, n).argtypes = [vp, C.c_float]
     L.mpm_grid_based_collisions.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int]
+    L.mpm_default_implicit_params.argtypes = [C.POINTER(MpmImplicitParams)]
+    L.mpm_default_implicit_params.restype = None
+    L.mpm_time_integration.argtypes = [vp, C.c_float, C.POINTER(MpmImplicitParams), C.POINTER(MpmImplicitStats)]
+    L.mpm_energy.argtypes = [vp, C.c_float, C.POINTER(MpmImplicitParams), fp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.mpm_energy_gradient.argtypes = [vp, C.c_float, C.POINTER(MpmImplicitParams), fp, C.c_int, fp]
     L.mpm_substep_end.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int]
     L.mpm_substep.argtypes = [vp, C.c_float, C.POINTER(MpmBoxCollider), C.c_int, C.c_int]
     L.mpm_download_grid.argtypes = [vp, fp]
@@ -156,6 +173,17 @@ def default_params(**kw):
         else:
             setattr(p, k, float(v))
     return p
+
+
+def default_implicit_params(**kw):
+    q = MpmImplicitParams()
+    lib().mpm_default_implicit_params(C.byref(q))
+    known = {f[0] for f in MpmImplicitParams._fields_}
+    for k, v in kw.items():
+        if k not in known:
+            raise TypeError(f"unknown implicit parameter {k!r}; fields are {sorted(known)}")
+        setattr(q, k, int(v) if k in ("hardening", "max_iters", "ls_max_iters") else float(v))
+    return q
 
 
 def make_colliders(w2l, half, vel=None):
@@ -342,6 +370,29 @@ class Sim:
 
     def updateParticlePositions(self, dt):
         _ck(self.L.mpm_update_particle_positions(self.h, dt))
+
+    # ---- implicit time integration (LagrangeEulerView::timeIntegration, cpp:211-233) ----
+    def timeIntegration(self, dt, params=None):
+        q = params if params is not None else default_implicit_params()
+        st = MpmImplicitStats()
+        _ck(self.L.mpm_time_integration(self.h, dt, C.byref(q), C.byref(st)))
+        return st
+
+    def energy(self, dt, trial_velocity=None, relative=False, params=None):
+        """(Energy, ElasticPotential) of cpp:160-185 at a dense (I*J*K, 3) trial velocity field (None: the grid's own)."""
+        q = params if params is not None else default_implicit_params()
+        tv = None if trial_velocity is None else _f32(trial_velocity, (self.MAX_I * self.MAX_J * self.MAX_K, 3))
+        e, el = C.c_double(0), C.c_double(0)
+        _ck(self.L.mpm_energy(self.h, dt, C.byref(q), None if tv is None else _fp(tv), int(relative), C.byref(e), C.byref(el)))
+        return e.value, el.value
+
+    def energy_gradient(self, dt, trial_velocity=None, relative=False, params=None):
+        q = params if params is not None else default_implicit_params()
+        n = self.MAX_I * self.MAX_J * self.MAX_K
+        tv = None if trial_velocity is None else _f32(trial_velocity, (n, 3))
+        g = np.empty((n, 3), np.float32)
+        _ck(self.L.mpm_energy_gradient(self.h, dt, C.byref(q), None if tv is None else _fp(tv), int(relative), _fp(g)))
+        return g
 
     def staged_substep(self, dt, colliders, nc):
         self.rasterizeParticlesToGrid(); self.computeExplicitGridForces(); self.gridVelocitiesUpdate(dt)

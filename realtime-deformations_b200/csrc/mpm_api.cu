@@ -4,6 +4,7 @@
 #include "../../include/mpm_b200.h"
 #include "mpm_kernels.cuh"
 #include "mpm_tile_kernels.cuh"
+#include "mpm_implicit.cuh"
 
 #ifndef MPM_HOST_EMU
 #include <nvtx3/nvToolsExt.h>        // header-only; no-ops unless a profiler (nsys / ncu --nvtx) is attached
@@ -79,6 +80,10 @@ struct mpm_sim {
     bool tau_valid = false, binned = false;
     bool hist_valid = false;   // key[] and blk_count[] already describe the current buffer (written by the fused substep's gather)
     bool hist_fuse = true;     // MPM_B200_FUSE_HIST=0 restores the separate k_bin_count pass (A/B)
+    // implicit time integration (mpm_implicit.cuh): node vectors in grid layout, allocated on first use
+    enum { IMP_X = 0, IMP_G, IMP_Q, IMP_XOLD, IMP_GOLD, IMP_TMP, IMP_LSG, IMP_S0, IMP_Y0 = IMP_S0 + 8, IMP_NVEC = IMP_Y0 + 8 };
+    float4* imp_vec[IMP_NVEC] = {};
+    double* imp_acc = nullptr;        // [0] inertia energy, [1] elastic energy, [2] dot product, [3] (int) |x|_inf bits
     bool mig_packed = false;   // slab handles: the gather of the last substep has already packed the leavers into out_buf (fused migration)
     // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
     PeerLayers peer = { nullptr, nullptr };
@@ -281,7 +286,9 @@ int mpm_destroy(mpm_t* s) {
     for (int b = 0; b < 2; ++b) { cudaFree(s->buf[b]); cudaFree(s->out_buf[b]); }
     cudaFree(s->key); cudaFree(s->sorted_ids); cudaFree(s->blk_count); cudaFree(s->blk_start); cudaFree(s->blk_cursor);
     cudaFree(s->pblock_list); cudaFree(s->gflag); cudaFree(s->gblock_list); cudaFree(s->partial);
-    cudaFree(s->grid); cudaFree(s->gforce); cudaFree(s->dc); cudaFree(s->slot_of_pid);
+    cudaFree(s->grid); cudaFree(s->gforce);
+    for (auto& v : s->imp_vec) cudaFree(v);
+    cudaFree(s->imp_acc); cudaFree(s->dc); cudaFree(s->slot_of_pid);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
@@ -721,6 +728,219 @@ int mpm_update_particle_positions(mpm_t* s, float dt) {        // cpp:344-350
     NEED(s);
     if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first");
     TRY((launch_g2p<G2P_ADVECT>(s, dt)));
+    return MPM_OK;
+}
+
+// ---- implicit (optimisation-based) time integration: LagrangeEulerView::timeIntegration, cpp:211-233 ------------------------
+void mpm_default_implicit_params(MpmImplicitParams* q) {
+    memset(q, 0, sizeof *q);
+    q->mu0 = 1.0f; q->lambda0 = 1.0f; q->xi = 10.0f;                       // hpp:212-214
+    q->hardening = 0;                                                      // exp(xi*1 - det FP), cpp:187-191 as written
+    q->max_iters = 50;                                                     // LBFGS.hpp:48
+    q->ls_decrease = 1e-4f; q->ls_tau = 0.7f; q->ls_max_iters = 100000;    // Minimizer.hpp:62-63, Backtracking.hpp:46
+    q->tol_grad = 1e-2f; q->tol_step = 1e-2f;                              // mathy.hpp:31-35
+}
+static int implicit_ready(mpm_sim* s, const MpmImplicitParams* q, int n_vec) {
+    if (!q) return fail(MPM_ERR_INVALID, "params is NULL");
+    if (!s->binned) return fail(MPM_ERR_INVALID, "call mpm_rasterize_particles_to_grid first (the objective is defined on its grid and used cells)");
+    if (s->prm.stencil != 0) return fail(MPM_ERR_INVALID, "implicit time integration is defined for the reference's cubic stencil only");
+    if (s->pid_base != 0 || s->gd.lo != 0 || s->gd.hi != s->gd.npbi_global) return fail(MPM_ERR_INVALID, "implicit time integration: single-domain handles only");
+    if (!(q->mu0 >= 0.0f) || !(q->lambda0 >= 0.0f) || q->max_iters < 0 || q->ls_max_iters < 1 || !(q->ls_tau > 0.0f && q->ls_tau < 1.0f) || (q->hardening != 0 && q->hardening != 1))
+        return fail(MPM_ERR_INVALID, "bad implicit parameters");
+    const size_t bytes = sizeof(float4) * 64 * (size_t)s->gd.n_gblocks;
+    for (int i = 0; i < n_vec; ++i)
+        if (!s->imp_vec[i]) {
+            CK(cudaMalloc(&s->imp_vec[i], bytes));
+            CK(cudaMemsetAsync(s->imp_vec[i], 0, bytes, s->stream));
+        }
+    if (!s->imp_acc) CK(cudaMalloc(&s->imp_acc, 4 * sizeof(double)));
+    return MPM_OK;
+}
+static ImplicitConst implicit_const(const MpmImplicitParams* q) { return ImplicitConst{ q->mu0, q->lambda0, q->xi, q->hardening }; }
+// E(x) (and its gradient into vector g when g >= 0); one host read-back
+static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x, int g, double* inertia, double* elastic) {
+    CK(cudaMemsetAsync(s->imp_acc, 0, 2 * sizeof(double), s->stream));
+    float4* G = g >= 0 ? s->imp_vec[g] : nullptr;
+    k_imp_nodes<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[x], G, s->imp_acc);
+    CKLAUNCH();
+    const int nb = grid_for(s->n_bound, 128);
+    if (G) k_imp_particles<true><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], G, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
+    else k_imp_particles<false><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], nullptr, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
+    CKLAUNCH();
+    s->stats.kernel_launches += 2;
+    double h[2];
+    CK(cudaMemcpyAsync(h, s->imp_acc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *inertia = h[0]; *elastic = h[1];
+    return MPM_OK;
+}
+static int implicit_dot(mpm_sim* s, int a, int b, double* out, float* absmax_a = nullptr) {
+    CK(cudaMemsetAsync(s->imp_acc + 2, 0, 2 * sizeof(double), s->stream));
+    k_vec_dot<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[a], s->imp_vec[b], s->imp_acc + 2, absmax_a ? (int*)(s->imp_acc + 3) : nullptr);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    double h[2];
+    CK(cudaMemcpyAsync(h, s->imp_acc + 2, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = h[0];
+    if (absmax_a) { int bits; memcpy(&bits, &h[1], sizeof bits); memcpy(absmax_a, &bits, sizeof bits); }
+    return MPM_OK;
+}
+static int implicit_lin(mpm_sim* s, int z, float a, int x, float b, int y) {      // z = a x + b y (y < 0: z = a x)
+    k_vec_lin<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[z], a, s->imp_vec[x], b, y >= 0 ? s->imp_vec[y] : nullptr);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    return MPM_OK;
+}
+static int implicit_load_trial(mpm_sim* s, const float* trial_velocity, int add) {
+    const size_t n = (size_t)s->gd.I * s->gd.J * s->gd.K;
+    if (!trial_velocity) {
+        k_imp_from_grid<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[mpm_sim::IMP_X]);
+        CKLAUNCH(); s->stats.kernel_launches++;
+        return MPM_OK;
+    }
+    float* d = nullptr;
+    CK(cudaMalloc(&d, n * 3 * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(d, trial_velocity, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) {
+        k_imp_import<<<grid_for((int64_t)n, 256), 256, 0, s->stream>>>(s->imp_vec[mpm_sim::IMP_X], s->grid, s->gd, d, add);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "implicit: trial velocity upload: %s", cudaGetErrorString(e));
+    return MPM_OK;
+}
+int mpm_energy(mpm_t* s, float dt, const MpmImplicitParams* q, const float* trial_velocity, int relative, double* energy, double* elastic) {
+    NEED(s);
+    if (!energy) return fail(MPM_ERR_INVALID, "energy is NULL");
+    TRY(implicit_ready(s, q, 1));
+    TRY(implicit_load_trial(s, trial_velocity, relative));
+    double ein, eel;
+    TRY(implicit_eval(s, dt, q, mpm_sim::IMP_X, -1, &ein, &eel));
+    *energy = ein + eel;
+    if (elastic) *elastic = eel;
+    return MPM_OK;
+}
+int mpm_energy_gradient(mpm_t* s, float dt, const MpmImplicitParams* q, const float* trial_velocity, int relative, float* gradient) {
+    NEED(s);
+    if (!gradient) return fail(MPM_ERR_INVALID, "gradient is NULL");
+    TRY(implicit_ready(s, q, 2));
+    TRY(implicit_load_trial(s, trial_velocity, relative));
+    double ein, eel;
+    // nodes outside the active blocks: zero (the vector was zero-initialised and only active blocks are ever written)
+    TRY(implicit_eval(s, dt, q, mpm_sim::IMP_X, mpm_sim::IMP_G, &ein, &eel));
+    const size_t n = (size_t)s->gd.I * s->gd.J * s->gd.K;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, n * 3 * sizeof(float)));
+    k_imp_export<<<grid_for((int64_t)n, 256), 256, 0, s->stream>>>(s->imp_vec[mpm_sim::IMP_G], s->gd, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(gradient, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(MPM_ERR_CUDA, "energy_gradient: %s", cudaGetErrorString(e));
+    return MPM_OK;
+}
+// mcl::optlib::LBFGS<float, Dynamic, 8>::minimize (LBFGS.hpp:52-152) with Backtracking::search (Backtracking.hpp:38-69) and the
+// convergence rule of mathy.hpp:31-35, driven from the host over device vectors; the objective's gradient is analytic.
+int mpm_time_integration(mpm_t* s, float dt, const MpmImplicitParams* q, MpmImplicitStats* st) {
+    NEED(s);
+    TRY(implicit_ready(s, q, mpm_sim::IMP_NVEC));
+    enum { M = 8 };
+    const int X = mpm_sim::IMP_X, G = mpm_sim::IMP_G, Q = mpm_sim::IMP_Q, XOLD = mpm_sim::IMP_XOLD, GOLD = mpm_sim::IMP_GOLD, TMP = mpm_sim::IMP_TMP,
+              LSG = mpm_sim::IMP_LSG, S0 = mpm_sim::IMP_S0, Y0 = mpm_sim::IMP_Y0;
+    int slot[M];                         // history column i lives in vectors S0 + slot[i], Y0 + slot[i] (rotated instead of copied)
+    for (int i = 0; i < M; ++i) slot[i] = i;
+    float alpha[M] = { 0 }, rho[M] = { 0 };
+    TRY(implicit_load_trial(s, nullptr, 0));
+    double ein, eel, d;
+    int evals = 0, result = 0;
+    TRY(implicit_eval(s, dt, q, X, G, &ein, &eel)); ++evals;
+    const double e_start = ein + eel;
+    double e_cur = e_start;
+    float gamma_k = 1.0f, alpha_init = 1.0f;
+    int global_iter = 0, max_iters = q->max_iters;
+    for (int k = 0; k < max_iters; ++k) {
+        TRY(implicit_lin(s, XOLD, 1.0f, X, 0.0f, -1));
+        TRY(implicit_lin(s, GOLD, 1.0f, G, 0.0f, -1));
+        TRY(implicit_lin(s, Q, 1.0f, G, 0.0f, -1));
+        global_iter++;
+        const int iter = k < M ? k : M;
+        for (int i = iter - 1; i >= 0; --i) {
+            TRY(implicit_dot(s, S0 + slot[i], Y0 + slot[i], &d)); rho[i] = (float)(1.0 / d);
+            TRY(implicit_dot(s, S0 + slot[i], Q, &d)); alpha[i] = rho[i] * (float)d;
+            TRY(implicit_lin(s, Q, 1.0f, Q, -alpha[i], Y0 + slot[i]));
+        }
+        TRY(implicit_lin(s, Q, gamma_k, Q, 0.0f, -1));
+        for (int i = 0; i < iter; ++i) {
+            TRY(implicit_dot(s, Q, Y0 + slot[i], &d));
+            const float beta = rho[i] * (float)d;
+            TRY(implicit_lin(s, Q, 1.0f, Q, alpha[i] - beta, S0 + slot[i]));
+        }
+        float ginf = 0.0f;
+        TRY(implicit_dot(s, G, Q, &d, &ginf));
+        if ((float)d <= 0) {                       // not a descent direction: steepest descent, restart the count (LBFGS.hpp:101-106)
+            TRY(implicit_lin(s, Q, 1.0f, G, 0.0f, -1));
+            max_iters -= k;
+            k = 0;
+            alpha_init = (float)std::min(1.0, 1.0 / (double)ginf);
+        }
+        float rate;
+        {   // Backtracking::search(x, p = -q): (the library re-evaluates value and gradient at x here; they are unchanged, so they are reused)
+            double pn;
+            TRY(implicit_dot(s, Q, Q, &pn));
+            if ((float)std::sqrt(pn) <= FLT_EPSILON) rate = q->ls_decrease;
+            else {
+                float a = alpha_init;
+                const float fx0 = (float)e_cur;
+                TRY(implicit_dot(s, G, Q, &d));
+                const float gtp = -(float)d;
+                int it = 0;
+                for (; it < q->ls_max_iters; ++it) {
+                    TRY(implicit_lin(s, TMP, 1.0f, X, -a, Q));
+                    TRY(implicit_eval(s, dt, q, TMP, -1, &ein, &eel)); ++evals;
+                    if ((float)(ein + eel) <= fx0 + a * q->ls_decrease * gtp) break;
+                    a *= q->ls_tau;
+                }
+                rate = it >= q->ls_max_iters ? -1.0f : a;
+            }
+        }
+        if (rate <= 0) { result = -1; break; }
+        TRY(implicit_lin(s, X, 1.0f, X, -rate, Q));
+        {   // Objective::converged(x_last, x, grad): |grad| < tol or |x_last - x| = rate |q| < tol
+            double gn, qn;
+            TRY(implicit_dot(s, G, G, &gn));
+            TRY(implicit_dot(s, Q, Q, &qn));
+            if ((float)std::sqrt(gn) < q->tol_grad || (float)(rate * std::sqrt(qn)) < q->tol_step) { result = global_iter; break; }
+        }
+        TRY(implicit_eval(s, dt, q, X, G, &ein, &eel)); ++evals;
+        e_cur = ein + eel;
+        int col;
+        if (k < M) col = slot[k];
+        else { col = slot[0]; for (int i = 0; i + 1 < M; ++i) slot[i] = slot[i + 1]; slot[M - 1] = col; }
+        TRY(implicit_lin(s, S0 + col, 1.0f, X, -1.0f, XOLD));
+        TRY(implicit_lin(s, Y0 + col, 1.0f, G, -1.0f, GOLD));
+        double yy, sy;
+        TRY(implicit_dot(s, Y0 + col, Y0 + col, &yy));
+        result = global_iter;
+        if (std::fabs((float)yy) <= 0) break;
+        TRY(implicit_dot(s, S0 + col, Y0 + col, &sy));
+        gamma_k = (float)sy / (float)yy;
+        alpha_init = 1.0f;
+    }
+    (void)LSG;
+    // the minimiser becomes the grid velocity of the used cells (cpp:227-232)
+    double e_end_in, e_end_el, gn;
+    TRY(implicit_eval(s, dt, q, X, G, &e_end_in, &e_end_el));
+    TRY(implicit_dot(s, G, G, &gn));
+    k_imp_to_grid<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[X]);
+    CKLAUNCH(); s->stats.kernel_launches++;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        st->iterations = result; st->evaluations = evals;
+        st->energy_start = e_start; st->energy_end = e_end_in + e_end_el; st->grad_norm_end = std::sqrt(gn);
+    }
+    if (result < 0) return fail(MPM_ERR_INVALID, "implicit time integration: line search failed (no step length satisfied the Armijo condition)");
     return MPM_OK;
 }
 

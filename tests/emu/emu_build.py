@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "realtime-deformations_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SRC_OUT = os.path.join(BUILD, "src")
 LIB = os.path.join(BUILD, "libmpm_b200_emu.so")
-FILES = ("mpm_api.cu", "mpm_tile_kernels.cuh", "mpm_kernels.cuh", "mpm_math.cuh")
+FILES = ("mpm_api.cu", "mpm_tile_kernels.cuh", "mpm_implicit.cuh", "mpm_kernels.cuh", "mpm_math.cuh")
 
 
 def _kernel_start(text, i):

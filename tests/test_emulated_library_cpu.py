@@ -56,6 +56,15 @@ def test_gpu_parity_logic_on_emulated_library(emu_lib):
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-4000:]
 
 
+def test_implicit_time_integration_on_emulated_library(emu_lib):
+    """tests/test_gpu_implicit.py (Energy vs the reference's golden values, gradient and minimiser vs the oracle, the
+    semi-implicit substep sequence, error paths) against the emulated build."""
+    env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_implicit.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-4000:]
+
+
 def test_default_scene_trajectory_on_emulated_library(emu_lib):
     """400 substeps of the reference's default scene through the fused path, against the reference's own trajectory."""
     r = _run_gpu_suite(emu_lib, "default_scene_trajectory and variants0")
