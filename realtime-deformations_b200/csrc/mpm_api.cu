@@ -83,6 +83,7 @@ struct mpm_sim {
     // implicit time integration (mpm_implicit.cuh): node vectors in grid layout, allocated on first use
     enum { IMP_X = 0, IMP_G, IMP_Q, IMP_XOLD, IMP_GOLD, IMP_TMP, IMP_LSG, IMP_S0, IMP_Y0 = IMP_S0 + 8, IMP_NVEC = IMP_Y0 + 8 };
     float4* imp_vec[IMP_NVEC] = {};
+    float4* imp_aux = nullptr;        // 3 float4 per sorted rank: I + dt grad v, then the stress matrix Gm (block-tile form)
     double* imp_acc = nullptr;        // [0] inertia energy, [1] elastic energy, [2] dot product, [3] (int) |x|_inf bits
     bool mig_packed = false;   // slab handles: the gather of the last substep has already packed the leavers into out_buf (fused migration)
     // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
@@ -270,6 +271,7 @@ static int create_impl(const MpmParams* params, int max_i, int max_j, int max_k,
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->colliders, 0, sizeof s->colliders);
     CK(tile_kernels_init());
+    CK(implicit_kernels_init());
     CK(cudaStreamSynchronize(s->stream));
     { int rc = validate_pos_div(s); if (rc) return rc; }
     return MPM_OK;
@@ -288,7 +290,7 @@ int mpm_destroy(mpm_t* s) {
     cudaFree(s->pblock_list); cudaFree(s->gflag); cudaFree(s->gblock_list); cudaFree(s->partial);
     cudaFree(s->grid); cudaFree(s->gforce);
     for (auto& v : s->imp_vec) cudaFree(v);
-    cudaFree(s->imp_acc); cudaFree(s->dc); cudaFree(s->slot_of_pid);
+    cudaFree(s->imp_acc); cudaFree(s->imp_aux); cudaFree(s->dc); cudaFree(s->slot_of_pid);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->ev_ok) for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->render_ready); cudaEventDestroy(s->copy_done); }
@@ -754,6 +756,7 @@ static int implicit_ready(mpm_sim* s, const MpmImplicitParams* q, int n_vec) {
             CK(cudaMemsetAsync(s->imp_vec[i], 0, bytes, s->stream));
         }
     if (!s->imp_acc) CK(cudaMalloc(&s->imp_acc, 4 * sizeof(double)));
+    if (!s->imp_aux) CK(cudaMalloc(&s->imp_aux, sizeof(float4) * 3 * (size_t)s->capacity));
     return MPM_OK;
 }
 static ImplicitConst implicit_const(const MpmImplicitParams* q) { return ImplicitConst{ q->mu0, q->lambda0, q->xi, q->hardening }; }
@@ -764,10 +767,28 @@ static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x
     k_imp_nodes<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[x], G, s->imp_acc);
     CKLAUNCH();
     const int nb = grid_for(s->n_bound, 128);
-    if (G) k_imp_particles<true><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], G, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
-    else k_imp_particles<false><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], nullptr, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
-    CKLAUNCH();
-    s->stats.kernel_launches += 2;
+    if (s->prm.p2g_variant == 1 || s->prm.g2p_variant == 1) {       // baseline: thread per particle, 64 gathers and 64 vector reds each
+        if (G) k_imp_particles<true><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], G, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
+        else k_imp_particles<false><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], nullptr, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
+        CKLAUNCH();
+        s->stats.kernel_launches += 2;
+    } else {                                                        // block tiles: TMA-staged gather | per-particle stress | register-accumulated scatter
+        const Planes C = s->planes(s->cur);
+        CK(cudaMemsetAsync(&s->dc->work_b, 0, sizeof(int), s->stream));
+        k_g2p_tile<G2P_GATHER | G2P_GRADW, 4><<<s->num_sms * G2P_MIN_CTAS, G2P_T, sizeof(G2PSmem), s->stream>>>(C, C, s->sorted_ids, s->pblock_list, s->dc, s->imp_vec[x], s->gd, s->sc, dt,
+                                                                                                         nullptr, nullptr, MigOut{ nullptr, nullptr, 0 }, s->imp_aux);
+        CKLAUNCH();
+        if (G) k_imp_stress<true><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), s->imp_acc);
+        else k_imp_stress<false><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), s->imp_acc);
+        CKLAUNCH();
+        s->stats.kernel_launches += 3;
+        if (G) {
+            CK(cudaMemsetAsync(&s->dc->work_a, 0, sizeof(int), s->stream));
+            k_imp_scatter_tile<<<s->num_sms * 2, P2G_T, sizeof(ImpScatterSmem), s->stream>>>(C, s->sorted_ids, s->pblock_list, s->dc, s->imp_aux, G, s->gd, s->sc);
+            CKLAUNCH();
+            s->stats.kernel_launches++;
+        }
+    }
     double h[2];
     CK(cudaMemcpyAsync(h, s->imp_acc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));

@@ -12,26 +12,11 @@
 // Precision: per-particle energies and the polar factor in double (the B200 has the fp64 rate to spare here), sums in
 // double atomics, the gradient scatter in float vector reds.
 #pragma once
-#include "mpm_kernels.cuh"
+#include "mpm_tile_kernels.cuh"
 
 namespace mpm {
 
 struct ImplicitConst { float mu0, lambda0, xi; int hardening; };
-
-// weights and weight derivatives of the four stencil nodes cell-1 .. cell+2 (offsets fx+1, fx, fx-1, fx-2: the branches of
-// hpp:20-52 are known statically)
-MPM_DI void axis_weights_and_derivatives(float x, const PosDiv& d, int cell, float w[4], float dw[4]) {
-    const float fx = sub_rn(pos_div(x, d), (float)cell);
-    const float gx = 1.0f - fx;
-    w[0] = 0.16666667163372040f * gx * gx * gx;
-    w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
-    w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
-    w[3] = 0.16666667163372040f * fx * fx * fx;
-    dw[0] = -0.5f * gx * gx;
-    dw[1] = fx * fmaf(1.5f, fx, -2.0f);
-    dw[2] = gx * fmaf(-1.5f, gx, 2.0f);
-    dw[3] = 0.5f * fx * fx;
-}
 
 // rotation factor of the polar decomposition by Newton's iteration R <- (R + R^-T)/2 in double; false if singular
 MPM_DI bool polar_rotation_d(const double (&F)[9], double (&R)[9]) {
@@ -160,6 +145,227 @@ k_imp_particles(Planes P, const int* __restrict__ sorted_ids, DevCounters* dc, c
     if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&acc[1], e);
 }
 
+// ---- block-tile form of the particle term (the default; k_imp_particles above is the baseline, p2g_variant / g2p_variant 1) ----
+// 1. k_g2p_tile<G2P_GATHER | G2P_GRADW> gathers A = I + dt grad v of the trial field from TMA-staged tiles into aux[3 j .. 3 j + 2]
+// 2. k_imp_stress: thread per sorted rank j: F = A FE, polar factor and energy in double; with GRAD the 3x3
+//    Gm = dt V0 (2 mu (F - R) + lambda (J - 1) J F^-T) FE^T overwrites aux[3 j ..]
+// 3. k_imp_scatter_tile: grad_i += Gm grad w_ip, accumulated per (cell, x-slab) thread in registers and folded like P2G
+template <bool GRAD>
+__global__ void __launch_bounds__(128)
+k_imp_stress(Planes P, const int* __restrict__ sorted_ids, DevCounters* dc, float4* __restrict__ aux, float dt, ImplicitConst ic, double* __restrict__ acc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (j < dc->n_binned) {
+        const int p = sorted_ids[j];
+        const float4 a6 = P.p[6][p], a7 = P.p[7][p], a8 = P.p[8][p], a9 = P.p[9][p], a10 = P.p[10][p];
+        const float4 q0 = aux[3 * (size_t)j], q1 = aux[3 * (size_t)j + 1], q2 = aux[3 * (size_t)j + 2];
+        const float FE[9] = { a6.z, a6.w, a7.x, a7.y, a7.z, a7.w, a8.x, a8.y, a8.z };
+        const float FP[9] = { a8.w, a9.x, a9.y, a9.z, a9.w, a10.x, a10.y, a10.z, a10.w };
+        const double A[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x };
+        const double V0 = a6.x;
+        double F[9], R[9];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) F[c * 3 + r] = A[0 + r] * FE[c * 3 + 0] + A[3 + r] * FE[c * 3 + 1] + A[6 + r] * FE[c * 3 + 2];
+        const double detFP = (double)m3_det_fast(FP);
+        const double hard = exp(ic.hardening == 0 ? (double)ic.xi - detFP : (double)ic.xi * (1.0 - detFP));
+        const double mu = ic.mu0 * hard, lambda = ic.lambda0 * hard;
+        if (!polar_rotation_d(F, R)) dc->svd_failed = 1;
+        double fn2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const double d = F[i] - R[i]; fn2 += d * d; }
+        const double c00 = F[4] * F[8] - F[7] * F[5], c01 = F[7] * F[2] - F[1] * F[8], c02 = F[1] * F[5] - F[4] * F[2];
+        const double J = F[0] * c00 + F[3] * c01 + F[6] * c02;
+        e = V0 * (mu * fn2 + 0.5 * lambda * (J - 1.0) * (J - 1.0));
+        if (GRAD) {
+            const double cof[9] = { c00, -(F[3] * F[8] - F[6] * F[5]), F[3] * F[7] - F[6] * F[4],
+                                    c01, F[0] * F[8] - F[6] * F[2], -(F[0] * F[7] - F[6] * F[1]),
+                                    c02, -(F[0] * F[5] - F[3] * F[2]), F[0] * F[4] - F[3] * F[1] };
+            double Pk[9];
+            float Gm[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Pk[i] = 2.0 * mu * (F[i] - R[i]) + lambda * (J - 1.0) * cof[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) Gm[c * 3 + r] = (float)((double)dt * V0 * (Pk[0 + r] * FE[0 + c] + Pk[3 + r] * FE[3 + c] + Pk[6 + r] * FE[6 + c]));
+            aux[3 * (size_t)j] = make_float4(Gm[0], Gm[1], Gm[2], Gm[3]);
+            aux[3 * (size_t)j + 1] = make_float4(Gm[4], Gm[5], Gm[6], Gm[7]);
+            aux[3 * (size_t)j + 2] = make_float4(Gm[8], 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&acc[1], e);
+}
+
+struct ImpScatterSmem {
+    union {
+        struct {
+            float4 wx[P2G_CH], wy[P2G_CH], wz[P2G_CH];      // weights of the four stencil nodes per axis
+            float4 dx[P2G_CH], dy[P2G_CH], dz[P2G_CH];      // their derivatives / h
+            float4 g0[P2G_CH], g1[P2G_CH];                  // Gm entries 0..3, 4..7 (column-major)
+            float g8[P2G_CH];
+            unsigned short order[P2G_CH];
+        } c;
+        float4 t1[4][4][4][42];                             // z-folded partial sums, as in P2GSmem
+    } u;
+    int cell_cnt[64];
+    int4 work;
+};
+// Thread t = cell*4 + a as in k_p2g_tile; three channels (no mass), value at node (a, b, c) of the particle's stencil:
+//   grad_r += G_r0 dwx_a wy_b wz_c + G_r1 wx_a dwy_b wz_c + G_r2 wx_a wy_b dwz_c
+//           = wz_c (pa_r wy_b + qa_r dwy_b) + dwz_c (ra_r wy_b),      pa = G_.0 dwx_a, qa = G_.1 wx_a, ra = G_.2 wx_a
+// as packed pairs over two consecutive z-nodes. sorted_ids is NOT re-ordered here: aux is indexed by sorted rank.
+__global__ void __launch_bounds__(P2G_T, 2)
+k_imp_scatter_tile(Planes P, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
+                   const float4* __restrict__ aux, float4* __restrict__ G, GridDims gd, SimConst sc) {
+    MPM_DYN_SMEM(imp_smem_raw, 16);
+    ImpScatterSmem& S = *reinterpret_cast<ImpScatterSmem*>(imp_smem_raw);
+    const int t = threadIdx.x, lane = t & 31;
+    const int my_cell = t >> 2, my_a = t & 3;
+    const int my_cx = my_cell >> 4, my_cy = (my_cell >> 2) & 3, my_cz = my_cell & 3;
+    const int n_work = dc->n_active_pblocks;
+    const float ih = 1.0f / sc.h;
+    for (;;) {
+        __syncthreads();          // the fold of the previous block is done with t1 and everyone has read S.work
+        if (t == 0) {
+            const int w = atomicAdd(&dc->work_a, 1);
+            S.work = w < n_work ? pblock_list[w] : make_int4(-1, 0, 0, 0);
+        }
+        if (t < 64) S.cell_cnt[t] = 0;
+        __syncthreads();
+        const int4 wk = S.work;
+        if (wk.x < 0) break;
+        const int start = wk.y, cnt = wk.z;
+        const int pbk = wk.w & (PB_COORD_MAX - 1), pbj = (wk.w >> PB_COORD_BITS) & (PB_COORD_MAX - 1), pbi = (wk.w >> (2 * PB_COORD_BITS)) + gd.lo;
+        f32x2_t AX[8], AY[8], AZ[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) AX[i] = AY[i] = AZ[i] = 0ull;
+        const int n_chunks = (cnt + P2G_CH - 1) / P2G_CH;
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            const int nch = n_chunks == 1 ? cnt : (cnt - ck + n_chunks - 1) / n_chunks;
+            if (ck > 0) {
+                if (t < 64) S.cell_cnt[t] = 0;
+                __syncthreads();
+            }
+            int cell_rank[P2G_PPT];
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) {
+                const int q = t + u * P2G_T;
+                cell_rank[u] = -1;
+                if (q < nch) {
+                    const int j = start + ck + q * n_chunks;
+                    const float4 xm = P.p[0][sorted_ids[j]];
+                    const float4 g0 = aux[3 * (size_t)j], g1 = aux[3 * (size_t)j + 1], g2 = aux[3 * (size_t)j + 2];
+                    float wx[4], wy[4], wz[4], dx[4], dy[4], dz[4];
+                    const int cx = cell_of_t<0>(xm.x, sc.pd), cy = cell_of_t<0>(xm.y, sc.pd), cz = cell_of_t<0>(xm.z, sc.pd);
+                    axis_weights_and_derivatives(xm.x, sc.pd, cx, wx, dx);
+                    axis_weights_and_derivatives(xm.y, sc.pd, cy, wy, dy);
+                    axis_weights_and_derivatives(xm.z, sc.pd, cz, wz, dz);
+                    S.u.c.wx[q] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                    S.u.c.wy[q] = make_float4(wy[0], wy[1], wy[2], wy[3]);
+                    S.u.c.wz[q] = make_float4(wz[0], wz[1], wz[2], wz[3]);
+                    S.u.c.dx[q] = make_float4(dx[0] * ih, dx[1] * ih, dx[2] * ih, dx[3] * ih);
+                    S.u.c.dy[q] = make_float4(dy[0] * ih, dy[1] * ih, dy[2] * ih, dy[3] * ih);
+                    S.u.c.dz[q] = make_float4(dz[0] * ih, dz[1] * ih, dz[2] * ih, dz[3] * ih);
+                    S.u.c.g0[q] = g0; S.u.c.g1[q] = g1; S.u.c.g8[q] = g2.x;
+                    const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
+                    cell_rank[u] = lc | (atomicAdd(&S.cell_cnt[lc], 1) << 8);
+                }
+            }
+            __syncthreads();
+            const int c0 = S.cell_cnt[2 * lane], c1 = S.cell_cnt[2 * lane + 1];
+            int inc = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            const int ex = inc - (c0 + c1);
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u) {
+                const int c = cell_rank[u] < 0 ? 0 : (cell_rank[u] & 255);
+                const int e = __shfl_sync(0xffffffffu, ex, c >> 1), f = __shfl_sync(0xffffffffu, c0, c >> 1);
+                if (cell_rank[u] >= 0) S.u.c.order[e + ((c & 1) ? f : 0) + (cell_rank[u] >> 8)] = (unsigned short)(t + u * P2G_T);
+            }
+            int i0, i1;
+            {
+                const int e = __shfl_sync(0xffffffffu, ex, my_cell >> 1), f = __shfl_sync(0xffffffffu, c0, my_cell >> 1), g = __shfl_sync(0xffffffffu, c1, my_cell >> 1);
+                i0 = e + ((my_cell & 1) ? f : 0);
+                i1 = i0 + ((my_cell & 1) ? g : f);
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int i = i0; i < i1; ++i) {
+                const int pi = S.u.c.order[i];
+                const float wxa = reinterpret_cast<const float*>(&S.u.c.wx[pi])[my_a], dxa = reinterpret_cast<const float*>(&S.u.c.dx[pi])[my_a];
+                const float4 wy = S.u.c.wy[pi], wz = S.u.c.wz[pi], dy = S.u.c.dy[pi], dz = S.u.c.dz[pi], g0 = S.u.c.g0[pi], g1 = S.u.c.g1[pi];
+                const float g8 = S.u.c.g8[pi];
+                // Gm column-major: G_r0 = (g0.x, g0.y, g0.z), G_r1 = (g0.w, g1.x, g1.y), G_r2 = (g1.z, g1.w, g8)
+                const float pa[3] = { g0.x * dxa, g0.y * dxa, g0.z * dxa }, qa[3] = { g0.w * wxa, g1.x * wxa, g1.y * wxa }, ra[3] = { g1.z * wxa, g1.w * wxa, g8 * wxa };
+                const float wyv[4] = { wy.x, wy.y, wy.z, wy.w }, dyv[4] = { dy.x, dy.y, dy.z, dy.w };
+                const f32x2_t wzp[2] = { pack2(wz.x, wz.y), pack2(wz.z, wz.w) }, dzp[2] = { pack2(dz.x, dz.y), pack2(dz.z, dz.w) };
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const float u0 = fmaf(pa[0], wyv[bb], qa[0] * dyv[bb]), u1 = fmaf(pa[1], wyv[bb], qa[1] * dyv[bb]), u2 = fmaf(pa[2], wyv[bb], qa[2] * dyv[bb]);
+                    const float v0 = ra[0] * wyv[bb], v1 = ra[1] * wyv[bb], v2 = ra[2] * wyv[bb];
+                    const f32x2_t U0 = pack2(u0, u0), U1 = pack2(u1, u1), U2 = pack2(u2, u2), V0 = pack2(v0, v0), V1 = pack2(v1, v1), V2 = pack2(v2, v2);
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp) {
+                        ffma2_acc(AX[bb * 2 + cp], wzp[cp], U0); ffma2_acc(AX[bb * 2 + cp], dzp[cp], V0);
+                        ffma2_acc(AY[bb * 2 + cp], wzp[cp], U1); ffma2_acc(AY[bb * 2 + cp], dzp[cp], V1);
+                        ffma2_acc(AZ[bb * 2 + cp], wzp[cp], U2); ffma2_acc(AZ[bb * 2 + cp], dzp[cp], V2);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        float4 acc[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[2 * i] = make_float4(0.f, lo2(AX[i]), lo2(AY[i]), lo2(AZ[i]));
+            acc[2 * i + 1] = make_float4(0.f, hi2(AX[i]), hi2(AY[i]), hi2(AZ[i]));
+        }
+        // z-fold with warp shuffles (k_p2g_tile phase 2a), then x/y fold from shared memory, one vector red per tile node
+        float4 s0[4], s1[4];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) { s0[bb] = acc[bb * 4]; s1[bb] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int cc = 1; cc < 4; ++cc) {
+            const int src = (lane & ~12) | (((my_cz - cc) & 3) << 2);
+            const bool lo = cc <= my_cz;
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                float4 v;
+                v.x = 0.f; v.y = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].y, src);
+                v.z = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].z, src); v.w = __shfl_sync(0xffffffffu, acc[bb * 4 + cc].w, src);
+                if (lo) { s0[bb].y += v.y; s0[bb].z += v.z; s0[bb].w += v.w; }
+                else { s1[bb].y += v.y; s1[bb].z += v.z; s1[bb].w += v.w; }
+            }
+        }
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz] = s0[bb];
+            if (my_cz < 3) S.u.t1[my_cx][my_cy][my_a][bb * 7 + my_cz + 4] = s1[bb];
+        }
+        __syncthreads();
+        for (int n = t; n < 343; n += P2G_T) {
+            const int ni = n / 49, nj = (n / 7) % 7, nk = n % 7;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+                for (int dy = 0; dy < 4; ++dy) {
+                    const int cx = ni - dx, cy = nj - dy;
+                    if (cx >= 0 && cx <= 3 && cy >= 0 && cy <= 3) {
+                        const float4 v = S.u.t1[cx][cy][dx][dy * 7 + nk];
+                        sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                }
+            if (sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) atomicAdd(&G[node_index(gd, 4 * pbi + ni, 4 * pbj + nj, 4 * pbk + nk)], sum);
+        }
+    }
+}
+
 // ---- vectors over the active nodes (float4 per node; .x unused and kept 0) ----
 // z = a x + b y (any of them may alias)
 __global__ void __launch_bounds__(256)
@@ -234,5 +440,11 @@ __global__ void k_imp_export(const float4* __restrict__ G, GridDims gd, float* _
     const float4 g = G[node_index(gd, i, j, k)];
     out3[t * 3] = g.y; out3[t * 3 + 1] = g.z; out3[t * 3 + 2] = g.w;
 }
+
+#if !defined(MPM_HOST_EMU) || defined(MPM_HOST_EMU_API)
+inline cudaError_t implicit_kernels_init() {
+    return cudaFuncSetAttribute(k_imp_scatter_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImpScatterSmem));
+}
+#endif
 
 }  // namespace mpm

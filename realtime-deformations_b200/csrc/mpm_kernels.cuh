@@ -557,7 +557,7 @@ __global__ void k_volumes(Planes P, const int* __restrict__ sorted_ids, const De
     P.p[6][p] = a6;
 }
 
-enum { G2P_F = 1, G2P_GATHER = 2, G2P_ADVECT = 4, G2P_REORDER = 8, G2P_HIST = 16 };
+enum { G2P_F = 1, G2P_GATHER = 2, G2P_ADVECT = 4, G2P_REORDER = 8, G2P_HIST = 16, G2P_GRADW = 32 };
 
 MPM_DI void advect_rn(ParticleRegs& r, const SimConst& sc, float dt) {   // cpp:344-350, 381-388
 #pragma unroll

@@ -128,6 +128,21 @@ MPM_DI void axis_weights(float x, const PosDiv& d, int cell, float w[4]) {
     w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
     w[3] = 0.16666667163372040f * fx * fx * fx;
 }
+// cubic weights and weight DERIVATIVES (hpp:32-52; implicit time integration, mpm_implicit.cuh) of the four stencil nodes
+// cell-1 .. cell+2: offsets fx+1, fx, fx-1, fx-2, so the branches of hpp:20-52 are known statically
+MPM_DI void axis_weights_and_derivatives(float x, const PosDiv& d, int cell, float w[4], float dw[4]) {
+    const float fx = sub_rn(pos_div(x, d), (float)cell);
+    const float gx = 1.0f - fx;
+    w[0] = 0.16666667163372040f * gx * gx * gx;
+    w[1] = fmaf(fmaf(0.5f, fx, -1.0f), fx * fx, 0.66666668653488159f);
+    w[2] = fmaf(fmaf(0.5f, gx, -1.0f), gx * gx, 0.66666668653488159f);
+    w[3] = 0.16666667163372040f * fx * fx * fx;
+    dw[0] = -0.5f * gx * gx;
+    dw[1] = fx * fmaf(1.5f, fx, -2.0f);
+    dw[2] = gx * fmaf(-1.5f, gx, 2.0f);
+    dw[3] = 0.5f * fx * fx;
+}
+
 // same as cell_of + axis_weights with the quotient formed once
 template <int Q>
 MPM_DI int cell_and_weights_t(float x, const PosDiv& d, float w[4]) {

@@ -404,11 +404,14 @@ struct G2PSmem {
 // Measured at 64 Mi particles (profiles/r2_ab_64M.md): blocked tile + scalar FMA 2.40 ms, linear tile 2.22, packed pairs
 // 2.19, both 1.99 -> only this form is kept.
 // FLAGS: G2P_GATHER always, optionally G2P_ADVECT, G2P_REORDER, G2P_HIST (the F-update runs in P2G or in k_fupdate).
+// G2P_GRADW (implicit time integration, mpm_implicit.cuh): the same separable gather with (w, dw/dx) pairs instead of
+// (w, w * (x_i - x_p)) pairs, i.e. the gradient of the field in `grid` with the true B-spline derivative (hpp:59-71); the
+// result I + dt * grad v goes to `aux` (3 float4 per sorted rank) and no particle plane is written.
 template <int FLAGS, int W = 4 /* stencil: 4 = cubic (compile time), 3 = quadratic (compile time: 27 tile reads instead of 64), 0 = either (run time) */>
 __global__ void __launch_bounds__(G2P_T, G2P_MIN_CTAS)
 k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int4* __restrict__ pblock_list, DevCounters* dc,
            const float4* __restrict__ grid, GridDims gd, SimConst sc, float dt, int* __restrict__ key_out = nullptr, int* __restrict__ blk_count = nullptr,
-           MigOut mo = MigOut{ nullptr, nullptr, 0 }) {
+           MigOut mo = MigOut{ nullptr, nullptr, 0 }, float4* __restrict__ aux = nullptr) {
     MPM_DYN_SMEM(g2p_smem_raw, 128);
     G2PSmem& S = *reinterpret_cast<G2PSmem*>(g2p_smem_raw);
     constexpr int SQ = W == 3 ? 1 : (W == 4 ? 0 : 2), WN = W == 3 ? 3 : 4;
@@ -470,16 +473,30 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 {
                     float wx[4], wy[4], wz[4];
                     // one pos/h quotient per axis feeds the cell index and the weights (same bits as cell_of + axis_weights)
-                    const int cx = cell_and_weights_t<SQ>(r.x[0], sc.pd, wx), cy = cell_and_weights_t<SQ>(r.x[1], sc.pd, wy), cz = cell_and_weights_t<SQ>(r.x[2], sc.pd, wz);
+                    int cx, cy, cz;
+                    float dwx[4], dwy[4], dwz[4];
+                    if constexpr ((FLAGS & G2P_GRADW) != 0) {
+                        cx = cell_of_t<SQ>(r.x[0], sc.pd); cy = cell_of_t<SQ>(r.x[1], sc.pd); cz = cell_of_t<SQ>(r.x[2], sc.pd);
+                        axis_weights_and_derivatives(r.x[0], sc.pd, cx, wx, dwx);
+                        axis_weights_and_derivatives(r.x[1], sc.pd, cy, wy, dwy);
+                        axis_weights_and_derivatives(r.x[2], sc.pd, cz, wz, dwz);
+                    } else {
+                        cx = cell_and_weights_t<SQ>(r.x[0], sc.pd, wx); cy = cell_and_weights_t<SQ>(r.x[1], sc.pd, wy); cz = cell_and_weights_t<SQ>(r.x[2], sc.pd, wz);
+                    }
                     const int ox = (cx - 1) - 4 * pbi, oy = (cy - 1) - 4 * pbj, oz = (cz - 1) - 4 * pbk;
                     const float4* __restrict__ lin = tile + (ox * G2P_LIN_PLANE + oy * G2P_LIN_ROW + oz);
                     // pairs: S = (s0, s1) <- (wz, wz dz) * n ;  T = (t0, t1y) <- (wy, wy dy) * s0 ;  V = (v, Bx) <- (wx, wx dx) * t0
                     f32x2_t WX[4], WY[4], WZ[4], V[3] = { 0ull, 0ull, 0ull };
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        WX[a] = pack2(wx[a], wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]));
-                        WY[a] = pack2(wy[a], wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]));
-                        WZ[a] = pack2(wz[a], wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]));
+                        if constexpr ((FLAGS & G2P_GRADW) != 0) {
+                            const float ih = 1.0f / sc.h;
+                            WX[a] = pack2(wx[a], dwx[a] * ih); WY[a] = pack2(wy[a], dwy[a] * ih); WZ[a] = pack2(wz[a], dwz[a] * ih);
+                        } else {
+                            WX[a] = pack2(wx[a], wx[a] * ((float)(cx - 1 + a) * sc.h - r.x[0]));
+                            WY[a] = pack2(wy[a], wy[a] * ((float)(cy - 1 + a) * sc.h - r.x[1]));
+                            WZ[a] = pack2(wz[a], wz[a] * ((float)(cz - 1 + a) * sc.h - r.x[2]));
+                        }
                     }
                     float By[3] = { 0, 0, 0 }, Bz[3] = { 0, 0, 0 };
 #pragma unroll
@@ -525,10 +542,16 @@ k_g2p_tile(Planes cur, Planes nxt, const int* __restrict__ sorted_ids, const int
                 }
                 const Planes& D = (FLAGS & G2P_REORDER) ? nxt : cur;
                 const int q = (FLAGS & G2P_REORDER) ? j : p_cur;
+                if constexpr ((FLAGS & G2P_GRADW) != 0) {      // I + dt grad v (column-major like every 3x3 here), by sorted rank
+                    aux[3 * (size_t)j + 0] = make_float4(fmaf(dt, r.B[0], 1.0f), dt * r.B[1], dt * r.B[2], dt * r.B[3]);
+                    aux[3 * (size_t)j + 1] = make_float4(fmaf(dt, r.B[4], 1.0f), dt * r.B[5], dt * r.B[6], dt * r.B[7]);
+                    aux[3 * (size_t)j + 2] = make_float4(fmaf(dt, r.B[8], 1.0f), 0.0f, 0.0f, 0.0f);
+                } else {
                 if (FLAGS & (G2P_ADVECT | G2P_REORDER)) D.p[0][q] = make_float4(r.x[0], r.x[1], r.x[2], r.m);
                 D.p[1][q] = make_float4(r.B[0], r.B[1], r.B[2], r.B[3]);
                 D.p[2][q] = make_float4(r.B[4], r.B[5], r.B[6], r.B[7]);
                 D.p[3][q] = make_float4(r.B[8], r.v[0], r.v[1], r.v[2]);
+                }
                 if (FLAGS & G2P_HIST) {
                     // next substep's binning, first half, done here where the new position is in registers: block key of slot j
                     // of the re-sorted buffer (what k_bin_count would re-read P0 for); a particle that left the slab goes
@@ -585,6 +608,7 @@ inline cudaError_t tile_kernels_init() {
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, 4>), G2PSmem); MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER, 0>), G2PSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, 4>), G2PSmem);
     MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_ADVECT | G2P_REORDER | G2P_HIST, 3>), G2PSmem);
+    MPM_SET_SMEM((k_g2p_tile<G2P_GATHER | G2P_GRADW, 4>), G2PSmem);
 #undef MPM_SET_SMEM
     return cudaSuccess;
 }

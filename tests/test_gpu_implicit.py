@@ -27,10 +27,14 @@ def _oracle_on(state, dims=(20, 20, 20)):
     return o
 
 
-def test_energy_matches_reference(kat):
+FORMS = [(0, 0), (1, 1)]      # block-tile form (TMA-staged gather, register-accumulated scatter) and the thread-per-particle baseline
+
+
+@pytest.mark.parametrize("variants", FORMS)
+def test_energy_matches_reference(kat, variants):
     # Energy and ElasticPotential of the unmodified reference at six trial fields; the device sums in double, the
     # reference in float (2147-term float sums: ~1e-6 relative)
-    sim = sim_from_state35(kat["energy_state"], (20, 20, 20))
+    sim = sim_from_state35(kat["energy_state"], (20, 20, 20), variants=variants)
     sim.rasterizeParticlesToGrid()
     assert sim.stats().n_active_nodes == int(kat["energy_ref"][0, 2])          # used_cells.size()
     for (amp, dt), ref in zip(kat["energy_cases"], kat["energy_ref"]):
@@ -42,11 +46,12 @@ def test_energy_matches_reference(kat):
     assert abs(e0 - kat["energy_ref"][0, 0]) <= 5e-6 * kat["energy_ref"][0, 0]
 
 
-def test_energy_gradient_matches_oracle(kat):
+@pytest.mark.parametrize("variants", FORMS)
+def test_energy_gradient_matches_oracle(kat, variants):
     st = kat["energy_state"]
     o = _oracle_on(st)
     used = o.used_cells()
-    sim = sim_from_state35(st, (20, 20, 20))
+    sim = sim_from_state35(st, (20, 20, 20), variants=variants)
     sim.rasterizeParticlesToGrid()
     for amp, dt in ((0.5, 1e-3), (0.05, 1e-5), (0.0, 1e-3)):
         pert = (kat["energy_pert_unit"] * np.float32(amp)).astype(np.float32)
@@ -59,7 +64,8 @@ def test_energy_gradient_matches_oracle(kat):
         assert abs(float(g.sum(0) @ np.ones(3)) - float(ref.sum())) <= 1e-4 * scale * np.sqrt(used.size)
 
 
-def test_time_integration_matches_oracle_minimiser(kat):
+@pytest.mark.parametrize("variants", FORMS)
+def test_time_integration_matches_oracle_minimiser(kat, variants):
     # timeIntegration (cpp:211-233) on 24 slow particles: same optimiser, same objective, analytic gradient on both sides.
     # The iterates are sensitive (the second L-BFGS step scales by s.y / y.y of a 1e-4 first step), so the minimiser is held
     # to the energy it reaches (1 %) and to 2 % of the distance moved, not bit-wise.
@@ -72,7 +78,7 @@ def test_time_integration_matches_oracle_minimiser(kat):
     check = _oracle_on(sub)
     e0, e_o = check.energy(v_star, dt), check.energy(v_o, dt)
 
-    sim = sim_from_state35(sub, (20, 20, 20))
+    sim = sim_from_state35(sub, (20, 20, 20), variants=variants)
     sim.rasterizeParticlesToGrid()
     st = sim.timeIntegration(dt)
     v_g = sim.grid()[used][:, 4:7]

@@ -123,3 +123,21 @@ def test_binning_uses_warp_aggregated_atomics(kernels):
     for name in ("k_bin_count", "k_bin_scatter"):
         k = _one(kernels, name)
         assert _count(k, "MATCH.ANY") == 4, "4 elements per thread, each warp-aggregated with match.any"
+
+
+def test_implicit_integration_tile_kernels_contract(kernels):
+    """The objective evaluation of mpm_time_integration in block-tile form (mpm_implicit.cuh): the trial field's gradient comes
+    from the same TMA-staged separable gather as G2P (other pair weights, result to the aux array instead of particle planes),
+    the gradient scatter accumulates in registers on packed pairs and issues one vector red per tile node."""
+    g = _one(kernels, "k_g2p_tileILi34ELi4EE")
+    assert g["regs"] <= 128 and _count(g, "UBLKCP") == 4 and _count(g, "LDS.128") == 64 and _count(g, "FFMA2") >= 200
+    assert _count(g, "STG.E.128") == 3, "I + dt grad v: three float4 per particle, no particle plane written"
+    s = _one(kernels, "k_imp_scatter_tile")
+    assert s["regs"] <= 128 and _count(s, "REDG.E.ADD.F32x4") == 1 and _count(s, "FFMA2") == 48
+    assert not any("CAST" in o for o in s["ops"]) and _count(s, "SHFL.IDX") >= 36
+    for name in ("k_imp_stressILb0E", "k_imp_stressILb1E"):
+        k = _one(kernels, name)
+        assert _count(k, "DFMA") >= 40, "polar factor and energy density in double"
+        assert k["regs"] <= 128
+    b = _one(kernels, "k_imp_particlesILb1E")
+    assert _count(b, "REDG.E.ADD.F32x4") >= 1 and _count(b, "REDG.E.ADD.F32x4") <= 64      # baseline: a vector red per (particle, node)

@@ -11,7 +11,9 @@ import mpm_b200
 grid, n = int(sys.argv[1]), int(sys.argv[2])
 dt = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-4
 sc = mpm_b200.scenes.snowball_drop(grid=grid, n=n)
-p = mpm_b200.capi.default_params()
+import os
+form = int(os.environ.get("MPM_PROBE_BASELINE", "0"))      # 1 = thread-per-particle baseline kernels instead of the block-tile form
+p = mpm_b200.capi.default_params(p2g_variant=form, g2p_variant=form)
 sim = mpm_b200.Sim(grid, grid, grid, sc["n"], p)
 sim.upload(sc["pos"], sc["vel"], sc["mass"])
 sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
@@ -24,7 +26,7 @@ for step in range(3):
     sim.rasterizeParticlesToGrid(); sim.gridVelocitiesUpdate(dt); sim.synchronize()
     t0 = time.perf_counter(); st = sim.timeIntegration(dt, q); sim.synchronize(); t = time.perf_counter() - t0
     sim.gridBasedCollisions(dt, cols, nc); sim.updateDeformationGradient(dt); sim.updateParticleVelocities(); sim.updateParticlePositions(dt)
-    print(f"step {step}: n={sc['n']} grid={grid} dt={dt} iterations={st.iterations} evaluations={st.evaluations} E {st.energy_start:.6g} -> {st.energy_end:.6g} |grad| {st.grad_norm_end:.3g} "
+    print(f"step {step}: form={'baseline' if form else 'tile'} n={sc['n']} grid={grid} dt={dt} iterations={st.iterations} evaluations={st.evaluations} E {st.energy_start:.6g} -> {st.energy_end:.6g} |grad| {st.grad_norm_end:.3g} "
           f"solve {t*1e3:.2f} ms = {t*1e3/max(st.evaluations,1):.3f} ms per evaluation, {sc['n']*st.evaluations/t/1e9:.3f} G particle-evaluations/s", flush=True)
 # evaluation alone (energy + gradient), timed over 10 calls
 sim.rasterizeParticlesToGrid(); sim.synchronize()
