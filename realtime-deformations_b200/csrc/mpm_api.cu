@@ -755,21 +755,26 @@ static int implicit_ready(mpm_sim* s, const MpmImplicitParams* q, int n_vec) {
             CK(cudaMalloc(&s->imp_vec[i], bytes));
             CK(cudaMemsetAsync(s->imp_vec[i], 0, bytes, s->stream));
         }
-    if (!s->imp_acc) CK(cudaMalloc(&s->imp_acc, 4 * sizeof(double)));
+    if (!s->imp_acc) { CK(cudaMalloc(&s->imp_acc, 32 * sizeof(double))); CK(cudaMemsetAsync(s->imp_acc, 0, 32 * sizeof(double), s->stream)); }
     if (!s->imp_aux) CK(cudaMalloc(&s->imp_aux, sizeof(float4) * 3 * (size_t)s->capacity));
     return MPM_OK;
 }
 static ImplicitConst implicit_const(const MpmImplicitParams* q) { return ImplicitConst{ q->mu0, q->lambda0, q->xi, q->hardening }; }
-// E(x) (and its gradient into vector g when g >= 0); one host read-back
-static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x, int g, double* inertia, double* elastic) {
-    CK(cudaMemsetAsync(s->imp_acc, 0, 2 * sizeof(double), s->stream));
+// device scalars of the implicit solve (doubles): [0..1] energies of a line-search evaluation, [2..3] energies of the
+// value + gradient evaluation, [4..6] dot products read back together, [7] |x|_inf bits, [8] the recursion's running dot product;
+// floats at (float*)(imp_acc + 16): alpha[8] and the current coefficient
+enum { ACC_LS = 0, ACC_VG = 2, ACC_DOT = 4, ACC_ABS = 7, ACC_RUN = 8, ACC_FLOATS = 16, ACC_DOUBLES = 32 };
+// E(x) (and its gradient into vector g when g >= 0) accumulated into imp_acc[slot], imp_acc[slot + 1]; no host read-back
+static int implicit_eval_async(mpm_sim* s, float dt, const MpmImplicitParams* q, int x, int g, int slot) {
+    CK(cudaMemsetAsync(s->imp_acc + slot, 0, 2 * sizeof(double), s->stream));
+    double* acc = s->imp_acc + slot;
     float4* G = g >= 0 ? s->imp_vec[g] : nullptr;
-    k_imp_nodes<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[x], G, s->imp_acc);
+    k_imp_nodes<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[x], G, acc);
     CKLAUNCH();
     const int nb = grid_for(s->n_bound, 128);
     if (s->prm.p2g_variant == 1 || s->prm.g2p_variant == 1) {       // baseline: thread per particle, 64 gathers and 64 vector reds each
-        if (G) k_imp_particles<true><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], G, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
-        else k_imp_particles<false><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], nullptr, s->gd, s->sc, dt, implicit_const(q), s->imp_acc);
+        if (G) k_imp_particles<true><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], G, s->gd, s->sc, dt, implicit_const(q), acc);
+        else k_imp_particles<false><<<nb, 128, 0, s->stream>>>(s->planes(s->cur), s->sorted_ids, s->dc, s->imp_vec[x], nullptr, s->gd, s->sc, dt, implicit_const(q), acc);
         CKLAUNCH();
         s->stats.kernel_launches += 2;
     } else {                                                        // block tiles: TMA-staged gather | per-particle stress | register-accumulated scatter
@@ -778,8 +783,8 @@ static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x
         k_g2p_tile<G2P_GATHER | G2P_GRADW, 4><<<s->num_sms * G2P_MIN_CTAS, G2P_T, sizeof(G2PSmem), s->stream>>>(C, C, s->sorted_ids, s->pblock_list, s->dc, s->imp_vec[x], s->gd, s->sc, dt,
                                                                                                          nullptr, nullptr, MigOut{ nullptr, nullptr, 0 }, s->imp_aux);
         CKLAUNCH();
-        if (G) k_imp_stress<true><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), s->imp_acc);
-        else k_imp_stress<false><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), s->imp_acc);
+        if (G) k_imp_stress<true><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), acc);
+        else k_imp_stress<false><<<nb, 128, 0, s->stream>>>(C, s->sorted_ids, s->dc, s->imp_aux, dt, implicit_const(q), acc);
         CKLAUNCH();
         s->stats.kernel_launches += 3;
         if (G) {
@@ -789,25 +794,29 @@ static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x
             s->stats.kernel_launches++;
         }
     }
-    double h[2];
-    CK(cudaMemcpyAsync(h, s->imp_acc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    return MPM_OK;
+}
+static int implicit_read(mpm_sim* s, int first, int count, double* h) {      // the one place the solve waits for the device
+    CK(cudaMemcpyAsync(h, s->imp_acc + first, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return MPM_OK;
+}
+static int implicit_eval(mpm_sim* s, float dt, const MpmImplicitParams* q, int x, int g, double* inertia, double* elastic) {
+    TRY(implicit_eval_async(s, dt, q, x, g, ACC_LS));
+    double h[2];
+    TRY(implicit_read(s, ACC_LS, 2, h));
     *inertia = h[0]; *elastic = h[1];
     return MPM_OK;
 }
-static int implicit_dot(mpm_sim* s, int a, int b, double* out, float* absmax_a = nullptr) {
-    CK(cudaMemsetAsync(s->imp_acc + 2, 0, 2 * sizeof(double), s->stream));
-    k_vec_dot<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[a], s->imp_vec[b], s->imp_acc + 2, absmax_a ? (int*)(s->imp_acc + 3) : nullptr);
+// imp_acc[slot] += a . b (the slot must be zero); optionally |a|_inf into ACC_ABS
+static int implicit_dot_async(mpm_sim* s, int a, int b, int slot, bool absmax_a = false) {
+    k_vec_dot<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[a], s->imp_vec[b], s->imp_acc + slot, absmax_a ? (int*)(s->imp_acc + ACC_ABS) : nullptr);
     CKLAUNCH(); s->stats.kernel_launches++;
-    double h[2];
-    CK(cudaMemcpyAsync(h, s->imp_acc + 2, sizeof h, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    *out = h[0];
-    if (absmax_a) { int bits; memcpy(&bits, &h[1], sizeof bits); memcpy(absmax_a, &bits, sizeof bits); }
     return MPM_OK;
 }
-static int implicit_lin(mpm_sim* s, int z, float a, int x, float b, int y) {      // z = a x + b y (y < 0: z = a x)
-    k_vec_lin<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[z], a, s->imp_vec[x], b, y >= 0 ? s->imp_vec[y] : nullptr);
+static int implicit_lin(mpm_sim* s, int z, float a, int x, float b, int y, bool b_on_device = false) {      // z = a x + b y (y < 0: z = a x)
+    k_vec_lin<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->imp_vec[z], a, s->imp_vec[x], b, y >= 0 ? s->imp_vec[y] : nullptr,
+                                                           b_on_device ? (const float*)(s->imp_acc + ACC_FLOATS) + 8 : nullptr);
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
@@ -863,21 +872,27 @@ int mpm_energy_gradient(mpm_t* s, float dt, const MpmImplicitParams* q, const fl
     return MPM_OK;
 }
 // mcl::optlib::LBFGS<float, Dynamic, 8>::minimize (LBFGS.hpp:52-152) with Backtracking::search (Backtracking.hpp:38-69) and the
-// convergence rule of mathy.hpp:31-35, driven from the host over device vectors; the objective's gradient is analytic.
+// convergence rule of mathy.hpp:31-35, driven from the host over device vectors; the objective's gradient is analytic. The
+// scalars of the two-loop recursion stay on the device (k_lbfgs_coef); the host waits three to four times per iteration: for
+// the direction's dot products, for each line-search value, and for the new point's energy together with s.y and y.y.
 int mpm_time_integration(mpm_t* s, float dt, const MpmImplicitParams* q, MpmImplicitStats* st) {
     NEED(s);
     TRY(implicit_ready(s, q, mpm_sim::IMP_NVEC));
     enum { M = 8 };
     const int X = mpm_sim::IMP_X, G = mpm_sim::IMP_G, Q = mpm_sim::IMP_Q, XOLD = mpm_sim::IMP_XOLD, GOLD = mpm_sim::IMP_GOLD, TMP = mpm_sim::IMP_TMP,
-              LSG = mpm_sim::IMP_LSG, S0 = mpm_sim::IMP_S0, Y0 = mpm_sim::IMP_Y0;
+              S0 = mpm_sim::IMP_S0, Y0 = mpm_sim::IMP_Y0;
     int slot[M];                         // history column i lives in vectors S0 + slot[i], Y0 + slot[i] (rotated instead of copied)
     for (int i = 0; i < M; ++i) slot[i] = i;
-    float alpha[M] = { 0 }, rho[M] = { 0 };
+    float rho[M] = { 0 };                // 1 / (s_i . y_i): the library recomputes it every iteration from the same vectors
+    double* sc = s->imp_acc;
+    float* fc = (float*)(s->imp_acc + ACC_FLOATS);
+    CK(cudaMemsetAsync(sc, 0, ACC_DOUBLES * sizeof(double), s->stream));
     TRY(implicit_load_trial(s, nullptr, 0));
-    double ein, eel, d;
+    double h[4];
     int evals = 0, result = 0;
-    TRY(implicit_eval(s, dt, q, X, G, &ein, &eel)); ++evals;
-    const double e_start = ein + eel;
+    TRY(implicit_eval_async(s, dt, q, X, G, ACC_VG)); ++evals;
+    TRY(implicit_read(s, ACC_VG, 2, h));
+    const double e_start = h[0] + h[1];
     double e_cur = e_start;
     float gamma_k = 1.0f, alpha_init = 1.0f;
     int global_iter = 0, max_iters = q->max_iters;
@@ -887,38 +902,47 @@ int mpm_time_integration(mpm_t* s, float dt, const MpmImplicitParams* q, MpmImpl
         TRY(implicit_lin(s, Q, 1.0f, G, 0.0f, -1));
         global_iter++;
         const int iter = k < M ? k : M;
-        for (int i = iter - 1; i >= 0; --i) {
-            TRY(implicit_dot(s, S0 + slot[i], Y0 + slot[i], &d)); rho[i] = (float)(1.0 / d);
-            TRY(implicit_dot(s, S0 + slot[i], Q, &d)); alpha[i] = rho[i] * (float)d;
-            TRY(implicit_lin(s, Q, 1.0f, Q, -alpha[i], Y0 + slot[i]));
+        for (int i = iter - 1; i >= 0; --i) {          // alpha_i = rho_i (s_i . q); q -= alpha_i y_i
+            TRY(implicit_dot_async(s, S0 + slot[i], Q, ACC_RUN));
+            k_lbfgs_coef<<<1, 1, 0, s->stream>>>(sc + ACC_RUN, fc, i, rho[i], 0);
+            CKLAUNCH();
+            TRY(implicit_lin(s, Q, 1.0f, Q, 0.0f, Y0 + slot[i], true));
         }
         TRY(implicit_lin(s, Q, gamma_k, Q, 0.0f, -1));
-        for (int i = 0; i < iter; ++i) {
-            TRY(implicit_dot(s, Q, Y0 + slot[i], &d));
-            const float beta = rho[i] * (float)d;
-            TRY(implicit_lin(s, Q, 1.0f, Q, alpha[i] - beta, S0 + slot[i]));
+        for (int i = 0; i < iter; ++i) {               // beta = rho_i (y_i . q); q += (alpha_i - beta) s_i
+            TRY(implicit_dot_async(s, Q, Y0 + slot[i], ACC_RUN));
+            k_lbfgs_coef<<<1, 1, 0, s->stream>>>(sc + ACC_RUN, fc, i, rho[i], 1);
+            CKLAUNCH();
+            TRY(implicit_lin(s, Q, 1.0f, Q, 0.0f, S0 + slot[i], true));
         }
-        float ginf = 0.0f;
-        TRY(implicit_dot(s, G, Q, &d, &ginf));
-        if ((float)d <= 0) {                       // not a descent direction: steepest descent, restart the count (LBFGS.hpp:101-106)
+        s->stats.kernel_launches += 2 * iter;
+        // g . q, |g|_inf, q . q, g . g in one read-back
+        CK(cudaMemsetAsync(sc + ACC_DOT, 0, 4 * sizeof(double), s->stream));
+        TRY(implicit_dot_async(s, G, Q, ACC_DOT, true));
+        TRY(implicit_dot_async(s, Q, Q, ACC_DOT + 1));
+        TRY(implicit_dot_async(s, G, G, ACC_DOT + 2));
+        TRY(implicit_read(s, ACC_DOT, 4, h));
+        double gq = h[0], qq = h[1];
+        const double gg = h[2];
+        if ((float)gq <= 0) {                          // not a descent direction: steepest descent, restart the count (LBFGS.hpp:101-106)
+            float ginf; { int bits; memcpy(&bits, &h[3], sizeof bits); memcpy(&ginf, &bits, sizeof bits); }
             TRY(implicit_lin(s, Q, 1.0f, G, 0.0f, -1));
+            gq = gg; qq = gg;
             max_iters -= k;
             k = 0;
             alpha_init = (float)std::min(1.0, 1.0 / (double)ginf);
         }
         float rate;
         {   // Backtracking::search(x, p = -q): (the library re-evaluates value and gradient at x here; they are unchanged, so they are reused)
-            double pn;
-            TRY(implicit_dot(s, Q, Q, &pn));
-            if ((float)std::sqrt(pn) <= FLT_EPSILON) rate = q->ls_decrease;
+            if ((float)std::sqrt(qq) <= FLT_EPSILON) rate = q->ls_decrease;
             else {
                 float a = alpha_init;
                 const float fx0 = (float)e_cur;
-                TRY(implicit_dot(s, G, Q, &d));
-                const float gtp = -(float)d;
+                const float gtp = -(float)gq;
                 int it = 0;
                 for (; it < q->ls_max_iters; ++it) {
                     TRY(implicit_lin(s, TMP, 1.0f, X, -a, Q));
+                    double ein, eel;
                     TRY(implicit_eval(s, dt, q, TMP, -1, &ein, &eel)); ++evals;
                     if ((float)(ein + eel) <= fx0 + a * q->ls_decrease * gtp) break;
                     a *= q->ls_tau;
@@ -928,38 +952,41 @@ int mpm_time_integration(mpm_t* s, float dt, const MpmImplicitParams* q, MpmImpl
         }
         if (rate <= 0) { result = -1; break; }
         TRY(implicit_lin(s, X, 1.0f, X, -rate, Q));
-        {   // Objective::converged(x_last, x, grad): |grad| < tol or |x_last - x| = rate |q| < tol
-            double gn, qn;
-            TRY(implicit_dot(s, G, G, &gn));
-            TRY(implicit_dot(s, Q, Q, &qn));
-            if ((float)std::sqrt(gn) < q->tol_grad || (float)(rate * std::sqrt(qn)) < q->tol_step) { result = global_iter; break; }
-        }
-        TRY(implicit_eval(s, dt, q, X, G, &ein, &eel)); ++evals;
-        e_cur = ein + eel;
+        // Objective::converged(x_last, x, grad): |grad| < tol or |x_last - x| = rate |q| < tol
+        if ((float)std::sqrt(gg) < q->tol_grad || (float)(rate * std::sqrt(qq)) < q->tol_step) { result = global_iter; break; }
+        TRY(implicit_eval_async(s, dt, q, X, G, ACC_VG)); ++evals;
         int col;
         if (k < M) col = slot[k];
         else { col = slot[0]; for (int i = 0; i + 1 < M; ++i) slot[i] = slot[i + 1]; slot[M - 1] = col; }
         TRY(implicit_lin(s, S0 + col, 1.0f, X, -1.0f, XOLD));
         TRY(implicit_lin(s, Y0 + col, 1.0f, G, -1.0f, GOLD));
-        double yy, sy;
-        TRY(implicit_dot(s, Y0 + col, Y0 + col, &yy));
+        CK(cudaMemsetAsync(sc + ACC_DOT, 0, 2 * sizeof(double), s->stream));
+        TRY(implicit_dot_async(s, Y0 + col, Y0 + col, ACC_DOT));
+        TRY(implicit_dot_async(s, S0 + col, Y0 + col, ACC_DOT + 1));
+        TRY(implicit_read(s, ACC_VG, 4, h));           // energies of the new point, y.y, s.y
+        e_cur = h[0] + h[1];
+        const double yy = h[2], sy = h[3];
+        {   // rho of the column as the next iterations' recursion will see it (columns shift when the window is full)
+            const int pos = k < M ? k : M - 1;
+            if (k >= M) for (int i = 0; i + 1 < M; ++i) rho[i] = rho[i + 1];
+            rho[pos] = (float)(1.0 / sy);
+        }
         result = global_iter;
         if (std::fabs((float)yy) <= 0) break;
-        TRY(implicit_dot(s, S0 + col, Y0 + col, &sy));
         gamma_k = (float)sy / (float)yy;
         alpha_init = 1.0f;
     }
-    (void)LSG;
     // the minimiser becomes the grid velocity of the used cells (cpp:227-232)
-    double e_end_in, e_end_el, gn;
-    TRY(implicit_eval(s, dt, q, X, G, &e_end_in, &e_end_el));
-    TRY(implicit_dot(s, G, G, &gn));
+    TRY(implicit_eval_async(s, dt, q, X, G, ACC_VG));
+    CK(cudaMemsetAsync(sc + ACC_DOT, 0, sizeof(double), s->stream));
+    TRY(implicit_dot_async(s, G, G, ACC_DOT));
     k_imp_to_grid<<<persistent_grid(s, 8), 256, 0, s->stream>>>(s->gblock_list, s->dc, s->grid, s->imp_vec[X]);
     CKLAUNCH(); s->stats.kernel_launches++;
+    TRY(implicit_read(s, ACC_VG, 3, h));
     if (st) {
         memset(st, 0, sizeof *st);
         st->iterations = result; st->evaluations = evals;
-        st->energy_start = e_start; st->energy_end = e_end_in + e_end_el; st->grad_norm_end = std::sqrt(gn);
+        st->energy_start = e_start; st->energy_end = h[0] + h[1]; st->grad_norm_end = std::sqrt(h[2]);
     }
     if (result < 0) return fail(MPM_ERR_INVALID, "implicit time integration: line search failed (no step length satisfied the Armijo condition)");
     return MPM_OK;

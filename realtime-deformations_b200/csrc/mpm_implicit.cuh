@@ -369,7 +369,9 @@ k_imp_scatter_tile(Planes P, const int* __restrict__ sorted_ids, const int4* __r
 // ---- vectors over the active nodes (float4 per node; .x unused and kept 0) ----
 // z = a x + b y (any of them may alias)
 __global__ void __launch_bounds__(256)
-k_vec_lin(const int* __restrict__ gblock_list, const DevCounters* __restrict__ dc, float4* z, float a, const float4* x, float b, const float4* y) {
+k_vec_lin(const int* __restrict__ gblock_list, const DevCounters* __restrict__ dc, float4* z, float a, const float4* x, float b, const float4* y,
+          const float* __restrict__ b_dev = nullptr) {
+    if (b_dev) b = *b_dev;                 // coefficient left on the device by k_lbfgs_coef
     const int nb = dc->n_active_gblocks;
     const int sub = threadIdx.x >> 6, t = threadIdx.x & 63, per = blockDim.x >> 6;
     for (int blk = blockIdx.x * per + sub; blk < nb; blk += gridDim.x * per) {
@@ -400,6 +402,15 @@ k_vec_dot(const int* __restrict__ gblock_list, const DevCounters* __restrict__ d
         if (s != 0.0) atomicAdd(out, s);
         if (absmax_bits && m > 0.0f) atomicMax(absmax_bits, __float_as_int(m));
     }
+}
+// scalars of the L-BFGS two-loop recursion (LBFGS.hpp:88-99) without a host round trip: sc[0] holds the dot product k_vec_dot
+// has just accumulated; first loop: alpha_i = rho_i (s_i . q), coefficient -alpha_i; second loop: beta = rho_i (y_i . q),
+// coefficient alpha_i - beta. fc[0..7] = alpha, fc[8] = the coefficient the next k_vec_lin reads. Float like the reference.
+__global__ void k_lbfgs_coef(double* __restrict__ sc, float* __restrict__ fc, int i, float rho, int second) {
+    const float d = (float)sc[0];
+    if (!second) { fc[i] = rho * d; fc[8] = -fc[i]; }
+    else fc[8] = fc[i] - rho * d;
+    sc[0] = 0.0;
 }
 // trial velocities <-> grid: X = (0, v) of the grid; grid velocity = X where the node has mass
 __global__ void __launch_bounds__(256)

