@@ -413,6 +413,83 @@ def expected_id_sums(n):
     return tot, h
 
 
+def implicit_line(args):
+    """SURVEY 8 row f4, opt-in (`--workload implicit`; the default contract line is the substep): one JSON line for the implicit
+    (optimisation-based) time integration, mpm_time_integration = LagrangeEulerView::timeIntegration (material_point_method.cpp:
+    211-233). A step is one solve (the vendored optimiser's up to 50 L-BFGS iterations) on a snowball mid-impact; the metric counts
+    objective evaluations (one pass over all particles each, most with the gradient scatter) per second. Timed on the host around
+    the C-ABI call, which ends with a device read-back (the library runs on its own stream, which torch events do not see)."""
+    import mpm_b200
+    import numpy as np
+    grid, n = args.grid or 256, args.particles or (1 << 22)
+    sc = mpm_b200.scenes.snowball_drop(grid=grid, n=n)
+    sim = mpm_b200.Sim(grid, grid, grid, sc["n"], mpm_b200.capi.default_params())
+    sim.upload(sc["pos"], sc["vel"], sc["mass"])
+    sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
+    cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
+    sim.substep(float(sc["dt"]), cols, nc, 400)                  # explicit substeps until the ball is well into the impact
+    dt, E, nu = 1e-4, 1.4e5, 0.2
+    q = mpm_b200.capi.default_implicit_params(mu0=E / (2 * (1 + nu)), lambda0=E * nu / ((1 + nu) * (1 - 2 * nu)), hardening=1)
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    launches0 = None
+    evals, iters, times, e_drop = 0, 0, [], []
+    sampler = ClockSampler(0)
+    for k in range(warm + steps):
+        sim.rasterizeParticlesToGrid(); sim.gridVelocitiesUpdate(dt); sim.synchronize()
+        if k == warm:
+            launches0 = sim.stats().kernel_launches
+            sampler.start()
+        t0 = time.perf_counter()
+        st = sim.timeIntegration(dt, q)
+        t1 = time.perf_counter() - t0
+        if k >= warm:
+            times.append(t1); evals += st.evaluations; iters += st.iterations; e_drop.append(st.energy_end / st.energy_start)
+        sim.gridBasedCollisions(dt, cols, nc); sim.updateDeformationGradient(dt); sim.updateParticleVelocities(); sim.updateParticlePositions(dt)
+    clocks = sampler.stop()
+    stt = sim.stats()
+    launches = stt.kernel_launches - launches0
+    total = sum(times)
+    n_p, n_active = sc["n"], stt.n_active_nodes
+    value = n_p * evals / total
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of one evaluation: read x, V0, FE, FP (88 B/particle); per active node read the trial velocity and (m, v*),
+    # write the gradient (48 B)
+    bytes_eval = 88.0 * n_p + 48.0 * n_active
+    achieved = bytes_eval * evals / total / 1e9
+    line = {"metric": "particle_evaluations_per_s", "value": value, "unit": "particle-evaluations/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+            "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f32 (polar factor and sums in f64)",
+            "data": "synthetic",
+            "config": {"workload": f"implicit_snowball_{grid}: one implicit time-integration solve per step on a {n_p}-particle snowball mid-impact, {grid}^3 grid, dt = 1e-4 "
+                                   "(SURVEY 8 row f4; not a BASELINE.json config: the reference never runs this path)",
+                       "particles": n_p, "grid": [grid] * 3, "dt": dt, "iterations_per_solve": iters / steps, "evaluations_per_solve": evals / steps,
+                       "energy_end_over_start": float(np.mean(e_drop)), "timing": "host clock around mpm_time_integration (ends with a device read-back)",
+                       "l2_policy": "particle state (88 B/particle read per evaluation) >> 126 MB L2 at 4 Mi particles"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_evaluation": bytes_eval, "n_active_nodes": n_active,
+                         "note": "whole solve, optimiser algebra and host waits included; the evaluation kernels alone are in profiles/ (ncu)"},
+            "e2e": {"value": value, "unit": "particle-evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(32 * (3 * iters + evals) / steps),
+                    "note": "same call: the grid the solve starts from is produced on the device by the preceding stages; the read-backs are the optimiser's scalars"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if not args.no_cpu_baseline:
+        # the oracle's evaluation of the same objective (value + analytic gradient) on one host core, bounded sample
+        sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_py as op
+        small = mpm_b200.scenes.small_ball(grid=48, radius_cells=12.0)
+        o = op.Oracle(48, 48, 48, small["n"], op.default_params(h=float(small["h"])))
+        o.set_state(op.initial_state(small["pos"], small["vel"], small["mass"])); o.rasterize(); o.volumes(); o.rasterize()
+        used = o.used_cells(); v = o.grid()[used][:, 4:7]
+        qo = op.default_implicit_params(mu0=q.mu0, lambda0=q.lambda0, hardening=1)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 10.0:
+            o.energy(v, dt, qo); o.energy_gradient(v, dt, qo); reps += 1
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": small["n"] * reps / tc, "unit": "particle-evaluations/s", "cores": 1, "kind": "port",
+                                "sample": f"{reps} value + gradient evaluations of the oracle (oracle_energy, oracle_energy_gradient) on a {small['n']}-particle ball, 48^3 grid",
+                                "cpu": cpu_model()}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,10 +501,13 @@ def main():
     ap.add_argument("--particles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi-check", action="store_true")
+    ap.add_argument("--workload", default="substep", choices=["substep", "implicit"])   # implicit: the f4 line (opt-in; one GPU)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload == "implicit":
+        return implicit_line(args)
 
     import torch
     import mpm_b200

@@ -13,5 +13,10 @@ sim.rasterizeParticlesToGrid(); sim.computeParticleVolumesAndDensities()
 cols, nc = mpm_b200.capi.make_colliders(sc["w2l"], sc["half"], sc["cvel"])
 sim.staged_substep(1e-5, cols, nc)
 sim.substep(1e-5, cols, nc, 3)
+# implicit time integration (mpm_implicit.cuh): gradient gather, stress, tile scatter, the optimiser's vector kernels
+sim.rasterizeParticlesToGrid(); sim.gridVelocitiesUpdate(1e-4)
+st = sim.timeIntegration(1e-4, mpm_b200.capi.default_implicit_params(mu0=5.8e4, lambda0=3.9e4, hardening=1, max_iters=4))
+print("implicit", st.iterations, st.evaluations, st.energy_start, st.energy_end)
+sim.gridBasedCollisions(1e-4, cols, nc); sim.updateDeformationGradient(1e-4); sim.updateParticleVelocities(); sim.updateParticlePositions(1e-4)
 s = sim.download_state35()
 print("ok", np.isfinite(s).all(), sim.stats().n_active_nodes)
