@@ -143,6 +143,42 @@ def test_semi_implicit_substeps_on_a_ball_vs_oracle():
     assert np.abs(a[:, 1:4] - b[:, 1:4]).max() < 5e-2 * 200.0                   # velocities: 5 % of the impact speed
 
 
+def _crowded_scene(n, seed=3):
+    """n particles inside ONE 4^3-cell particle block (several chunks of the tile scatter, ragged 32-slices in the gather) plus a
+    few isolated ones, on a 32^3 grid (the scene of test_gpu_parity.test_ragged_block_occupancy_vs_oracle)."""
+    rng = np.random.default_rng(seed)
+    lo = np.float32(13 * 0.05 + 1e-4)
+    pos = (lo + rng.uniform(0, 4 * 0.05 - 2e-4, size=(n, 3))).astype(np.float32)
+    pos = np.concatenate([pos, np.array([[0.31, 0.52, 0.77], [1.2, 0.4, 0.9], [0.8, 1.3, 0.2]], np.float32)])
+    vel = rng.normal(scale=5.0, size=pos.shape).astype(np.float32)
+    sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=2.0, with_ground=False)
+    sc.update(pos=pos, vel=vel, mass=np.full(len(pos), 6e-5, np.float32), n=len(pos))
+    return sc
+
+
+@pytest.mark.parametrize("n", [1, 31, 700, 3000])
+def test_objective_on_ragged_block_occupancy_vs_oracle(n):
+    # energy and gradient with everything in one particle block (1 .. 6 chunks of 512 in the tile scatter) against the oracle,
+    # at trial velocities away from the grid's own
+    sc = _crowded_scene(n)
+    o, _, _ = oracle_from_scene(sc)
+    sim, _, _ = sim_from_scene(sc)
+    o.rasterize(); sim.rasterizeParticlesToGrid()
+    used = o.used_cells()
+    rng = np.random.default_rng(11)
+    pert = np.zeros((32 ** 3, 3), np.float32)
+    pert[used] = rng.standard_normal((used.size, 3)).astype(np.float32)
+    dt = 2e-4
+    qo, qg = op.default_implicit_params(mu0=50.0, lambda0=30.0), mpm_b200.capi.default_implicit_params(mu0=50.0, lambda0=30.0)
+    v = o.grid()[used][:, 4:7] + pert[used]
+    e_o = o.energy(v, dt, qo)
+    e_g, _ = sim.energy(dt, pert, relative=True, params=qg)
+    assert abs(e_g - e_o) <= 2e-4 * abs(e_o), (n, e_g, e_o)          # |F - R| ~ 1e-2 here: the reference's float F - R carries ~1e-5 relative noise, the device's is double
+    g_o = o.energy_gradient(v, dt, qo)
+    g_g = sim.energy_gradient(dt, pert, relative=True, params=qg)[used]
+    assert np.abs(g_g - g_o).max() <= 5e-4 * np.abs(g_o).max(), (n, np.abs(g_g - g_o).max(), np.abs(g_o).max())      # same float-vs-double F - R noise; a lost chunk would be O(1)
+
+
 def test_implicit_error_paths():
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
     sim, cols, nc = sim_from_scene(sc)
