@@ -18,10 +18,35 @@ namespace mpm {
 
 struct ImplicitConst { float mu0, lambda0, xi; int hardening; };
 
-// rotation factor of the polar decomposition by Newton's iteration R <- (R + R^-T)/2 in double; false if singular
+// rotation factor of the polar decomposition by Newton's iteration R <- (R + R^-T)/2; false if singular. The iteration is
+// self-correcting and quadratically convergent, so it runs in float down to ~1e-6 and only the last steps in double (from an
+// error e one double step leaves e^2 / 2): the fp64 work of the stress kernel drops from ~7 steps to 2.
 MPM_DI bool polar_rotation_d(const double (&F)[9], double (&R)[9]) {
+    {
+        float X[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = F[i];
+        for (int i = 0; i < 9; ++i) X[i] = (float)F[i];
+        for (int it = 0; it < 40; ++it) {
+            const float a = X[0], b = X[3], c = X[6], d = X[1], e = X[4], f = X[7], g = X[2], hh = X[5], k = X[8];
+            const float c00 = e * k - f * hh, c01 = -(d * k - f * g), c02 = d * hh - e * g;
+            const float c10 = -(b * k - c * hh), c11 = a * k - c * g, c12 = -(a * hh - b * g);
+            const float c20 = b * f - c * e, c21 = -(a * f - c * d), c22 = a * e - b * d;
+            const float det = a * c00 + b * c01 + c * c02;
+            if (det == 0.0f || !isfinite(det)) return false;
+            const float id = 1.0f / det;
+            const float cof[9] = { c00, c10, c20, c01, c11, c21, c02, c12, c22 };
+            float diff = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const float v = 0.5f * (X[i] + cof[i] * id);
+                diff = fmaxf(diff, fabsf(v - X[i]));
+                X[i] = v;
+            }
+            if (diff < 2e-6f) break;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = (double)X[i];
+    }
     for (int it = 0; it < 60; ++it) {
         // column-major: element (r, c) = R[c*3 + r]
         const double a = R[0], b = R[3], c = R[6], d = R[1], e = R[4], f = R[7], g = R[2], hh = R[5], k = R[8];
@@ -39,7 +64,7 @@ MPM_DI bool polar_rotation_d(const double (&F)[9], double (&R)[9]) {
             diff = fmax(diff, fabs(v - R[i]));
             R[i] = v;
         }
-        if (diff < 1e-15) break;
+        if (diff < 1e-13) break;      // the step that produced it squared the error once more
     }
     return true;
 }
