@@ -81,7 +81,7 @@ struct mpm_sim {
     bool hist_valid = false;   // key[] and blk_count[] already describe the current buffer (written by the fused substep's gather)
     bool hist_fuse = true;     // MPM_B200_FUSE_HIST=0 restores the separate k_bin_count pass (A/B)
     // implicit time integration (mpm_implicit.cuh): node vectors in grid layout, allocated on first use
-    enum { IMP_X = 0, IMP_G, IMP_Q, IMP_XOLD, IMP_GOLD, IMP_TMP, IMP_LSG, IMP_S0, IMP_Y0 = IMP_S0 + 8, IMP_NVEC = IMP_Y0 + 8 };
+    enum { IMP_X = 0, IMP_G, IMP_Q, IMP_XOLD, IMP_GOLD, IMP_TMP, IMP_S0, IMP_Y0 = IMP_S0 + 8, IMP_NVEC = IMP_Y0 + 8 };
     float4* imp_vec[IMP_NVEC] = {};
     float4* imp_aux = nullptr;        // 3 float4 per sorted rank: I + dt grad v, then the stress matrix Gm (block-tile form)
     double* imp_acc = nullptr;        // [0] inertia energy, [1] elastic energy, [2] dot product, [3] (int) |x|_inf bits
