@@ -62,7 +62,7 @@ def test_implicit_time_integration_on_emulated_library(emu_lib):
     env = dict(os.environ, MPM_B200_LIB=emu_lib, MPM_B200_ALLOW_EMULATION="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_implicit.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500, env=env, cwd=ROOT)
-    assert r.returncode == 0 and "12 passed" in r.stdout, r.stdout[-4000:]
+    assert r.returncode == 0 and "13 passed" in r.stdout, r.stdout[-4000:]
 
 
 def test_default_scene_trajectory_on_emulated_library(emu_lib):

@@ -179,6 +179,35 @@ def test_objective_on_ragged_block_occupancy_vs_oracle(n):
     assert np.abs(g_g - g_o).max() <= 5e-4 * np.abs(g_o).max(), (n, np.abs(g_g - g_o).max(), np.abs(g_o).max())      # same float-vs-double F - R noise; a lost chunk would be O(1)
 
 
+def test_time_integration_full_size_ball_vs_oracle():
+    # 58 k particles (a 12-cell-radius ball at 200 m/s, 48^3 grid, ~190 particle blocks), three optimiser iterations with the
+    # explicit path's material at 10 x the explicit time step, against the oracle running the same three iterations. The
+    # reference's stopping rule (|grad| < 1e-2, mathy.hpp:31) would stop at once in these units, so it is tightened on both sides.
+    sc = mpm_b200.scenes.small_ball(grid=48, radius_cells=12.0)
+    dt = 1e-4
+    E, nu = 1.4e5, 0.2
+    kw = dict(mu0=E / (2 * (1 + nu)), lambda0=E * nu / ((1 + nu) * (1 - 2 * nu)), hardening=1, max_iters=3, tol_grad=1e-9, tol_step=1e-9)
+    o, _, _ = oracle_from_scene(sc)
+    sim, _, _ = sim_from_scene(sc)
+    st = sim.download_state35()
+    st[:, 12] *= 0.99                                      # a uniform 1 % compression along y in FE: something to solve
+    o.set_state(st); sim.upload_state35(st)
+    o.rasterize(); o.grid_velocities(dt)
+    sim.rasterizeParticlesToGrid(); sim.gridVelocitiesUpdate(dt)
+    used = o.used_cells()
+    vo_star, vg_star = o.grid()[used][:, 4:7].copy(), sim.grid()[used][:, 4:7].copy()
+    it_o, _ = o.time_integration(dt, op.default_implicit_params(**kw))
+    stt = sim.timeIntegration(dt, mpm_b200.capi.default_implicit_params(**kw))
+    d_o, d_g = o.grid()[used][:, 4:7] - vo_star, sim.grid()[used][:, 4:7] - vg_star          # what each solve did to its own v*
+    assert stt.iterations == 3 and it_o == 3
+    moved = np.abs(d_o).max()
+    assert moved > 1e-3 and stt.energy_end < stt.energy_start
+    # velocities near 200 m/s carry 1.5e-5 per ulp, so differences of two of them resolve the move to ~3e-5
+    assert np.abs(d_g - d_o).max() <= 5e-2 * moved + 6e-5, (np.abs(d_g - d_o).max(), moved)
+    m = o.grid()[used][:, :1]
+    assert np.abs((m * d_o).sum(0) - (m * d_g).sum(0)).max() <= 5e-2 * np.abs(m * d_o).sum() + 1e-9
+
+
 def test_implicit_error_paths():
     sc = mpm_b200.scenes.small_ball(grid=32, radius_cells=3.0)
     sim, cols, nc = sim_from_scene(sc)
