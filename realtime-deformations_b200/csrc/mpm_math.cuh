@@ -24,7 +24,7 @@ MPM_DI float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 MPM_DI float rcp_rn(float a) { return __frcp_rn(a); }      // correctly rounded 1/a == IEEE 1.0f / a
 
 // packed fp32 pairs (sm_100a FFMA2 / FADD2: two IEEE-rounded operations per lane per instruction; ptxas folds a duplicated
-// {x, x} operand into a scalar broadcast). Used only by the experimental kernel variants below.
+// {x, x} operand into a scalar broadcast). Used by the accumulation loop of P2G, the gather and the implicit scatter.
 #ifndef MPM_HOST_EMU
 typedef unsigned long long f32x2_t;
 MPM_DI f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }

