@@ -58,6 +58,15 @@ struct P2GSmem {
     int4 work;
 };
 typedef P2GInG P2GIn;
+// L2 prefetch: no register, no shared memory, one instruction per 128-byte line. P2G uses it twice per block (measured at 64 Mi,
+// profiles/r2_experiments.md: P2G + F-update 5.09 -> 4.84 ms): the five planes the in-kernel F-update will read are requested
+// while the derive phase has the particle's id in hand, and the six planes of the NEXT block's first chunk right after this
+// block's fold, when its ids (requested before the fold) have arrived.
+#ifndef MPM_HOST_EMU
+MPM_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+MPM_DI void prefetch_l2(const void*) {}
+#endif
 // first-chunk ids of a work item (chunks interleave the block's segment: slot q of chunk 0 is rank start + q * n_chunks)
 MPM_DI void p2g_first_chunk_ids(const int4& wk, const int* __restrict__ sorted_ids, int t, int (&gid)[P2G_PPT], int& nch0) {
     const int nck0 = (wk.z + P2G_CH - 1) / P2G_CH;
@@ -166,6 +175,9 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     S.u.c.hA1[q] = make_float4(A[4] * sc.h, A[5] * sc.h, A[6] * sc.h, A[7] * sc.h);
                     S.u.c.hA8[q] = A[8] * sc.h;
                     gids[u] = gid;
+                    if (FUPD) {      // the F-update of this block reads these five planes a few microseconds from now: pull them into L2
+                        prefetch_l2(&P.p[6][gid]); prefetch_l2(&P.p[7][gid]); prefetch_l2(&P.p[8][gid]); prefetch_l2(&P.p[9][gid]); prefetch_l2(&P.p[10][gid]);
+                    }
                     const int lc = (((cx - 1) - 4 * pbi) * 4 + ((cy - 1) - 4 * pbj)) * 4 + ((cz - 1) - 4 * pbk);
                     cell_rank[u] = lc | (atomicAdd(&S.cell_cnt[lc], 1) << 8);
                 }
@@ -326,6 +338,17 @@ k_p2g_tile(Planes P, int* __restrict__ sorted_ids, const int4* __restrict__ pblo
                     else if (layer == 0) { if (peer.dn) atomicAdd(&peer.dn[idx], sum); }
                 }
             }
+        }
+        {   // the next block's first chunk: its ids have arrived during the fold; pull its six P2G planes into L2 ahead of the derive loads
+            const int nck_n = (S.work.z + P2G_CH - 1) / P2G_CH;
+            const int nch_n = S.work.x < 0 ? 0 : (nck_n <= 1 ? S.work.z : (S.work.z + nck_n - 1) / nck_n);
+#pragma unroll
+            for (int u = 0; u < P2G_PPT; ++u)
+                if (t + u * P2G_T < nch_n) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (k == 0 || (k <= 3 ? MODE != P2G_FORCE : MODE != P2G_MOMENTUM)) prefetch_l2(&P.p[k][gid_pref[u]]);      // the planes p2g_load_planes<MODE> reads
+                }
         }
         MPM_PROF(6);              // x/y fold + reds
         if (FUPD) {
